@@ -1,0 +1,353 @@
+"""Pins the CPU oracle against the golden vectors and known-answer tests that the
+reference's own test module holds for the hot path (RUMDEED src/mod_tests.F90;
+SURVEY.md section 8c).  Tolerances: the reference asserts 2 % (tolerance_rel,
+mod_global.F90:419-420); where the expected value is a closed form we assert far
+tighter, and say so.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.oracle import (REMOVE_BOT, REMOVE_TOP, SPECIES_ELEC, SPECIES_ION)
+
+NM = 1.0e-9
+
+
+def rel_vec(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+# --------------------------------------------------------------------------------------
+# constants: mod_global.F90:26-75,333
+def test_constants(orc):
+    k = orc.k
+    assert k.epsilon_0 == 1.0 / (1.25663706212e-6 * 299792458.0 ** 2)
+    assert abs(k.epsilon_0 - 8.8541878128e-12) / 8.8541878128e-12 < 1e-9
+    assert k.div_fac_c == 1.0 / (4.0 * k.pi * k.epsilon_0 * 1.0)
+    assert k.m_N2p == 28.0134 * 1.66053906660e-27 - 9.1093837015e-31
+    assert k.length_scale == 1e-9 and k.time_scale == 1e-12
+
+
+# --------------------------------------------------------------------------------------
+# Test_Acceleration_Without_Image_Charge, mod_tests.F90:405-518
+def _three_particles():
+    R = np.array([[3.0, -10.0, 2.0], [-9.0, 26.0, 80.0], [6.0, -24.0, 56.53]]) * NM
+    return R
+
+
+def test_acceleration_without_image_charge(orc):
+    k = orc.k
+    d, V = 100.0 * NM, 2.0
+    p = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 0)
+    R = _three_particles()
+    q = np.array([-k.q_0, -k.q_0, +k.q_0])
+    m = np.array([k.m_0, k.m_0, k.m_N2p])
+    sp = np.array([SPECIES_ELEC, SPECIES_ELEC, SPECIES_ION], dtype=np.int32)
+    pre = k.q_0 ** 2 / (4.0 * k.pi * k.epsilon_0)
+    E = np.array([0.0, 0.0, -V / d])
+
+    def coul(a, b):
+        return (a - b) / np.linalg.norm(a - b) ** 3
+
+    a1 = (+pre * coul(R[0], R[1]) - pre * coul(R[0], R[2])) / k.m_0 - k.q_0 / k.m_0 * E
+    a2 = (+pre * coul(R[1], R[0]) - pre * coul(R[1], R[2])) / k.m_0 - k.q_0 / k.m_0 * E
+    a3 = (-pre * coul(R[2], R[0]) - pre * coul(R[2], R[1])) / k.m_N2p + k.q_0 / k.m_N2p * E
+    want = np.stack([a1, a2, a3])
+
+    for fn in (orc.accel_planar, orc.accel_generic):
+        got = fn(p, R, q, m, sp)
+        # closed form: the only difference is the 1e-18 m softening (~1e-10 relative)
+        assert rel_vec(got, want) < 1e-8
+    got = orc.accel_gather(p, R, q, m)
+    assert rel_vec(got, want) < 1e-8
+
+    # vacuum field, and the "Python script" golden field vector (:500-515).  The probe point
+    # is built from single-precision literals in the Fortran source.
+    probe = np.array([np.float32(-4.55), np.float32(-2.34), np.float32(96.44)], dtype=np.float64) * NM
+    assert np.allclose(orc.calc_field_at(p, np.zeros((0, 3)), np.zeros(0), probe), E)
+    E_python = np.array([-314559.29097098, 1423979.07058996, -20246038.87978313])
+    got = orc.calc_field_at(p, R, q, probe, sp)
+    assert np.all(np.abs(got - E_python) / np.abs(E_python) < 0.02)  # the reference's tolerance
+    # with double-precision probe literals the vector is reproduced to 8 digits
+    got_d = orc.calc_field_at(p, R, q, np.array([-4.55, -2.34, 96.44]) * NM, sp)
+    assert np.all(np.abs(got_d - E_python) / np.abs(E_python) < 1e-7)
+
+
+# Test_Acceleration_With_Image_Charge, mod_tests.F90:703-900 (n = 0 partners only)
+def test_field_with_image_charge_golden(orc):
+    k = orc.k
+    d, V = 100.0 * NM, 2.0
+    p = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, True, 0)
+    R = _three_particles()
+    q = np.array([-k.q_0, -k.q_0, +k.q_0])
+    probe = np.array([-4.55, -2.34, 96.44]) * NM
+    # The routine holding this vector is DISABLED in Run_Tests (mod_tests.F90:256): it was
+    # generated for an older two-partner model (partners at -z and at 2d - z, see R_1a/R_1b
+    # at :740-765), not for today's series.  It still pins the Coulomb summation: adding
+    # those two partners of every particle as explicit opposite charges reproduces it.
+    E_python = np.array([-102526.05673208, 421022.84663293, -20456407.74487634])
+    Ra = R.copy(); Ra[:, 2] = 2.0 * d - Ra[:, 2]
+    Rb = R.copy(); Rb[:, 2] = -Rb[:, 2]
+    p_noic = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 0)
+    got = orc.calc_field_at(p_noic, np.concatenate([R, Ra, Rb]), np.concatenate([q, -q, -q]), probe)
+    assert np.all(np.abs(got - E_python) / np.abs(E_python) < 1e-7)
+    # today's N_ic_max = 0 series keeps only the partner at -z
+    got0 = orc.calc_field_at(p, R, q, probe)
+    want0 = orc.calc_field_at(p_noic, np.concatenate([R, Rb]), np.concatenate([q, -q]), probe)
+    assert rel_vec(got0, want0) < 1e-13
+    assert rel_vec(got0, [-320542.29311032, 1419794.5752913, -20114901.11090498]) < 1e-9  # numpy cross-check
+
+
+# Test_Image_Charge, mod_tests.F90:523-691
+def test_image_charge_series(orc):
+    k = orc.k
+    d, V = 100.0 * NM, 2.0
+    R1 = np.array([3.0, -10.0, 2.0]) * NM
+    R2 = np.array([6.0, -24.0, 98.53]) * NM
+    q1, q2 = -k.q_0, +k.q_0
+    kC = 1.0 / (4.0 * k.pi * k.epsilon_0)
+
+    p0 = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, True, 0)
+    # self interaction: -q^2/(4 pi eps0 (2z)^2) in z only
+    for R, q in ((R1, q1), (R2, q2)):
+        f = q * q * k.div_fac_c * orc.force_image_charges_v2(p0, R, R)
+        want = np.array([0.0, 0.0, -q * q * kC / (2.0 * R[2]) ** 2])
+        assert abs(f[0]) < 1e-30 and abs(f[1]) < 1e-30
+        assert abs(f[2] - want[2]) / abs(want[2]) < 1e-8
+
+    def coul(qa, qb, a, b):
+        return qa * qb * kC * (a - b) / np.linalg.norm(a - b) ** 3
+
+    mirror = lambda r: np.array([r[0], r[1], -r[2]])
+    f12 = q1 * q2 * k.div_fac_c * orc.force_image_charges_v2(p0, R1, R2)
+    assert rel_vec(f12, coul(q1, -q2, R1, mirror(R2))) < 1e-8
+    f21 = q2 * q1 * k.div_fac_c * orc.force_image_charges_v2(p0, R2, R1)
+    assert rel_vec(f21, coul(q2, -q1, R2, mirror(R1))) < 1e-8
+
+    # N_ic_max = 1: five partners
+    p1 = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, True, 1)
+
+    def partners(r, q):
+        z = r[2]
+        return [(-q, -z), (-q, -2 * d - z), (+q, -2 * d + z), (-q, 2 * d - z), (+q, 2 * d + z)]
+
+    for (Ra, qa, Rb, qb) in ((R1, q1, R1, q1), (R2, q2, R2, q2), (R1, q1, R2, q2)):
+        want = sum(coul(qa, qi, Ra, np.array([Rb[0], Rb[1], zi])) for qi, zi in partners(Rb, qb))
+        got = qa * qb * k.div_fac_c * orc.force_image_charges_v2(p1, Ra, Rb)
+        assert rel_vec(got, want) < 1e-8
+
+    # image_charge = .false. returns zero (mod_verlet.F90:1933-1935)
+    pn = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 3)
+    assert np.all(orc.force_image_charges_v2(pn, R1, R2) == 0.0)
+
+
+# Test_Planar_Specialized_Acceleration, mod_tests.F90:1610-1676
+def _forty(orc, box):
+    k = orc.k
+    i = np.arange(1, 41, dtype=np.float64)
+    pos = np.stack([(0.5 + 0.45 * np.sin(1.7 * i)) * box[0],
+                    (0.5 + 0.45 * np.cos(2.3 * i)) * box[1],
+                    (0.5 + 0.45 * np.sin(3.1 * i + 0.5)) * box[2]], axis=1)
+    ion = (np.arange(1, 41) % 5) == 0
+    q = np.where(ion, k.q_0, -k.q_0)
+    m = np.where(ion, k.m_N2p, k.m_0)
+    sp = np.where(ion, SPECIES_ION, SPECIES_ELEC).astype(np.int32)
+    return pos, q, m, sp
+
+
+@pytest.mark.parametrize("use_ic,nic", [(True, 2), (False, 0), (True, 1), (True, 0)])
+def test_specialised_equals_generic_equals_gather(orc, use_ic, nic):
+    d, V = 1000.0 * NM, 2.0e3
+    box = (100 * NM, 100 * NM, d)
+    p = orc.params_planar(V, d, box, 0.25e-15, use_ic, nic)
+    pos, q, m, sp = _forty(orc, box)
+    a_gen = orc.accel_generic(p, pos, q, m, sp)
+    a_pl = orc.accel_planar(p, pos, q, m, sp)
+    a_ga = orc.accel_gather(p, pos, q, m)
+    a_ld = orc.accel_gather_ld(p, pos, q, m)
+    scale = np.maximum(np.linalg.norm(a_gen, axis=1), 1.0)
+    # the reference's own bar is 1e-10 (:1664-1675); all three forms agree far tighter
+    assert np.max(np.linalg.norm(a_pl - a_gen, axis=1) / scale) < 1e-12
+    assert np.max(np.linalg.norm(a_ga - a_gen, axis=1) / scale) < 1e-12
+    assert np.max(np.linalg.norm(a_ld - a_gen, axis=1) / scale) < 1e-12
+
+
+# Test_Planar_Batch_Field, mod_tests.F90:1554-1603
+def test_planar_batch_field(orc):
+    k = orc.k
+    d, V = 100.0 * NM, 2.0
+    p = orc.params_planar(V, d, (100 * NM, 100 * NM, d), 0.25e-15, True, 1)
+    pts = np.array([[0, 0, 10.0], [12, -4, 21], [-20, 30, 80], [40, 40, 95]]) * NM
+    vac = orc.calc_field_at_batch(p, np.zeros((0, 3)), np.zeros(0), pts)
+    assert np.all(vac[:, :2] == 0.0) and np.all(vac[:, 2] == -V / d)
+    R = np.array([[10, -5, 20.0], [-15, 8, 60], [5, 25, 40]]) * NM
+    q = np.array([-k.q_0, -k.q_0, k.q_0])
+    batch = orc.calc_field_at_batch(p, R, q, pts)
+    for i in range(4):
+        single = orc.calc_field_at(p, R, q, pts[i])
+        assert np.array_equal(batch[i], single)
+        truth = orc.calc_field_at(p, R, q, pts[i], ld=True)
+        assert rel_vec(single, truth) < 1e-13
+
+
+# Test_Tip_Acceleration, mod_tests.F90:988-1084
+def test_tip_acceleration_and_field(orc):
+    k = orc.k
+    p = orc.params_tip(2.0e3, 900 * NM, 100 * NM, 100 * NM, (100 * NM, 100 * NM, 1000 * NM), 0.25e-3 * 1e-12, True)
+    # derived parameters (mod_emission_tip.f90:105-125)
+    assert abs(p.d - 1000 * NM) < 1e-20
+    assert abs(p.max_xi - (100.0 / 900.0 + 1.0)) < 1e-15
+    a = math.sqrt(900.0 ** 2 * 100.0 ** 2 / (100.0 ** 2 + 2 * 900.0 * 100.0) + 900.0 ** 2) * NM
+    assert abs(p.a_foci - a) / a < 1e-14
+    assert abs(p.eta_1 + 900 * NM / a) < 1e-14
+    # the apex sits at z = h_tip: eta(0,0,h) == eta_1, xi == 1
+    assert abs(orc.lib.orc_eta_coor(p, 0.0, 0.0, p.h_tip) - p.eta_1) < 1e-12
+    assert abs(orc.lib.orc_xi_coor(p, 0.0, 0.0, p.h_tip) - 1.0) < 1e-12
+
+    R = np.array([[2.0, 1.0, 103.0], [-2.0, 2.5, 106.0], [1.5, -3.0, 110.0]]) * NM
+    q = np.array([-k.q_0, -k.q_0, k.q_0])
+    m = np.array([k.m_0, k.m_0, k.m_N2p])
+    sp = np.array([SPECIES_ELEC, SPECIES_ELEC, SPECIES_ION], dtype=np.int32)
+    # expected: the generic pair loop written out in the test (:1032-1055)
+    want = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(i + 1, 3):
+            pre = q[i] * q[j] * k.div_fac_c
+            diff = R[i] - R[j]
+            r = math.sqrt(np.sum(diff ** 2)) + NM ** 2
+            fc = pre / (r * r * r) * diff
+            fic = pre * orc.image_charge_effect(p, R[i], R[j])
+            ficN = np.array([-fic[0], -fic[1], fic[2]])
+            want[j] += (ficN - fc) / m[j]
+            want[i] += (fc + fic) / m[i]
+        want[i] += q[i] * orc.field_E(p, R[i]) / m[i]
+    a_gen = orc.accel_generic(p, R, q, m, sp)
+    a_ga = orc.accel_gather(p, R, q, m)
+    a_ld = orc.accel_gather_ld(p, R, q, m)
+    for got in (a_gen, a_ga, a_ld):
+        assert rel_vec(got, want) < 1e-12
+    pts = np.array([[0, 0, 102.0], [30, -10, 130], [-50, 40, 300], [15, 8, 500]]) * NM
+    batch = orc.calc_field_at_batch(p, R, q, pts)
+    for i in range(4):
+        assert np.array_equal(batch[i], orc.calc_field_at(p, R, q, pts[i]))
+        assert rel_vec(batch[i], orc.calc_field_at(p, R, q, pts[i], ld=True)) < 1e-12
+    # F8-iii: the tip image term carries q_0/(4 pi eps0) inside Sphere_IC_field
+    ic = orc.sphere_ic_field(p, R[0], R[1])
+    diff = R[0] - R[1]
+    direct = k.q_0 * k.div_fac_c * diff / np.linalg.norm(diff) ** 3
+    assert np.linalg.norm(ic) < 10 * np.linalg.norm(direct)  # same magnitude class as a field in V/m
+
+
+# Test_Beeman_Kinematics, mod_tests.F90:1403-1452
+def test_beeman_kinematics(orc):
+    k = orc.k
+    d, V, dt, vx0 = 1000 * NM, 2.0e3, 0.25e-15, 1.0e3
+    p = orc.params_planar(V, d, (100 * NM, 100 * NM, d), dt, False, 0)
+    s = orc.store(16)
+    s.add(p, [0.0, 0.0, 500 * NM], [vx0, 0.0, 0.0], SPECIES_ELEC, 1, 1)
+    for _ in range(3):
+        s.step(p)
+    a_z = k.q_0 * V / (k.m_0 * d)
+    assert abs((s.pos[0, 2] - 500 * NM) - 4.5 * a_z * dt ** 2) / (4.5 * a_z * dt ** 2) < 1e-9
+    assert abs(s.vel[0, 2] - 3.0 * a_z * dt) / (3.0 * a_z * dt) < 1e-12
+    assert abs(s.pos[0, 0] - 3.0 * vx0 * dt) / (3.0 * vx0 * dt) < 1e-12
+    assert s.vel[0, 0] == vx0 and s.pos[0, 1] == 0.0
+    ramo = k.q_0 * 3.0 * a_z * dt / d
+    assert abs(s.s.ramo_current[SPECIES_ELEC] - ramo) / ramo < 1e-12
+
+
+# Test_Transit_Time, mod_tests.F90:912-977
+def test_transit_time(orc):
+    k = orc.k
+    d, V, dt = 1000 * NM, 2.0e3, 0.25e-15
+    p = orc.params_planar(V, d, (100 * NM, 100 * NM, d), dt, True, 0)
+    z0 = 1.0 * NM
+    steps_exp = math.ceil(math.sqrt(2.0 * d * (d - z0) * k.m_0 / (k.q_0 * V)) / dt)
+    s = orc.store(4)
+    s.add(p, [0.0, 0.0, z0], [0.0, 0.0, 0.0], SPECIES_ELEC, 1, 1)
+    steps_res = None
+    for i in range(1, steps_exp + 1001):
+        s.step(p)
+        s.remove(i)
+        if s.n == 0:
+            steps_res = i
+            break
+    assert steps_res is not None
+    assert abs(steps_exp - steps_res) < 0.01 * steps_exp
+    ev = s.events()
+    assert len(ev) == 1 and ev[0]["kind"] == 1 and ev[0]["id"] == 0
+
+
+# Test_Particle_Bookkeeping / Test_Particle_Removal / Test_Remove_All_Particles, mod_tests.F90:1091-1328
+def test_particle_removal_bit_exact(orc):
+    k = orc.k
+    d = 100 * NM
+    p = orc.params_planar(2.0, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 0)
+    s = orc.store(16)
+    spc = [SPECIES_ELEC] * 7
+    spc[2] = SPECIES_ION
+    spc[5] = SPECIES_ION
+    R = np.array([[1.0 * i, -2.0 * i, 10.0 * i] for i in range(1, 8)]) * NM
+    Vel = np.array([[100.0 * i, -50.0 * i, 25.0 * i] for i in range(1, 8)])
+    for i in range(7):
+        assert s.add(p, R[i], Vel[i], spc[i], 1, 1) == i
+    Rprev = R + 0.5 * NM
+    s.prev_pos[:] = Rprev
+    assert (s.s.nrPart, s.s.nrElec, s.s.nrIon) == (7, 5, 2)
+    s.mark(1, REMOVE_TOP)
+    s.mark(1, REMOVE_TOP)  # double mark is a no-op
+    s.mark(3, REMOVE_BOT)
+    s.mark(5, REMOVE_TOP)
+    assert s.s.nrPart_remove == 3 and s.s.nrElec_remove == 2 and s.s.nrIon_remove == 1
+    assert s.s.nrElec_remove_top == 1 and s.s.nrElec_remove_bot == 1 and s.s.nrIon_remove_top == 1
+    assert s.charge[1] == 0.0
+    s.remove(11)
+    assert (s.s.nrPart, s.s.nrElec, s.s.nrIon) == (4, 3, 1)
+    keep = [0, 2, 4, 6]
+    assert np.array_equal(s.pos, R[keep])
+    assert np.array_equal(s.prev_pos, Rprev[keep])
+    assert np.array_equal(s.vel, Vel[keep])
+    assert list(s.species) == [SPECIES_ELEC, SPECIES_ION, SPECIES_ELEC, SPECIES_ELEC]
+    assert list(s.ids) == [0, 2, 4, 6]
+    assert list(s.emitter) == [1] * 4 and list(s.section) == [1] * 4
+    assert s.charge[0] == -k.q_0 and s.charge[1] == +k.q_0
+    assert s.mass[0] == k.m_0 and s.mass[1] == k.m_N2p
+    assert s.life_time(10, SPECIES_ELEC) == 2 and s.life_time(10, SPECIES_ION) == 1
+    assert np.all(s.mask(7) == 1)
+    assert s.s.nrPart_remove == 0 and s.s.nrElec_remove == 0 and s.s.nrIon_remove == 0
+
+
+def test_remove_all_particles(orc):
+    d = 100 * NM
+    p = orc.params_planar(2.0, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 0)
+    s = orc.store(8)
+    s.add(p, np.array([3, -10, 2.0]) * NM, [0, 0, 0], SPECIES_ELEC, 1, 1)
+    s.add(p, np.array([-9, 26, 80.0]) * NM, [0, 0, 0], SPECIES_ELEC, 1, 1)
+    s.mark(0, REMOVE_TOP)
+    s.mark(1, REMOVE_TOP)
+    s.remove(21)
+    assert s.s.nrPart == 0 and s.s.nrElec == 0 and s.s.nrPart_remove == 0
+    assert np.all(s.mask(2) == 1)
+    s.add(p, np.array([5, 6, 50.0]) * NM, [0, 0, 0], SPECIES_ELEC, 2, 1)
+    assert s.s.nrPart == 1 and s.s.nrElec == 1
+    assert np.array_equal(s.pos[0], np.array([5, 6, 50.0]) * NM)
+    assert s.ids[0] == 2  # ids keep counting
+
+
+# Test_FN_Functions, mod_tests.F90:1688-1735 (high-precision Python references, phi = 4.7 eV)
+def test_fn_functions(orc):
+    d = 1000 * NM
+    p_off = orc.params_planar(2.0e3, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 0)
+    p_on = orc.params_planar(2.0e3, d, (100 * NM, 100 * NM, d), 0.25e-15, True, 0)
+    w = 4.7
+    assert orc.fn_v_y(p_off, -2.0e9, w) == 1.0 and orc.fn_t_y(p_off, -2.0e9, w) == 1.0
+    assert abs(orc.fn_v_y(p_on, -2.0e9, w) - 0.8253581935658024) < 1e-12
+    assert abs(orc.fn_t_y(p_on, -2.0e9, w) - 1.0292422630703880) < 1e-12
+    assert abs(orc.fn_escape_prob_log(p_on, -2.0e9, w) - (-28.723444978828507)) < 1e-9
+    assert abs(orc.fn_v_y(p_on, -4.0e9, w) - 0.6808388366998485) < 1e-12
+    assert abs(orc.fn_t_y(p_on, -4.0e9, w) - 1.0484437096180323) < 1e-12
+    assert abs(orc.fn_escape_prob_log(p_on, -4.0e9, w) - (-11.846999895226958)) < 1e-9
+    assert orc.fn_v_y(p_on, -1.0e12, w) == 0.0
+    # tip variant (mod_emission_tip.f90:1734) is exp of the same exponent
+    assert abs(math.log(orc.tip_escape_prob(p_on, -2.0e9, w)) - (-28.723444978828507)) < 1e-9
