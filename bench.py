@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- RUMDEED hot-path benchmark (contract: see the task statement / DESIGN.md section 6).
+
+Workload (BASELINE.json configs[4]): synthetic planar-diode electron cloud,
+d = 1000 nm, V = 2000 V, image_charge on, N_ic_max = 1, dt = 1e-4 ps, N electrons i.i.d.
+uniform in x,y in [-500,500] nm, z in [1,999] nm, NumPy PCG64(20261017).  Default N = 1e6.
+
+A step is one MD step of the hot path: Beeman position update + boundary/plane checks,
+all-pairs Coulomb + image-charge acceleration, velocity update + Ramo current, with the
+particle state resident in HBM.  value = N(N-1) ordered pair interactions per step / time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n PARTICLES] [--impl ours|reference]
+
+N > 1: one process per GPU (torchrun); i-particles are partitioned, every rank integrates
+a replica of the O(N) state and the acceleration slices are all-gathered over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NM = 1.0e-9
+FLOPS_PER_PAIR = {(-1): 21, 0: 39, 1: 99, 2: 159}  # 21 + ic*(18 + 60*N_ic_max)
+METRIC = "pair_interactions_per_s"
+UNIT = "pair-interactions/s"
+
+
+def make_cloud(n, seed=20261017):
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    pos = np.empty((n, 3))
+    pos[:, 0] = rng.uniform(-500.0, 500.0, n) * NM
+    pos[:, 1] = rng.uniform(-500.0, 500.0, n) * NM
+    pos[:, 2] = rng.uniform(1.0, 999.0, n) * NM
+    return pos
+
+
+def flops_per_pair(image_charge, nic):
+    return 21 + (18 + 60 * nic if image_charge else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, pw, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def load_fast_oracle():
+    """The CPU restatement built with the reference's flags (-O3 -march=native -fopenmp).
+    Rebuilt natively on this box when gcc is here, else the prebuilt x86-64-v3 file."""
+    from oracle import oracle as om
+    path = None
+    try:
+        td = tempfile.mkdtemp(prefix="rb2_oracle_")
+        om.build(force=True, march="native", out_dir=td)
+        path = os.path.join(td, "liboracle_fast.so")
+        if not os.path.exists(path):
+            path = None
+    except Exception:
+        path = None
+    if path is None:
+        om.build()
+        return om.Oracle(fast=True), "prebuilt -O3 -march=x86-64-v3 -fopenmp"
+    return om.Oracle(path=path), "-O3 -march=native -fopenmp (built on this host)"
+
+
+def cpu_sample(orc, p, pos, q, m, target_s=12.0):
+    """Time a bounded, strided sample of the rows of the reference's CPU pair loop
+    (Calculate_Acceleration_Particles_Planar, i<j scatter).  Returns ordered pair-interactions/s."""
+    n = pos.shape[0]
+    # calibration: a handful of rows
+    stride = max(1, n // 16)
+    t0 = time.perf_counter()
+    _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
+    t = time.perf_counter() - t0
+    rate = pairs / max(t, 1e-9)
+    want_pairs = rate * target_s
+    total_pairs = n * (n - 1) / 2
+    if want_pairs >= total_pairs:
+        stride = 1
+    else:
+        stride = max(1, int(round(total_pairs / want_pairs)))
+    t0 = time.perf_counter()
+    _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
+    t = time.perf_counter() - t0
+    frac = pairs / total_pairs
+    sample = (f"rows i = 0, {stride}, 2*{stride}, ... of the i<j pair loop at N = {n} "
+              f"({pairs} unordered pair evaluations = {100 * frac:.3g}% of a full evaluation, {t:.1f} s)")
+    return 2.0 * pairs / t, t, sample
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the Fortran binary cannot
+    be built in this image) on the host cores, same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, how = load_fast_oracle()
+    n = args.n
+    pos = make_cloud(n)
+    q = np.full(n, -orc.k.q_0)
+    m = np.full(n, orc.k.m_0)
+    p = orc.params_planar(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic)
+    cores = orc.max_threads()
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    vals, times, sample = [], [], ""
+    for it in range(args.warmup + args.steps):
+        v, t, sample = cpu_sample(orc, p, pos, q, m, target_s=per_step)
+        if it >= args.warmup:
+            vals.append(v); times.append(t)
+    value = float(np.mean(vals))
+    ms_full = n * (n - 1) / value * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + f"; {how}; ms_per_step is the full-step extrapolation"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic planar-diode electron cloud N={args.n}, d=1000nm, V=2000V, image_charge, "
+                        f"N_ic_max={args.nic}, dt=1e-4ps (BASELINE.json configs[4])",
+            "n_particles": args.n, "N_ic_max": args.nic, "image_charge": True,
+            "flops_per_pair": flops_per_pair(True, args.nic),
+            "parallelism": f"i-partition x{world}" + (" + NCCL all-gather of accelerations" if world > 1 else ""),
+            "l2": "256 MiB L2-flush write between timed steps (outside the per-step CUDA-event pairs)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rumdeed_b200 as rb
+    from rumdeed_b200.api import M_0, Q_0
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.n
+    pos = make_cloud(n)
+    q = np.full(n, -Q_0)
+    m = np.full(n, M_0)
+    chunk = (n + world - 1) // world
+    cap = chunk * world
+    cfg = rb.planar_config(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic,
+                           capacity=cap, device=local)
+    hp = rb.HotPath(cfg)
+    hp.upload(pos, q, m)
+    i0, i1 = rank * chunk, min(n, (rank + 1) * chunk)
+    hp.set_partition(i0, i1)
+    ext = torch.cuda.ExternalStream(hp.stream(), device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    class _Alias:  # expose the library's acceleration buffer to torch without a copy
+        def __init__(self, ptr, nelem):
+            self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    def acc_tensor():
+        ptr, nbytes = hp.device_buffer("acc")
+        return torch.as_tensor(_Alias(ptr, nbytes // 8), device=f"cuda:{local}")
+
+    def one_step(step):
+        if world == 1:
+            return hp.Update_Position(step)
+        hp.Update_Particle_Position(step)
+        hp.Calculate_Acceleration_Particles()
+        t = acc_tensor()
+        with torch.cuda.stream(ext):
+            dist.all_gather_into_tensor(t[: 3 * cap], t[3 * i0: 3 * (i0 + chunk)])
+        return hp.Update_Particle_Velocity()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP64 peak of this GPU (independent DFMA chains), burst and sustained
+    peak_burst, _ = hp.fp64_peak(30.0)
+    peak_sust, _ = hp.fp64_peak(1500.0)
+
+    for w in range(args.warmup):
+        one_step(w + 1)
+    barrier()
+    hp.launch_count(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    accel_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush on torch's stream ...
+        torch.cuda.current_stream().synchronize()
+        ev[k][0].record(ext)               # ... timed region on the library's launching stream
+        one_step(args.warmup + k + 1)
+        ev[k][1].record(ext)
+        accel_ms.append(hp.last_accel_info()["ms"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop() if rank == 0 else None
+    launches = hp.launch_count()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    info = hp.last_accel_info()
+
+    # end to end through the C ABI with HOST buffers: pinned pos/q/m in, accelerations out
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_pos, h_q, h_m = pin(pos), pin(q), pin(m)
+    h_acc = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+    hp.accel_host_ptr(n, h_pos.data_ptr(), h_q.data_ptr(), h_m.data_ptr(), h_acc.data_ptr())  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hp.accel_host_ptr(n, h_pos.data_ptr(), h_q.data_ptr(), h_m.data_ptr(), h_acc.data_ptr())
+    barrier()
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+
+    stats = torch.tensor([dev_ms, t_wall * 1e3, t_e2e * 1e3, float(np.mean(accel_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    dev_ms, wall_ms, e2e_ms, acc_ms = [float(x) for x in stats.tolist()]
+
+    if rank == 0:
+        pairs = float(n) * float(n - 1)
+        ms_per_step = dev_ms / args.steps
+        value = pairs / (ms_per_step * 1e-3)
+        fpp = flops_per_pair(True, args.nic)
+        n_local = i1 - i0
+        achieved = fpp * float(n_local) * float(n - 1) / (acc_ms * 1e-3) / 1e12
+        peak = peak_sust if acc_ms > 200.0 else peak_burst
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"k_pair_n{n}", None)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "md_steps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic,
+                         "kernel": "k_pair<planar, N_ic_max=%d> (+ finalize)" % args.nic,
+                         "kernel_ms": acc_ms, "flops_per_pair": fpp, "fp64_instr_per_pair": 74 if args.nic == 1 else None,
+                         "peak_source": "measured in this run: rb2_fp64_peak independent-DFMA-chain kernel "
+                                        f"(burst {peak_burst:.2f}, sustained 1.5 s {peak_sust:.2f} TFLOP/s; nominal 37.2); "
+                                        "MEASURED_PEAKS.json holds no FP64 figure",
+                         "launch": info},
+            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 24 * n,
+                    "ms_per_step": e2e_ms, "what": "rb2_accel_host: pinned host pos/q/m -> device, pair kernel, accelerations -> host"},
+            "gpu_launches": launches, "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                orc, how = load_fast_oracle()
+                p = orc.params_planar(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic)
+                v, t, sample = cpu_sample(orc, p, pos, q, m, target_s=12.0)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": orc.max_threads(), "kind": "port",
+                                        "sample": sample + "; " + how}
+            except Exception as e:  # the baseline is a reported extra, never the product path
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    hp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=1_000_000, help="particles (headline 1e6; 1e4 / 1e5 for the sweep)")
+    ap.add_argument("--nic", type=int, default=1, help="N_ic_max")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

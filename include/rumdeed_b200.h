@@ -1,0 +1,195 @@
+/*
+ * rumdeed_b200.h -- C ABI of the B200-native replacement for RUMDEED's
+ * per-timestep hot path (all-pairs Coulomb + image charges, Beeman step,
+ * batched surface-field evaluation).
+ *
+ * This is the drop-in boundary: every entry point replaces one call site of the
+ * reference Fortran host (cited per function, paths relative to the RUMDEED
+ * tree) and is what `fortran/mod_b200_bridge.F90` binds with ISO_C_BINDING
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - Every function returns RB2_OK (0) or a negative RB2_ERR_* code and never
+ *     throws or calls exit(); rb2_last_error_string() describes the last error.
+ *   - (3,n) arrays use the Fortran host layout: column-major, i.e. xyzxyz...
+ *   - Particle indices are 0-based on this side (Fortran slot - 1).
+ *   - The caller owns all host arrays; the library owns all device memory and
+ *     the authoritative particle state between rb2_upload_particles and
+ *     rb2_download_particles.
+ *   - Calls are made from ONE host thread (the Fortran master thread, outside
+ *     any OpenMP region); the library is not re-entrant.
+ *   - There is NO CPU fallback: every compute entry point fails with
+ *     RB2_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RUMDEED_B200_H
+#define RUMDEED_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB2_OK              0
+#define RB2_ERR_NOT_INIT   -1
+#define RB2_ERR_CUDA       -2
+#define RB2_ERR_ARG        -3
+#define RB2_ERR_CAPACITY   -4
+#define RB2_ERR_GEOMETRY   -5
+
+/* src/mod_verlet.F90:62-65 (ACC_GEOM_*) */
+#define RB2_GEOM_PLANAR 1
+#define RB2_GEOM_TIP    2
+/* src/mod_global.F90:101-118 */
+#define RB2_SPECIES_ELEC 1
+#define RB2_SPECIES_ION  2
+#define RB2_SPECIES_ATOM 3
+#define RB2_REMOVE_TOP   1
+#define RB2_REMOVE_BOT   2
+#define RB2_REMOVE_RECOM 3
+#define RB2_REMOVE_ION   4
+
+#define RB2_PLANES_MAX    10    /* planes_N_max, src/mod_global.F90:337 */
+#define RB2_MAX_LIFE_TIME 1000  /* src/mod_global.F90:280 */
+
+/* Scalars the hot path reads from mod_global / mod_hyperboloid_tip after Init_*.
+ * (E_z, d, N_ic_max, image_charge: src/mod_verlet.F90:1238-1248.) */
+typedef struct rb2_config {
+    int    geometry;        /* RB2_GEOM_* == ACC_Geometry(), src/mod_verlet.F90:1168 */
+    int    image_charge;    /* logical image_charge */
+    int    N_ic_max;
+    int    planes_N;
+    double V_s;
+    double d;               /* gap spacing */
+    double E_z;             /* -V_d/d, src/mod_verlet.F90:2052 */
+    double box_dim[3];
+    double time_step;
+    double planes_z[RB2_PLANES_MAX];
+    /* hyperboloid tip, src/mod_hyperboloid_tip.f90:11-21 */
+    double a_foci, eta_1, shift_z, pre_fac_E_tip, pre_fac_E_tip_unit_voltage, h_tip, r_tip, max_xi;
+    int    capacity;        /* MAX_PARTICLES, src/mod_global.F90:98 */
+    int    device;          /* CUDA ordinal, -1 = keep the current device */
+} rb2_config;
+
+/* Counters of mod_global (nrPart, nrElec, ... and the nr*_remove* family). */
+typedef struct rb2_counts {
+    int nrPart, nrElec, nrIon, nrAtom, nrID, nrPart_dropped;
+    int nrPart_remove, nrElec_remove, nrIon_remove, nrAtom_remove;
+    int nrPart_remove_top, nrPart_remove_bot;
+    int nrElec_remove_top, nrElec_remove_bot;
+    int nrIon_remove_top, nrIon_remove_bot;
+} rb2_counts;
+
+/* One absorbed-electron or plane-crossing record, in the order the serial
+ * reference writes them (ascending particle index; absorb before planes).
+ * kind 1: density_absorb_top.bin, 2: density_absorb_bot.bin (src/mod_pair.F90:243-257),
+ * kind 3: planes-<plane+1>.bin (src/mod_verlet.F90:360). x,y in length_scale units. */
+typedef struct rb2_event {
+    int    kind, plane, index;
+    double x, y, vx, vy, vz;
+    int    emit, sec, id;
+} rb2_event;
+
+/* What Update_Position(step) leaves in mod_global for the writers. */
+typedef struct rb2_step_result {
+    double ramo_current[4];      /* per species, index = species id (src/mod_verlet.F90:488) */
+    double avg_part_vel[3];      /* already divided by the counts (src/mod_verlet.F90:428-447) */
+    double avg_elec_vel[3];
+    double avg_ion_vel[3];
+    int    n_events;             /* records waiting in rb2_get_events */
+    rb2_counts counts;
+    float  accel_ms;             /* device time of the pair kernel(s), CUDA events */
+    float  step_ms;              /* device time of the whole step */
+} rb2_step_result;
+
+/* ---- life cycle: end of Init_* / Clean_up (src/main.F90:146, :266) ------------ */
+int rb2_init(const rb2_config *cfg);
+int rb2_finalize(void);
+/* Re-read the scalar parameters (Set_Voltage changes E_z; tests switch image_charge). */
+int rb2_update_config(const rb2_config *cfg);
+const char *rb2_last_error_string(void);
+/* 1 when a usable sm_100 device is present (no state needed). */
+int rb2_device_available(void);
+
+/* ---- particle state: replaces the `!$acc update device` sites
+ *      (src/mod_verlet.F90:92-94, :1256-1263).  NULL int arrays default to
+ *      species=elec, step=0, emitter=1, section=1, life=-1, id=slot. ---------- */
+int rb2_upload_particles(int n, const double *pos, const double *prev_pos, const double *vel,
+                         const double *acc, const double *acc_prev, const double *acc_prev2,
+                         const double *charge, const double *mass,
+                         const int *species, const int *step, const int *emitter,
+                         const int *section, const int *life, const int *id, int nrID);
+/* Any output pointer may be NULL.  Arrays must hold nrPart entries. */
+int rb2_download_particles(double *pos, double *prev_pos, double *vel,
+                           double *acc, double *acc_prev, double *acc_prev2,
+                           double *charge, double *mass,
+                           int *species, int *step, int *emitter, int *section, int *life, int *id,
+                           int *mask);
+int rb2_get_counts(rb2_counts *out);
+
+/* Add_Particle (src/mod_pair.F90:29-159) for k particles, appended in call order;
+ * ids are assigned from the library's nrID.  Particles beyond capacity are counted
+ * in nrPart_dropped, like the reference. */
+int rb2_add_particles(int k, const double *pos, const double *vel, const int *species,
+                      int step, const int *emit, const int *sec, const int *life);
+/* Mark_Particles_Remove (src/mod_pair.F90:169-339) for k host-chosen particles. */
+int rb2_mark_remove(int k, const int *index, const int *reason);
+/* Remove_Particles (src/mod_pair.F90:352-562): stable compaction, counters reset. */
+int rb2_remove_marked(int step, rb2_counts *out);
+/* life_time(1:MAX_LIFE_TIME, 1:nrSpecies) as [lt][species] with lt, species 0-based +1
+ * padding, i.e. out[(lt)*4 + species]; (RB2_MAX_LIFE_TIME+1)*4 entries. */
+int rb2_get_life_time(long long *out);
+
+/* ---- dynamics ------------------------------------------------------------------ */
+/* Update_Position(step) (src/main.F90:190 -> src/mod_verlet.F90:123-162):
+ * Beeman position update + boundary + planes, acceleration, velocity + Ramo. */
+int rb2_step(int step, rb2_step_result *out);
+/* The three phases separately (the reference's unit tests call them one by one). */
+int rb2_update_position(int step);                 /* src/mod_verlet.F90:197-232 */
+int rb2_accel_only(void);                          /* Calculate_Acceleration_Particles, :597 (overwrites) */
+int rb2_update_velocity(rb2_step_result *out);     /* src/mod_verlet.F90:449-509 */
+int rb2_get_events(int max_events, rb2_event *out, int *n_out);
+/* Stateless form of the reference's OpenACC call (upload positions, run the
+ * kernel, copy the accelerations out: src/mod_verlet.F90:1254-1340) with HOST
+ * buffers; used for the end-to-end measurement. */
+int rb2_accel_host(int n, const double *pos, const double *charge, const double *mass, double *acc_out);
+
+/* ---- field evaluation ------------------------------------------------------------- */
+/* Calc_Field_at_Batch (src/mod_verlet.F90:1635); M = 1 is Calc_Field_at (:1466).
+ * Synchronous on return. */
+int rb2_field_batch(int M, const double *pos_in, double *field_out);
+/* Same, plus the contribution of n_new particles that are not in the store yet
+ * (exact by linearity): keeps the serial semantics of the default samplers
+ * (src/mod_field_emission_v2.F90:1122, src/mod_photo_emission.f90:603-686). */
+int rb2_field_batch_delta(int M, const double *pos_in, int n_new, const double *new_pos,
+                          const double *new_charge, double *field_out);
+/* Particles_To_Device / Release_Device_Particles (src/mod_verlet.F90:85-111): the
+ * state is already device resident, kept for source compatibility. */
+int rb2_field_window_open(void);
+int rb2_field_window_close(void);
+
+/* ---- multi-GPU plumbing --------------------------------------------------
+ * The i-range [i_begin, i_end) of the acceleration evaluation this process owns
+ * (global, 0-based).  Default: everything. */
+int rb2_set_partition(int i_begin, int i_end);
+/* Device pointer + byte size of the (3,capacity) acceleration buffer so that the
+ * host plumbing (torch.distributed / NCCL) can all-gather the slices in place. */
+int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes);
+/* Block the host until the library's stream is idle. */
+int rb2_synchronize(void);
+/* CUDA stream handle (cudaStream_t) the library launches on. */
+int rb2_stream(void **stream_out);
+
+/* ---- measurement helpers --------------------------------------------------------------- */
+/* Independent-DFMA-chain micro-benchmark: measured FP64 peak of this GPU in TFLOP/s
+ * (FMA = 2 flops) over about `ms_target` milliseconds. */
+int rb2_fp64_peak(double ms_target, double *tflops_out, float *ms_out);
+/* Launch statistics since init / last reset: kernels launched by this library. */
+int rb2_launch_count(long long *out, int reset);
+/* Device time of the last acceleration evaluation (ms), and its launch geometry. */
+int rb2_last_accel_info(float *ms, int *grid_x, int *grid_y, int *block, int *j_split);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUMDEED_B200_H */

@@ -22,7 +22,7 @@ SPECIES_ELEC, SPECIES_ION, SPECIES_ATOM = 1, 2, 3
 REMOVE_TOP, REMOVE_BOT = 1, 2
 GEOM_PLANAR, GEOM_TIP = 1, 2
 PLANES_MAX = 10
-MAX_LIFE_TIME = 10000
+MAX_LIFE_TIME = 1000
 
 
 class Constants(C.Structure):

@@ -26,7 +26,7 @@ enum { ORC_REMOVE_UNKNOWN = 0, ORC_REMOVE_TOP = 1, ORC_REMOVE_BOT = 2, ORC_REMOV
 enum { ORC_GEOM_OTHER = 0, ORC_GEOM_PLANAR = 1, ORC_GEOM_TIP = 2 };  /* src/mod_verlet.F90:62-65 */
 
 #define ORC_PLANES_MAX 10        /* src/mod_global.F90:337 */
-#define ORC_MAX_LIFE_TIME 10000  /* histogram length used by the oracle store */
+#define ORC_MAX_LIFE_TIME 1000   /* src/mod_global.F90:280 */
 
 /* Physical constants, src/mod_global.F90:26-75,333 */
 typedef struct {

@@ -1,0 +1,744 @@
+// rb2_api.cu -- the C ABI declared in include/rumdeed_b200.h: state management, host<->device
+// plumbing and the per-step orchestration.  All compute is in rb2_pair.cu / rb2_integrate.cu;
+// there is no CPU fallback anywhere in this library.
+#include <stdarg.h>
+#include <string.h>
+
+#include "rb2_internal.cuh"
+
+Rb2Ctx g_rb2;
+char   g_rb2_err[512] = "no error";
+
+int rb2_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_rb2_err, sizeof(g_rb2_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+StepParams rb2_make_step_params(const rb2_config &c)
+{
+    StepParams P{};
+    P.geometry = c.geometry;
+    P.dt = c.time_step;
+    P.dt2 = c.time_step * c.time_step;  // time_step2 = time_step**2
+    P.box_z = c.box_dim[2];
+    P.d = c.d;
+    P.planes_N = c.planes_N < 0 ? 0 : (c.planes_N > RB2_PLANES_MAX ? RB2_PLANES_MAX : c.planes_N);
+    for (int k = 0; k < RB2_PLANES_MAX; ++k) P.planes_z[k] = c.planes_z[k];
+    P.pl.two_d = 2.0 * c.d;
+    P.pl.E_z = c.E_z;
+    P.pl.nic = c.N_ic_max;
+    P.pl.do_ic = c.image_charge;
+    P.tip.a_foci = c.a_foci;
+    P.tip.shift_z = c.shift_z;
+    P.tip.pre_fac_E_tip = c.pre_fac_E_tip;
+    P.tip.eta_1 = c.eta_1;
+    P.tip.z_0 = c.h_tip - c.r_tip;
+    P.tip.r_tip = c.r_tip;
+    P.tip.unit_scale_num = c.pre_fac_E_tip_unit_voltage;
+    P.tip.unit_scale_den = c.pre_fac_E_tip;
+    P.tip.do_ic = c.image_charge;
+    return P;
+}
+
+namespace {
+
+template <class T>
+int dev_alloc(T **p, size_t count)
+{
+    RB2_CUDA(cudaMalloc((void **)p, (count > 0 ? count : 1) * sizeof(T)));
+    return RB2_OK;
+}
+
+int alloc_arrays(DevArrays &A, size_t cap)
+{
+    int rc;
+    if ((rc = dev_alloc(&A.pq, cap))) return rc;
+    if ((rc = dev_alloc(&A.prev_pos, 3 * cap))) return rc;
+    if ((rc = dev_alloc(&A.vel, 3 * cap))) return rc;
+    if ((rc = dev_alloc(&A.acc, 3 * cap))) return rc;
+    if ((rc = dev_alloc(&A.acc_prev, 3 * cap))) return rc;
+    if ((rc = dev_alloc(&A.acc_prev2, 3 * cap))) return rc;
+    if ((rc = dev_alloc(&A.mass, cap))) return rc;
+    if ((rc = dev_alloc(&A.species, cap))) return rc;
+    if ((rc = dev_alloc(&A.step, cap))) return rc;
+    if ((rc = dev_alloc(&A.emitter, cap))) return rc;
+    if ((rc = dev_alloc(&A.section, cap))) return rc;
+    if ((rc = dev_alloc(&A.life, cap))) return rc;
+    if ((rc = dev_alloc(&A.id, cap))) return rc;
+    return RB2_OK;
+}
+void free_arrays(DevArrays &A)
+{
+    cudaFree(A.pq); cudaFree(A.prev_pos); cudaFree(A.vel); cudaFree(A.acc); cudaFree(A.acc_prev); cudaFree(A.acc_prev2);
+    cudaFree(A.mass); cudaFree(A.species); cudaFree(A.step); cudaFree(A.emitter); cudaFree(A.section); cudaFree(A.life);
+    cudaFree(A.id);
+    A = DevArrays{};
+}
+
+int check_config(const rb2_config *cfg)
+{
+    if (!cfg) return rb2_fail(RB2_ERR_ARG, "config is NULL");
+    if (cfg->geometry != RB2_GEOM_PLANAR && cfg->geometry != RB2_GEOM_TIP)
+        return rb2_fail(RB2_ERR_GEOMETRY, "geometry %d: only planar (1) and hyperboloid tip (2) run on the device", cfg->geometry);
+    if (cfg->planes_N < 0 || cfg->planes_N > RB2_PLANES_MAX) return rb2_fail(RB2_ERR_ARG, "planes_N out of range");
+    if (cfg->N_ic_max < 0) return rb2_fail(RB2_ERR_ARG, "N_ic_max < 0");
+    return RB2_OK;
+}
+
+void fill_counts_from_device(Rb2Ctx &c)
+{
+    const DevCounters &h = *c.h_counters;
+    c.counts.nrPart_remove = h.mark_part;
+    c.counts.nrElec_remove = h.mark_elec;
+    c.counts.nrIon_remove = h.mark_ion;
+    c.counts.nrAtom_remove = h.mark_atom;
+    c.counts.nrPart_remove_top = h.top_part;
+    c.counts.nrPart_remove_bot = h.bot_part;
+    c.counts.nrElec_remove_top = h.top_elec;
+    c.counts.nrElec_remove_bot = h.bot_elec;
+    c.counts.nrIon_remove_top = h.top_ion;
+    c.counts.nrIon_remove_bot = h.bot_ion;
+}
+
+int fetch_counters(Rb2Ctx &c)
+{
+    RB2_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    fill_counts_from_device(c);
+    return RB2_OK;
+}
+
+void fill_velocity_result(Rb2Ctx &c, rb2_step_result *out)
+{
+    const double *r = c.h_red;
+    for (int k = 0; k < 4; ++k) out->ramo_current[k] = r[k];
+    for (int k = 0; k < 3; ++k) {
+        // Average_Velocities, src/mod_verlet.F90:428-447
+        out->avg_part_vel[k] = (c.counts.nrPart != 0) ? r[4 + k] / c.counts.nrPart : r[4 + k];
+        out->avg_elec_vel[k] = (c.counts.nrElec != 0) ? r[7 + k] / c.counts.nrElec : r[7 + k];
+        out->avg_ion_vel[k] = (c.counts.nrIon != 0) ? r[10 + k] / c.counts.nrIon : r[10 + k];
+    }
+}
+
+// position update + (ordered) event records; leaves the stream busy with nothing pending on the host
+int do_update_position(Rb2Ctx &c, bool overlap_accel, int *rc_accel)
+{
+    c.host_events.clear();
+    if (c.n < 1) {
+        if (overlap_accel && rc_accel) *rc_accel = RB2_OK;
+        return RB2_OK;
+    }
+    RB2_CUDA(cudaMemsetAsync(&c.d_counters->n_events, 0, sizeof(int), c.stream));
+    int rc = rb2_launch_update_position(c);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(cudaEventRecord(c.ev_c, c.stream));
+    if (overlap_accel) {
+        // queue the O(N^2) kernel behind the counter copy; the host learns the record count
+        // while it runs
+        int i0 = c.part_begin, i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
+        if (i0 < 0) i0 = 0;
+        *rc_accel = rb2_launch_accel(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
+        if (*rc_accel) return *rc_accel;
+        c.accel_timed = true;
+    }
+    RB2_CUDA(cudaEventSynchronize(c.ev_c));
+    fill_counts_from_device(c);
+    const int nev = c.h_counters->n_events;
+    if (nev > 0) {
+        rc = rb2_launch_events(c, nev);
+        if (rc) return rc;
+        c.host_events.resize((size_t)nev);
+        RB2_CUDA(cudaMemcpyAsync(c.host_events.data(), c.d_events, (size_t)nev * sizeof(rb2_event), cudaMemcpyDeviceToHost, c.stream));
+    }
+    return RB2_OK;
+}
+
+}  // namespace
+
+int rb2_ensure_stage(Rb2Ctx &c, size_t n_doubles, size_t n_ints)
+{
+    if (n_doubles > c.stage_d_cap) {
+        if (c.d_stage_d) RB2_CUDA(cudaFree(c.d_stage_d));
+        c.d_stage_d = nullptr; c.stage_d_cap = 0;
+        const size_t want = n_doubles + n_doubles / 2 + 1024;
+        RB2_CUDA(cudaMalloc(&c.d_stage_d, want * sizeof(double)));
+        c.stage_d_cap = want;
+    }
+    if (n_ints > c.stage_i_cap) {
+        if (c.d_stage_i) RB2_CUDA(cudaFree(c.d_stage_i));
+        c.d_stage_i = nullptr; c.stage_i_cap = 0;
+        const size_t want = n_ints + n_ints / 2 + 1024;
+        RB2_CUDA(cudaMalloc(&c.d_stage_i, want * sizeof(int)));
+        c.stage_i_cap = want;
+    }
+    return RB2_OK;
+}
+
+extern "C" {
+
+const char *rb2_last_error_string(void) { return g_rb2_err; }
+
+int rb2_device_available(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) { cudaGetLastError(); return 0; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    return prop.major >= 10 ? 1 : 0;
+}
+
+int rb2_init(const rb2_config *cfg)
+{
+    Rb2Ctx &c = g_rb2;
+    if (c.init) rb2_finalize();
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (cfg->capacity < 1) return rb2_fail(RB2_ERR_ARG, "capacity must be >= 1");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+        cudaGetLastError();
+        return rb2_fail(RB2_ERR_CUDA, "no CUDA device: librumdeed_b200 has no CPU fallback");
+    }
+    if (cfg->device >= 0) RB2_CUDA(cudaSetDevice(cfg->device));
+    RB2_CUDA(cudaGetDevice(&c.dev));
+    cudaDeviceProp prop;
+    RB2_CUDA(cudaGetDeviceProperties(&prop, c.dev));
+    if (prop.major < 10)
+        return rb2_fail(RB2_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.dev, prop.major, prop.minor);
+    c.sm_count = prop.multiProcessorCount;
+    c.cfg = *cfg;
+    c.cap = cfg->capacity;
+    c.n = 0;
+    c.counts = rb2_counts{};
+    c.part_begin = 0;
+    c.part_end = -1;
+    c.launches = 0;
+    RB2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    RB2_CUDA(cudaEventCreate(&c.ev_a0));
+    RB2_CUDA(cudaEventCreate(&c.ev_a1));
+    RB2_CUDA(cudaEventCreate(&c.ev_s0));
+    RB2_CUDA(cudaEventCreate(&c.ev_s1));
+    RB2_CUDA(cudaEventCreateWithFlags(&c.ev_c, cudaEventDisableTiming));
+    const size_t cap = (size_t)c.cap;
+    if ((rc = alloc_arrays(c.a, cap))) return rc;
+    if ((rc = alloc_arrays(c.b, cap))) return rc;
+    if ((rc = dev_alloc(&c.mask, cap))) return rc;
+    if ((rc = dev_alloc(&c.evcnt, cap))) return rc;
+    if ((rc = dev_alloc(&c.evbits, cap))) return rc;
+    if ((rc = dev_alloc(&c.prefix, cap))) return rc;
+    if ((rc = dev_alloc(&c.blocksum, cap / 1024 + 8))) return rc;
+    if ((rc = dev_alloc(&c.life_hist, (size_t)(RB2_MAX_LIFE_TIME + 1) * 4))) return rc;
+    if ((rc = dev_alloc(&c.d_counters, 1))) return rc;
+    if ((rc = dev_alloc(&c.d_red, 16))) return rc;
+    if ((rc = dev_alloc(&c.d_total, 4))) return rc;
+    RB2_CUDA(cudaMallocHost(&c.h_counters, sizeof(DevCounters)));
+    RB2_CUDA(cudaMallocHost(&c.h_red, 16 * sizeof(double)));
+    RB2_CUDA(cudaMallocHost(&c.h_total, 4 * sizeof(int)));
+    memset(c.h_counters, 0, sizeof(DevCounters));
+    memset(c.h_red, 0, 16 * sizeof(double));
+    RB2_CUDA(cudaMemsetAsync(c.d_counters, 0, sizeof(DevCounters), c.stream));
+    RB2_CUDA(cudaMemsetAsync(c.d_red, 0, 16 * sizeof(double), c.stream));
+    RB2_CUDA(cudaMemsetAsync(c.life_hist, 0, (size_t)(RB2_MAX_LIFE_TIME + 1) * 4 * sizeof(unsigned long long), c.stream));
+    c.init = true;
+    if ((rc = rb2_launch_fill_mask(c, c.cap))) return rc;
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    return RB2_OK;
+}
+
+int rb2_finalize(void)
+{
+    Rb2Ctx &c = g_rb2;
+    if (!c.init) return RB2_OK;
+    cudaStreamSynchronize(c.stream);
+    free_arrays(c.a);
+    free_arrays(c.b);
+    cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);
+    cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
+    cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
+    cudaFreeHost(c.h_counters); cudaFreeHost(c.h_red); cudaFreeHost(c.h_total); cudaFreeHost(c.h_pts); cudaFreeHost(c.h_fld);
+    cudaFreeHost(c.h_stage);
+    cudaEventDestroy(c.ev_a0); cudaEventDestroy(c.ev_a1); cudaEventDestroy(c.ev_s0); cudaEventDestroy(c.ev_s1);
+    cudaEventDestroy(c.ev_c);
+    cudaStreamDestroy(c.stream);
+    c = Rb2Ctx{};
+    return RB2_OK;
+}
+
+int rb2_update_config(const rb2_config *cfg)
+{
+    RB2_REQUIRE_INIT();
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    const int cap = g_rb2.cfg.capacity, dev = g_rb2.cfg.device;
+    g_rb2.cfg = *cfg;
+    g_rb2.cfg.capacity = cap;  // capacity and device are fixed at init
+    g_rb2.cfg.device = dev;
+    return RB2_OK;
+}
+
+int rb2_upload_particles(int n, const double *pos, const double *prev_pos, const double *vel, const double *acc,
+                         const double *acc_prev, const double *acc_prev2, const double *charge, const double *mass,
+                         const int *species, const int *step, const int *emitter, const int *section, const int *life,
+                         const int *id, int nrID)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (n < 0 || n > c.cap) return rb2_fail(RB2_ERR_CAPACITY, "n = %d exceeds capacity %d", n, c.cap);
+    if (n > 0 && (!pos || !charge || !mass)) return rb2_fail(RB2_ERR_ARG, "pos, charge and mass are required");
+    const size_t b3 = (size_t)n * 3 * sizeof(double), b1 = (size_t)n * sizeof(double), bi = (size_t)n * sizeof(int);
+    cudaStream_t st = c.stream;
+    if (n > 0) {
+        // pos + charge travel through the spare set and are packed into pq on the device
+        RB2_CUDA(cudaMemcpyAsync(c.b.prev_pos, pos, b3, cudaMemcpyHostToDevice, st));
+        RB2_CUDA(cudaMemcpyAsync(c.b.mass, charge, b1, cudaMemcpyHostToDevice, st));
+        int rc = rb2_launch_pack(c, c.b.prev_pos, c.b.mass, n, c.a.pq);
+        if (rc) return rc;
+        RB2_CUDA(cudaMemcpyAsync(c.a.mass, mass, b1, cudaMemcpyHostToDevice, st));
+#define RB2_UP3(dst, src)                                                          \
+    if (src) RB2_CUDA(cudaMemcpyAsync(dst, src, b3, cudaMemcpyHostToDevice, st)); \
+    else RB2_CUDA(cudaMemsetAsync(dst, 0, b3, st))
+        RB2_UP3(c.a.prev_pos, prev_pos);
+        RB2_UP3(c.a.vel, vel);
+        RB2_UP3(c.a.acc, acc);
+        RB2_UP3(c.a.acc_prev, acc_prev);
+        RB2_UP3(c.a.acc_prev2, acc_prev2);
+#undef RB2_UP3
+        if (species) RB2_CUDA(cudaMemcpyAsync(c.a.species, species, bi, cudaMemcpyHostToDevice, st));
+        if (step) RB2_CUDA(cudaMemcpyAsync(c.a.step, step, bi, cudaMemcpyHostToDevice, st));
+        if (emitter) RB2_CUDA(cudaMemcpyAsync(c.a.emitter, emitter, bi, cudaMemcpyHostToDevice, st));
+        if (section) RB2_CUDA(cudaMemcpyAsync(c.a.section, section, bi, cudaMemcpyHostToDevice, st));
+        if (life) RB2_CUDA(cudaMemcpyAsync(c.a.life, life, bi, cudaMemcpyHostToDevice, st));
+        if (id) RB2_CUDA(cudaMemcpyAsync(c.a.id, id, bi, cudaMemcpyHostToDevice, st));
+        rc = rb2_launch_fill_defaults(c, n, !species, !step, !emitter, !section, !life, !id);
+        if (rc) return rc;
+    }
+    int rc = rb2_launch_fill_mask(c, c.n > n ? c.n : n);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemsetAsync(c.d_counters, 0, sizeof(DevCounters), st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    memset(c.h_counters, 0, sizeof(DevCounters));
+    c.n = n;
+    rb2_counts k{};
+    k.nrPart = n;
+    if (species) {
+        for (int i = 0; i < n; ++i) {
+            if (species[i] == RB2_SPECIES_ELEC) k.nrElec++;
+            else if (species[i] == RB2_SPECIES_ION) k.nrIon++;
+            else if (species[i] == RB2_SPECIES_ATOM) k.nrAtom++;
+        }
+    } else {
+        k.nrElec = n;
+    }
+    k.nrID = nrID >= 0 ? nrID : n;
+    k.nrPart_dropped = c.counts.nrPart_dropped;
+    c.counts = k;
+    c.host_events.clear();
+    return RB2_OK;
+}
+
+int rb2_download_particles(double *pos, double *prev_pos, double *vel, double *acc, double *acc_prev, double *acc_prev2,
+                           double *charge, double *mass, int *species, int *step, int *emitter, int *section, int *life,
+                           int *id, int *mask)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    const int n = c.n;
+    if (n < 1) return RB2_OK;
+    const size_t b3 = (size_t)n * 3 * sizeof(double), b1 = (size_t)n * sizeof(double), bi = (size_t)n * sizeof(int);
+    cudaStream_t st = c.stream;
+    if (pos || charge) {
+        int rc = rb2_launch_unpack(c, c.a.pq, n, pos ? c.b.prev_pos : nullptr, charge ? c.b.mass : nullptr);
+        if (rc) return rc;
+        if (pos) RB2_CUDA(cudaMemcpyAsync(pos, c.b.prev_pos, b3, cudaMemcpyDeviceToHost, st));
+        if (charge) RB2_CUDA(cudaMemcpyAsync(charge, c.b.mass, b1, cudaMemcpyDeviceToHost, st));
+    }
+    if (prev_pos) RB2_CUDA(cudaMemcpyAsync(prev_pos, c.a.prev_pos, b3, cudaMemcpyDeviceToHost, st));
+    if (vel) RB2_CUDA(cudaMemcpyAsync(vel, c.a.vel, b3, cudaMemcpyDeviceToHost, st));
+    if (acc) RB2_CUDA(cudaMemcpyAsync(acc, c.a.acc, b3, cudaMemcpyDeviceToHost, st));
+    if (acc_prev) RB2_CUDA(cudaMemcpyAsync(acc_prev, c.a.acc_prev, b3, cudaMemcpyDeviceToHost, st));
+    if (acc_prev2) RB2_CUDA(cudaMemcpyAsync(acc_prev2, c.a.acc_prev2, b3, cudaMemcpyDeviceToHost, st));
+    if (mass) RB2_CUDA(cudaMemcpyAsync(mass, c.a.mass, b1, cudaMemcpyDeviceToHost, st));
+    if (species) RB2_CUDA(cudaMemcpyAsync(species, c.a.species, bi, cudaMemcpyDeviceToHost, st));
+    if (step) RB2_CUDA(cudaMemcpyAsync(step, c.a.step, bi, cudaMemcpyDeviceToHost, st));
+    if (emitter) RB2_CUDA(cudaMemcpyAsync(emitter, c.a.emitter, bi, cudaMemcpyDeviceToHost, st));
+    if (section) RB2_CUDA(cudaMemcpyAsync(section, c.a.section, bi, cudaMemcpyDeviceToHost, st));
+    if (life) RB2_CUDA(cudaMemcpyAsync(life, c.a.life, bi, cudaMemcpyDeviceToHost, st));
+    if (id) RB2_CUDA(cudaMemcpyAsync(id, c.a.id, bi, cudaMemcpyDeviceToHost, st));
+    if (mask) RB2_CUDA(cudaMemcpyAsync(mask, c.mask, bi, cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    return RB2_OK;
+}
+
+int rb2_get_counts(rb2_counts *out)
+{
+    RB2_REQUIRE_INIT();
+    if (!out) return rb2_fail(RB2_ERR_ARG, "out is NULL");
+    int rc = fetch_counters(g_rb2);
+    if (rc) return rc;
+    *out = g_rb2.counts;
+    return RB2_OK;
+}
+
+int rb2_add_particles(int k, const double *pos, const double *vel, const int *species, int step, const int *emit,
+                      const int *sec, const int *life)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (k < 0) return rb2_fail(RB2_ERR_ARG, "k < 0");
+    if (k == 0) return RB2_OK;
+    if (!pos || !vel || !species) return rb2_fail(RB2_ERR_ARG, "pos, vel and species are required");
+    for (int t = 0; t < k; ++t)
+        if (species[t] < RB2_SPECIES_ELEC || species[t] > RB2_SPECIES_ATOM)
+            return rb2_fail(RB2_ERR_ARG, "unknown particle species %d", species[t]);  // reference: ERROR UNKNOWN PARTICLE TYPE
+    int room = c.cap - c.n;
+    int kk = k <= room ? k : (room > 0 ? room : 0);
+    c.counts.nrPart_dropped += (k - kk);  // src/mod_pair.F90:37-43
+    if (kk == 0) return RB2_OK;
+    int rc = rb2_ensure_stage(c, (size_t)6 * kk, (size_t)4 * kk);
+    if (rc) return rc;
+    std::vector<int> tmp((size_t)3 * kk);
+    for (int t = 0; t < kk; ++t) {
+        tmp[t] = emit ? emit[t] : 1;
+        int s = sec ? sec[t] : 1;
+        if (s > 96 * 96) s = 96 * 96;  // MAX_SECTIONS clamp, src/mod_pair.F90:46-51
+        tmp[kk + t] = s;
+        tmp[2 * kk + t] = life ? life[t] : -1;
+    }
+    cudaStream_t st = c.stream;
+    double *d_pos = c.d_stage_d, *d_vel = c.d_stage_d + (size_t)3 * kk;
+    int *d_sp = c.d_stage_i, *d_emit = d_sp + kk, *d_sec = d_sp + 2 * kk, *d_life = d_sp + 3 * kk;
+    RB2_CUDA(cudaMemcpyAsync(d_pos, pos, (size_t)3 * kk * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemcpyAsync(d_vel, vel, (size_t)3 * kk * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemcpyAsync(d_sp, species, (size_t)kk * sizeof(int), cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemcpyAsync(d_emit, tmp.data(), (size_t)3 * kk * sizeof(int), cudaMemcpyHostToDevice, st));
+    rc = rb2_launch_add(c, kk, c.n, c.counts.nrID, step, d_pos, d_vel, d_sp, d_emit, d_sec, d_life);
+    if (rc) return rc;
+    RB2_CUDA(cudaStreamSynchronize(st));  // tmp and the caller's arrays may go away
+    for (int t = 0; t < kk; ++t) {
+        if (species[t] == RB2_SPECIES_ELEC) c.counts.nrElec++;
+        else if (species[t] == RB2_SPECIES_ION) c.counts.nrIon++;
+        else c.counts.nrAtom++;
+    }
+    c.n += kk;
+    c.counts.nrPart = c.n;
+    c.counts.nrID += kk;
+    return RB2_OK;
+}
+
+int rb2_mark_remove(int k, const int *index, const int *reason)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (k < 0) return rb2_fail(RB2_ERR_ARG, "k < 0");
+    if (k == 0) return RB2_OK;
+    if (!index || !reason) return rb2_fail(RB2_ERR_ARG, "index and reason are required");
+    int rc = rb2_ensure_stage(c, 0, (size_t)2 * k);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.d_stage_i, index, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    RB2_CUDA(cudaMemcpyAsync(c.d_stage_i + k, reason, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    rc = rb2_launch_mark(c, k, c.d_stage_i, c.d_stage_i + k);
+    if (rc) return rc;
+    return fetch_counters(c);
+}
+
+int rb2_remove_marked(int step, rb2_counts *out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    int rc = fetch_counters(c);
+    if (rc) return rc;
+    const DevCounters h = *c.h_counters;
+    if (h.mark_part > 0 && c.n > 0) {  // src/mod_pair.F90:358
+        const int n_old = c.n;
+        if (n_old - h.mark_part > 0) {
+            rc = rb2_launch_compact(c, step);
+            if (rc) return rc;
+        }
+        c.counts.nrElec -= h.mark_elec;
+        c.counts.nrIon -= h.mark_ion;
+        c.counts.nrAtom -= h.mark_atom;
+        if (c.counts.nrElec < 0) c.counts.nrElec = 0;
+        if (c.counts.nrIon < 0) c.counts.nrIon = 0;
+        c.counts.nrPart = c.counts.nrElec + c.counts.nrIon + c.counts.nrAtom;
+        c.n = c.counts.nrPart;
+        rc = rb2_launch_fill_mask(c, n_old);
+        if (rc) return rc;
+        RB2_CUDA(cudaMemsetAsync(c.d_counters, 0, sizeof(DevCounters), c.stream));
+        RB2_CUDA(cudaStreamSynchronize(c.stream));
+        memset(c.h_counters, 0, sizeof(DevCounters));
+        fill_counts_from_device(c);
+    }
+    if (out) *out = c.counts;
+    return RB2_OK;
+}
+
+int rb2_get_life_time(long long *out)
+{
+    RB2_REQUIRE_INIT();
+    if (!out) return rb2_fail(RB2_ERR_ARG, "out is NULL");
+    RB2_CUDA(cudaMemcpyAsync(out, g_rb2.life_hist, (size_t)(RB2_MAX_LIFE_TIME + 1) * 4 * sizeof(long long),
+                             cudaMemcpyDeviceToHost, g_rb2.stream));
+    RB2_CUDA(cudaStreamSynchronize(g_rb2.stream));
+    return RB2_OK;
+}
+
+int rb2_update_position(int step)
+{
+    (void)step;
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    int rc = do_update_position(c, false, nullptr);
+    if (rc) return rc;
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    return RB2_OK;
+}
+
+int rb2_accel_only(void)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    int i0 = c.part_begin < 0 ? 0 : c.part_begin;
+    int i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
+    int rc = rb2_launch_accel(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
+    if (rc) return rc;
+    c.accel_timed = (c.n > 0 && i1 > i0);
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    return RB2_OK;
+}
+
+int rb2_update_velocity(rb2_step_result *out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    int rc = rb2_launch_update_velocity(c);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        fill_velocity_result(c, out);
+        out->n_events = (int)c.host_events.size();
+        out->counts = c.counts;
+    }
+    return RB2_OK;
+}
+
+int rb2_step(int step, rb2_step_result *out)
+{
+    (void)step;
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    RB2_CUDA(cudaEventRecord(c.ev_s0, c.stream));
+    int rc_accel = RB2_OK;
+    c.accel_timed = false;
+    int rc = do_update_position(c, true, &rc_accel);
+    if (rc) return rc;
+    rc = rb2_launch_update_velocity(c);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(cudaEventRecord(c.ev_s1, c.stream));
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        fill_velocity_result(c, out);
+        out->n_events = (int)c.host_events.size();
+        out->counts = c.counts;
+        if (c.accel_timed) RB2_CUDA(cudaEventElapsedTime(&out->accel_ms, c.ev_a0, c.ev_a1));
+        RB2_CUDA(cudaEventElapsedTime(&out->step_ms, c.ev_s0, c.ev_s1));
+    }
+    return RB2_OK;
+}
+
+int rb2_get_events(int max_events, rb2_event *out, int *n_out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    const int n = (int)c.host_events.size();
+    if (n_out) *n_out = n;
+    if (out && max_events > 0) {
+        const int m = n < max_events ? n : max_events;
+        if (m > 0) memcpy(out, c.host_events.data(), (size_t)m * sizeof(rb2_event));
+    }
+    return RB2_OK;
+}
+
+int rb2_accel_host(int n, const double *pos, const double *charge, const double *mass, double *acc_out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (n < 0 || n > c.cap) return rb2_fail(RB2_ERR_CAPACITY, "n = %d exceeds capacity %d", n, c.cap);
+    if (n == 0) return RB2_OK;
+    if (!pos || !charge || !mass || !acc_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    // scratch = the spare array set; the resident particle state is untouched
+    const size_t b3 = (size_t)n * 3 * sizeof(double), b1 = (size_t)n * sizeof(double);
+    cudaStream_t st = c.stream;
+    RB2_CUDA(cudaMemcpyAsync(c.b.prev_pos, pos, b3, cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemcpyAsync(c.b.mass, charge, b1, cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemcpyAsync(c.b.vel, mass, b1, cudaMemcpyHostToDevice, st));
+    int rc = rb2_launch_pack(c, c.b.prev_pos, c.b.mass, n, c.b.pq);
+    if (rc) return rc;
+    // honours the i-partition: this process evaluates and returns rows [i0, i1) only
+    int i0 = c.part_begin < 0 ? 0 : c.part_begin;
+    int i1 = (c.part_end < 0 || c.part_end > n) ? n : c.part_end;
+    if (i0 > i1) i0 = i1;
+    rc = rb2_launch_accel(c, c.b.pq, c.b.vel, n, i0, i1, c.b.acc);
+    if (rc) return rc;
+    c.accel_timed = (i1 > i0);
+    if (i1 > i0)
+        RB2_CUDA(cudaMemcpyAsync(acc_out + (size_t)3 * i0, c.b.acc + (size_t)3 * i0, (size_t)(i1 - i0) * 3 * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    return RB2_OK;
+}
+
+static int ensure_field_buffers(Rb2Ctx &c, int M)
+{
+    if (M > c.fld_cap) {
+        if (c.d_pts) RB2_CUDA(cudaFree(c.d_pts));
+        if (c.d_fld) RB2_CUDA(cudaFree(c.d_fld));
+        if (c.h_pts) RB2_CUDA(cudaFreeHost(c.h_pts));
+        if (c.h_fld) RB2_CUDA(cudaFreeHost(c.h_fld));
+        c.d_pts = c.d_fld = c.h_pts = c.h_fld = nullptr;
+        c.fld_cap = 0;
+        const int want = M < 1024 ? 1024 : M + M / 2;  // like the reference's max(M, 1024), src/mod_verlet.F90:1710
+        RB2_CUDA(cudaMalloc(&c.d_pts, (size_t)3 * want * sizeof(double)));
+        RB2_CUDA(cudaMalloc(&c.d_fld, (size_t)3 * want * sizeof(double)));
+        RB2_CUDA(cudaMallocHost(&c.h_pts, (size_t)3 * want * sizeof(double)));
+        RB2_CUDA(cudaMallocHost(&c.h_fld, (size_t)3 * want * sizeof(double)));
+        c.fld_cap = want;
+    }
+    return RB2_OK;
+}
+
+int rb2_field_batch_delta(int M, const double *pos_in, int n_new, const double *new_pos, const double *new_charge,
+                          double *field_out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (M < 1) return RB2_OK;  // src/mod_verlet.F90:1658
+    if (!pos_in || !field_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    if (n_new < 0 || (n_new > 0 && (!new_pos || !new_charge))) return rb2_fail(RB2_ERR_ARG, "bad pending-particle arguments");
+    int rc = ensure_field_buffers(c, M);
+    if (rc) return rc;
+    cudaStream_t st = c.stream;
+    const size_t b3 = (size_t)3 * M * sizeof(double);
+    memcpy(c.h_pts, pos_in, b3);
+    RB2_CUDA(cudaMemcpyAsync(c.d_pts, c.h_pts, b3, cudaMemcpyHostToDevice, st));
+    if (n_new > 0) {
+        if (n_new > c.extra_cap) {
+            if (c.d_extra) RB2_CUDA(cudaFree(c.d_extra));
+            c.d_extra = nullptr; c.extra_cap = 0;
+            const int want = n_new + n_new / 2 + 256;
+            RB2_CUDA(cudaMalloc(&c.d_extra, (size_t)want * sizeof(double4)));
+            c.extra_cap = want;
+        }
+        rc = rb2_ensure_stage(c, (size_t)4 * n_new, 0);
+        if (rc) return rc;
+        RB2_CUDA(cudaMemcpyAsync(c.d_stage_d, new_pos, (size_t)3 * n_new * sizeof(double), cudaMemcpyHostToDevice, st));
+        RB2_CUDA(cudaMemcpyAsync(c.d_stage_d + (size_t)3 * n_new, new_charge, (size_t)n_new * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = rb2_launch_pack(c, c.d_stage_d, c.d_stage_d + (size_t)3 * n_new, n_new, c.d_extra);
+        if (rc) return rc;
+    }
+    rc = rb2_launch_field(c, c.a.pq, c.n, c.d_extra, n_new, c.d_pts, M, c.d_fld);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.h_fld, c.d_fld, b3, cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    memcpy(field_out, c.h_fld, b3);
+    return RB2_OK;
+}
+
+int rb2_field_batch(int M, const double *pos_in, double *field_out)
+{
+    return rb2_field_batch_delta(M, pos_in, 0, nullptr, nullptr, field_out);
+}
+
+int rb2_field_window_open(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
+int rb2_field_window_close(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
+
+int rb2_set_partition(int i_begin, int i_end)
+{
+    RB2_REQUIRE_INIT();
+    if (i_begin < 0 || (i_end >= 0 && i_end < i_begin)) return rb2_fail(RB2_ERR_ARG, "bad partition [%d, %d)", i_begin, i_end);
+    g_rb2.part_begin = i_begin;
+    g_rb2.part_end = i_end;
+    return RB2_OK;
+}
+
+int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (!name || !dev_ptr) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    const size_t cap = (size_t)c.cap;
+    void *p = nullptr;
+    size_t b = 0;
+    if (!strcmp(name, "acc")) { p = c.a.acc; b = 3 * cap * sizeof(double); }
+    else if (!strcmp(name, "pq")) { p = c.a.pq; b = cap * sizeof(double4); }
+    else if (!strcmp(name, "vel")) { p = c.a.vel; b = 3 * cap * sizeof(double); }
+    else if (!strcmp(name, "acc_prev")) { p = c.a.acc_prev; b = 3 * cap * sizeof(double); }
+    else if (!strcmp(name, "acc_prev2")) { p = c.a.acc_prev2; b = 3 * cap * sizeof(double); }
+    else if (!strcmp(name, "mass")) { p = c.a.mass; b = cap * sizeof(double); }
+    else return rb2_fail(RB2_ERR_ARG, "unknown buffer '%s'", name);
+    *dev_ptr = p;
+    if (bytes) *bytes = b;
+    return RB2_OK;
+}
+
+int rb2_synchronize(void)
+{
+    RB2_REQUIRE_INIT();
+    RB2_CUDA(cudaStreamSynchronize(g_rb2.stream));
+    return RB2_OK;
+}
+
+int rb2_stream(void **stream_out)
+{
+    RB2_REQUIRE_INIT();
+    if (!stream_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    *stream_out = (void *)g_rb2.stream;
+    return RB2_OK;
+}
+
+int rb2_fp64_peak(double ms_target, double *tflops_out, float *ms_out)
+{
+    RB2_REQUIRE_INIT();
+    if (!tflops_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    if (ms_target <= 0.0) ms_target = 50.0;
+    return rb2_launch_fp64_peak(g_rb2, ms_target, tflops_out, ms_out);
+}
+
+int rb2_launch_count(long long *out, int reset)
+{
+    RB2_REQUIRE_INIT();
+    if (out) *out = g_rb2.launches;
+    if (reset) g_rb2.launches = 0;
+    return RB2_OK;
+}
+
+int rb2_last_accel_info(float *ms, int *grid_x, int *grid_y, int *block, int *j_split)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (ms) {
+        *ms = 0.f;
+        if (c.accel_timed) {
+            RB2_CUDA(cudaEventSynchronize(c.ev_a1));
+            RB2_CUDA(cudaEventElapsedTime(ms, c.ev_a0, c.ev_a1));
+        }
+    }
+    if (grid_x) *grid_x = c.last_grid_x;
+    if (grid_y) *grid_y = c.last_grid_y;
+    if (block) *block = c.last_block;
+    if (j_split) *j_split = c.last_split;
+    return RB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// rb2_internal.cuh -- shared declarations of librumdeed_b200.so (not installed).
+//
+// Data layout in HBM (one allocation per array, capacity = rb2_config.capacity; every array
+// exists twice so that the stable compaction of Remove_Particles is one gather pass into
+// the spare set followed by a pointer swap):
+//   pq        double4[cap]   {x, y, z, q}: the only thing the O(N^2) kernels read
+//                            (32 B/particle, 16 B aligned rows for TMA bulk copies)
+//   prev_pos, vel, acc, acc_prev, acc_prev2   double[3*cap]  Fortran (3,N) order
+//   mass      double[cap]
+//   species, step, emitter, section, life, id   int[cap]
+//   mask      int[cap]       1 = live, 0 = marked for removal
+//   evcnt     uint8[cap]     records this particle produced in the position update
+//   evbits    uint16[cap]    bit 0/1: absorbed top/bot record, bit 2+k: plane k crossed
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "rumdeed_b200.h"
+
+// ---- physical constants (reference src/mod_global.F90:26-75, :333) -------------------
+#define RB2_PI 3.141592653589793238462643383279502884197169399375105820974944592307816406286
+namespace rb2k {
+constexpr double mu_0 = 1.25663706212e-6;
+constexpr double c = 299792458.0;
+constexpr double epsilon_0 = 1.0 / (mu_0 * (c * c));  // derived, like the reference
+constexpr double div_fac_c = 1.0 / (4.0 * RB2_PI * epsilon_0 * 1.0);
+constexpr double q_0 = 1.602176634e-19;
+constexpr double m_0 = 9.1093837015e-31;
+constexpr double m_u = 1.66053906660e-27;
+constexpr double m_N2 = 28.0134 * m_u;
+constexpr double m_N2p = m_N2 - m_0;
+constexpr double length_scale = 1.0e-9;
+constexpr double soft = length_scale * length_scale;  // 1e-18 m, added to r
+}  // namespace rb2k
+
+// ---- kernel parameter blocks (passed by value) -----------------------------------------
+struct PlanarParams {
+    double two_d;  // 2*d
+    double E_z;
+    int    nic;    // N_ic_max
+    int    do_ic;
+};
+struct TipParams {
+    double a_foci, shift_z, pre_fac_E_tip, eta_1;
+    double z_0, r_tip;  // sphere centre height (h_tip - r_tip) and radius
+    double unit_scale_num, unit_scale_den;  // pre_fac_E_tip_unit_voltage, pre_fac_E_tip
+    int    do_ic;
+};
+struct StepParams {
+    int    geometry;
+    double dt, dt2;
+    double box_z;
+    double d;
+    int    planes_N;
+    double planes_z[RB2_PLANES_MAX];
+    PlanarParams pl;
+    TipParams    tip;
+};
+
+struct DevCounters {  // cumulative since the last rb2_remove_marked
+    int mark_part, mark_elec, mark_ion, mark_atom;
+    int top_part, bot_part, top_elec, bot_elec, top_ion, bot_ion;
+    int n_events, pad;
+};
+
+struct DevArrays {
+    double4 *pq = nullptr;
+    double *prev_pos = nullptr, *vel = nullptr, *acc = nullptr, *acc_prev = nullptr, *acc_prev2 = nullptr;
+    double *mass = nullptr;
+    int *species = nullptr, *step = nullptr, *emitter = nullptr, *section = nullptr, *life = nullptr, *id = nullptr;
+};
+
+struct Rb2Ctx {
+    bool         init = false;
+    rb2_config   cfg{};
+    int          dev = 0;
+    int          sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int          cap = 0;
+    int          n = 0;  // nrPart
+    rb2_counts   counts{};
+    int          part_begin = 0, part_end = -1;  // i-partition (end<0: all)
+
+    DevArrays a, b;  // current / spare
+    int *mask = nullptr;
+    unsigned char *evcnt = nullptr;
+    unsigned short *evbits = nullptr;
+    int *prefix = nullptr, *blocksum = nullptr;  // scan scratch
+    unsigned long long *life_hist = nullptr;     // [(RB2_MAX_LIFE_TIME+1)*4]
+
+    DevCounters *d_counters = nullptr, *h_counters = nullptr;  // device / pinned host
+    double *d_red = nullptr, *h_red = nullptr;                  // velocity-update reductions (16 doubles)
+    double *d_redpart = nullptr; int redpart_blocks = 0;
+    int *d_total = nullptr, *h_total = nullptr;                 // scan totals
+
+    double *partial = nullptr; size_t partial_bytes = 0;       // pair-kernel partial sums
+    rb2_event *d_events = nullptr; int ev_cap = 0;
+    std::vector<rb2_event> host_events;
+
+    // staging (grow-only): field points / fields, add/mark arguments, rb2_accel_host
+    double *d_pts = nullptr, *d_fld = nullptr, *h_pts = nullptr, *h_fld = nullptr; int fld_cap = 0;
+    double4 *d_extra = nullptr; int extra_cap = 0;
+    double *d_stage_d = nullptr; size_t stage_d_cap = 0;  // doubles
+    int *d_stage_i = nullptr; size_t stage_i_cap = 0;     // ints
+    double *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned
+
+    cudaEvent_t ev_a0 = nullptr, ev_a1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_c = nullptr;
+    bool  accel_timed = false;
+    int   last_grid_x = 0, last_grid_y = 0, last_block = 0, last_split = 0;
+    long long launches = 0;
+};
+
+extern Rb2Ctx g_rb2;
+extern char   g_rb2_err[512];
+
+int rb2_fail(int code, const char *fmt, ...);
+
+#define RB2_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return rb2_fail(RB2_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+#define RB2_REQUIRE_INIT()                                                     \
+    do {                                                                       \
+        if (!g_rb2.init) return rb2_fail(RB2_ERR_NOT_INIT, "rb2_init has not been called"); \
+    } while (0)
+#define RB2_LAUNCHED(n_) (g_rb2.launches += (n_))
+
+StepParams rb2_make_step_params(const rb2_config &c);
+int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
+
+// pair / field kernels (rb2_pair.cu)
+int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, int i_begin, int i_end, double *acc_out);
+int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra, int n_extra,
+                     const double *d_pts, int M, double *d_fld);
+// integrate kernels (rb2_integrate.cu)
+int rb2_launch_pack(Rb2Ctx &ctx, const double *pos3, const double *q, int n, double4 *pq);
+int rb2_launch_unpack(Rb2Ctx &ctx, const double4 *pq, int n, double *pos3, double *q);
+int rb2_launch_update_position(Rb2Ctx &ctx);
+int rb2_launch_events(Rb2Ctx &ctx, int n_events);
+int rb2_launch_update_velocity(Rb2Ctx &ctx);
+int rb2_launch_compact(Rb2Ctx &ctx, int step);
+int rb2_launch_add(Rb2Ctx &ctx, int k, int slot0, int id0, int step, const double *d_pos, const double *d_vel,
+                   const int *d_species, const int *d_emit, const int *d_sec, const int *d_life);
+int rb2_launch_mark(Rb2Ctx &ctx, int k, const int *d_index, const int *d_reason);
+int rb2_launch_fill_defaults(Rb2Ctx &ctx, int n, bool species, bool step, bool emitter, bool section, bool life, bool id);
+int rb2_launch_fill_mask(Rb2Ctx &ctx, int n);
+int rb2_launch_fp64_peak(Rb2Ctx &ctx, double ms_target, double *tflops, float *ms);
+
+// ---- device math ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+// High word of 1e-80: below this the rsqrt seed is clamped so that s == 0 (coincident
+// points) yields a finite weight that the zero offset then multiplies to exactly 0,
+// like the reference's softened 1/r^3 does.
+#define RB2_SEED_CLAMP_HI 0x2F52F8AC
+
+__device__ __forceinline__ double rb2_rsqrt_seed(double s_clamped)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s_clamped));  // MUFU.RSQ64H
+    return y;
+}
+
+// w = 1 / (sqrt(s) + 1e-18)^3   (reference: r = sqrt(..) + length_scale**2; inv_r3 = 1/(r*r*r),
+// src/mod_verlet.F90:1302-1303, src/acc_ic_planar_series.inc:22-23).
+// 7 FP64-pipe instructions + 1 MUFU + 1 integer max instead of sqrt + add + 2 mul + divide:
+//   y0 ~ s^-1/2 (>= 18 good bits), e = 1 - s*y0^2,
+//   s^-3/2 = y0^3 (1-e)^-3/2 = y0^3 (1 + 3/2 e + 15/8 e^2 + O(e^3)),   |e^3| < 1e-15
+//   (r+eps)^-3 = r^-3 (1 - 3 eps/r + O((eps/r)^2)),  eps/r <= 1e-6 for r >= 1e-12 m
+__device__ __forceinline__ double rb2_inv_r3_soft(double s)
+{
+    int hi = __double2hiint(s);
+    hi = max(hi, RB2_SEED_CLAMP_HI);
+    const double y0 = rb2_rsqrt_seed(__hiloint2double(hi, 0));
+    const double t = y0 * y0;
+    const double e = fma(-s, t, 1.0);
+    const double c0 = fma(-3.0 * rb2k::soft, y0, 1.0);
+    const double p = fma(e, fma(1.875, e, 1.5), c0);
+    return (y0 * t) * p;
+}
+
+// Vacuum field of the hyperboloid tip, src/acc_tip_field_E.inc:13-34 ==
+// field_E_Hyperboloid, src/mod_hyperboloid_tip.f90:115-154.
+__device__ __forceinline__ void rb2_tip_field_E(const TipParams &T, double x_1, double y_1, double z_1, double &fE_x,
+                                                double &fE_y, double &fE_z)
+{
+    const double zp = z_1 + T.a_foci - T.shift_z, zm = z_1 - T.a_foci - T.shift_z;
+    const double r_p = sqrt(x_1 * x_1 + y_1 * y_1 + zp * zp);
+    const double r_m = sqrt(x_1 * x_1 + y_1 * y_1 + zm * zm);
+    const double xi = (r_p + r_m) / (2.0 * T.a_foci);
+    const double eta = (r_p - r_m) / (2.0 * T.a_foci);
+    double phi;
+    if ((fabs(x_1) < 1.0e-18) && (fabs(y_1) < 1.0e-18)) phi = 0.0;
+    else phi = atan2(y_1, x_1);
+    const double pre_fac_xyz = T.pre_fac_E_tip * 1.0 / (xi * xi - eta * eta);
+    double fac_xy;
+    if (fabs(xi - 1.0) < 1.0e-6) fac_xy = 0.0;
+    else fac_xy = eta * sqrt((xi * xi - 1.0) / (1.0 - eta * eta));
+    fE_x = -1.0 * pre_fac_xyz * fac_xy * cos(phi);
+    fE_y = -1.0 * pre_fac_xyz * fac_xy * sin(phi);
+    fE_z = pre_fac_xyz * xi;
+}
+#endif

@@ -1,0 +1,453 @@
+"""GPU parity tests: the CUDA hot path, called through the C ABI, against the CPU oracle on
+identical seeded inputs (oracle = tests' checker only).
+
+Tolerances (BASELINE.json north_star): fields and forces within 1e-11 relative in FP64,
+measured like the reference does (mod_tests.F90:1664-1675): ||a - a_ref|| / max(||a_ref||, 1)
+per particle; particle indexing, removal and the Beeman update are bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import rumdeed_b200 as rb
+from rumdeed_b200.api import M_0, M_N2P, Q_0, REMOVE_BOT, REMOVE_TOP, SPECIES_ELEC, SPECIES_ION
+
+pytestmark = pytest.mark.gpu
+
+NM = 1.0e-9
+TOL = 1.0e-11
+
+
+def cloud(n, seed, box=(1000.0, 1000.0, 1000.0), ions=True, zmin=1.0):
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    pos = np.stack([rng.uniform(-0.5 * box[0], 0.5 * box[0], n),
+                    rng.uniform(-0.5 * box[1], 0.5 * box[1], n),
+                    rng.uniform(zmin, box[2] - zmin, n)], axis=1) * NM
+    ion = ((np.arange(n) % 10) == 9) if ions else np.zeros(n, dtype=bool)
+    q = np.where(ion, Q_0, -Q_0)
+    m = np.where(ion, M_N2P, M_0)
+    sp = np.where(ion, SPECIES_ION, SPECIES_ELEC).astype(np.int32)
+    return pos, q, m, sp
+
+
+def relerr(a, ref):
+    scale = np.maximum(np.linalg.norm(ref, axis=-1), 1.0)
+    return float(np.max(np.linalg.norm(a - ref, axis=-1) / scale))
+
+
+def planar(orc, V=2000.0, d=1000.0 * NM, ic=True, nic=1, dt=1.0e-16, cap=1 << 16, planes=()):
+    box = (1000 * NM, 1000 * NM, d)
+    cfg = rb.planar_config(V, d, box, dt, ic, nic, capacity=cap, planes_z=planes)
+    p = orc.params_planar(V, d, box, dt, ic, nic)
+    p.set_planes(planes)
+    return cfg, p
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ic,nic", [(False, 0), (True, 0), (True, 1), (True, 2), (True, 3)])
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 1000, 2500])
+def test_planar_acceleration_vs_oracle(orc, ic, nic, n):
+    cfg, p = planar(orc, ic=ic, nic=nic)
+    pos, q, m, sp = cloud(n, 20261017 + n)
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+    truth = orc.accel_gather_ld(p, pos, q, m)
+    ref = orc.accel_gather(p, pos, q, m)
+    assert relerr(acc, truth) < TOL
+    assert relerr(acc, ref) < TOL
+    if n <= 1000:
+        scat = orc.accel_planar(p, pos, q, m, sp)  # the CPU pair loop (i<j scatter)
+        assert relerr(acc, scat) < TOL
+
+
+def test_reference_golden_three_particles(orc):
+    """mod_tests.F90:405-518: closed-form Coulomb accelerations and the Python field vector."""
+    d, V = 100 * NM, 2.0
+    box = (100 * NM, 100 * NM, d)
+    R = np.array([[3.0, -10.0, 2.0], [-9.0, 26.0, 80.0], [6.0, -24.0, 56.53]]) * NM
+    q = np.array([-Q_0, -Q_0, Q_0]); m = np.array([M_0, M_0, M_N2P])
+    sp = np.array([1, 1, 2], dtype=np.int32)
+    cfg = rb.planar_config(V, d, box, 0.25e-15, False, 0, capacity=64)
+    pre = Q_0 ** 2 * rb.api.DIV_FAC_C
+    E = np.array([0, 0, -V / d])
+    coul = lambda a, b: (a - b) / np.linalg.norm(a - b) ** 3
+    want = np.stack([(pre * coul(R[0], R[1]) - pre * coul(R[0], R[2])) / M_0 - Q_0 / M_0 * E,
+                     (pre * coul(R[1], R[0]) - pre * coul(R[1], R[2])) / M_0 - Q_0 / M_0 * E,
+                     (-pre * coul(R[2], R[0]) - pre * coul(R[2], R[1])) / M_N2P + Q_0 / M_N2P * E])
+    with rb.HotPath(cfg) as hp:
+        probe = np.array([-4.55, -2.34, 96.44]) * NM
+        assert np.allclose(hp.Calc_Field_at(probe), E, rtol=0, atol=0)  # empty system: vacuum field
+        hp.Add_Particle(R[0], [0, 0, 0], SPECIES_ELEC, 1, 0)
+        hp.Add_Particle(R[1], [0, 0, 0], SPECIES_ELEC, 1, 0)
+        hp.Add_Particle(R[2], [0, 0, 0], SPECIES_ION, 1, 0)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        assert relerr(acc, want) < 1e-8  # closed form differs by the 1e-18 m softening only
+        E_python = np.array([-314559.29097098, 1423979.07058996, -20246038.87978313])
+        got = hp.Calc_Field_at(probe)
+        assert np.all(np.abs(got - E_python) / np.abs(E_python) < 1e-7)
+        p = orc.params_planar(V, d, box, 0.25e-15, False, 0)
+        assert relerr(got[None], orc.calc_field_at(p, R, q, probe, ld=True)[None]) < TOL
+
+
+def test_forty_particle_reference_case(orc):
+    """mod_tests.F90:1610-1676: 40 sin/cos-placed particles, every 5th an ion, N_ic_max = 2 and IC off."""
+    d, V = 1000 * NM, 2.0e3
+    box = (100 * NM, 100 * NM, d)
+    i = np.arange(1, 41, dtype=np.float64)
+    pos = np.stack([(0.5 + 0.45 * np.sin(1.7 * i)) * box[0], (0.5 + 0.45 * np.cos(2.3 * i)) * box[1],
+                    (0.5 + 0.45 * np.sin(3.1 * i + 0.5)) * box[2]], axis=1)
+    ion = (np.arange(1, 41) % 5) == 0
+    q = np.where(ion, Q_0, -Q_0); m = np.where(ion, M_N2P, M_0)
+    sp = np.where(ion, 2, 1).astype(np.int32)
+    for ic, nic in ((True, 2), (False, 0)):
+        cfg = rb.planar_config(V, d, box, 0.25e-15, ic, nic, capacity=64)
+        p = orc.params_planar(V, d, box, 0.25e-15, ic, nic)
+        with rb.HotPath(cfg) as hp:
+            hp.upload(pos, q, m, species=sp)
+            hp.Calculate_Acceleration_Particles()
+            acc = hp.download(("acc",))["acc"]
+        assert relerr(acc, orc.accel_generic(p, pos, q, m, sp)) < 1e-12
+        assert relerr(acc, orc.accel_planar(p, pos, q, m, sp)) < 1e-12
+
+
+def test_coincident_and_marked_particles(orc):
+    """Exact coincidence gives a zero Coulomb term (softened 1/r^3 times a zero offset), and a
+    marked particle (q = 0) neither exerts nor feels pair forces (mod_pair.F90:207)."""
+    cfg, p = planar(orc, ic=True, nic=1)
+    pos, q, m, sp = cloud(300, 7)
+    pos[17] = pos[3]
+    q = q.copy(); q[40] = 0.0; q[41] = 0.0
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+    assert np.all(np.isfinite(acc))
+    assert relerr(acc, orc.accel_gather(p, pos, q, m)) < TOL
+    assert np.all(acc[40] == 0.0) and np.all(acc[41] == 0.0)
+
+
+def test_partition_and_host_buffer_paths(orc):
+    cfg, p = planar(orc, ic=True, nic=1)
+    pos, q, m, sp = cloud(1500, 11)
+    ref = orc.accel_gather(p, pos, q, m)
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        hp.Calculate_Acceleration_Particles()
+        full = hp.download(("acc",))["acc"]
+        # i-partition: two halves written in place give the same bits as the full evaluation
+        hp.upload(pos, q, m, species=sp)
+        hp.set_partition(0, 700)
+        hp.Calculate_Acceleration_Particles()
+        hp.set_partition(700, 1500)
+        hp.Calculate_Acceleration_Particles()
+        hp.set_partition(0, -1)
+        halves = hp.download(("acc",))["acc"]
+        host = hp.accel_host(pos, q, m)
+    assert relerr(full, ref) < TOL
+    assert relerr(halves, ref) < TOL
+    assert relerr(host, ref) < TOL
+    assert np.array_equal(host, full)
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ic,nic", [(False, 0), (True, 0), (True, 1), (True, 2)])
+@pytest.mark.parametrize("M", [1, 4, 33, 300])
+def test_planar_field_batch_vs_oracle(orc, ic, nic, M):
+    cfg, p = planar(orc, ic=ic, nic=nic)
+    pos, q, m, sp = cloud(2000, 5)
+    rng = np.random.default_rng(99 + M)
+    pts = np.stack([rng.uniform(-500, 500, M), rng.uniform(-500, 500, M), np.zeros(M)], axis=1) * NM
+    if M >= 4:
+        pts[1, 2] = 1.0 * NM    # the photo-emission probe height
+        pts[2, 2] = 500.0 * NM
+    with rb.HotPath(cfg) as hp:
+        vac = hp.Calc_Field_at_Batch(pts)
+        assert np.all(vac[:, :2] == 0.0) and np.all(vac[:, 2] == cfg.E_z)
+        hp.upload(pos, q, m, species=sp)
+        hp.Particles_To_Device()
+        fld = hp.Calc_Field_at_Batch(pts)
+        one = hp.Calc_Field_at(pts[0])
+        hp.Release_Device_Particles()
+    want = np.stack([orc.calc_field_at(p, pos, q, pts[k], sp, ld=True) for k in range(M)])
+    assert relerr(fld, want) < TOL
+    assert relerr(fld, orc.calc_field_at_batch(p, pos, q, pts, sp)) < TOL
+    assert relerr(one[None], want[:1]) < TOL
+
+
+def test_reference_planar_batch_case(orc):
+    """mod_tests.F90:1554-1603 (N_ic_max = 1, 3 particles, 4 points; vacuum check)."""
+    d, V = 100 * NM, 2.0
+    box = (100 * NM, 100 * NM, d)
+    cfg = rb.planar_config(V, d, box, 0.25e-15, True, 1, capacity=64)
+    p = orc.params_planar(V, d, box, 0.25e-15, True, 1)
+    pts = np.array([[0, 0, 10.0], [12, -4, 21], [-20, 30, 80], [40, 40, 95]]) * NM
+    R = np.array([[10, -5, 20.0], [-15, 8, 60], [5, 25, 40]]) * NM
+    q = np.array([-Q_0, -Q_0, Q_0])
+    with rb.HotPath(cfg) as hp:
+        vac = hp.Calc_Field_at_Batch(pts)
+        assert np.all(vac == np.array([0.0, 0.0, -V / d]))
+        for r, s in zip(R, (1, 1, 2)):
+            hp.Add_Particle(r, [0, 0, 0], s, 1, 1)
+        batch = hp.Calc_Field_at_Batch(pts)
+        singles = np.stack([hp.Calc_Field_at(pt) for pt in pts])
+    assert relerr(batch, orc.calc_field_at_batch(p, R, q, pts)) < TOL
+    assert relerr(batch, singles) < 1e-13
+
+
+def test_field_delta_is_linear(orc):
+    """snapshot + delta == field of the enlarged system (serial sampler semantics)."""
+    cfg, p = planar(orc, ic=True, nic=1)
+    pos, q, m, sp = cloud(900, 21)
+    new_pos, new_q, _, _ = cloud(37, 22, ions=False)
+    new_pos[:, 2] = 1.0 * NM
+    rng = np.random.default_rng(3)
+    pts = np.stack([rng.uniform(-500, 500, 50), rng.uniform(-500, 500, 50), np.zeros(50)], axis=1) * NM
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        delta = hp.Calc_Field_at_Batch_delta(pts, new_pos, new_q)
+    want = orc.calc_field_at_batch(p, np.concatenate([pos, new_pos]), np.concatenate([q, new_q]), pts)
+    assert relerr(delta, want) < TOL
+
+
+# --------------------------------------------------------------------------------------------------
+def tip_setup(orc, V=2.0e3, cap=4096, dt=0.25e-3 * 1e-12, boxz=1000 * NM):
+    box = (100 * NM, 100 * NM, boxz)
+    cfg = rb.tip_config(V, 900 * NM, 100 * NM, 100 * NM, box, dt, True, capacity=cap)
+    p = orc.params_tip(V, 900 * NM, 100 * NM, 100 * NM, box, dt, True)
+    return cfg, p
+
+
+def test_tip_config_matches_oracle(orc):
+    cfg, p = tip_setup(orc)
+    for name in ("a_foci", "eta_1", "shift_z", "pre_fac_E_tip", "pre_fac_E_tip_unit_voltage", "h_tip", "r_tip", "max_xi", "d"):
+        assert getattr(cfg, name) == pytest.approx(getattr(p, name), rel=1e-15), name
+
+
+def test_tip_reference_case(orc):
+    """mod_tests.F90:988-1084: three particles at the apex; batch == point."""
+    cfg, p = tip_setup(orc)
+    R = np.array([[2.0, 1.0, 103.0], [-2.0, 2.5, 106.0], [1.5, -3.0, 110.0]]) * NM
+    q = np.array([-Q_0, -Q_0, Q_0]); m = np.array([M_0, M_0, M_N2P])
+    sp = np.array([1, 1, 2], dtype=np.int32)
+    pts = np.array([[0, 0, 102.0], [30, -10, 130], [-50, 40, 300], [15, 8, 500]]) * NM
+    with rb.HotPath(cfg) as hp:
+        for r, s in zip(R, sp):
+            hp.Add_Particle(r, [0, 0, 0], int(s), 1, 0)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        batch = hp.Calc_Field_at_Batch(pts)
+        singles = np.stack([hp.Calc_Field_at(pt) for pt in pts])
+    assert relerr(acc, orc.accel_generic(p, R, q, m, sp)) < TOL
+    assert relerr(acc, orc.accel_gather_ld(p, R, q, m)) < TOL
+    assert relerr(batch, orc.calc_field_at_batch(p, R, q, pts, sp)) < TOL
+    assert relerr(batch, singles) < 1e-13
+
+
+@pytest.mark.parametrize("n", [5, 130, 700])
+def test_tip_cloud_vs_oracle(orc, n):
+    cfg, p = tip_setup(orc)
+    rng = np.random.default_rng(n)
+    pos = np.stack([rng.uniform(-40, 40, n), rng.uniform(-40, 40, n), rng.uniform(105, 900, n)], axis=1) * NM
+    ion = (np.arange(n) % 7) == 6
+    q = np.where(ion, Q_0, -Q_0); m = np.where(ion, M_N2P, M_0)
+    pts = np.stack([rng.uniform(-30, 30, 40), rng.uniform(-30, 30, 40), rng.uniform(101, 400, 40)], axis=1) * NM
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=np.where(ion, 2, 1).astype(np.int32))
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        fld = hp.Calc_Field_at_Batch(pts)
+        vac_only = None
+    assert relerr(acc, orc.accel_gather_ld(p, pos, q, m)) < TOL
+    assert relerr(acc, orc.accel_gather(p, pos, q, m)) < TOL
+    want = np.stack([orc.calc_field_at(p, pos, q, pts[k], ld=True) for k in range(40)])
+    assert relerr(fld, want) < TOL
+
+
+# --------------------------------------------------------------------------------------------------
+def test_beeman_kinematics_reference_case(orc):
+    """mod_tests.F90:1403-1452."""
+    d, V, dt, vx0 = 1000 * NM, 2.0e3, 0.25e-15, 1.0e3
+    cfg = rb.planar_config(V, d, (100 * NM, 100 * NM, d), dt, False, 0, capacity=16)
+    with rb.HotPath(cfg) as hp:
+        hp.Add_Particle([0.0, 0.0, 500 * NM], [vx0, 0.0, 0.0], SPECIES_ELEC, 1, 1)
+        for i in range(1, 4):
+            r = hp.Update_Position(i)
+        s = hp.download(("pos", "vel"))
+    a_z = Q_0 * V / (M_0 * d)
+    assert abs((s["pos"][0, 2] - 500 * NM) - 4.5 * a_z * dt ** 2) / (4.5 * a_z * dt ** 2) < 1e-9
+    assert abs(s["vel"][0, 2] - 3.0 * a_z * dt) / (3.0 * a_z * dt) < 1e-12
+    assert abs(s["pos"][0, 0] - 3.0 * vx0 * dt) / (3.0 * vx0 * dt) < 1e-12
+    assert s["vel"][0, 0] == vx0 and s["pos"][0, 1] == 0.0
+    ramo = Q_0 * 3.0 * a_z * dt / d
+    assert abs(r.ramo_current[SPECIES_ELEC] - ramo) / ramo < 1e-12
+
+
+def test_particle_removal_reference_case(orc):
+    """mod_tests.F90:1193-1328: survivors 1,3,5,7 in order, ids 0,2,4,6, life-time bin 10."""
+    d = 100 * NM
+    cfg = rb.planar_config(2.0, d, (100 * NM, 100 * NM, d), 0.25e-15, False, 0, capacity=16)
+    spc = [1, 1, 2, 1, 1, 2, 1]
+    R = np.array([[1.0 * i, -2.0 * i, 10.0 * i] for i in range(1, 8)]) * NM
+    Vel = np.array([[100.0 * i, -50.0 * i, 25.0 * i] for i in range(1, 8)])
+    with rb.HotPath(cfg) as hp:
+        for i in range(7):
+            hp.Add_Particle(R[i], Vel[i], spc[i], 1, 1)
+        k = hp.counts()
+        assert (k.nrPart, k.nrElec, k.nrIon, k.nrID) == (7, 5, 2, 7)
+        hp.Mark_Particles_Remove(1, REMOVE_TOP)
+        hp.Mark_Particles_Remove(1, REMOVE_TOP)  # no-op
+        hp.Mark_Particles_Remove(3, REMOVE_BOT)
+        hp.Mark_Particles_Remove(5, REMOVE_TOP)
+        k = hp.counts()
+        assert (k.nrPart_remove, k.nrElec_remove, k.nrIon_remove) == (3, 2, 1)
+        assert (k.nrElec_remove_top, k.nrElec_remove_bot, k.nrIon_remove_top) == (1, 1, 1)
+        assert hp.download(("charge",))["charge"][1] == 0.0
+        k = hp.Remove_Particles(11)
+        assert (k.nrPart, k.nrElec, k.nrIon) == (4, 3, 1)
+        s = hp.download(("pos", "prev_pos", "vel", "charge", "mass", "species", "id", "emitter", "section", "mask"))
+        keep = [0, 2, 4, 6]
+        assert np.array_equal(s["pos"], R[keep]) and np.array_equal(s["vel"], Vel[keep])
+        assert np.all(s["prev_pos"] == -1.0 * NM)
+        assert list(s["species"]) == [1, 2, 1, 1] and list(s["id"]) == [0, 2, 4, 6]
+        assert list(s["emitter"]) == [1] * 4 and list(s["section"]) == [1] * 4
+        assert s["charge"][0] == -Q_0 and s["charge"][1] == Q_0 and s["mass"][0] == M_0 and s["mass"][1] == M_N2P
+        lt = hp.life_time()
+        assert lt[10, SPECIES_ELEC] == 2 and lt[10, SPECIES_ION] == 1
+        assert np.all(s["mask"] == 1)
+        k = hp.counts()
+        assert (k.nrPart_remove, k.nrElec_remove, k.nrIon_remove) == (0, 0, 0)
+        # remove everything (the branch that skips the compaction), then reuse the store
+        hp.Mark_Particles_Remove(np.arange(4), REMOVE_TOP)
+        k = hp.Remove_Particles(21)
+        assert k.nrPart == 0 and k.nrElec == 0
+        hp.Add_Particle(np.array([5, 6, 50.0]) * NM, [0, 0, 0], SPECIES_ELEC, 22, 1)
+        s = hp.download(("pos", "id"))
+        assert np.array_equal(s["pos"][0], np.array([5, 6, 50.0]) * NM) and s["id"][0] == 7
+
+
+@pytest.mark.parametrize("geom", ["planar", "tip"])
+def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom):
+    """Many Beeman steps with absorption at both electrodes, plane crossings, mid-run additions:
+    particle order, ids, records and counters must match the oracle exactly; positions and
+    velocities agree to rounding (the accelerations feeding them agree to ~1e-13)."""
+    rng = np.random.default_rng(5)
+    if geom == "planar":
+        d = 200 * NM
+        planes = (5 * NM, 50 * NM, 150 * NM)
+        box = (100 * NM, 100 * NM, d)
+        dt = 2.0e-16
+        cfg = rb.planar_config(40.0, d, box, dt, True, 1, capacity=2048, planes_z=planes)
+        p = orc.params_planar(40.0, d, box, dt, True, 1)
+        n0 = 300
+        pos = np.stack([rng.uniform(-50, 50, n0), rng.uniform(-50, 50, n0), rng.uniform(1, 199, n0)], axis=1) * NM
+        vel = np.stack([rng.normal(0, 2e4, n0), rng.normal(0, 2e4, n0), rng.normal(0, 4e5, n0)], axis=1)
+    else:
+        planes = (150 * NM, 400 * NM)
+        box = (100 * NM, 100 * NM, 600 * NM)
+        dt = 2.0e-16
+        cfg = rb.tip_config(500.0, 900 * NM, 100 * NM, 100 * NM, box, dt, True, capacity=2048, planes_z=planes)
+        p = orc.params_tip(500.0, 900 * NM, 100 * NM, 100 * NM, box, dt, True)
+        n0 = 200
+        pos = np.stack([rng.uniform(-20, 20, n0), rng.uniform(-20, 20, n0), rng.uniform(102, 590, n0)], axis=1) * NM
+        vel = np.stack([rng.normal(0, 2e4, n0), rng.normal(0, 2e4, n0), rng.normal(0, 6e5, n0)], axis=1)
+    p.set_planes(planes)
+    species = np.where((np.arange(n0) % 9) == 8, 2, 1).astype(np.int32)
+    st = orc.store(2048)
+    with rb.HotPath(cfg) as hp:
+        for i in range(n0):
+            st.add(p, pos[i], vel[i], int(species[i]), 0, 1, -1, 1 + (i % 5))
+        hp.Add_Particles(pos, vel, species, 0, emit=np.ones(n0, dtype=np.int32), sec=(1 + (np.arange(n0) % 5)).astype(np.int32))
+        total_events = 0
+        for step in range(1, 121):
+            st.clear_events()
+            st.step(p)
+            r = hp.Update_Position(step)
+            ev_o, ev_g = st.events(), hp.events()
+            assert r.n_events == len(ev_o) == len(ev_g)
+            for a, b in zip(ev_o, ev_g):
+                assert (a["kind"], a["plane"], a["index"], a["emit"], a["sec"], a["id"]) == \
+                       (b["kind"], b["plane"], b["index"], b["emit"], b["sec"], b["id"])
+                for key in ("x", "y", "vx", "vy", "vz"):
+                    assert b[key] == pytest.approx(a[key], rel=1e-9, abs=1e-30)
+            total_events += len(ev_o)
+            k = hp.counts()
+            assert (k.nrPart_remove, k.nrElec_remove, k.nrIon_remove) == (st.s.nrPart_remove, st.s.nrElec_remove, st.s.nrIon_remove)
+            assert (k.nrElec_remove_top, k.nrElec_remove_bot) == (st.s.nrElec_remove_top, st.s.nrElec_remove_bot)
+            for sp_ in (1, 2):
+                assert r.ramo_current[sp_] == pytest.approx(st.s.ramo_current[sp_], rel=1e-9, abs=1e-30)
+            st.remove(step)
+            k = hp.Remove_Particles(step)
+            assert (k.nrPart, k.nrElec, k.nrIon) == (st.s.nrPart, st.s.nrElec, st.s.nrIon)
+            if step % 10 == 0:  # emission: new electrons 1 nm above the cathode / tip
+                kadd = 7
+                if geom == "planar":
+                    npos = np.stack([rng.uniform(-50, 50, kadd), rng.uniform(-50, 50, kadd), np.full(kadd, 1.0)], axis=1) * NM
+                else:
+                    npos = np.stack([rng.uniform(-5, 5, kadd), rng.uniform(-5, 5, kadd), np.full(kadd, 102.0)], axis=1) * NM
+                for i in range(kadd):
+                    st.add(p, npos[i], [0, 0, 0], 1, step, 1, -1, 3)
+                hp.Add_Particles(npos, np.zeros((kadd, 3)), np.ones(kadd, dtype=np.int32), step,
+                                 emit=np.ones(kadd, dtype=np.int32), sec=np.full(kadd, 3, dtype=np.int32))
+            if step % 20 == 0:
+                s = hp.download(("pos", "vel", "id", "species", "step", "section"))
+                assert np.array_equal(s["id"], st.ids) and np.array_equal(s["species"], st.species)
+                assert np.array_equal(s["step"], st.step_born) and np.array_equal(s["section"], st.section)
+                assert np.allclose(s["pos"], st.pos, rtol=1e-10, atol=1e-22)
+                assert np.allclose(s["vel"], st.vel, rtol=1e-8, atol=1e-6)
+        assert total_events > 20 and st.s.nrPart < n0 + 12 * 7
+        lt = hp.life_time()
+        for sp_ in (1, 2):
+            ref = np.array([st.life_time(t, sp_) for t in range(rb.api.MAX_LIFE_TIME + 1)])
+            assert np.array_equal(lt[:, sp_], ref)
+
+
+def test_beeman_update_is_bit_exact_without_pair_forces(orc):
+    """With the pair forces off (single species far apart is not needed: use q = 0 atoms-free
+    trick: one particle per run) the position/velocity arithmetic itself is bit-identical."""
+    d, V, dt = 300 * NM, 30.0, 1.0e-16
+    cfg = rb.planar_config(V, d, (100 * NM, 100 * NM, d), dt, False, 0, capacity=8)
+    p = orc.params_planar(V, d, (100 * NM, 100 * NM, d), dt, False, 0)
+    rng = np.random.default_rng(1)
+    for trial in range(5):
+        pos = np.array([rng.uniform(-50, 50), rng.uniform(-50, 50), rng.uniform(1, 299)]) * NM
+        vel = rng.normal(0, 1e5, 3)
+        st = orc.store(8)
+        st.add(p, pos, vel, 1, 0, 1)
+        with rb.HotPath(cfg) as hp:
+            hp.Add_Particle(pos, vel, 1, 0, 1)
+            for step in range(1, 40):
+                st.step(p)
+                hp.Update_Position(step)
+            s = hp.download(("pos", "vel", "acc", "prev_pos"))
+        assert np.array_equal(s["pos"], st.pos) and np.array_equal(s["vel"], st.vel)
+        assert np.array_equal(s["acc"], st.acc) and np.array_equal(s["prev_pos"], st.prev_pos)
+
+
+# --------------------------------------------------------------------------------------------------
+def test_large_cloud_properties(orc):
+    """BASELINE sizes: rows sampled against the long-double oracle, Newton's third law on the
+    Coulomb-only variant, and linearity of the field in the sources."""
+    n = 100_000
+    cfg, p = planar(orc, ic=True, nic=1, cap=n)
+    pos, q, m, sp = cloud(n, 20261017, ions=True)
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        info = hp.last_accel_info()
+        assert info["ms"] > 0 and info["grid_x"] * info["grid_y"] >= 148
+        rows = [0, 1, 127, 128, 5000, 49999, 50000, 77777, n - 2, n - 1]
+        for i in rows:
+            truth = orc.accel_gather_ld(p, pos, q, m, i, i + 1)
+            assert relerr(acc[i:i + 1], truth) < TOL, i
+        # Coulomb only, no vacuum field: sum_i m_i a_i = 0
+        cfg0 = rb.planar_config(0.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1e-16, False, 0, capacity=n)
+        hp.update_config(cfg0)
+        hp.Calculate_Acceleration_Particles()
+        a0 = hp.download(("acc",))["acc"]
+        f = a0 * m[:, None]
+        assert np.linalg.norm(f.sum(axis=0)) < 1e-9 * np.abs(f).sum()
