@@ -212,13 +212,12 @@ def run_ours(args):
     pos = make_cloud(n)
     q = np.full(n, -Q_0)
     m = np.full(n, M_0)
-    chunk = (n + world - 1) // world
-    cap = chunk * world
+    from rumdeed_b200.partition import row_partition
+    chunk, i0, i1, cap = row_partition(n, world, rank)
     cfg = rb.planar_config(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic,
                            capacity=cap, device=local)
     hp = rb.HotPath(cfg)
     hp.upload(pos, q, m)
-    i0, i1 = rank * chunk, min(n, (rank + 1) * chunk)
     hp.set_partition(i0, i1)
     ext = torch.cuda.ExternalStream(hp.stream(), device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

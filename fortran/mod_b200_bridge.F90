@@ -1,0 +1,320 @@
+!-------------------------------------------------------------------------------
+! mod_b200_bridge -- ISO_C_BINDING layer between the RUMDEED Fortran host and
+! librumdeed_b200.so (C ABI: include/rumdeed_b200.h).
+!
+! NOTE: no Fortran compiler exists in the image this repository is built in, so
+! this file has never been compiled there.  It is kept deliberately mechanical:
+! one interface block per C entry point plus thin wrappers with the names and
+! argument conventions of the reference routines they replace.  The same C
+! symbols are exercised by tests/ through ctypes with Fortran-layout arrays.
+!
+! Build (with the reference's makefile):  add mod_b200_bridge.o after
+! mod_hyperboloid_tip.o, compile with -DRUMDEED_B200 and link
+! -L<repo>/rumdeed_b200 -lrumdeed_b200.  See INTEGRATION.md for the five call
+! sites in mod_verlet.F90 / mod_pair.F90 / main.F90 that dispatch here.
+!-------------------------------------------------------------------------------
+module mod_b200_bridge
+  use, intrinsic :: iso_c_binding
+  use mod_global
+  use mod_hyperboloid_tip, only: a_foci, eta_1, shift_z, pre_fac_E_tip, &
+                               & pre_fac_E_tip_unit_voltage, h_tip, r_tip, max_xi
+  implicit none
+  private
+
+  public :: B200_Init, B200_Finalize, B200_Sync_Config
+  public :: B200_Upload_Particles, B200_Download_Particles
+  public :: B200_Add_Particle, B200_Mark_Particles_Remove, B200_Remove_Particles
+  public :: B200_Update_Position, B200_Calculate_Acceleration_Particles
+  public :: B200_Calc_Field_at, B200_Calc_Field_at_Batch
+  public :: B200_Particles_To_Device, B200_Release_Device_Particles
+
+  integer, parameter :: RB2_GEOM_PLANAR = 1, RB2_GEOM_TIP = 2
+  integer, parameter :: RB2_PLANES_MAX = 10
+
+  ! struct rb2_config (include/rumdeed_b200.h)
+  type, bind(C) :: rb2_config
+    integer(c_int) :: geometry, image_charge, N_ic_max, planes_N
+    real(c_double) :: V_s, d, E_z
+    real(c_double) :: box_dim(3)
+    real(c_double) :: time_step
+    real(c_double) :: planes_z(RB2_PLANES_MAX)
+    real(c_double) :: a_foci, eta_1, shift_z, pre_fac_E_tip, pre_fac_E_tip_unit_voltage, h_tip, r_tip, max_xi
+    integer(c_int) :: capacity, device
+  end type rb2_config
+
+  type, bind(C) :: rb2_counts
+    integer(c_int) :: nrPart, nrElec, nrIon, nrAtom, nrID, nrPart_dropped
+    integer(c_int) :: nrPart_remove, nrElec_remove, nrIon_remove, nrAtom_remove
+    integer(c_int) :: nrPart_remove_top, nrPart_remove_bot
+    integer(c_int) :: nrElec_remove_top, nrElec_remove_bot
+    integer(c_int) :: nrIon_remove_top, nrIon_remove_bot
+  end type rb2_counts
+
+  type, bind(C) :: rb2_event
+    integer(c_int) :: kind, plane, index
+    real(c_double) :: x, y, vx, vy, vz
+    integer(c_int) :: emit, sec, id
+  end type rb2_event
+
+  type, bind(C) :: rb2_step_result
+    real(c_double) :: ramo_current(4)
+    real(c_double) :: avg_part_vel(3), avg_elec_vel(3), avg_ion_vel(3)
+    integer(c_int) :: n_events
+    type(rb2_counts) :: counts
+    real(c_float)  :: accel_ms, step_ms
+  end type rb2_step_result
+
+  interface
+    integer(c_int) function rb2_init(cfg) bind(C, name='rb2_init')
+      import :: c_int, rb2_config
+      type(rb2_config), intent(in) :: cfg
+    end function
+    integer(c_int) function rb2_finalize() bind(C, name='rb2_finalize')
+      import :: c_int
+    end function
+    integer(c_int) function rb2_update_config(cfg) bind(C, name='rb2_update_config')
+      import :: c_int, rb2_config
+      type(rb2_config), intent(in) :: cfg
+    end function
+    integer(c_int) function rb2_upload_particles(n, pos, prev_pos, vel, acc, acc_prev, acc_prev2, charge, mass, &
+                          & species, step, emitter, section, life, id, nrID) bind(C, name='rb2_upload_particles')
+      import :: c_int, c_double
+      integer(c_int), value :: n, nrID
+      real(c_double), intent(in) :: pos(3, *), prev_pos(3, *), vel(3, *), acc(3, *), acc_prev(3, *), acc_prev2(3, *)
+      real(c_double), intent(in) :: charge(*), mass(*)
+      integer(c_int), intent(in) :: species(*), step(*), emitter(*), section(*), life(*), id(*)
+    end function
+    integer(c_int) function rb2_download_particles(pos, prev_pos, vel, acc, acc_prev, acc_prev2, charge, mass, &
+                          & species, step, emitter, section, life, id, mask) bind(C, name='rb2_download_particles')
+      import :: c_int, c_double, c_ptr
+      real(c_double), intent(out) :: pos(3, *), prev_pos(3, *), vel(3, *), acc(3, *), acc_prev(3, *), acc_prev2(3, *)
+      real(c_double), intent(out) :: charge(*), mass(*)
+      integer(c_int), intent(out) :: species(*), step(*), emitter(*), section(*), life(*), id(*)
+      type(c_ptr), value :: mask ! pass c_null_ptr: the Fortran masks are all .true. after Remove_Particles
+    end function
+    integer(c_int) function rb2_add_particles(k, pos, vel, species, step, emit, sec, life) bind(C, name='rb2_add_particles')
+      import :: c_int, c_double
+      integer(c_int), value :: k, step
+      real(c_double), intent(in) :: pos(3, *), vel(3, *)
+      integer(c_int), intent(in) :: species(*), emit(*), sec(*), life(*)
+    end function
+    integer(c_int) function rb2_mark_remove(k, index, reason) bind(C, name='rb2_mark_remove')
+      import :: c_int
+      integer(c_int), value :: k
+      integer(c_int), intent(in) :: index(*), reason(*)
+    end function
+    integer(c_int) function rb2_remove_marked(step, counts) bind(C, name='rb2_remove_marked')
+      import :: c_int, rb2_counts
+      integer(c_int), value :: step
+      type(rb2_counts), intent(out) :: counts
+    end function
+    integer(c_int) function rb2_step(step, res) bind(C, name='rb2_step')
+      import :: c_int, rb2_step_result
+      integer(c_int), value :: step
+      type(rb2_step_result), intent(out) :: res
+    end function
+    integer(c_int) function rb2_accel_only() bind(C, name='rb2_accel_only')
+      import :: c_int
+    end function
+    integer(c_int) function rb2_get_events(max_events, events, n_out) bind(C, name='rb2_get_events')
+      import :: c_int, rb2_event
+      integer(c_int), value :: max_events
+      type(rb2_event), intent(out) :: events(*)
+      integer(c_int), intent(out) :: n_out
+    end function
+    integer(c_int) function rb2_field_batch(M, pos_in, field_out) bind(C, name='rb2_field_batch')
+      import :: c_int, c_double
+      integer(c_int), value :: M
+      real(c_double), intent(in)  :: pos_in(3, *)
+      real(c_double), intent(out) :: field_out(3, *)
+    end function
+    integer(c_int) function rb2_field_window_open() bind(C, name='rb2_field_window_open')
+      import :: c_int
+    end function
+    integer(c_int) function rb2_field_window_close() bind(C, name='rb2_field_window_close')
+      import :: c_int
+    end function
+    function rb2_last_error_string() bind(C, name='rb2_last_error_string') result(p)
+      import :: c_ptr
+      type(c_ptr) :: p
+    end function
+  end interface
+
+  type(rb2_event), allocatable :: ev_buf(:)
+
+contains
+
+  subroutine Check(rc, where)
+    integer(c_int), intent(in)   :: rc
+    character(len=*), intent(in) :: where
+    if (rc /= 0) then
+      print '(a, a, a, i0)', 'RUMDEED: librumdeed_b200 error in ', where, ', code ', rc
+      error stop 2
+    end if
+  end subroutine Check
+
+  ! Geometry id: the same test ACC_Geometry() does (mod_verlet.F90:1168); 0 = not on the device.
+  subroutine Fill_Config(cfg, geom)
+    type(rb2_config), intent(out) :: cfg
+    integer, intent(in)           :: geom
+    cfg%geometry = geom
+    cfg%image_charge = merge(1, 0, image_charge)
+    cfg%N_ic_max = N_ic_max
+    cfg%planes_N = planes_N
+    cfg%V_s = V_s
+    cfg%d = d
+    cfg%E_z = E_z
+    cfg%box_dim = box_dim
+    cfg%time_step = time_step
+    cfg%planes_z = planes_z
+    cfg%a_foci = a_foci;  cfg%eta_1 = eta_1;  cfg%shift_z = shift_z
+    cfg%pre_fac_E_tip = pre_fac_E_tip
+    cfg%pre_fac_E_tip_unit_voltage = pre_fac_E_tip_unit_voltage
+    cfg%h_tip = h_tip;  cfg%r_tip = r_tip;  cfg%max_xi = max_xi
+    cfg%capacity = MAX_PARTICLES
+    cfg%device = -1
+  end subroutine Fill_Config
+
+  ! Call at the end of Init_* (main.F90:146), once the procedure pointers are bound.
+  subroutine B200_Init(geom)
+    integer, intent(in) :: geom
+    type(rb2_config)    :: cfg
+    call Fill_Config(cfg, geom)
+    call Check(rb2_init(cfg), 'rb2_init')
+  end subroutine B200_Init
+
+  subroutine B200_Finalize()
+    call Check(rb2_finalize(), 'rb2_finalize')
+  end subroutine B200_Finalize
+
+  ! After Set_Voltage or any change of image_charge / N_ic_max (the unit tests do that).
+  subroutine B200_Sync_Config(geom)
+    integer, intent(in) :: geom
+    type(rb2_config)    :: cfg
+    call Fill_Config(cfg, geom)
+    call Check(rb2_update_config(cfg), 'rb2_update_config')
+  end subroutine B200_Sync_Config
+
+  ! One-off synchronisation points (e.g. before Write_Position or a host-only module runs).
+  subroutine B200_Upload_Particles()
+    if (nrPart > 0) then
+      call Check(rb2_upload_particles(int(nrPart, c_int), particles_cur_pos, particles_prev_pos, particles_cur_vel, &
+               & particles_cur_accel, particles_prev_accel, particles_prev2_accel, particles_charge, particles_mass, &
+               & particles_species, particles_step, particles_emitter, particles_section, particles_life, particles_id, &
+               & int(nrID, c_int)), 'rb2_upload_particles')
+    end if
+  end subroutine B200_Upload_Particles
+
+  subroutine B200_Download_Particles()
+    if (nrPart > 0) then
+      call Check(rb2_download_particles(particles_cur_pos, particles_prev_pos, particles_cur_vel, particles_cur_accel, &
+               & particles_prev_accel, particles_prev2_accel, particles_charge, particles_mass, particles_species, &
+               & particles_step, particles_emitter, particles_section, particles_life, particles_id, c_null_ptr), &
+               & 'rb2_download_particles')
+    end if
+  end subroutine B200_Download_Particles
+
+  ! Add_Particle (mod_pair.F90:29): the host keeps doing its own bookkeeping and file
+  ! writes; this mirrors the new particle into the device store (slot nrPart, id nrID).
+  subroutine B200_Add_Particle(par_pos, par_vel, par_species, step, emit, life, sec)
+    double precision, dimension(1:3), intent(in) :: par_pos, par_vel
+    integer, intent(in)                          :: par_species, step, emit, life, sec
+    real(c_double) :: p(3, 1), v(3, 1)
+    integer(c_int) :: s(1), e(1), c(1), l(1)
+    p(:, 1) = par_pos;  v(:, 1) = par_vel
+    s(1) = par_species;  e(1) = emit;  c(1) = sec;  l(1) = life
+    call Check(rb2_add_particles(1_c_int, p, v, s, int(step, c_int), e, c, l), 'rb2_add_particles')
+  end subroutine B200_Add_Particle
+
+  ! Mark_Particles_Remove (mod_pair.F90:169) for marks decided on the host (collisions).
+  subroutine B200_Mark_Particles_Remove(i, m)
+    integer, intent(in) :: i, m
+    integer(c_int)      :: idx(1), why(1)
+    idx(1) = i - 1 ! 0-based on the C side
+    why(1) = m
+    call Check(rb2_mark_remove(1_c_int, idx, why), 'rb2_mark_remove')
+  end subroutine B200_Mark_Particles_Remove
+
+  ! Remove_Particles (mod_pair.F90:352): compaction on the device, counters back to mod_global.
+  subroutine B200_Remove_Particles(step)
+    integer, intent(in) :: step
+    type(rb2_counts)    :: k
+    call Check(rb2_remove_marked(int(step, c_int), k), 'rb2_remove_marked')
+    nrPart = k%nrPart;  nrElec = k%nrElec;  nrIon = k%nrIon;  nrAtom = k%nrAtom
+    nrElecIon = nrElec + nrIon
+    nrPart_remove = 0;  nrElec_remove = 0;  nrIon_remove = 0;  nrAtom_remove = 0
+    nrPart_remove_top = 0;  nrPart_remove_bot = 0
+    nrElec_remove_top = 0;  nrElec_remove_bot = 0
+    nrIon_remove_top = 0;  nrIon_remove_bot = 0
+  end subroutine B200_Remove_Particles
+
+  ! Update_Position(step) (main.F90:190): one fused device step.  Fills ramo_current, the
+  ! velocity averages and the remove counters, and writes the absorb / plane records in the
+  ! serial order (ascending particle index) with the units the reference uses.
+  subroutine B200_Update_Position(step)
+    integer, intent(in)   :: step
+    type(rb2_step_result) :: r
+    integer(c_int)        :: n_ev
+    integer               :: k
+    call Check(rb2_step(int(step, c_int), r), 'rb2_step')
+    ramo_current(1:nrSpecies) = r%ramo_current(2:nrSpecies+1) ! C index = species id
+    avg_part_vel = r%avg_part_vel;  avg_elec_vel = r%avg_elec_vel;  avg_ion_vel = r%avg_ion_vel
+    nrPart_remove = r%counts%nrPart_remove;  nrElec_remove = r%counts%nrElec_remove
+    nrIon_remove = r%counts%nrIon_remove;    nrAtom_remove = r%counts%nrAtom_remove
+    nrPart_remove_top = r%counts%nrPart_remove_top;  nrPart_remove_bot = r%counts%nrPart_remove_bot
+    nrElec_remove_top = r%counts%nrElec_remove_top;  nrElec_remove_bot = r%counts%nrElec_remove_bot
+    nrIon_remove_top = r%counts%nrIon_remove_top;    nrIon_remove_bot = r%counts%nrIon_remove_bot
+    if (r%n_events > 0) then
+      if (.not. allocated(ev_buf)) allocate(ev_buf(max(1024, int(r%n_events))))
+      if (size(ev_buf) < r%n_events) then
+        deallocate(ev_buf);  allocate(ev_buf(2*int(r%n_events)))
+      end if
+      call Check(rb2_get_events(int(size(ev_buf), c_int), ev_buf, n_ev), 'rb2_get_events')
+      do k = 1, n_ev
+        select case (ev_buf(k)%kind)
+        case (1) ! mod_pair.F90:243-245
+          write(unit=ud_density_absorb_top) ev_buf(k)%x, ev_buf(k)%y, ev_buf(k)%vx, ev_buf(k)%vy, ev_buf(k)%vz, &
+                                          & ev_buf(k)%emit, ev_buf(k)%sec, ev_buf(k)%id
+        case (2) ! mod_pair.F90:255-256
+          write(unit=ud_density_absorb_bot) ev_buf(k)%x, ev_buf(k)%y, ev_buf(k)%emit, ev_buf(k)%sec, ev_buf(k)%id
+        case (3) ! mod_verlet.F90:360-362
+          write(unit=planes_ud(ev_buf(k)%plane + 1)) ev_buf(k)%x, ev_buf(k)%y, ev_buf(k)%vx, ev_buf(k)%vy, ev_buf(k)%vz, &
+                                          & ev_buf(k)%emit, ev_buf(k)%sec, ev_buf(k)%id
+        end select
+      end do
+    end if
+  end subroutine B200_Update_Position
+
+  ! Calculate_Acceleration_Particles (mod_verlet.F90:597), used directly by the unit tests.
+  subroutine B200_Calculate_Acceleration_Particles()
+    call Check(rb2_accel_only(), 'rb2_accel_only')
+  end subroutine B200_Calculate_Acceleration_Particles
+
+  ! Calc_Field_at_Batch (mod_verlet.F90:1635)
+  subroutine B200_Calc_Field_at_Batch(M, pos_in, field_out)
+    integer, intent(in)                                :: M
+    double precision, dimension(1:3, 1:M), intent(in)  :: pos_in
+    double precision, dimension(1:3, 1:M), intent(out) :: field_out
+    if (M < 1) return
+    call Check(rb2_field_batch(int(M, c_int), pos_in, field_out), 'rb2_field_batch')
+  end subroutine B200_Calc_Field_at_Batch
+
+  ! Calc_Field_at (mod_verlet.F90:1466)
+  function B200_Calc_Field_at(pos_xyz) result(field)
+    double precision, dimension(1:3), intent(in) :: pos_xyz
+    double precision, dimension(1:3)             :: field
+    double precision                             :: p(3, 1), f(3, 1)
+    p(:, 1) = pos_xyz
+    call Check(rb2_field_batch(1_c_int, p, f), 'rb2_field_batch')
+    field = f(:, 1)
+  end function B200_Calc_Field_at
+
+  subroutine B200_Particles_To_Device()
+    call Check(rb2_field_window_open(), 'rb2_field_window_open')
+  end subroutine B200_Particles_To_Device
+
+  subroutine B200_Release_Device_Particles()
+    call Check(rb2_field_window_close(), 'rb2_field_window_close')
+  end subroutine B200_Release_Device_Particles
+
+end module mod_b200_bridge

@@ -13,8 +13,8 @@
 //   * the planar image series shares dx, dy, dx^2+dy^2 over all partners, sums the lateral
 //     weights first (2 FMAs per pair instead of 2 per partner) and evaluates
 //     1/(sqrt(s)+1e-18)^3 with one MUFU.RSQ64H seed + 7 FP64 instructions
-//     (rb2_inv_r3_soft) instead of sqrt + divide: 74 FP64-pipe instructions per ordered
-//     pair at N_ic_max = 1 against 99 algorithmic flops;
+//     (rb2_inv_r3_soft) instead of sqrt + divide: 74 FP64-pipe instructions + 6 MUFU per
+//     ordered pair at N_ic_max = 1 against 99 algorithmic flops;
 //   * the reference's index-ordered image roles (j>i evaluates at (z_i,z_j), j<i at
 //     (z_j,z_i)) reduce to a sign on the same-charge z-sum, resolved per tile except in
 //     the tiles that overlap the CTA's own i-range.
@@ -22,9 +22,22 @@
 
 namespace {
 
-constexpr int TJ = 128;      // j-particles per shared-memory tile (4 KB)
-constexpr int STAGES = 3;    // ring depth
-constexpr int BLOCK = 128;   // i-particles (or field points) per CTA, one per thread
+#ifndef RB2_BLOCK
+#define RB2_BLOCK 128
+#endif
+#ifndef RB2_MINB
+#define RB2_MINB 4
+#endif
+#ifndef RB2_UNROLL
+#define RB2_UNROLL 4
+#endif
+#ifndef RB2_TJ
+#define RB2_TJ 128
+#endif
+constexpr int TJ = RB2_TJ;        // j-particles per shared-memory tile (32 B each)
+constexpr int STAGES = 3;         // ring depth
+constexpr int UNROLL = RB2_UNROLL;
+constexpr int BLOCK = RB2_BLOCK;  // i-particles (or field points) per CTA, one per thread
 
 // ---- TMA bulk copy + mbarrier (sm_90+ PTX, UBLKCP / SYNCS in SASS) -----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,7 +89,7 @@ __device__ __forceinline__ void planar_term(double xi, double yi, double zi, con
     const double dx = xi - pj.x;
     const double dy = yi - pj.y;
     const double dz = zi - pj.z;
-    const double dxy2 = fma(dy, dy, dx * dx);
+    const double dxy2 = fma(dy, dy, fma(dx, dx, RB2_S_FLOOR));
     const double wc = rb2_inv_r3_soft(fma(dz, dz, dxy2));
     if (NIC < 0) {
         const double t = qj * wc;
@@ -156,7 +169,7 @@ __device__ __forceinline__ void tip_ic_force(const TipParams &T, const TipImage 
 // partial[(slot*3 + c)*n_tgt + (i - i_begin)] receives  sum_j q_j * (Coulomb + image)_c  over
 // this CTA's j-chunk.
 template <int GEOM, int NIC, bool FIELD>
-__global__ void __launch_bounds__(BLOCK, 4)
+__global__ void __launch_bounds__(BLOCK, RB2_MINB)
 k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ tgt_pq, const double *__restrict__ tgt_pts,
        int i_begin, int i_end, int j_chunk, int slot0, PlanarParams P, TipParams T, double *__restrict__ partial)
 {
@@ -230,7 +243,7 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                     }
                     az += a.t;
                 } else {
-#pragma unroll 2
+#pragma unroll UNROLL
                     for (int jj = 0; jj < cnt; ++jj) {
                         const double4 pj = tile[jj];
                         planar_term<NIC>(xi, yi, zi, pj, pj.w, pj.w, P, a);
@@ -342,7 +355,7 @@ Split choose_split(int n_tgt, int n_src, int sm_count)
 {
     Split s;
     s.nblk = (n_tgt + BLOCK - 1) / BLOCK;
-    const int want_units = sm_count * 4 * 8;
+    const int want_units = sm_count * RB2_MINB * 8;
     int ns = (want_units + s.nblk - 1) / s.nblk;
     const int max_ns = (n_src + TJ - 1) / TJ;
     if (ns > max_ns) ns = max_ns;
