@@ -87,7 +87,8 @@ def build(force: bool = False, march: str | None = None, out_dir: str | None = N
     need = force or not (os.path.exists(os.path.join(out, "liboracle.so"))
                          and os.path.exists(os.path.join(out, "liboracle_fast.so")))
     if not need:
-        src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("rumdeed_oracle.c", "rumdeed_oracle.h"))
+        src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in (
+            "rumdeed_oracle.c", "rumdeed_oracle.h", "rumdeed_oracle_emission.c", "rumdeed_oracle_emission.h"))
         need = src_m > min(os.path.getmtime(os.path.join(out, f)) for f in ("liboracle.so", "liboracle_fast.so"))
     if need:
         cmd = ["make", "-C", _HERE, "-B", f"OUT={out}"]
@@ -362,3 +363,130 @@ class Store:
 
     def life_time(self, lt, species):
         return int(self.s.life_time[lt][species])
+
+
+# ------------------------------------------------------------------------------------------------------
+# emission samplers (oracle/rumdeed_oracle_emission.c)
+SUPPLY_FE, SUPPLY_GTF = 1, 2
+
+
+class Rng(C.Structure):
+    _fields_ = [("s", C.c_uint64 * 4)]
+
+
+class EmissionStruct(C.Structure):
+    _fields_ = [("p", C.POINTER(Params)), ("store", C.POINTER(StoreStruct)),
+                ("emit_pos", C.c_double * 3), ("emit_dim", C.c_double * 3),
+                ("y_num", C.c_int), ("x_num", C.c_int), ("w_theta_arr", _PD),
+                ("T_temp", C.c_double), ("a_rate", C.c_double), ("MH_std", C.c_double),
+                ("MH_std_tip", C.c_double), ("residual", C.c_double)]
+
+
+class Emission:
+    """One rectangular emitter with a checkerboard work function on top of an oracle Store."""
+
+    def __init__(self, orc: Oracle, p: Params, store: Store, emit_pos, emit_dim, w_theta=((2.0,),), T_temp=293.15, seed=1):
+        self.orc, self.p, self.store = orc, p, store
+        lib = orc.lib
+        self.w = np.ascontiguousarray(np.atleast_2d(np.asarray(w_theta, dtype=np.float64)))
+        e = self.e = EmissionStruct()
+        e.p = C.pointer(p)
+        e.store = store.ptr
+        e.emit_pos[:] = list(emit_pos)
+        e.emit_dim[:] = list(emit_dim)
+        e.y_num, e.x_num = self.w.shape
+        e.w_theta_arr = _d(self.w)
+        e.T_temp = T_temp
+        e.a_rate, e.MH_std, e.MH_std_tip, e.residual = 1.0, 0.0125, 1.0, 0.0
+        self.rng = Rng()
+        PE, PR = C.POINTER(EmissionStruct), C.POINTER(Rng)
+        if not getattr(lib, "_emission_bound", False):
+            lib.orc_rng_seed.argtypes = [PR, C.c_uint64]
+            lib.orc_rng_uniform.argtypes = [PR]; lib.orc_rng_uniform.restype = C.c_double
+            lib.orc_box_muller.argtypes = [PR, _PD, _PD, _PD]
+            lib.orc_rand_poisson.argtypes = [PR, C.c_double]; lib.orc_rand_poisson.restype = C.c_int
+            lib.orc_get_mb_velocity.argtypes = [PR, C.c_double, _PD]
+            lib.orc_w_theta_xy.argtypes = [PE, _PD, _PI]; lib.orc_w_theta_xy.restype = C.c_double
+            lib.orc_kevin_jgtf_v2.argtypes = [C.c_double] * 3; lib.orc_kevin_jgtf_v2.restype = C.c_double
+            lib.orc_supply_integrand.argtypes = [PE, C.c_int, _PD, _PD]; lib.orc_supply_integrand.restype = C.c_double
+            lib.orc_supply_grid.argtypes = [PE, C.c_int, C.c_int, _PD]; lib.orc_supply_grid.restype = C.c_double
+            lib.orc_mh_rectangle_J.argtypes = [PE, PR, _PD, _PD, _PD]; lib.orc_mh_rectangle_J.restype = C.c_int
+            lib.orc_mh_rectangle_J_batch.argtypes = [PE, PR, C.c_int, _PD, _PD, _PD]
+            lib.orc_do_field_emission_planar.argtypes = [PE, PR, C.c_int, C.c_double, C.c_int, _PD]
+            lib.orc_do_field_emission_planar.restype = C.c_int
+            lib.orc_mh_rectangle_J_thermo.argtypes = [PE, PR, _PD]; lib.orc_mh_rectangle_J_thermo.restype = C.c_int
+            lib.orc_do_field_thermo_emission_planar.argtypes = [PE, PR, C.c_int, C.c_double]
+            lib.orc_do_field_thermo_emission_planar.restype = C.c_int
+            lib.orc_do_photo_emission_rectangle.argtypes = [PE, PR, C.c_int, C.c_double, C.c_int, C.c_int]
+            lib.orc_do_photo_emission_rectangle.restype = C.c_int
+            lib.orc_tip_supply_grid.argtypes = [PE, C.c_int, C.c_int, _PD]; lib.orc_tip_supply_grid.restype = C.c_double
+            lib.orc_metro_algo_tip_v3.argtypes = [PE, PR, C.c_int, _PD, _PD, _PD, _PD, _PD]
+            lib.orc_metro_algo_tip_v3.restype = C.c_int
+            lib.orc_do_field_emission_tip.argtypes = [PE, PR, C.c_int, C.c_double]; lib.orc_do_field_emission_tip.restype = C.c_int
+            lib._emission_bound = True
+        lib.orc_rng_seed(C.byref(self.rng), seed)
+
+    def _E(self):
+        return C.byref(self.e)
+
+    def _R(self):
+        return C.byref(self.rng)
+
+    def uniform(self):
+        return self.orc.lib.orc_rng_uniform(self._R())
+
+    def w_theta_xy(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        sec = C.c_int(0)
+        w = self.orc.lib.orc_w_theta_xy(self._E(), _d(pos), C.byref(sec))
+        return w, sec.value
+
+    def kevin_jgtf_v2(self, F, T, w):
+        return self.orc.lib.orc_kevin_jgtf_v2(F, T, w)
+
+    def supply_integrand(self, kind, xx):
+        xx = np.ascontiguousarray(xx, dtype=np.float64)
+        f = np.zeros(3)
+        return self.orc.lib.orc_supply_integrand(self._E(), kind, _d(xx), _d(f)), f
+
+    def supply_grid(self, kind, n):
+        f = np.zeros(3)
+        return self.orc.lib.orc_supply_grid(self._E(), kind, n, _d(f)), f
+
+    def mh_rectangle_J(self):
+        df, F, pos = np.zeros(1), np.zeros(1), np.zeros(3)
+        rc = self.orc.lib.orc_mh_rectangle_J(self._E(), self._R(), _d(df), _d(F), _d(pos))
+        return rc, df[0], F[0], pos
+
+    def mh_rectangle_J_batch(self, M):
+        df, F, pos = np.zeros(M), np.zeros(M), np.zeros((M, 3))
+        self.orc.lib.orc_mh_rectangle_J_batch(self._E(), self._R(), M, _d(df), _d(F), _d(pos))
+        return df, F, pos
+
+    def do_field_emission_planar(self, step, N_sup, mh_batch=False):
+        dfa = np.zeros(1)
+        n = self.orc.lib.orc_do_field_emission_planar(self._E(), self._R(), step, N_sup, int(mh_batch), _d(dfa))
+        return n, dfa[0]
+
+    def mh_rectangle_J_thermo(self):
+        pos = np.zeros(3)
+        rc = self.orc.lib.orc_mh_rectangle_J_thermo(self._E(), self._R(), _d(pos))
+        return rc, pos
+
+    def do_field_thermo_emission_planar(self, step, N_sup):
+        return self.orc.lib.orc_do_field_thermo_emission_planar(self._E(), self._R(), step, N_sup)
+
+    def do_photo_emission_rectangle(self, step, p_eV, photon_mode=1, max_elec_emit=-1):
+        return self.orc.lib.orc_do_photo_emission_rectangle(self._E(), self._R(), step, p_eV, photon_mode, max_elec_emit)
+
+    def tip_supply_grid(self, nr_xi=100, nr_phi=100):
+        fa = np.zeros(1)
+        return self.orc.lib.orc_tip_supply_grid(self._E(), nr_xi, nr_phi, _d(fa)), fa[0]
+
+    def metro_algo_tip_v3(self, ndim=80):
+        xi, phi, eta_f, df, pos = np.zeros(1), np.zeros(1), np.zeros(1), np.zeros(1), np.zeros(3)
+        rc = self.orc.lib.orc_metro_algo_tip_v3(self._E(), self._R(), ndim, _d(xi), _d(phi), _d(eta_f), _d(df), _d(pos))
+        return rc, xi[0], phi[0], eta_f[0], df[0], pos
+
+    def do_field_emission_tip(self, step, n_s):
+        return self.orc.lib.orc_do_field_emission_tip(self._E(), self._R(), step, n_s)

@@ -6,5 +6,7 @@ package is the thin Python host mirror used by the tests and the benchmark.
 from .api import (Config, Counts, Event, HotPath, Rb2Error, StepResult, device_available, load_library,  # noqa: F401
                   planar_config, tip_config)
 
-__all__ = ["Config", "Counts", "Event", "HotPath", "Rb2Error", "StepResult", "device_available", "load_library",
+from .host_api import Simulation  # noqa: F401,E402
+
+__all__ = ["Simulation", "Config", "Counts", "Event", "HotPath", "Rb2Error", "StepResult", "device_available", "load_library",
            "planar_config", "tip_config"]

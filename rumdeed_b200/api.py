@@ -209,6 +209,15 @@ class HotPath:
         self._check(self.lib.rb2_init(C.byref(config)))
         self.closed = False
 
+    @classmethod
+    def attach(cls):
+        """View on the store another host (e.g. host_api.Simulation) has already initialised."""
+        obj = cls.__new__(cls)
+        obj.lib = load_library()
+        obj.cfg = None
+        obj.closed = True  # never finalises somebody else's state
+        return obj
+
     # -- plumbing -----------------------------------------------------------------------------
     def _check(self, rc):
         if rc != 0:
