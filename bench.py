@@ -347,7 +347,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=1_000_000, help="particles (headline 1e6; 1e4 / 1e5 for the sweep)")
+    ap.add_argument("--particles", "--n", dest="n", type=int, default=1_000_000,
+                    help="particles (headline 1e6; 1e4 / 1e5 for the sweep); use --particles under torchrun")
     ap.add_argument("--nic", type=int, default=1, help="N_ic_max")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

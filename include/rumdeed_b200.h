@@ -172,6 +172,14 @@ int rb2_field_window_close(void);
  * The i-range [i_begin, i_end) of the acceleration evaluation this process owns
  * (global, 0-based).  Default: everything. */
 int rb2_set_partition(int i_begin, int i_end);
+/* Pair-symmetric evaluation split over processes: (target superblock, source group) work units are
+ * dealt round-robin to `world` processes; each computes partial raw sums (rb2_accel_partial), the host
+ * plumbing all-reduces the buffer "raw" (3 x padded-N doubles), then every process finalises. */
+int rb2_set_pair_rank(int rank, int world);
+int rb2_accel_partial(void);
+int rb2_accel_finalize(void);
+/* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb". */
+int rb2_set_option(const char *name, double value);
 /* Device pointer + byte size of the (3,capacity) acceleration buffer so that the
  * host plumbing (torch.distributed / NCCL) can all-gather the slices in place. */
 int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes);

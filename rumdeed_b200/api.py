@@ -92,7 +92,7 @@ EXPORTS = (
     "rb2_add_particles", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_accel_host",
     "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close",
-    "rb2_set_partition", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
+    "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
 )
 
@@ -128,6 +128,8 @@ def load_library(path: str | None = None):
     lib.rb2_field_batch.argtypes = [C.c_int, _PD, _PD]
     lib.rb2_field_batch_delta.argtypes = [C.c_int, _PD, C.c_int, _PD, _PD, _PD]
     lib.rb2_set_partition.argtypes = [C.c_int, C.c_int]
+    lib.rb2_set_pair_rank.argtypes = [C.c_int, C.c_int]
+    lib.rb2_set_option.argtypes = [C.c_char_p, C.c_double]
     lib.rb2_device_buffer.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.rb2_stream.argtypes = [C.POINTER(C.c_void_p)]
     lib.rb2_fp64_peak.argtypes = [C.c_double, _PD, C.POINTER(C.c_float)]
@@ -382,6 +384,18 @@ class HotPath:
     # -- multi-GPU / measurement ---------------------------------------------------------------------
     def set_partition(self, i_begin, i_end):
         self._check(self.lib.rb2_set_partition(int(i_begin), int(i_end)))
+
+    def set_option(self, name: str, value: float):
+        self._check(self.lib.rb2_set_option(name.encode(), float(value)))
+
+    def set_pair_rank(self, rank, world):
+        self._check(self.lib.rb2_set_pair_rank(int(rank), int(world)))
+
+    def accel_partial(self):
+        self._check(self.lib.rb2_accel_partial())
+
+    def accel_finalize(self):
+        self._check(self.lib.rb2_accel_finalize())
 
     def device_buffer(self, name: str):
         p = C.c_void_p()

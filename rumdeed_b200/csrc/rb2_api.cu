@@ -124,6 +124,31 @@ void fill_velocity_result(Rb2Ctx &c, rb2_step_result *out)
     }
 }
 
+// Which pair kernel evaluates Calculate_Acceleration_Particles: the pair-symmetric kernel for the planar
+// geometry when the whole i-range is evaluated here (pair_mode 2, or auto from sym_min_n particles on),
+// the gather kernel otherwise (tip geometry, i-partition in effect, small N).
+bool use_sym_kernel(const Rb2Ctx &c, int n, int i0, int i1)
+{
+    if (c.cfg.geometry != RB2_GEOM_PLANAR || c.pair_mode == 1) return false;
+    if (i0 != 0 || i1 != n) return false;
+    if (c.pair_mode == 2) return true;
+    return n >= c.sym_min_n;
+}
+
+int launch_accel_any(Rb2Ctx &c, const double4 *pq, const double *mass, int n, int i0, int i1, double *acc)
+{
+    if (use_sym_kernel(c, n, i0, i1)) {
+        if (c.pair_world > 1)
+            return rb2_fail(RB2_ERR_ARG, "pair work is split over %d processes: use rb2_accel_partial / rb2_accel_finalize", c.pair_world);
+        int rc = rb2_launch_accel_sym_partial(c, pq, n);
+        if (rc) return rc;
+        c.last_pair_kernel = 2;
+        return rb2_launch_accel_sym_finalize(c, pq, mass, n, acc);
+    }
+    c.last_pair_kernel = 1;
+    return rb2_launch_accel(c, pq, mass, n, i0, i1, acc);
+}
+
 // position update + (ordered) event records; leaves the stream busy with nothing pending on the host
 int do_update_position(Rb2Ctx &c, bool overlap_accel, int *rc_accel)
 {
@@ -142,7 +167,7 @@ int do_update_position(Rb2Ctx &c, bool overlap_accel, int *rc_accel)
         // while it runs
         int i0 = c.part_begin, i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
         if (i0 < 0) i0 = 0;
-        *rc_accel = rb2_launch_accel(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
+        *rc_accel = launch_accel_any(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
         if (*rc_accel) return *rc_accel;
         c.accel_timed = true;
     }
@@ -261,6 +286,7 @@ int rb2_finalize(void)
     free_arrays(c.b);
     cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);
     cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
+    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw);
     cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
     cudaFreeHost(c.h_counters); cudaFreeHost(c.h_red); cudaFreeHost(c.h_total); cudaFreeHost(c.h_pts); cudaFreeHost(c.h_fld);
     cudaFreeHost(c.h_stage);
@@ -506,7 +532,7 @@ int rb2_accel_only(void)
     Rb2Ctx &c = g_rb2;
     int i0 = c.part_begin < 0 ? 0 : c.part_begin;
     int i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
-    int rc = rb2_launch_accel(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
+    int rc = launch_accel_any(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
     if (rc) return rc;
     c.accel_timed = (c.n > 0 && i1 > i0);
     RB2_CUDA(cudaStreamSynchronize(c.stream));
@@ -589,7 +615,7 @@ int rb2_accel_host(int n, const double *pos, const double *charge, const double 
     int i0 = c.part_begin < 0 ? 0 : c.part_begin;
     int i1 = (c.part_end < 0 || c.part_end > n) ? n : c.part_end;
     if (i0 > i1) i0 = i1;
-    rc = rb2_launch_accel(c, c.b.pq, c.b.vel, n, i0, i1, c.b.acc);
+    rc = launch_accel_any(c, c.b.pq, c.b.vel, n, i0, i1, c.b.acc);
     if (rc) return rc;
     c.accel_timed = (i1 > i0);
     if (i1 > i0)
@@ -663,6 +689,58 @@ int rb2_field_batch(int M, const double *pos_in, double *field_out)
 int rb2_field_window_open(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 int rb2_field_window_close(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 
+int rb2_set_option(const char *name, double value)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (!name) return rb2_fail(RB2_ERR_ARG, "NULL option name");
+    if (!strcmp(name, "pair_mode")) {
+        if (value < 0 || value > 2) return rb2_fail(RB2_ERR_ARG, "pair_mode must be 0 (auto), 1 (gather) or 2 (pair-symmetric)");
+        c.pair_mode = (int)value;
+    } else if (!strcmp(name, "sym_min_n")) {
+        c.sym_min_n = (int)value;
+    } else if (!strcmp(name, "sym_budget_mb")) {
+        if (value <= 0) return rb2_fail(RB2_ERR_ARG, "sym_budget_mb must be > 0");
+        c.sym_budget_bytes = (size_t)(value * 1048576.0);
+    } else {
+        return rb2_fail(RB2_ERR_ARG, "unknown option '%s'", name);
+    }
+    return RB2_OK;
+}
+
+int rb2_set_pair_rank(int rank, int world)
+{
+    RB2_REQUIRE_INIT();
+    if (world < 1 || rank < 0 || rank >= world) return rb2_fail(RB2_ERR_ARG, "bad rank %d of %d", rank, world);
+    g_rb2.pair_rank = rank;
+    g_rb2.pair_world = world;
+    return RB2_OK;
+}
+
+int rb2_accel_partial(void)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (c.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_accel_partial: planar geometry only");
+    int rc = rb2_launch_accel_sym_partial(c, c.a.pq, c.n);
+    if (rc) return rc;
+    c.last_pair_kernel = 2;
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    return RB2_OK;
+}
+
+int rb2_accel_finalize(void)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (c.n > 0 && (!c.sym_raw || c.sym_n_pad < c.n)) return rb2_fail(RB2_ERR_ARG, "rb2_accel_finalize without rb2_accel_partial");
+    int rc = rb2_launch_accel_sym_finalize(c, c.a.pq, c.a.mass, c.n, c.a.acc);
+    if (rc) return rc;
+    c.accel_timed = c.n > 0;
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    return RB2_OK;
+}
+
 int rb2_set_partition(int i_begin, int i_end)
 {
     RB2_REQUIRE_INIT();
@@ -686,6 +764,7 @@ int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes)
     else if (!strcmp(name, "acc_prev")) { p = c.a.acc_prev; b = 3 * cap * sizeof(double); }
     else if (!strcmp(name, "acc_prev2")) { p = c.a.acc_prev2; b = 3 * cap * sizeof(double); }
     else if (!strcmp(name, "mass")) { p = c.a.mass; b = cap * sizeof(double); }
+    else if (!strcmp(name, "raw")) { p = c.sym_raw; b = (size_t)3 * c.sym_n_pad * sizeof(double); }
     else return rb2_fail(RB2_ERR_ARG, "unknown buffer '%s'", name);
     *dev_ptr = p;
     if (bytes) *bytes = b;

@@ -98,6 +98,15 @@ struct Rb2Ctx {
     int *d_total = nullptr, *h_total = nullptr;                 // scan totals
 
     double *partial = nullptr; size_t partial_bytes = 0;       // pair-kernel partial sums
+    // pair-symmetric kernel (rb2_pair_sym.cu)
+    int    pair_mode = 0;                 // 0 auto, 1 gather, 2 pair-symmetric
+    int    sym_min_n = 16384;             // auto: use the symmetric kernel from this N on
+    int    pair_rank = 0, pair_world = 1; // ownership of (target, group) CTAs across processes
+    size_t sym_budget_bytes = (size_t)2048 << 20;
+    double *sym_bufI = nullptr, *sym_bufJ = nullptr, *sym_raw = nullptr;
+    size_t sym_bufI_bytes = 0, sym_bufJ_bytes = 0, sym_raw_bytes = 0;
+    int    sym_n_pad = 0;
+    int    last_pair_kernel = 0;          // 1 gather, 2 symmetric
     rb2_event *d_events = nullptr; int ev_cap = 0;
     std::vector<rb2_event> host_events;
 
@@ -138,6 +147,9 @@ int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
 int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, int i_begin, int i_end, double *acc_out);
 int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra, int n_extra,
                      const double *d_pts, int M, double *d_fld);
+// pair-symmetric kernel (rb2_pair_sym.cu)
+int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n);
+int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);
 // integrate kernels (rb2_integrate.cu)
 int rb2_launch_pack(Rb2Ctx &ctx, const double *pos3, const double *q, int n, double4 *pq);
 int rb2_launch_unpack(Rb2Ctx &ctx, const double4 *pq, int n, double *pos3, double *q);

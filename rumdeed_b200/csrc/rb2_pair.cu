@@ -19,6 +19,7 @@
 //     (z_j,z_i)) reduce to a sign on the same-charge z-sum, resolved per tile except in
 //     the tiles that overlap the CTA's own i-range.
 #include "rb2_internal.cuh"
+#include "rb2_planar_math.cuh"
 
 namespace {
 
@@ -69,67 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-}
-
-struct Acc4 {
-    double x, y, z, t;  // t: same-charge partner z-sum, signed by the caller (image roles)
-};
-
-// ---- planar pair term ----------------------------------------------------------------------
-// Coulomb (src/mod_verlet.F90:1297-1306) + image series (src/acc_ic_planar_series.inc:20-63)
-// of source j evaluated at (xi, yi, zi), WITHOUT q_i/(4 pi eps0) (applied in the finalize
-// kernel).  Partner heights relative to the evaluation height, with S = z_i + z_j and
-// D = z_i - z_j:  opposite charge  S, S-2nd, S+2nd ;  same charge  D-2nd, D+2nd.
-// With the roles swapped (reference j < i) S is unchanged and D -> -D, which maps the two
-// same-charge partners onto each other with dz negated: same weights, opposite z-sum.
-template <int NIC>
-__device__ __forceinline__ void planar_term(double xi, double yi, double zi, const double4 pj, double qj, double qs,
-                                            const PlanarParams &P, Acc4 &a)
-{
-    const double dx = xi - pj.x;
-    const double dy = yi - pj.y;
-    const double dz = zi - pj.z;
-    const double dxy2 = fma(dy, dy, fma(dx, dx, RB2_S_FLOOR));
-    const double wc = rb2_inv_r3_soft(fma(dz, dz, dxy2));
-    if (NIC < 0) {
-        const double t = qj * wc;
-        a.x = fma(dx, t, a.x);
-        a.y = fma(dy, t, a.y);
-        a.z = fma(dz, t, a.z);
-        return;
-    }
-    const double S = zi + pj.z;
-    const double w0 = rb2_inv_r3_soft(fma(S, S, dxy2));
-    double W = -w0;        // sum of signed lateral weights
-    double Zopp = S * w0;  // opposite-charge z-sum (enters with a minus)
-    double Zsame = 0.0;    // same-charge z-sum (sign = image role)
-    if (NIC == 1) {
-        const double a1 = S - P.two_d, a2 = S + P.two_d, b1 = dz - P.two_d, b2 = dz + P.two_d;
-        const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
-        const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
-        const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
-        const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
-        W = (w3 + w4) - ((w0 + w1) + w2);
-        Zopp = fma(a2, w2, fma(a1, w1, Zopp));
-        Zsame = fma(b2, w4, b1 * w3);
-    } else if (NIC >= 2) {
-        for (int n = 1; n <= P.nic; ++n) {
-            const double h = P.two_d * (double)n;
-            const double a1 = S - h, a2 = S + h, b1 = dz - h, b2 = dz + h;
-            const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
-            const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
-            const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
-            const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
-            W += (w3 + w4) - (w1 + w2);
-            Zopp = fma(a2, w2, fma(a1, w1, Zopp));
-            Zsame = fma(b2, w4, fma(b1, w3, Zsame));
-        }
-    }
-    const double t = qj * (wc + W);
-    a.x = fma(dx, t, a.x);
-    a.y = fma(dy, t, a.y);
-    a.z = fma(qj, fma(dz, wc, -Zopp), a.z);
-    a.t = fma(qs, Zsame, a.t);
 }
 
 // ---- hyperboloid tip math (IEEE sqrt / divide: N is small for this geometry) -----------------

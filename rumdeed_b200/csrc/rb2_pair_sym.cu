@@ -1,0 +1,268 @@
+// rb2_pair_sym.cu -- pair-symmetric all-pairs acceleration for the planar geometry.
+//
+// The reference's CPU pair loop (src/mod_verlet.F90:763-884) evaluates every unordered pair
+// ONCE and applies the result to both particles: Coulomb with the opposite sign, the image
+// series with x, y mirrored and z unchanged (:862-871).  Its OpenACC kernel gives that up and
+// gathers N(N-1) ordered pairs (:1187-1200).  This kernel keeps the halved arithmetic on the GPU
+// without atomics and with a fixed summation order:
+//
+//   * particles are grouped in superblocks of 128 (one CTA = 4 warps); a CTA owns a target
+//     superblock I and sweeps a group of source superblocks J >= I;
+//   * inside a 128 x 128 tile each warp pairs its 32 targets (registers) with 32 "visitors"
+//     that ROTATE through the lanes with warp shuffles, so every lane sees every visitor once;
+//     the lane accumulates the force on its own particle and, in the visitor's travelling
+//     accumulators, the reaction on the visitor.  Four rounds (warp w takes source warp-block
+//     (w + r) mod 4) cover the tile; after each round the visitors' sums are added to
+//     shared-memory slots that no other warp touches in that round;
+//   * per tile the 128 source sums are stored once to a partial buffer indexed by
+//     (source superblock, target superblock); the target sums are stored once per
+//     (group, target superblock).  A reduce kernel adds both in ascending order.  To bound the
+//     buffer the source superblocks are processed in bands (one launch pair per band);
+//   * the diagonal tile (J == I) uses the gather form with per-element self mask and role sign.
+//
+// Per unordered pair at N_ic_max = 1: 81 FP64-pipe instructions + 6 MUFU + 14 SHFL, i.e. about
+// 40 FP64 instructions per ordered pair interaction against 74 in the gather kernel.  Image roles
+// (F8-ii) need no test here: J > I implies i < j for every pair of the tile.
+#include "rb2_internal.cuh"
+#include "rb2_planar_math.cuh"
+
+namespace {
+
+constexpr int SB = 128;  // particles per superblock = threads per CTA
+
+struct SymGeom {
+    int n, nsb, n_pad;
+    int band_start, band_len;  // source superblocks [band_start, band_start + band_len)
+    int G, ngroups;            // source superblocks per CTA group, groups in this band
+    int rank, world;           // CTA (I, grp) is owned by rank (I + grp) % world
+};
+
+__device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
+
+template <int NIC>
+__global__ void __launch_bounds__(SB, 4)
+k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
+{
+    const int I = blockIdx.x;
+    const int grp = blockIdx.y;
+    if (((I + grp) % g.world) != g.rank) return;
+    const int J0 = g.band_start + grp * g.G;
+    const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
+    const int Jbeg = max(J0, I);
+    if (Jbeg >= J1) return;
+
+    __shared__ double xs[SB], ys[SB], zs[SB], qs[SB];
+    __shared__ double jacc[3][SB];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = I * SB + tid;
+    const int last = g.n - 1;
+    double xi, yi, zi, qi;
+    {
+        const double4 p = pq[i < g.n ? i : last];
+        xi = p.x; yi = p.y; zi = p.z;
+        qi = (i < g.n) ? p.w : 0.0;  // padding lanes: charge 0, any finite position
+    }
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    const int src_lane = (lane + 1) & 31;
+
+    for (int J = Jbeg; J < J1; ++J) {
+        const int j = J * SB + tid;
+        const double4 pj = pq[j < g.n ? j : last];
+        __syncthreads();  // everybody is done with the previous tile's shared memory
+        xs[tid] = pj.x; ys[tid] = pj.y; zs[tid] = pj.z;
+        qs[tid] = (j < g.n) ? pj.w : 0.0;
+        jacc[0][tid] = 0.0; jacc[1][tid] = 0.0; jacc[2][tid] = 0.0;
+        __syncthreads();
+
+        if (J == I) {
+            // diagonal tile: ordered evaluation of this superblock against itself
+            Acc4 a = {0.0, 0.0, 0.0, 0.0};
+            for (int jj = 0; jj < SB; ++jj) {
+                const double4 s = make_double4(xs[jj], ys[jj], zs[jj], qs[jj]);
+                const double qe = (jj == tid) ? 0.0 : s.w;
+                const double qsg = (jj > tid) ? qe : -qe;
+                planar_term<NIC>(xi, yi, zi, s, qe, qsg, P, a);
+            }
+            ax += a.x; ay += a.y; az += a.z + a.t;
+        } else {
+            for (int r = 0; r < 4; ++r) {
+                const int home = ((warp + r) & 3) * 32 + lane;
+                double vx = xs[home], vy = ys[home], vz = zs[home], vq = qs[home];
+                double bx = 0.0, by = 0.0, bz = 0.0;   // reaction on the visitor, travels with it
+                double tx = 0.0, ty = 0.0, tz = 0.0;   // force on my particle from this round
+#pragma unroll 2
+                for (int k = 0; k < 32; ++k) {
+                    const PairW w = planar_weights<NIC>(xi, yi, zi, vx, vy, vz, P);
+                    // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
+                    const double ti = vq * w.U, tj = qi * w.U;
+                    tx = fma(w.dx, ti, tx);
+                    ty = fma(w.dy, ti, ty);
+                    bx = fma(-w.dx, tj, bx);
+                    by = fma(-w.dy, tj, by);
+                    if (NIC < 0) {
+                        tz = fma(w.dz, ti, tz);
+                        bz = fma(-w.dz, tj, bz);
+                    } else {
+                        const double czz = w.dz * w.wc;
+                        const double icz = w.Zsame - w.Zopp;
+                        tz = fma(vq, icz + czz, tz);
+                        bz = fma(qi, icz - czz, bz);
+                    }
+                    vx = rot1(vx, src_lane); vy = rot1(vy, src_lane); vz = rot1(vz, src_lane); vq = rot1(vq, src_lane);
+                    bx = rot1(bx, src_lane); by = rot1(by, src_lane); bz = rot1(bz, src_lane);
+                }
+                // 32 rotations by one lane: every visitor is back at its home lane
+                ax += tx; ay += ty; az += tz;
+                jacc[0][home] += bx; jacc[1][home] += by; jacc[2][home] += bz;
+                __syncthreads();  // the next round's owner of this warp-block sees the sums
+            }
+            const size_t base = (((size_t)(J - g.band_start) * g.nsb + I) * 3) * SB + tid;
+            bufJ[base] = jacc[0][tid];
+            bufJ[base + SB] = jacc[1][tid];
+            bufJ[base + 2 * SB] = jacc[2][tid];
+        }
+    }
+    const size_t ib = (size_t)grp * 3 * g.n_pad + i;
+    bufI[ib] = ax;
+    bufI[ib + g.n_pad] = ay;
+    bufI[ib + 2 * (size_t)g.n_pad] = az;
+}
+
+// raw[c][p] += (sum over this band's groups of the target sums) + (sum over I < J(p) of the source sums),
+// both in ascending order; only slots written by this rank are read.
+__global__ void __launch_bounds__(SB)
+k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restrict__ bufJ, double *__restrict__ raw)
+{
+    const int Jp = blockIdx.x;  // superblock of this particle
+    const int tid = threadIdx.x;
+    const int p = Jp * SB + tid;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    // as a target (I = Jp)
+    for (int grp = 0; grp < g.ngroups; ++grp) {
+        const int J0 = g.band_start + grp * g.G;
+        const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
+        if (max(J0, Jp) >= J1) continue;
+        if (((Jp + grp) % g.world) != g.rank) continue;
+        const size_t ib = (size_t)grp * 3 * g.n_pad + p;
+        s0 += bufI[ib];
+        s1 += bufI[ib + g.n_pad];
+        s2 += bufI[ib + 2 * (size_t)g.n_pad];
+    }
+    // as a source (J = Jp), when Jp lies in this band
+    if (Jp >= g.band_start && Jp < g.band_start + g.band_len) {
+        const int grp = (Jp - g.band_start) / g.G;
+        const size_t col = (size_t)(Jp - g.band_start) * g.nsb;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll 4
+        for (int I = 0; I < Jp; ++I) {
+            if (((I + grp) % g.world) != g.rank) continue;
+            const size_t base = ((col + I) * 3) * SB + tid;
+            t0 += bufJ[base];
+            t1 += bufJ[base + SB];
+            t2 += bufJ[base + 2 * SB];
+        }
+        s0 += t0; s1 += t1; s2 += t2;
+    }
+    raw[p] += s0;
+    raw[(size_t)g.n_pad + p] += s1;
+    raw[2 * (size_t)g.n_pad + p] += s2;
+}
+
+// a_i = ( q_i/(4 pi eps0) * raw_i + q_i * E_z zhat ) / m_i   (src/mod_verlet.F90:1333-1338)
+__global__ void k_sym_finalize(int n, int n_pad, const double *__restrict__ raw, const double4 *__restrict__ pq,
+                               const double *__restrict__ mass, PlanarParams P, double *__restrict__ acc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double q_1 = pq[i].w;
+    const double qd_1 = q_1 * rb2k::div_fac_c;
+    const double im_1 = 1.0 / mass[i];
+    acc[3 * i] = (qd_1 * raw[i]) * im_1;
+    acc[3 * i + 1] = (qd_1 * raw[(size_t)n_pad + i]) * im_1;
+    acc[3 * i + 2] = (qd_1 * raw[2 * (size_t)n_pad + i] + q_1 * P.E_z) * im_1;
+}
+
+int ensure_bytes(double **p, size_t *have, size_t want)
+{
+    if (want > *have) {
+        if (*p) RB2_CUDA(cudaFree(*p));
+        *p = nullptr;
+        *have = 0;
+        RB2_CUDA(cudaMalloc(p, want));
+        *have = want;
+    }
+    return RB2_OK;
+}
+
+}  // namespace
+
+// Partial raw sums of this rank (rank 0 of 1: everything) into ctx.sym_raw[3][n_pad].
+int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
+{
+    if (n < 1) return RB2_OK;
+    const rb2_config &c = ctx.cfg;
+    if (c.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "the pair-symmetric kernel implements the planar geometry only");
+    SymGeom g{};
+    g.n = n;
+    g.nsb = (n + SB - 1) / SB;
+    g.n_pad = g.nsb * SB;
+    g.rank = ctx.pair_rank;
+    g.world = ctx.pair_world < 1 ? 1 : ctx.pair_world;
+    // band width from the scratch budget (3 KB per (source, target) superblock pair)
+    const size_t col_bytes = (size_t)g.nsb * 3 * SB * sizeof(double);
+    size_t wb = ctx.sym_budget_bytes / col_bytes;
+    if (wb < 1) wb = 1;
+    if (wb > (size_t)g.nsb) wb = (size_t)g.nsb;
+    const int Wb = (int)wb;
+    // group size: enough CTAs to fill 4 CTAs/SM for ~8 waves
+    const double want_ctas = (double)ctx.sm_count * 4 * 8;
+    int G = (int)((double)g.nsb * Wb / want_ctas);
+    if (G < 1) G = 1;
+    if (G > Wb) G = Wb;
+    const int ngroups_max = (Wb + G - 1) / G;
+    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, (size_t)Wb * col_bytes);
+    if (rc) return rc;
+    rc = ensure_bytes(&ctx.sym_bufI, &ctx.sym_bufI_bytes, (size_t)ngroups_max * 3 * g.n_pad * sizeof(double));
+    if (rc) return rc;
+    rc = ensure_bytes(&ctx.sym_raw, &ctx.sym_raw_bytes, (size_t)3 * g.n_pad * sizeof(double));
+    if (rc) return rc;
+    ctx.sym_n_pad = g.n_pad;
+    cudaStream_t st = ctx.stream;
+    const StepParams SP = rb2_make_step_params(c);
+    RB2_CUDA(cudaEventRecord(ctx.ev_a0, st));
+    RB2_CUDA(cudaMemsetAsync(ctx.sym_raw, 0, (size_t)3 * g.n_pad * sizeof(double), st));
+    int launches = 0;
+    for (int b0 = 0; b0 < g.nsb; b0 += Wb) {
+        g.band_start = b0;
+        g.band_len = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
+        g.G = G;
+        g.ngroups = (g.band_len + G - 1) / G;
+        const int nI = b0 + g.band_len;  // targets I <= last source superblock of the band
+        dim3 grid(nI, g.ngroups), block(SB);
+#define RB2_GO(N) k_pair_sym<N><<<grid, block, 0, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ)
+        if (!c.image_charge) RB2_GO(-1);
+        else if (c.N_ic_max == 0) RB2_GO(0);
+        else if (c.N_ic_max == 1) RB2_GO(1);
+        else RB2_GO(2);
+#undef RB2_GO
+        RB2_CUDA(cudaGetLastError());
+        k_sym_reduce<<<g.nsb, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw);
+        RB2_CUDA(cudaGetLastError());
+        launches += 2;
+    }
+    RB2_LAUNCHED(launches);
+    ctx.last_grid_x = g.nsb; ctx.last_grid_y = (g.nsb + Wb - 1) / Wb; ctx.last_block = SB; ctx.last_split = G;
+    return RB2_OK;
+}
+
+int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out)
+{
+    if (n < 1) return RB2_OK;
+    const StepParams SP = rb2_make_step_params(ctx.cfg);
+    k_sym_finalize<<<(n + 255) / 256, 256, 0, ctx.stream>>>(n, ctx.sym_n_pad, ctx.sym_raw, pq, mass, SP.pl, acc_out);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(1);
+    RB2_CUDA(cudaEventRecord(ctx.ev_a1, ctx.stream));
+    return RB2_OK;
+}
