@@ -187,7 +187,9 @@ def workload_config(args, world):
                         f"N_ic_max={args.nic}, dt=1e-4ps (BASELINE.json configs[4])",
             "n_particles": args.n, "N_ic_max": args.nic, "image_charge": True,
             "flops_per_pair": flops_per_pair(True, args.nic),
-            "parallelism": f"i-partition x{world}" + (" + NCCL all-gather of accelerations" if world > 1 else ""),
+            "parallelism": (f"pair work units x{world}" + (" + NCCL all-reduce of the partial pair sums" if world > 1 else ""))
+            if (getattr(args, "pair_mode", "auto") == "sym" or (getattr(args, "pair_mode", "auto") == "auto" and args.n >= 16384))
+            else (f"i-partition x{world}" + (" + NCCL all-gather of accelerations" if world > 1 else "")),
             "l2": "256 MiB L2-flush write between timed steps (outside the per-step CUDA-event pairs)"}
 
 
@@ -218,26 +220,45 @@ def run_ours(args):
                            capacity=cap, device=local)
     hp = rb.HotPath(cfg)
     hp.upload(pos, q, m)
-    hp.set_partition(i0, i1)
+    # pair kernel: "sym" = each unordered pair once (default from 16384 particles on), "gather" = ordered pairs
+    sym = (args.pair_mode == "sym") or (args.pair_mode == "auto" and n >= 16384)
+    hp.set_option("pair_mode", 2 if sym else 1)
+    if sym:
+        hp.set_pair_rank(rank, world)   # (target superblock, source group) work units dealt round-robin
+    else:
+        hp.set_partition(i0, i1)        # contiguous i-rows per rank
     ext = torch.cuda.ExternalStream(hp.stream(), device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    class _Alias:  # expose the library's acceleration buffer to torch without a copy
+    class _Alias:  # expose a device buffer of the library to torch without a copy
         def __init__(self, ptr, nelem):
             self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
-    def acc_tensor():
-        ptr, nbytes = hp.device_buffer("acc")
+    def dev_tensor(name):
+        ptr, nbytes = hp.device_buffer(name)
         return torch.as_tensor(_Alias(ptr, nbytes // 8), device=f"cuda:{local}")
+
+    def exchange():
+        """The one exchange step of the path: partial pair sums are all-reduced (pair-symmetric kernel),
+        or the acceleration rows are all-gathered in place (gather kernel)."""
+        with torch.cuda.stream(ext):
+            if sym:
+                dist.all_reduce(dev_tensor("raw"), op=dist.ReduceOp.SUM)
+            else:
+                t = dev_tensor("acc")
+                dist.all_gather_into_tensor(t[: 3 * cap], t[3 * i0: 3 * (i0 + chunk)])
 
     def one_step(step):
         if world == 1:
             return hp.Update_Position(step)
         hp.Update_Particle_Position(step)
-        hp.Calculate_Acceleration_Particles()
-        t = acc_tensor()
-        with torch.cuda.stream(ext):
-            dist.all_gather_into_tensor(t[: 3 * cap], t[3 * i0: 3 * (i0 + chunk)])
+        if sym:
+            hp.accel_partial()
+            exchange()
+            hp.accel_finalize()
+        else:
+            hp.Calculate_Acceleration_Particles()
+            exchange()
         return hp.Update_Particle_Velocity()
 
     def barrier():
@@ -279,11 +300,24 @@ def run_ours(args):
     h_pos, h_q, h_m = pin(pos), pin(q), pin(m)
     h_acc = torch.empty((n, 3), dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
-    hp.accel_host_ptr(n, h_pos.data_ptr(), h_q.data_ptr(), h_m.data_ptr(), h_acc.data_ptr())  # warm
+
+    def e2e_once():
+        if world == 1 or not sym:
+            # stateless C-ABI call: host pos/q/m in, this rank's acceleration rows out
+            hp.accel_host_ptr(n, h_pos.data_ptr(), h_q.data_ptr(), h_m.data_ptr(), h_acc.data_ptr())
+        else:
+            # split pair work: upload, partial sums, all-reduce, finalise, rows back to the host
+            hp.upload(h_pos.numpy(), h_q.numpy(), h_m.numpy())
+            hp.accel_partial()
+            exchange()
+            hp.accel_finalize()
+            h_acc.numpy()[:] = hp.download(("acc",))["acc"]
+
+    e2e_once()  # warm
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        hp.accel_host_ptr(n, h_pos.data_ptr(), h_q.data_ptr(), h_m.data_ptr(), h_acc.data_ptr())
+        e2e_once()
     barrier()
     t_e2e = (time.perf_counter() - t0) / e2e_steps
 
@@ -300,8 +334,8 @@ def run_ours(args):
         ms_per_step = dev_ms / args.steps
         value = pairs / (ms_per_step * 1e-3)
         fpp = flops_per_pair(True, args.nic)
-        n_local = i1 - i0
-        achieved = fpp * float(n_local) * float(n - 1) / (acc_ms * 1e-3) / 1e12
+        # algorithmic flops of the slowest rank's share of the N(N-1) ordered pair interactions
+        achieved = fpp * pairs / world / (acc_ms * 1e-3) / 1e12
         peak = peak_sust if acc_ms > 200.0 else peak_burst
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -317,14 +351,23 @@ def run_ours(args):
             "md_steps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": "k_pair<planar, N_ic_max=%d> (+ finalize)" % args.nic,
-                         "kernel_ms": acc_ms, "flops_per_pair": fpp, "fp64_instr_per_pair": 74 if args.nic == 1 else None,
+                         "kernel": ("k_pair_sym<N_ic_max=%d> + k_sym_reduce per band, k_sym_finalize (each unordered pair "
+                                    "evaluated once and applied to both particles, like the reference's CPU pair loop; "
+                                    "achieved = ALGORITHMIC flops of the N(N-1) ordered interactions, so it can exceed "
+                                    "the executed-flop peak)" % args.nic) if sym
+                         else "k_pair<planar, N_ic_max=%d> + k_accel_finalize (ordered pairs)" % args.nic,
+                         "kernel_ms": acc_ms, "flops_per_pair": fpp,
+                         "fp64_instr_per_ordered_pair": (40.5 if sym else 74) if args.nic == 1 else None,
+                         "fp64_pipe_util_est": ((40.5 if sym else 74) * 2.0 / fpp) * (achieved / peak) if args.nic == 1 else None,
                          "peak_source": "measured in this run: rb2_fp64_peak independent-DFMA-chain kernel "
                                         f"(burst {peak_burst:.2f}, sustained 1.5 s {peak_sust:.2f} TFLOP/s; nominal 37.2); "
                                         "MEASURED_PEAKS.json holds no FP64 figure",
                          "launch": info},
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 24 * n,
-                    "ms_per_step": e2e_ms, "what": "rb2_accel_host: pinned host pos/q/m -> device, pair kernel, accelerations -> host"},
+                    "ms_per_step": e2e_ms,
+                    "what": "rb2_accel_host: pinned host pos/q/m -> device, pair kernel, accelerations -> host" if (world == 1 or not sym)
+                    else "rb2_upload_particles (host pos/q/m) -> rb2_accel_partial -> NCCL all-reduce -> rb2_accel_finalize -> rb2_download_particles(acc)"},
+            "pair_kernel": "pair-symmetric" if sym else "gather",
             "gpu_launches": launches, "clocks": clk,
         }
         if world == 1 and not args.no_cpu:
@@ -352,6 +395,8 @@ def main():
     ap.add_argument("--nic", type=int, default=1, help="N_ic_max")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pair-mode", default="auto", choices=["auto", "sym", "gather"],
+                    help="pair kernel: sym = each unordered pair once (default for N >= 16384), gather = ordered pairs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

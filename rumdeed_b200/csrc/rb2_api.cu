@@ -699,6 +699,9 @@ int rb2_set_option(const char *name, double value)
         c.pair_mode = (int)value;
     } else if (!strcmp(name, "sym_min_n")) {
         c.sym_min_n = (int)value;
+    } else if (!strcmp(name, "sym_waves")) {
+        if (value < 1) return rb2_fail(RB2_ERR_ARG, "sym_waves must be >= 1");
+        c.sym_waves = value;
     } else if (!strcmp(name, "sym_budget_mb")) {
         if (value <= 0) return rb2_fail(RB2_ERR_ARG, "sym_budget_mb must be > 0");
         c.sym_budget_bytes = (size_t)(value * 1048576.0);

@@ -28,7 +28,17 @@
 
 namespace {
 
+#ifndef RB2_SYM_UNROLL
+#define RB2_SYM_UNROLL 2
+#endif
+#ifndef RB2_SYM_LDSVIS
+#define RB2_SYM_LDSVIS 1
+#endif
+#ifndef RB2_SYM_MINB
+#define RB2_SYM_MINB 3
+#endif
 constexpr int SB = 128;  // particles per superblock = threads per CTA
+constexpr int SYM_UNROLL = RB2_SYM_UNROLL;
 
 struct SymGeom {
     int n, nsb, n_pad;
@@ -40,7 +50,7 @@ struct SymGeom {
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
 
 template <int NIC>
-__global__ void __launch_bounds__(SB, 4)
+__global__ void __launch_bounds__(SB, RB2_SYM_MINB)
 k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
 {
     const int I = blockIdx.x;
@@ -66,9 +76,18 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
     double ax = 0.0, ay = 0.0, az = 0.0;
     const int src_lane = (lane + 1) & 31;
 
+    double4 pj_next;
+    {
+        const int j = Jbeg * SB + tid;
+        pj_next = pq[j < g.n ? j : last];
+    }
     for (int J = Jbeg; J < J1; ++J) {
         const int j = J * SB + tid;
-        const double4 pj = pq[j < g.n ? j : last];
+        const double4 pj = pj_next;
+        if (J + 1 < J1) {  // software prefetch of the next source superblock: the load flies during this tile
+            const int jn = j + SB;
+            pj_next = pq[jn < g.n ? jn : last];
+        }
         __syncthreads();  // everybody is done with the previous tile's shared memory
         xs[tid] = pj.x; ys[tid] = pj.y; zs[tid] = pj.z;
         qs[tid] = (j < g.n) ? pj.w : 0.0;
@@ -88,11 +107,18 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
         } else {
             for (int r = 0; r < 4; ++r) {
                 const int home = ((warp + r) & 3) * 32 + lane;
+                const int wb0 = ((warp + r) & 3) * 32;
                 double vx = xs[home], vy = ys[home], vz = zs[home], vq = qs[home];
                 double bx = 0.0, by = 0.0, bz = 0.0;   // reaction on the visitor, travels with it
                 double tx = 0.0, ty = 0.0, tz = 0.0;   // force on my particle from this round
-#pragma unroll 2
+#pragma unroll SYM_UNROLL
                 for (int k = 0; k < 32; ++k) {
+#if RB2_SYM_LDSVIS
+                    // visitor coordinates straight from shared memory (conflict-free rotated index);
+                    // only the travelling accumulators go through the shuffle unit
+                    const int vi = wb0 + ((lane + k) & 31);
+                    vx = xs[vi]; vy = ys[vi]; vz = zs[vi]; vq = qs[vi];
+#endif
                     const PairW w = planar_weights<NIC>(xi, yi, zi, vx, vy, vz, P);
                     // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
                     const double ti = vq * w.U, tj = qi * w.U;
@@ -109,7 +135,9 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
                         tz = fma(vq, icz + czz, tz);
                         bz = fma(qi, icz - czz, bz);
                     }
+#if !RB2_SYM_LDSVIS
                     vx = rot1(vx, src_lane); vy = rot1(vy, src_lane); vz = rot1(vz, src_lane); vq = rot1(vq, src_lane);
+#endif
                     bx = rot1(bx, src_lane); by = rot1(by, src_lane); bz = rot1(bz, src_lane);
                 }
                 // 32 rotations by one lane: every visitor is back at its home lane
@@ -211,12 +239,20 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     g.world = ctx.pair_world < 1 ? 1 : ctx.pair_world;
     // band width from the scratch budget (3 KB per (source, target) superblock pair)
     const size_t col_bytes = (size_t)g.nsb * 3 * SB * sizeof(double);
-    size_t wb = ctx.sym_budget_bytes / col_bytes;
+    size_t budget = ctx.sym_budget_bytes;
+    {
+        size_t fr = 0, tot = 0;  // never ask for more than half of what is free (plus what we already hold)
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+            const size_t cap = (fr + ctx.sym_bufJ_bytes) / 2;
+            if (budget > cap) budget = cap;
+        }
+    }
+    size_t wb = budget / col_bytes;
     if (wb < 1) wb = 1;
     if (wb > (size_t)g.nsb) wb = (size_t)g.nsb;
     const int Wb = (int)wb;
     // group size: enough CTAs to fill 4 CTAs/SM for ~8 waves
-    const double want_ctas = (double)ctx.sm_count * 4 * 8;
+    const double want_ctas = (double)ctx.sm_count * 4 * ctx.sym_waves;
     int G = (int)((double)g.nsb * Wb / want_ctas);
     if (G < 1) G = 1;
     if (G > Wb) G = Wb;
