@@ -132,16 +132,21 @@ def cpu_sample(orc, p, pos, q, m, target_s=12.0):
     t0 = time.perf_counter()
     _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
     t = time.perf_counter() - t0
-    rate = pairs / max(t, 1e-9)
-    want_pairs = rate * target_s
     total_pairs = n * (n - 1) / 2
-    if want_pairs >= total_pairs:
-        stride = 1
-    else:
-        stride = max(1, int(round(total_pairs / want_pairs)))
-    t0 = time.perf_counter()
-    _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
-    t = time.perf_counter() - t0
+    # grow the sample until it takes about target_s (the first estimates are dominated by the fixed cost of
+    # the per-thread reduction arrays, so the rate is refined from each run)
+    for _ in range(4):
+        if stride == 1 or t >= 0.5 * target_s:
+            break
+        rate = pairs / max(t, 1e-9)
+        want_pairs = min(total_pairs, rate * target_s * (1.0 if t > 0.1 * target_s else 3.0))
+        new_stride = max(1, int(round(total_pairs / want_pairs)))
+        if new_stride >= stride:
+            break
+        stride = new_stride
+        t0 = time.perf_counter()
+        _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
+        t = time.perf_counter() - t0
     frac = pairs / total_pairs
     sample = (f"rows i = 0, {stride}, 2*{stride}, ... of the i<j pair loop at N = {n} "
               f"({pairs} unordered pair evaluations = {100 * frac:.3g}% of a full evaluation, {t:.1f} s)")
