@@ -188,6 +188,37 @@ int rb2_synchronize(void);
 /* CUDA stream handle (cudaStream_t) the library launches on. */
 int rb2_stream(void **stream_out);
 
+/* E_z only, at M points ON the cathode plane (pos_in[3k+2] must be 0), planar geometry.  Same value as
+ * the z component of rb2_field_batch (Calc_Field_at_Batch, src/mod_verlet.F90:1635) at such points, but
+ * computed from the mirror-antisymmetric form of the image series (E_x = E_y = 0 there when image charges
+ * are on): less than half the arithmetic.  What the planar emission integrands and samplers need
+ * (field(3) in src/mod_field_emission_v2.F90:668-745, :1122-1458). */
+int rb2_field_surface_z(int M, const double *pos_in, double *Ez_out);
+
+/* ---- device-resident emission sampler ------------------------------------------------- */
+/* Lock-step Metropolis-Hastings over the planar emitter: replaces the host loop of
+ * Metropolis_Hastings_rectangle_J_batch (src/mod_field_emission_v2.F90:1284-1458; kind 1) and, with
+ * kind 2, runs the chains of src/mod_field_thermo_emission.F90:198-364 in the same lock-step form.
+ * All jump iterations (proposal, M x N surface field, accept / reject, shared step adaptation) are
+ * enqueued on the device; the host is blocked once, for the result. */
+typedef struct rb2_mh_config {
+    int    kind;          /* 1: log electron supply (Elec_Supply_log :589); 2: ln J_GTF (thermal-field) */
+    int    ndim;          /* jump iterations (25*8 for kind 1, 25 for kind 2) */
+    int    ndim_first;    /* warm-up iterations using init_std and leaving MH_std alone */
+    int    image_charge;  /* Schottky-Nordheim barrier functions t_y / v_y on (1) or 1.0 (0) */
+    int    y_num, x_num;  /* work-function checkerboard, src/mod_work_function.F90:389-487 */
+    double emit_pos[2], emit_dim[2];
+    double T_temp;        /* kind 2 */
+    double init_std;      /* warm-up step as a fraction of the emitter side (0.10) */
+    double target_rate, std_gain, std_min, std_max; /* MH_std_update :603-612: 0.35, 0.025, 0.00005 / 0.005, 0.125 */
+} rb2_mh_config;
+/* M chains; w_theta is the [y_num][x_num] work-function table (host).  Outputs (host): log escape
+ * probability df_out[M] (kind 1; -HUGE for a chain that found no favourable spot), surface field
+ * F_out[M] (>= 0 marks a failed chain) and positions pos_out[3M].  a_rate_io / mh_std_io carry the
+ * sampler's adaptive state across calls (a_rate / MH_std of the reference module). */
+int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed,
+                  double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* Independent-DFMA-chain micro-benchmark: measured FP64 peak of this GPU in TFLOP/s
  * (FMA = 2 flops) over about `ms_target` milliseconds. */

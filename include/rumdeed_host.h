@@ -21,7 +21,7 @@ typedef struct rh_setup {
     double emitters_pos[3], emitters_dim[3]; /* m; for the tip: d_tip, R_base, h_tip */
     int    emitters_type, emitters_delay;
     double T_temp;
-    int    mh_batch;
+    int    mh_batch;           /* 0 serial chains, 1 lock-step chains (host loop), 2 lock-step chains resident on the GPU */
     int    planes_N;
     double planes_z[10];       /* m */
     double cuba_epsabs, cuba_epsrel;
@@ -65,6 +65,8 @@ int rh_cuba_integrate(void *sim, int kind, double *integral, double *error, int 
 int rh_mh_rectangle_J(void *sim, double *df_out, double *F_out, double *pos_out);
 int rh_mh_rectangle_J_batch(void *sim, int M, double *df_out, double *F_out, double *pos_out);
 int rh_mh_rectangle_J_thermo(void *sim, double *pos_out);
+/* mh_batch = 2 only: all M thermal-field chains in lock-step on the device (rb2_mh_planar kind 2) */
+int rh_mh_rectangle_J_thermo_batch(void *sim, int M, double *pos_out, int *ok_out);
 int rh_metro_algo_tip_v3(void *sim, int ndim, double *xi, double *phi, double *eta_f, double *df_cur, double *par_pos);
 int rh_metro_algo_tip_v3_batch(void *sim, int M, int ndim, double *eta_f, double *df_cur, double *par_pos);
 int rh_tip_supply_grid(void *sim, int nr_xi, int nr_phi, double *n_s, double *F_avg);

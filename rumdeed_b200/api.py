@@ -82,6 +82,15 @@ class StepResult(C.Structure):
                 ("accel_ms", C.c_float), ("step_ms", C.c_float)]
 
 
+class MhConfig(C.Structure):
+    """rb2_mh_config."""
+    _fields_ = [("kind", C.c_int), ("ndim", C.c_int), ("ndim_first", C.c_int), ("image_charge", C.c_int),
+                ("y_num", C.c_int), ("x_num", C.c_int),
+                ("emit_pos", C.c_double * 2), ("emit_dim", C.c_double * 2), ("T_temp", C.c_double),
+                ("init_std", C.c_double), ("target_rate", C.c_double), ("std_gain", C.c_double),
+                ("std_min", C.c_double), ("std_max", C.c_double)]
+
+
 _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int)
 
@@ -91,7 +100,7 @@ EXPORTS = (
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
     "rb2_add_particles", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_accel_host",
-    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close",
+    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
 )
@@ -127,6 +136,8 @@ def load_library(path: str | None = None):
     lib.rb2_accel_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rb2_field_batch.argtypes = [C.c_int, _PD, _PD]
     lib.rb2_field_batch_delta.argtypes = [C.c_int, _PD, C.c_int, _PD, _PD, _PD]
+    lib.rb2_field_surface_z.argtypes = [C.c_int, _PD, _PD]
+    lib.rb2_mh_planar.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
     lib.rb2_set_partition.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_pair_rank.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_option.argtypes = [C.c_char_p, C.c_double]
@@ -374,6 +385,37 @@ class HotPath:
         if pts.shape[0]:
             self._check(self.lib.rb2_field_batch_delta(pts.shape[0], _d(pts), npos.shape[0], _d(npos), _d(nq), _d(out)))
         return out
+
+    def field_surface_z(self, pos_in):
+        """E_z at points of the cathode plane z = 0 (planar geometry), see rb2_field_surface_z."""
+        pts = np.ascontiguousarray(pos_in, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(pts.shape[0])
+        if pts.shape[0]:
+            self._check(self.lib.rb2_field_surface_z(pts.shape[0], _d(pts), _d(out)))
+        return out
+
+    def mh_planar(self, M, emit_pos, emit_dim, w_theta, seed, kind=1, image_charge=True, T_temp=293.15,
+                  a_rate=1.0, MH_std=0.0125, ndim=None, ndim_first=None):
+        """Device-resident lock-step chains (src/mod_field_emission_v2.F90:1284-1458).
+        Returns (df, F, pos, a_rate, MH_std)."""
+        w = np.ascontiguousarray(w_theta, dtype=np.float64)
+        if w.ndim != 2:
+            w = w.reshape(1, -1)
+        c = MhConfig()
+        c.kind = kind
+        c.ndim = (25 if kind == 2 else 200) if ndim is None else ndim
+        c.ndim_first = (0 if kind == 2 else int(round(c.ndim * 0.25))) if ndim_first is None else ndim_first
+        c.image_charge = int(bool(image_charge))
+        c.y_num, c.x_num = w.shape
+        c.emit_pos[:] = list(emit_pos)[:2]
+        c.emit_dim[:] = list(emit_dim)[:2]
+        c.T_temp = T_temp
+        c.init_std, c.target_rate, c.std_gain = 0.10, 0.35, 0.025
+        c.std_min, c.std_max = (0.005 if kind == 2 else 0.00005), 0.1250
+        df, F, pos = np.zeros(M), np.zeros(M), np.zeros((M, 3))
+        ar, sd = C.c_double(a_rate), C.c_double(MH_std)
+        self._check(self.lib.rb2_mh_planar(C.byref(c), _d(w), M, seed, _d(df), _d(F), _d(pos), C.byref(ar), C.byref(sd)))
+        return df, F, pos, ar.value, sd.value
 
     def Particles_To_Device(self):
         self._check(self.lib.rb2_field_window_open())

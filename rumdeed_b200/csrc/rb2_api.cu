@@ -686,6 +686,42 @@ int rb2_field_batch(int M, const double *pos_in, double *field_out)
     return rb2_field_batch_delta(M, pos_in, 0, nullptr, nullptr, field_out);
 }
 
+int rb2_field_surface_z(int M, const double *pos_in, double *Ez_out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (M < 1) return RB2_OK;
+    if (!pos_in || !Ez_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    if (c.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_field_surface_z: planar geometry only");
+    for (int k = 0; k < M; ++k)
+        if (pos_in[3 * (size_t)k + 2] != 0.0) return rb2_fail(RB2_ERR_ARG, "rb2_field_surface_z: point %d is not on the cathode plane z = 0", k);
+    int rc = ensure_field_buffers(c, M);
+    if (rc) return rc;
+    cudaStream_t st = c.stream;
+    const size_t b3 = (size_t)3 * M * sizeof(double);
+    memcpy(c.h_pts, pos_in, b3);
+    RB2_CUDA(cudaMemcpyAsync(c.d_pts, c.h_pts, b3, cudaMemcpyHostToDevice, st));
+    rc = rb2_launch_surface_field(c, c.d_pts, M, c.d_fld);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.h_fld, c.d_fld, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    memcpy(Ez_out, c.h_fld, (size_t)M * sizeof(double));
+    return RB2_OK;
+}
+
+int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed, double *df_out,
+                  double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (M < 1) return RB2_OK;
+    if (!cfg || !w_theta || !df_out || !F_out || !pos_out || !a_rate_io || !mh_std_io) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    if (c.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_mh_planar: planar geometry only");
+    if (cfg->kind != 1 && cfg->kind != 2) return rb2_fail(RB2_ERR_ARG, "rb2_mh_planar: kind must be 1 or 2");
+    if (cfg->ndim < 0 || cfg->emit_dim[0] <= 0.0 || cfg->emit_dim[1] <= 0.0) return rb2_fail(RB2_ERR_ARG, "rb2_mh_planar: bad chain setup");
+    return rb2_launch_mh_planar(c, cfg, w_theta, M, seed, df_out, F_out, pos_out, a_rate_io, mh_std_io);
+}
+
 int rb2_field_window_open(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 int rb2_field_window_close(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 

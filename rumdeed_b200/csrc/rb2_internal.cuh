@@ -148,6 +148,10 @@ int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
 int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, int i_begin, int i_end, double *acc_out);
 int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra, int n_extra,
                      const double *d_pts, int M, double *d_fld);
+// device-resident Metropolis-Hastings sampler (rb2_mh.cu)
+int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
+                         double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
+int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez);
 // pair-symmetric kernel (rb2_pair_sym.cu)
 int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n);
 int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);

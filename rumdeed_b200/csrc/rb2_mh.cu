@@ -1,0 +1,538 @@
+// rb2_mh.cu -- device-resident lock-step Metropolis-Hastings sampler for the planar emitters.
+//
+// Replaces the host loop of Metropolis_Hastings_rectangle_J_batch (reference
+// src/mod_field_emission_v2.F90:1284-1458): M chains advance together.  ONE persistent cooperative kernel
+// runs the search for favourable start spots and all jump iterations; per iteration
+//   phase A  every CTA takes (tile of 32 chains) x (chunk of particles) work units: the proposals
+//            (Marsaglia polar normals, reflection at the emitter edges :1466-1516) are recomputed from the
+//            counter-based generator wherever they are needed, and the surface field sum runs over the
+//            particle records staged in shared memory;
+//   phase B  one warp per chain joins the chunk sums in a fixed order, adds the vacuum field and does the
+//            accept / reject step on the log electron supply (Elec_Supply_log :589, or ln J_GTF for the
+//            thermal-field mode, src/mod_field_thermo_emission.F90:257);
+// with a grid barrier after each phase, after which every thread applies the same MH_std update
+// (:603-612, one per iteration after the warm-up) from the iteration's accept / reject counters.
+//
+// Surface field.  The chains live on the cathode plane z = 0, where the image series of
+// src/acc_ic_planar_series.inc is mirror-antisymmetric: the partner of charge q at height h = z_j + 2nd is
+// the charge -q at -h, so E_x = E_y = 0 and
+//   E_z(p) = E_vac - 2 / (4 pi eps0) * sum_j q_j sum_{n=-N..N} h_jn / (rho^2 + h_jn^2)^(3/2)
+// (one partner of each mirrored couple is evaluated and doubled; without image charges only n = 0, not
+// doubled).  h_jn and q_j h_jn are precomputed once per call into 64-byte particle records, which leaves
+// 31 FP64 instructions per (chain, particle) at N_ic_max = 1 instead of the 74 of the general field kernel.
+// Random numbers: Philox4x32-10 keyed by (seed, chain), counter = (iteration, purpose, attempt): the
+// reference's RANDOM_NUMBER is compiler specific, so parity is statistical (tests/test_emission.py).
+#include "rb2_internal.cuh"
+
+#include <algorithm>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int MHB = 128;
+constexpr double TINY = 2.2250738585072014e-308;
+constexpr double HUGE_NEG = -1.7976931348623157e308;
+
+struct MhParams {
+    rb2_mh_config c;
+    const double *w_theta;  // [y_num][x_num] on the device
+    double b_FN, l_const;
+};
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo)
+{
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+// two uniforms in [0,1) for (chain, iteration, purpose, attempt)
+__device__ __forceinline__ void rand2(unsigned long long seed, int chain, int iter, int purpose, int attempt, double &u, double &v)
+{
+    const uint2 key = make_uint2((unsigned)seed ^ (unsigned)(chain * 0x9E3779B1u), (unsigned)(seed >> 32) + (unsigned)chain);
+    const uint4 r = philox(make_uint4((unsigned)iter, (unsigned)purpose, (unsigned)attempt, (unsigned)chain), key);
+    u = u53(r.x, r.y);
+    v = u53(r.z, r.w);
+}
+
+// ---- work function + target densities ------------------------------------------------------------------
+// w_theta_checkerboard, src/mod_work_function.F90:389-487
+__device__ __forceinline__ double w_theta_xy(const MhParams &P, double x, double y)
+{
+    const rb2_mh_config &c = P.c;
+    const double xs = (x - c.emit_pos[0]) / c.emit_dim[0], ys = (y - c.emit_pos[1]) / c.emit_dim[1];
+    int x_i = (int)floor(xs / (1.0 / c.x_num)) + 1, y_i = (int)floor(ys / (1.0 / c.y_num)) + 1;
+    x_i = min(max(x_i, 1), c.x_num);
+    y_i = min(max(y_i, 1), c.y_num);
+    y_i = c.y_num - y_i + 1;
+    return P.w_theta[(y_i - 1) * c.x_num + (x_i - 1)];
+}
+// t_y / v_y, src/mod_field_emission_v2.F90:515-553
+__device__ __forceinline__ double fn_l(const MhParams &P, double F, double w)
+{
+    double l = P.l_const * (-1.0 * F) / (w * w);
+    return l > 1.0 ? 1.0 : l;
+}
+__device__ __forceinline__ double t_y(const MhParams &P, double F, double w)
+{
+    if (!P.c.image_charge) return 1.0;
+    const double l = fn_l(P, F, w);
+    return 1.0 + l * (1.0 / 9.0 - 1.0 / 18.0 * log(l));
+}
+__device__ __forceinline__ double v_y(const MhParams &P, double F, double w)
+{
+    if (!P.c.image_charge) return 1.0;
+    const double l = fn_l(P, F, w);
+    return 1.0 - l + 1.0 / 6.0 * l * log(l);
+}
+// Jensen GTF current density, src/mod_kevin_rjgtf_v2.f90:56-175
+__device__ double Nns(double n, double s)
+{
+    if (n == 1.0) return (s + 1.0) * exp(-s);
+    const double x = n * n, y = 1.0 / x, z = (n - 1.0) * s;
+    double sng;
+    if (fabs(z) > 1.0e-5) sng = (x + 1.0) * (x * exp(-s) - exp(-n * s)) / (x - 1.0);
+    else sng = (0.5 * (x + 1.0) * exp(-s) / (n + 1.0)) * ((1.0 - n) * s * s + 2.0 * (1.0 + n) + 2.0 * s);
+    const double sn = -x * (0.10593434 * x + 0.35506593), sd = -y * (0.10593434 * y + 0.35506593);
+    return fmax(sng + sn * exp(-n * s) + x * sd * exp(-s), x * exp(-s));
+}
+__device__ double kevin_jgtf_v2(double F, double T, double Phi)
+{
+    const double kpi = 3.14159265358979324, kb = 1.0 / 11604.50635, hbar = 0.6582119571, c = 299.7924580;
+    const double mo = 5.685630103, afs = 1.0 / 137.035999084, Qo = afs * hbar * c / 4.0, cm = 1.0e7, Amp = 6.241509074e3;
+    const double Arld = (mo * (kb * kb) / (2.0 * (kpi * kpi) * (hbar * hbar * hbar))) * (cm * cm) / Amp;
+    const double Fo = fabs(F) * 1.0e-9;
+    if (Fo < 1.0e-9) return 0.0;
+    const double yo = sqrt(4.0 * Qo * Fo) / Phi, phix = Phi - sqrt(4.0 * Qo * Fo);
+    const double ty = 1.0 + (yo * yo) * (1.0 - log(yo)) / 9.0, vy = 1.0 - (yo * yo) * (3.0 - log(yo)) / 3.0;
+    const double Tmin = (hbar * Fo / (4.0 * kb * ty)) * sqrt(2.0 / (mo * Phi)), Tmax = hbar * Fo / (kb * kpi * sqrt(mo * Phi * yo));
+    const double betaT = 1.0 / (kb * T), betau = (2.0 / (hbar * Fo)) * sqrt(2.0 * mo * Phi) * ty;
+    const double betap = (kpi / (hbar * Fo)) * sqrt(mo * Phi * yo), theto = (4.0 * sqrt(2.0 * mo * (Phi * Phi * Phi)) / (3.0 * hbar * Fo)) * vy;
+    double nft, sft;
+    if (T < Tmin) { nft = betaT / betau; sft = theto; }
+    else if (T > Tmax) { nft = betaT / betap; sft = betap * phix; }
+    else {
+        const double Ap = 3.0 * (betap + betau) - 6.0 * theto / phix, Bp = -2.0 * (betap + 2.0 * betau) + 6.0 * theto / phix, Cp = betau - betaT;
+        const double po = (-Bp - sqrt(Bp * Bp - 4.0 * Ap * Cp)) / (2.0 * Ap);
+        const double theta = ((1.0 - po) * (1.0 - po)) * (2.0 * po + 1.0) * theto - phix * po * (1.0 - po) * ((1.0 - po) * betau - po * betap);
+        nft = 1.0;
+        sft = theta + betaT * (po * phix);
+    }
+    return (Arld * Nns(nft, sft) * (T * T)) * 1.0e4;
+}
+// log of the chain target at a favourable field F < 0
+__device__ __forceinline__ double target_log(const MhParams &P, double F, double x, double y)
+{
+    const double w = w_theta_xy(P, x, y);
+    if (P.c.kind == 2) return log(fmax(kevin_jgtf_v2(F, P.c.T_temp, w), TINY));
+    return 2.0 * log(-1.0 * F) - 2.0 * log(t_y(P, F, w)) - log(w);  // Elec_Supply_log
+}
+
+struct __align__(16) SurfRec {
+    double x, y, h0, g0, h1, g1, h2, g2;  // g_n = q * h_n;  N_ic_max >= 2: h0 = z, g1 = q, the rest on the fly
+};
+
+struct MhState {
+    double *cur_x, *cur_y, *sup_cur, *F_cur;  // [M]
+    int *ok;                                   // [M]
+    double *partial;                           // [nsplit][M]
+    int *cnt;                                  // [2 * (ndim + 1)] accepted / rejected per iteration
+    int *bad;                                  // [max_init] chains still without a favourable spot per round
+    const SurfRec *recs;                       // [n]
+    double *df_out, *F_out, *pos_out, *scal_out;
+};
+
+struct MhPlan {
+    int M, n, n_tiles, nsplit, j_chunk, units, max_init;
+    unsigned long long seed;
+    double two_d, E_vac, fac, mh_std0, a_rate0;
+    int nic;
+};
+
+// one particle against one surface point: sum of g_n / (rho^2 + h_n^2)^(3/2)
+template <int NIC>
+__device__ __forceinline__ double surf_term(const SurfRec &r, double px, double py, double acc, const MhPlan &L)
+{
+    const double dx = px - r.x, dy = py - r.y;
+    const double d2 = fma(dy, dy, fma(dx, dx, RB2_S_FLOOR));
+    acc = fma(r.g0, rb2_inv_r3_soft(fma(r.h0, r.h0, d2)), acc);
+    if (NIC == 1) {
+        acc = fma(r.g1, rb2_inv_r3_soft(fma(r.h1, r.h1, d2)), acc);
+        acc = fma(r.g2, rb2_inv_r3_soft(fma(r.h2, r.h2, d2)), acc);
+    } else if (NIC >= 2) {
+        for (int n = 1; n <= L.nic; ++n) {
+            const double h = L.two_d * (double)n, hm = r.h0 - h, hp = r.h0 + h;
+            acc = fma(r.g1 * hm, rb2_inv_r3_soft(fma(hm, hm, d2)), acc);
+            acc = fma(r.g1 * hp, rb2_inv_r3_soft(fma(hp, hp, d2)), acc);
+        }
+    }
+    return acc;
+}
+
+__global__ void k_surf_pack(const double4 *__restrict__ pq, int n, double two_d, int nic, SurfRec *__restrict__ recs)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double4 p = pq[j];
+    SurfRec r;
+    r.x = p.x; r.y = p.y; r.h0 = p.z; r.g0 = p.w * p.z;
+    if (nic >= 2) { r.h1 = 0.0; r.g1 = p.w; r.h2 = 0.0; r.g2 = 0.0; }
+    else { r.h1 = p.z - two_d; r.g1 = p.w * r.h1; r.h2 = p.z + two_d; r.g2 = p.w * r.h2; }
+    recs[j] = r;
+}
+
+// Proposal of chain c at iteration iter: a pure function of (seed, chain, iteration, chain state, step), so any
+// thread that needs it recomputes it.  iter < 0: search rounds for a favourable start (uniform over the emitter).
+__device__ __forceinline__ void propose(const MhParams &P, const MhState &S, const MhPlan &L, int iter, int k, double mh_std,
+                                        double &x, double &y)
+{
+    const rb2_mh_config &c = P.c;
+    x = __ldcg(&S.cur_x[k]);
+    y = __ldcg(&S.cur_y[k]);
+    const int ok = __ldcg(&S.ok[k]);
+    if (iter < 0) {
+        if (!ok) {
+            double u, v;
+            rand2(L.seed, k, iter, 0, 0, u, v);
+            x = u * c.emit_dim[0] + c.emit_pos[0];
+            y = v * c.emit_dim[1] + c.emit_pos[1];
+        }
+        return;
+    }
+    if (!ok) return;
+    const double frac = (iter > c.ndim_first) ? mh_std : c.init_std;
+    double g0 = 0.0, g1 = 0.0;
+    for (int attempt = 0; attempt < 64; ++attempt) {  // Marsaglia polar method, src/mod_global.F90:578-595
+        double u, v;
+        rand2(L.seed, k, iter, 1, attempt, u, v);
+        const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
+        if (w < 1.0 && w > 0.0) {
+            const double f = sqrt((-2.0 * log(w)) / w);
+            g0 = a * f; g1 = b * f;
+            break;
+        }
+    }
+    x += g0 * (c.emit_dim[0] * frac);
+    y += g1 * (c.emit_dim[1] * frac);
+    if (c.kind == 2) {  // src/mod_field_thermo_emission.F90:369-389
+        double qx = (x - c.emit_pos[0]) / c.emit_dim[0], qy = (y - c.emit_pos[1]) / c.emit_dim[1];
+        if (qx > 1.0 || qx < 0.0) qx = 1.0 - (qx - floor(qx));
+        if (qy > 1.0 || qy < 0.0) qy = 1.0 - (qy - floor(qy));
+        x = qx * c.emit_dim[0] + c.emit_pos[0];
+        y = qy * c.emit_dim[1] + c.emit_pos[1];
+    } else {  // src/mod_field_emission_v2.F90:1466-1516
+        const double x_max = c.emit_pos[0] + c.emit_dim[0], x_min = c.emit_pos[0];
+        const double y_max = c.emit_pos[1] + c.emit_dim[1], y_min = c.emit_pos[1];
+        if (x > x_max) x = x_max - (x - x_max); else if (x < x_min) x = (x_min - x) + x_min;
+        if (y > y_max) y = y_max - (y - y_max); else if (y < y_min) y = (y_min - y) + y_min;
+    }
+}
+
+// One work unit: 32 surface points (one per lane, the same in all four warps) against the particle records
+// [j0, j1).  The CTA stages 128-record sub-tiles in shared memory (double buffered), warp w takes records
+// 32w .. 32w+31 of each, and the four warp sums are joined in a fixed order.  The result is valid in warp 0.
+template <int NIC>
+__device__ __forceinline__ double surf_unit_sum(const SurfRec *__restrict__ g_recs, int j0, int j1, double px, double py,
+                                                const MhPlan &L, SurfRec (*recs)[MHB], double (*red)[32])
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsub = (j1 - j0 + MHB - 1) / MHB;
+    SurfRec nxt;
+    auto fetch = [&](int t) {
+        const int j = j0 + t * MHB + tid;
+        if (j < j1) nxt = g_recs[j];
+        else { nxt.x = 0.0; nxt.y = 0.0; nxt.h0 = 1.0; nxt.g0 = 0.0; nxt.h1 = 1.0; nxt.g1 = 0.0; nxt.h2 = 1.0; nxt.g2 = 0.0; }
+    };
+    fetch(0);
+    double acc = 0.0;
+    for (int t = 0; t < nsub; ++t) {
+        recs[t & 1][tid] = nxt;
+        __syncthreads();
+        if (t + 1 < nsub) fetch(t + 1);
+        const SurfRec *rr = &recs[t & 1][warp * 32];
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    const double sum = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+    __syncthreads();
+    return sum;
+}
+
+// phase A: partial surface sums of every (chain tile, particle chunk) unit
+template <int NIC>
+__device__ __forceinline__ void phase_field(const MhParams &P, const MhState &S, const MhPlan &L, int iter, double mh_std,
+                                            SurfRec (*recs)[MHB], double (*red)[32])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int u = blockIdx.x; u < L.units; u += gridDim.x) {
+        const int tile = u / L.nsplit, s = u - tile * L.nsplit;
+        const int c = tile * 32 + lane;
+        double px = 0.0, py = 0.0;
+        if (c < L.M) propose(P, S, L, iter, c, mh_std, px, py);
+        const int j0 = s * L.j_chunk, j1 = min(L.n, j0 + L.j_chunk);
+        const double sum = surf_unit_sum<NIC>(S.recs, j0, j1, px, py, L, recs, red);
+        if (warp == 0 && c < L.M) S.partial[(size_t)s * L.M + c] = sum;
+    }
+}
+
+// rb2_field_surface_z: the same unit sums for M caller-supplied surface points, then a warp per point joins them
+template <int NIC>
+__global__ void __launch_bounds__(MHB, 4) k_surface_field(const double *__restrict__ pts, const SurfRec *__restrict__ g_recs,
+                                                          MhPlan L, double *__restrict__ partial)
+{
+    __shared__ SurfRec recs[2][MHB];
+    __shared__ double red[MHB / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int u = blockIdx.x; u < L.units; u += gridDim.x) {
+        const int tile = u / L.nsplit, s = u - tile * L.nsplit;
+        const int c = tile * 32 + lane;
+        double px = 0.0, py = 0.0;
+        if (c < L.M) { px = pts[3 * c]; py = pts[3 * c + 1]; }
+        const int j0 = s * L.j_chunk, j1 = min(L.n, j0 + L.j_chunk);
+        const double sum = surf_unit_sum<NIC>(g_recs, j0, j1, px, py, L, recs, red);
+        if (warp == 0 && c < L.M) partial[(size_t)s * L.M + c] = sum;
+    }
+}
+__global__ void k_surface_join(const double *__restrict__ partial, MhPlan L, double *__restrict__ Ez)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= L.M) return;
+    double sum = 0.0;
+    for (int s = lane; s < L.nsplit; s += 32) sum += partial[(size_t)s * L.M + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) Ez[c] = L.E_vac - L.fac * sum;
+}
+
+// phase B: one warp per chain -- join the chunk sums, finish the field, accept / reject
+__device__ __forceinline__ void phase_accept(const MhParams &P, const MhState &S, const MhPlan &L, int iter, double mh_std)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * (MHB / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (MHB / 32);
+    int n_acc = 0, n_rej = 0, n_bad = 0;
+    for (int c = gwarp; c < L.M; c += nwarps) {
+        double sum = 0.0;
+        for (int s = lane; s < L.nsplit; s += 32) sum += __ldcg(&S.partial[(size_t)s * L.M + c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane != 0) continue;
+        const double Fz = L.E_vac - L.fac * sum;
+        double x, y;
+        propose(P, S, L, iter, c, mh_std, x, y);
+        const int ok = __ldcg(&S.ok[c]);
+        if (iter < 0) {
+            if (ok) continue;
+            if (Fz < 0.0) {
+                S.cur_x[c] = x; S.cur_y[c] = y; S.F_cur[c] = Fz;
+                S.sup_cur[c] = target_log(P, Fz, x, y);
+                S.ok[c] = 1;
+            } else n_bad++;
+            continue;
+        }
+        if (!ok) continue;
+        const bool unfav = (P.c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
+        bool accept = false;
+        if (!unfav) {
+            const double sup_new = target_log(P, Fz, x, y), sup_old = S.sup_cur[c];
+            accept = sup_new >= sup_old;
+            if (!accept) {
+                double u, v;
+                rand2(L.seed, c, iter, 2, 0, u, v);
+                accept = log(u) <= sup_new - sup_old;
+            }
+            if (accept) { S.cur_x[c] = x; S.cur_y[c] = y; S.sup_cur[c] = sup_new; S.F_cur[c] = Fz; }
+        }
+        if (accept) n_acc++; else n_rej++;
+    }
+    if (lane == 0) {
+        if (iter < 0) { if (n_bad) atomicAdd(&S.bad[-iter - 1], n_bad); }
+        else {
+            if (n_acc) atomicAdd(&S.cnt[2 * iter], n_acc);
+            if (n_rej) atomicAdd(&S.cnt[2 * iter + 1], n_rej);
+        }
+    }
+}
+
+template <int NIC>
+__global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S, MhPlan L)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ SurfRec recs[2][MHB];
+    __shared__ double red[MHB / 32][32];
+    double mh_std = L.mh_std0, a_rate = L.a_rate0;
+    // a favourable start for every chain (:1303-1361): rounds of uniform draws until the field is negative
+    int bad = L.M;
+    for (int r = 0; r < L.max_init && bad > 0; ++r) {
+        phase_field<NIC>(P, S, L, -(r + 1), mh_std, recs, red);
+        grid.sync();
+        phase_accept(P, S, L, -(r + 1), mh_std);
+        grid.sync();
+        bad = __ldcg(&S.bad[r]);
+    }
+    for (int i = 1; i <= P.c.ndim; ++i) {
+        phase_field<NIC>(P, S, L, i, mh_std, recs, red);
+        grid.sync();
+        phase_accept(P, S, L, i, mh_std);
+        grid.sync();
+        const int a = __ldcg(&S.cnt[2 * i]), r = __ldcg(&S.cnt[2 * i + 1]);
+        if (i > P.c.ndim_first && a + r > 0) {  // MH_std_update, :603-612 -- identical in every thread
+            a_rate = (double)a / (double)(a + r);
+            mh_std = fmin(fmax(mh_std * exp(P.c.std_gain * (a_rate - P.c.target_rate)), P.c.std_min), P.c.std_max);
+        }
+    }
+    // outputs: position, surface field and the log escape probability (Escape_Prob_log :568) of every chain
+    for (int k = blockIdx.x * MHB + threadIdx.x; k < L.M; k += gridDim.x * MHB) {
+        if (__ldcg(&S.ok[k])) {
+            const double x = __ldcg(&S.cur_x[k]), y = __ldcg(&S.cur_y[k]), F = __ldcg(&S.F_cur[k]);
+            const double w = w_theta_xy(P, x, y), sw = sqrt(w);
+            S.pos_out[3 * k] = x; S.pos_out[3 * k + 1] = y; S.pos_out[3 * k + 2] = 0.0;
+            S.F_out[k] = F;
+            S.df_out[k] = (P.c.kind == 2) ? 0.0 : P.b_FN * (sw * sw * sw) * v_y(P, F, w) / (-1.0 * F);
+        } else {  // failed chain: defined outputs, no emission (:1346-1361)
+            S.pos_out[3 * k] = P.c.emit_pos[0]; S.pos_out[3 * k + 1] = P.c.emit_pos[1]; S.pos_out[3 * k + 2] = 0.0;
+            S.F_out[k] = 1.0;
+            S.df_out[k] = HUGE_NEG;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
+}
+
+// work units: (tiles of 32 points) x (particle chunks, whole 128-record sub-tiles)
+MhPlan make_plan(const Rb2Ctx &ctx, int M, int G_max)
+{
+    const rb2_config &gc = ctx.cfg;
+    const int n = ctx.n;
+    MhPlan L{};
+    L.M = M; L.n = n; L.n_tiles = (M + 31) / 32;
+    if (n > 0) {
+        const long long max_ns = (n + MHB - 1) / MHB;
+        // one wave when the work is small (cheap joins), up to 16 waves when it is large (even finish)
+        const long long avail = (long long)L.n_tiles * max_ns;
+        long long units = std::min<long long>(avail, (long long)G_max * std::min<long long>(16, std::max<long long>(1, avail / ((long long)8 * G_max))));
+        long long ns = std::min<long long>(std::max<long long>((units + L.n_tiles - 1) / L.n_tiles, 1), max_ns);
+        int chunk = (int)((n + ns - 1) / ns);
+        chunk = ((chunk + MHB - 1) / MHB) * MHB;
+        L.j_chunk = chunk;
+        L.nsplit = (n + chunk - 1) / chunk;
+    }
+    L.units = L.n_tiles * L.nsplit;
+    L.two_d = 2.0 * gc.d;
+    L.E_vac = rb2_make_step_params(gc).pl.E_z;
+    L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
+    L.nic = gc.N_ic_max;
+    return L;
+}
+
+}  // namespace
+
+// E_z at M points of the cathode plane (z = 0), planar geometry: the mirror-antisymmetric form of the image
+// series (file header), 31 FP64 instructions per (point, particle) at N_ic_max = 1.
+int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez)
+{
+    if (M < 1) return RB2_OK;
+    const rb2_config &gc = ctx.cfg;
+    const int n = ctx.n;
+    const int NIC = !gc.image_charge ? -1 : (gc.N_ic_max >= 2 ? 2 : gc.N_ic_max);
+    const MhPlan L = make_plan(ctx, M, 4 * ctx.sm_count);
+    int rc = rb2_ensure_stage(ctx, (size_t)L.nsplit * M + (size_t)8 * n + 2, 0);
+    if (rc) return rc;
+    cudaStream_t st = ctx.stream;
+    double *partial = ctx.d_stage_d;
+    SurfRec *d_recs = reinterpret_cast<SurfRec *>(ctx.d_stage_d + ((((size_t)L.nsplit * M) + 1) & ~(size_t)1));
+    int launches = 1;
+    if (n > 0) {
+        k_surf_pack<<<(n + 255) / 256, 256, 0, st>>>(ctx.a.pq, n, L.two_d, gc.image_charge ? gc.N_ic_max : 0, d_recs);
+#define RB2_GO(N) k_surface_field<N><<<L.units, MHB, 0, st>>>(d_pts, d_recs, L, partial)
+        if (NIC < 0) RB2_GO(-1); else if (NIC == 0) RB2_GO(0); else if (NIC == 1) RB2_GO(1); else RB2_GO(2);
+#undef RB2_GO
+        launches += 2;
+    }
+    k_surface_join<<<(M + 3) / 4, 128, 0, st>>>(partial, L, d_Ez);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(launches);
+    return RB2_OK;
+}
+
+int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
+                         double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io)
+{
+    if (M < 1) return RB2_OK;
+    const int nw = cfg->y_num * cfg->x_num;
+    if (nw < 1 || nw > 96 * 96) return rb2_fail(RB2_ERR_ARG, "work function table must have 1..9216 cells");
+    const rb2_config &gc = ctx.cfg;
+    const int n = ctx.n, max_init = 10000;
+    const int NIC = !gc.image_charge ? -1 : (gc.N_ic_max >= 2 ? 2 : gc.N_ic_max);
+    void *kern = NIC < 0 ? (void *)k_mh_persistent<-1> : NIC == 0 ? (void *)k_mh_persistent<0>
+               : NIC == 1 ? (void *)k_mh_persistent<1> : (void *)k_mh_persistent<2>;
+    int occ = 0;
+    RB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MHB, 0));
+    if (occ < 1) return rb2_fail(RB2_ERR_CUDA, "sampler kernel does not fit on an SM");
+    const int G_max = occ * ctx.sm_count;
+    MhPlan L = make_plan(ctx, M, G_max);
+    const int warps_needed = (M + 3) / 4;  // CTAs so that phase B has one warp per chain
+    const int G = std::max(1, std::min(G_max, std::max(L.units, warps_needed)));
+    L.max_init = max_init;
+    L.seed = seed;
+    L.mh_std0 = *mh_std_io; L.a_rate0 = *a_rate_io;
+    // scratch (doubles): 4M state + nsplit*M partial + 5M outputs + table + 2 scalars + 8n records
+    const size_t nd = (size_t)9 * M + (size_t)L.nsplit * M + nw + 4 + (size_t)8 * n + 2;
+    const size_t ni = (size_t)M + 2 * ((size_t)cfg->ndim + 1) + max_init;
+    int rc = rb2_ensure_stage(ctx, nd, ni);
+    if (rc) return rc;
+    cudaStream_t st = ctx.stream;
+    double *d = ctx.d_stage_d;
+    MhState S{};
+    S.cur_x = d; S.cur_y = d + M; S.sup_cur = d + 2 * (size_t)M; S.F_cur = d + 3 * (size_t)M;
+    S.df_out = d + 4 * (size_t)M; S.F_out = d + 5 * (size_t)M; S.pos_out = d + 6 * (size_t)M;
+    S.partial = d + 9 * (size_t)M;
+    double *d_w = S.partial + (size_t)L.nsplit * M;
+    S.scal_out = d_w + nw;
+    size_t off = (size_t)(S.scal_out + 2 - d);
+    off = (off + 1) & ~(size_t)1;  // 16-byte alignment for the records
+    SurfRec *d_recs = reinterpret_cast<SurfRec *>(d + off);
+    S.recs = d_recs;
+    S.ok = ctx.d_stage_i;
+    S.cnt = ctx.d_stage_i + M;
+    S.bad = S.cnt + 2 * ((size_t)cfg->ndim + 1);
+    MhParams P;
+    P.c = *cfg;
+    P.w_theta = d_w;
+    const double pi = RB2_PI, h_bar = 6.62607015e-34 / (2.0 * pi);
+    P.b_FN = -4.0 / (3.0 * h_bar) * sqrt(2.0 * rb2k::m_0 * rb2k::q_0);
+    P.l_const = rb2k::q_0 / (4.0 * pi * rb2k::epsilon_0);
+    RB2_CUDA(cudaMemcpyAsync(d_w, w_theta_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemsetAsync(ctx.d_stage_i, 0, ni * sizeof(int), st));
+    RB2_CUDA(cudaMemsetAsync(d, 0, (size_t)4 * M * sizeof(double), st));
+    int launches = 1;
+    if (n > 0) {
+        k_surf_pack<<<(n + 255) / 256, 256, 0, st>>>(ctx.a.pq, n, L.two_d, gc.image_charge ? gc.N_ic_max : 0, d_recs);
+        launches++;
+    }
+    void *args[] = {&P, &S, &L};
+    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(MHB), args, 0, st));
+    RB2_LAUNCHED(launches);
+    double scal1[2];
+    RB2_CUDA(cudaMemcpyAsync(df_out, S.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(F_out, S.F_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(pos_out, S.pos_out, (size_t)3 * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(scal1, S.scal_out, sizeof(scal1), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    *mh_std_io = scal1[0];
+    *a_rate_io = scal1[1];
+    return RB2_OK;
+}

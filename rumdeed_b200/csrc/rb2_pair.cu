@@ -285,6 +285,36 @@ __global__ void k_field_finalize(const double *__restrict__ partial, int nslots,
     fld[3 * k + 2] = fE_z + rb2k::div_fac_c * sz;
 }
 
+// Few points against many j-chunks (the samplers' small batches): one CTA per point, strided slot sums
+// and a fixed-shape tree, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(128) k_field_finalize_wide(const double *__restrict__ partial, int nslots, int M,
+                                                             const double *__restrict__ pts, int geometry, PlanarParams P,
+                                                             TipParams T, double *__restrict__ fld)
+{
+    __shared__ double sh[3][128];
+    const int k = blockIdx.x, t = threadIdx.x;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int s = t; s < nslots; s += 128) {
+        const size_t base = (size_t)s * 3 * (size_t)M + (size_t)k;
+        sx += partial[base];
+        sy += partial[base + (size_t)M];
+        sz += partial[base + 2 * (size_t)M];
+    }
+    sh[0][t] = sx; sh[1][t] = sy; sh[2][t] = sz;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (t < w) { sh[0][t] += sh[0][t + w]; sh[1][t] += sh[1][t + w]; sh[2][t] += sh[2][t + w]; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        double fE_x = 0.0, fE_y = 0.0, fE_z = P.E_z;
+        if (geometry == RB2_GEOM_TIP) rb2_tip_field_E(T, pts[3 * k], pts[3 * k + 1], pts[3 * k + 2], fE_x, fE_y, fE_z);
+        fld[3 * k] = fE_x + rb2k::div_fac_c * sh[0][0];
+        fld[3 * k + 1] = fE_y + rb2k::div_fac_c * sh[1][0];
+        fld[3 * k + 2] = fE_z + rb2k::div_fac_c * sh[2][0];
+    }
+}
+
 struct Split {
     int nblk, nsplit, j_chunk;
 };
@@ -399,7 +429,10 @@ int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra
     const StepParams P = rb2_make_step_params(ctx.cfg);
     if (ctx.cfg.geometry != RB2_GEOM_PLANAR && ctx.cfg.geometry != RB2_GEOM_TIP)
         return rb2_fail(RB2_ERR_GEOMETRY, "geometry %d is not implemented on the device", ctx.cfg.geometry);
-    k_field_finalize<<<(M + 127) / 128, 128, 0, ctx.stream>>>(ctx.partial, nslots, M, d_pts, ctx.cfg.geometry, P.pl, P.tip, d_fld);
+    if (nslots >= 32)
+        k_field_finalize_wide<<<M, 128, 0, ctx.stream>>>(ctx.partial, nslots, M, d_pts, ctx.cfg.geometry, P.pl, P.tip, d_fld);
+    else
+        k_field_finalize<<<(M + 127) / 128, 128, 0, ctx.stream>>>(ctx.partial, nslots, M, d_pts, ctx.cfg.geometry, P.pl, P.tip, d_fld);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(1);
     return RB2_OK;

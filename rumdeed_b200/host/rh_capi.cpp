@@ -48,6 +48,7 @@ void *rh_create(const rh_setup *u)
     g.emitters_delay = u->emitters_delay;
     g.T_temp = u->T_temp;
     g.mh_batch = u->mh_batch != 0;
+    g.mh_device = u->mh_batch >= 2;
     g.planes_N = u->planes_N;
     for (int k = 0; k < 10; ++k) g.planes_z[k] = u->planes_z[k];
     if (u->cuba_epsabs > 0) g.cuba_epsabs = u->cuba_epsabs;
@@ -137,6 +138,12 @@ int rh_cuba_integrate(void *p, int kind, double *integral, double *error, int *n
 int rh_mh_rectangle_J(void *p, double *df, double *F, double *pos) { return Metropolis_Hastings_rectangle_J(*(Sim *)p, 1, df, F, pos); }
 int rh_mh_rectangle_J_batch(void *p, int M, double *df, double *F, double *pos) { return Metropolis_Hastings_rectangle_J_batch(*(Sim *)p, M, 1, df, F, pos); }
 int rh_mh_rectangle_J_thermo(void *p, double *pos) { return Metropolis_Hastings_rectangle_J_thermo(*(Sim *)p, 1, pos); }
+int rh_mh_rectangle_J_thermo_batch(void *p, int M, double *pos, int *ok)
+{
+    Sim &s = *(Sim *)p;
+    if (!s.g.mh_device) { s.err = "rh_mh_rectangle_J_thermo_batch needs mh_batch = 2 (device-resident chains)"; return -2; }
+    return Metropolis_Hastings_rectangle_J_thermo_batch(s, M, pos, ok);
+}
 int rh_metro_algo_tip_v3(void *p, int ndim, double *xi, double *phi, double *eta_f, double *df_cur, double *par_pos)
 {
     return Metro_algo_tip_v3(*(Sim *)p, ndim, xi, phi, eta_f, df_cur, par_pos);

@@ -112,6 +112,17 @@ int Sim::Calc_Field_at_Batch(int M, const double *pos_in, double *field_out)
     if (M < 1) return 0;
     return check(rb2_field_batch(M, pos_in, field_out), "rb2_field_batch");
 }
+// Calc_Field_at_Batch for points ON the planar cathode (z = 0), which is all the planar emission modules ask
+// for: with image charges on, E_x = E_y = 0 there and E_z comes from the cheaper rb2_field_surface_z.
+int Sim::Calc_Field_at_Surface(int M, const double *pos_in, double *field_out)
+{
+    if (M < 1) return 0;
+    if (!g.image_charge) return check(rb2_field_batch(M, pos_in, field_out), "rb2_field_batch");
+    scratch_ez.resize(M);
+    if (check(rb2_field_surface_z(M, pos_in, scratch_ez.data()), "rb2_field_surface_z")) return -1;
+    for (int k = 0; k < M; ++k) { field_out[3 * k] = 0.0; field_out[3 * k + 1] = 0.0; field_out[3 * k + 2] = scratch_ez[k]; }
+    return 0;
+}
 int Sim::Add_Particle(const double par_pos[3], const double par_vel[3], int species, int step, int emit, int life, int sec)
 {
     int rc = check(rb2_add_particles(1, par_pos, par_vel, &species, step, &emit, &sec, &life), "rb2_add_particles");
@@ -189,7 +200,7 @@ int Cuba_Integrate(Sim &s, int kind, int emit, QuadResult *out)
                 p[1] = g.emitters_pos[1] + v * g.emitters_dim[1];
                 p[2] = 0.0;
             }
-        if (s.Calc_Field_at_Batch(M, s.scratch_pts.data(), s.scratch_fld.data())) return -1;
+        if (s.Calc_Field_at_Surface(M, s.scratch_pts.data(), s.scratch_fld.data())) return -1;
         for (int r = 0; r < K; ++r)
             for (int k = 0; k < n_new; ++k) {
                 const size_t o = (size_t)3 * (r * n_new + k);
@@ -253,7 +264,7 @@ int Metropolis_Hastings_rectangle_J(Sim &s, int emit, double *df_out, double *F_
         cur_pos[0] = s.rng.uniform() * g.emitters_dim[0] + g.emitters_pos[0];
         cur_pos[1] = s.rng.uniform() * g.emitters_dim[1] + g.emitters_pos[1];
         cur_pos[2] = 0.0;
-        if (s.Calc_Field_at(cur_pos, field)) return -2;
+        if (s.Calc_Field_at_Surface(1, cur_pos, field)) return -2;
         if (field[2] < 0.0) break;
         if (++count > 10000) {
             *F_out = 1.0; *df_out = HUGE_NEG;
@@ -269,7 +280,7 @@ int Metropolis_Hastings_rectangle_J(Sim &s, int emit, double *df_out, double *F_
         s.rng.box_muller(cur_pos, std, new_pos);
         new_pos[2] = 0.0;
         check_limits_metro_rec(g, new_pos);
-        if (s.Calc_Field_at(new_pos, field)) return -2;
+        if (s.Calc_Field_at_Surface(1, new_pos, field)) return -2;
         if (field[2] >= 0.0) { if (i > ndim_first) jump_r++; continue; }
         const double sup_new = Elec_Supply_log(s, field[2], s.work.w_theta_xy(g, new_pos, nullptr));
         const double alpha = sup_new - sup_cur;
@@ -289,11 +300,32 @@ int Metropolis_Hastings_rectangle_J(Sim &s, int emit, double *df_out, double *F_
     return 0;
 }
 
+// mh_device: the same lock-step chains with every jump iteration enqueued on the GPU (rb2_mh_planar);
+// kind 1 = field emission (:1284-1458), kind 2 = thermal-field chains (src/mod_field_thermo_emission.F90:198-364)
+static int MH_planar_device(Sim &s, int kind, int M, double *df_out, double *F_out, double *pos_out)
+{
+    const Globals &g = s.g;
+    rb2_mh_config c{};
+    c.kind = kind;
+    c.ndim = (kind == 2) ? 25 : 25 * 8;
+    c.ndim_first = (kind == 2) ? 0 : (int)lround(c.ndim * 0.25);
+    c.image_charge = g.image_charge ? 1 : 0;
+    c.y_num = s.work.y_num; c.x_num = s.work.x_num;
+    for (int k = 0; k < 2; ++k) { c.emit_pos[k] = g.emitters_pos[k]; c.emit_dim[k] = g.emitters_dim[k]; }
+    c.T_temp = g.T_temp;
+    c.init_std = 0.10; c.target_rate = 0.35; c.std_gain = 0.025;
+    c.std_min = (kind == 2) ? 0.005 : 0.00005; c.std_max = 0.1250;
+    if (s.check(rb2_mh_planar(&c, s.work.w_theta_arr.data(), M, s.rng.next(), df_out, F_out, pos_out, &s.a_rate, &s.MH_std), "rb2_mh_planar"))
+        return -2;
+    return 0;
+}
+
 // Lock-step batch, :1284-1458: one device batch per jump iteration
 int Metropolis_Hastings_rectangle_J_batch(Sim &s, int M, int emit, double *df_out, double *F_out, double *pos_out)
 {
     (void)emit;
     const Globals &g = s.g;
+    if (g.mh_device) return MH_planar_device(s, 1, M, df_out, F_out, pos_out);
     const int ndim = 25 * 8, ndim_first = (int)lround(ndim * 0.25);
     std::vector<int> act(M), ok(M, 0);
     std::vector<double> cur((size_t)3 * M, 0.0), w_pos((size_t)3 * M), w_field((size_t)3 * M), sup_cur(M);
@@ -306,7 +338,7 @@ int Metropolis_Hastings_rectangle_J_batch(Sim &s, int M, int emit, double *df_ou
             w_pos[3 * k + 1] = s.rng.uniform() * g.emitters_dim[1] + g.emitters_pos[1];
             w_pos[3 * k + 2] = 0.0;
         }
-        if (s.Calc_Field_at_Batch(n_act, w_pos.data(), w_field.data())) return -2;
+        if (s.Calc_Field_at_Surface(n_act, w_pos.data(), w_field.data())) return -2;
         const int old = n_act;
         n_act = 0;
         for (int k = 0; k < old; ++k) {
@@ -342,7 +374,7 @@ int Metropolis_Hastings_rectangle_J_batch(Sim &s, int M, int emit, double *df_ou
             n_act++;
         }
         if (n_act == 0) break;
-        if (s.Calc_Field_at_Batch(n_act, w_pos.data(), w_field.data())) return -2;
+        if (s.Calc_Field_at_Surface(n_act, w_pos.data(), w_field.data())) return -2;
         for (int k = 0; k < n_act; ++k) {
             const int mc = act[k];
             if (w_field[3 * k + 2] >= 0.0) { it_r++; continue; }
@@ -463,7 +495,7 @@ int Metropolis_Hastings_rectangle_J_thermo(Sim &s, int emit, double pos_out[3])
         cur_pos[0] = s.rng.uniform() * g.emitters_dim[0] + g.emitters_pos[0];
         cur_pos[1] = s.rng.uniform() * g.emitters_dim[1] + g.emitters_pos[1];
         cur_pos[2] = 0.0;
-        if (s.Calc_Field_at(cur_pos, field)) return -2;
+        if (s.Calc_Field_at_Surface(1, cur_pos, field)) return -2;
         cur_w = s.work.w_theta_xy(g, cur_pos, nullptr);
         if (field[2] < 0.0) break;
         if (++count > 10000) {
@@ -477,7 +509,7 @@ int Metropolis_Hastings_rectangle_J_thermo(Sim &s, int emit, double pos_out[3])
         s.rng.box_muller(cur_pos, std, new_pos);
         new_pos[2] = 0.0;
         check_limits_metro_rec_tfe(g, new_pos);
-        if (s.Calc_Field_at(new_pos, field)) return -2;
+        if (s.Calc_Field_at_Surface(1, new_pos, field)) return -2;
         const double new_w = s.work.w_theta_xy(g, new_pos, nullptr);
         if (field[2] > 0.0) { jump_r++; continue; }
         const double df_new = log(std::max(Get_Kevin_Jgtf_v2(field[2], g.T_temp, new_w), TINY));
@@ -493,6 +525,18 @@ int Metropolis_Hastings_rectangle_J_thermo(Sim &s, int emit, double pos_out[3])
         if (s.MH_std > 0.1250) s.MH_std = 0.1250; else if (s.MH_std < 0.005) s.MH_std = 0.005;
     }
     memcpy(pos_out, cur_pos, sizeof(cur_pos));
+    return 0;
+}
+
+// All chains of one time step in lock-step on the device (mh_device); ok_out[k] = 0 for a chain that
+// found no favourable spot (the serial routine's "failed" return).
+int Metropolis_Hastings_rectangle_J_thermo_batch(Sim &s, int M, double *pos_out, int *ok_out)
+{
+    if (M < 1) return 0;
+    std::vector<double> df(M), F(M);
+    const int rc = MH_planar_device(s, 2, M, df.data(), F.data(), pos_out);
+    if (rc) return rc;
+    for (int k = 0; k < M; ++k) ok_out[k] = F[k] <= 0.0;
     return 0;
 }
 
@@ -521,11 +565,22 @@ static int Do_Field_Thermo_Emission(Sim &s, int step)
     memcpy(s.slog.F_avg, q.F_avg, sizeof(q.F_avg));
     const int N_round = s.rng.poisson(N_sup);
     int nrElecEmit = 0;
+    std::vector<double> b_pos;
+    std::vector<int> b_ok;
+    if (g.mh_device && N_round > 0) {
+        b_pos.resize((size_t)3 * N_round); b_ok.resize(N_round);
+        if (Metropolis_Hastings_rectangle_J_thermo_batch(s, N_round, b_pos.data(), b_ok.data())) return -1;
+    }
     for (int i = 0; i < N_round; ++i) {
         double par_pos[3], par_vel[3];
-        const int rc = Metropolis_Hastings_rectangle_J_thermo(s, 1, par_pos);
-        if (rc == -2) return -1;
-        if (rc < 0) continue;
+        if (g.mh_device) {
+            if (!b_ok[i]) continue;
+            memcpy(par_pos, &b_pos[(size_t)3 * i], sizeof(par_pos));
+        } else {
+            const int rc = Metropolis_Hastings_rectangle_J_thermo(s, 1, par_pos);
+            if (rc == -2) return -1;
+            if (rc < 0) continue;
+        }
         par_pos[2] = 1.0 * length_scale;
         Get_MB_Velocity(s, par_vel);
         int sec = 1;

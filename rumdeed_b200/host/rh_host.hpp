@@ -69,6 +69,7 @@ struct Globals {
     int planes_N = 10;
     double planes_z[RB2_PLANES_MAX] = {5.0, 10.0, 25.0, 50.0, 75.0, 100.0, 125.0, 250.0, 500.0, 750.0};
     bool mh_batch = false;
+    bool mh_device = false;  // lock-step chains run by rb2_mh_planar (implies mh_batch)
     int cuba_method = 2;
     double cuba_epsabs = 0.5, cuba_epsrel = 1.0e-3;
     int cuba_mineval = 1000, cuba_maxeval = 5000000;
@@ -143,7 +144,7 @@ struct Sim {
     FILE *ud_ramo = nullptr, *ud_emit = nullptr, *ud_absorb = nullptr, *ud_absorb_top = nullptr, *ud_absorb_bot = nullptr;
     FILE *ud_field = nullptr, *ud_integrand = nullptr, *ud_volt = nullptr, *ud_density_emit = nullptr;
     FILE *ud_density_absorb_top = nullptr, *ud_density_absorb_bot = nullptr, *planes_ud[RB2_PLANES_MAX] = {nullptr};
-    std::vector<double> scratch_pts, scratch_fld;
+    std::vector<double> scratch_pts, scratch_fld, scratch_ez;
 
     int fail(const std::string &m) { err = m; return -1; }
     int check(int rc, const char *where);
@@ -151,6 +152,7 @@ struct Sim {
     // mod_verlet / mod_pair through the C ABI
     int Calc_Field_at(const double pos[3], double field[3]);
     int Calc_Field_at_Batch(int M, const double *pos_in, double *field_out);
+    int Calc_Field_at_Surface(int M, const double *pos_in, double *field_out);
     int Add_Particle(const double par_pos[3], const double par_vel[3], int species, int step, int emit, int life, int sec);
     // geometry helpers (src/mod_hyperboloid_tip.f90:25-112, 156-163)
     void xyz_corr(double xi, double eta, double phi, double out[3]) const;
@@ -185,6 +187,7 @@ double Get_Kevin_Jgtf_v2(double F, double T, double w_theta);  // src/mod_kevin_
 int Metropolis_Hastings_rectangle_J(Sim &s, int emit, double *df_out, double *F_out, double pos_out[3]);
 int Metropolis_Hastings_rectangle_J_batch(Sim &s, int M, int emit, double *df_out, double *F_out, double *pos_out);
 int Metropolis_Hastings_rectangle_J_thermo(Sim &s, int emit, double pos_out[3]);
+int Metropolis_Hastings_rectangle_J_thermo_batch(Sim &s, int M, double *pos_out, int *ok_out);
 int Metro_algo_tip_v3(Sim &s, int ndim, double *xi, double *phi, double *eta_f, double *df_cur, double par_pos[3]);
 int Metro_algo_tip_v3_batch(Sim &s, int M, int ndim, double *eta_f_out, double *df_out, double *pos_out);
 int Tip_Supply_Grid(Sim &s, int nr_xi, int nr_phi, double *n_s, double *F_avg);

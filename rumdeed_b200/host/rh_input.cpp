@@ -146,6 +146,8 @@ int Read_Input_Variables(const std::string &path, Globals &g, std::string &err)
     integer("PLANES_N", g.planes_N);
     vec("PLANES_Z", g.planes_z, RB2_PLANES_MAX);
     logical("MH_BATCH", g.mh_batch);
+    logical("MH_DEVICE", g.mh_device);  // extension: lock-step chains resident on the GPU (rb2_mh_planar)
+    if (g.mh_device) g.mh_batch = true;
     integer("CUBA_METHOD", g.cuba_method);
     dbl("CUBA_EPSABS", g.cuba_epsabs);
     dbl("CUBA_EPSREL", g.cuba_epsrel);

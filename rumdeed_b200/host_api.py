@@ -75,6 +75,7 @@ def load_host_library():
     lib.rh_mh_rectangle_J.argtypes = [V, _PD, _PD, _PD]
     lib.rh_mh_rectangle_J_batch.argtypes = [V, C.c_int, _PD, _PD, _PD]
     lib.rh_mh_rectangle_J_thermo.argtypes = [V, _PD]
+    lib.rh_mh_rectangle_J_thermo_batch.argtypes = [V, C.c_int, _PD, _PI]
     lib.rh_metro_algo_tip_v3.argtypes = [V, C.c_int, _PD, _PD, _PD, _PD, _PD]
     lib.rh_metro_algo_tip_v3_batch.argtypes = [V, C.c_int, C.c_int, _PD, _PD, _PD]
     lib.rh_tip_supply_grid.argtypes = [V, C.c_int, C.c_int, _PD, _PD]
@@ -186,6 +187,12 @@ class Simulation:
         df, F, pos = np.zeros(M), np.zeros(M), np.zeros((M, 3))
         self._check(self.lib.rh_mh_rectangle_J_batch(self.ptr, M, _d(df), _d(F), _d(pos)))
         return df, F, pos
+
+    def Metropolis_Hastings_rectangle_J_thermo_batch(self, M):
+        """mh_batch=2: M thermal-field chains in lock-step on the device.  Returns (pos, ok)."""
+        pos, ok = np.zeros((M, 3)), np.zeros(M, dtype=np.int32)
+        self._check(self.lib.rh_mh_rectangle_J_thermo_batch(self.ptr, M, _d(pos), ok.ctypes.data_as(_PI)))
+        return pos, ok
 
     def Metropolis_Hastings_rectangle_J_thermo(self):
         pos = np.zeros(3)

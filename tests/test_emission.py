@@ -169,6 +169,59 @@ def test_fe_samplers_match_oracle_distribution(orc):
 
 
 @gpu
+def test_device_resident_fe_sampler(orc):
+    """mh_batch = 2 (rb2_mh_planar): the lock-step chains of mod_field_emission_v2.F90:1284-1458 run on the
+    device; same distributions as the oracle's chains, reproducible for a given seed, adaptive step in range."""
+    w = ((2.0, 2.4), (2.4, 2.0))
+    sim, p, st, em = _planar_pair(orc, 22, w=w, mh_batch=2)
+    emit = 100 * NM
+    with sim:
+        _preload(sim, st, p, 120, 5)
+        M = 800
+        df_d, F_d, pos_d = sim.Metropolis_Hastings_rectangle_J_batch(M)
+        df_o, F_o, pos_o = em.mh_rectangle_J_batch(M)
+        hp = rb.HotPath.attach()
+        args = dict(emit_pos=(-0.5 * emit, -0.5 * emit), emit_dim=(emit, emit), w_theta=w, seed=987654321)
+        r1 = hp.mh_planar(257, **args)
+        r2 = hp.mh_planar(257, **args)
+        r3 = hp.mh_planar(257, **{**args, "seed": 5})
+    assert np.all(F_d < 0) and np.all(np.abs(pos_d[:, :2]) <= 0.5 * emit) and np.all(pos_d[:, 2] == 0)
+    for k in (0, 1):
+        assert _ks(pos_d[:, k], pos_o[:, k]) > 1e-3
+    assert _ks(F_d, F_o) > 1e-3 and _ks(df_d, df_o) > 1e-3
+    in_low = lambda ps: np.mean(((ps[:, 0] < 0) & (ps[:, 1] > 0)) | ((ps[:, 0] > 0) & (ps[:, 1] < 0)))
+    assert abs(in_low(pos_d) - in_low(pos_o)) < 0.1
+    for a, b in zip(r1[:3], r2[:3]):
+        assert np.array_equal(a, b)                      # counter-based RNG: same seed, same chains
+    assert r1[3:] == r2[3:] and not np.array_equal(r1[2], r3[2])
+    assert 0.0 < r1[3] <= 1.0 and 0.00005 <= r1[4] <= 0.125
+    # escape exponent consistent with the returned field and position (Escape_Prob_log, :568)
+    k = 7
+    col, row = int((r1[2][k, 0] / emit + 0.5) * 2), 1 - int((r1[2][k, 1] / emit + 0.5) * 2)
+    assert r1[0][k] == pytest.approx(orc.fn_escape_prob_log(p, r1[1][k], w[row][col]), rel=1e-12)
+
+
+@gpu
+def test_device_resident_thermo_sampler(orc):
+    w = ((2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0), (2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0))
+    sim, p, st, em = _planar_pair(orc, 32, w=w, mode=9, T=1000.0, V=2000.0, d=1000 * NM, dt=1e-16, mh_batch=2)
+    with sim:
+        _preload(sim, st, p, 80, 6, d=1000 * NM)
+        # MH_std adapts once per chain in the serial routine and once per jump iteration in lock-step: let
+        # both settle (it grows from 1.25 % of the emitter side towards its cap) before comparing
+        for _ in range(30):
+            sim.Metropolis_Hastings_rectangle_J_thermo_batch(40)
+        a, ok = sim.Metropolis_Hastings_rectangle_J_thermo_batch(600)
+        b = np.array([em.mh_rectangle_J_thermo()[1] for _ in range(900)])[500:]
+        assert sim.state().MH_std > 0.05
+    assert np.all(ok == 1)
+    for k in (0, 1):
+        assert _ks(a[:, k], b[:, k]) > 1e-3
+    cell = lambda ps: ((np.floor((ps[:, 0] / (100 * NM) + 0.5) * 4) + np.floor((ps[:, 1] / (100 * NM) + 0.5) * 4)) % 2)
+    assert abs(np.mean(cell(a)) - np.mean(cell(b))) < 0.1
+
+
+@gpu
 def test_thermo_sampler_matches_oracle_distribution(orc):
     w = ((2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0), (2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0))
     sim, p, st, em = _planar_pair(orc, 31, w=w, mode=9, T=1000.0, V=2000.0, d=1000 * NM, dt=1e-16)
@@ -223,7 +276,7 @@ def test_tip_supply_and_sampler_match_oracle(orc):
 # ---------------------------------------------------------------------------------------------------------
 # GPU: whole-system runs
 @gpu
-@pytest.mark.parametrize("mh_batch", [False, True])
+@pytest.mark.parametrize("mh_batch", [False, True, 2])
 def test_planar_system_reference_test(orc, mh_batch):
     """mod_tests.F90:2013-2125 (Test_Planar_System): 250 steps, 1 kV over 500 nm, 100 x 100 nm emitter,
     2.0 eV, N_ic_max = 0.  Same assertions as the reference, plus agreement with an oracle run."""
@@ -254,7 +307,7 @@ def test_planar_system_reference_test(orc, mh_batch):
     Qo = 0.0
     for i in range(1, n_steps + 1):
         N_sup, _ = em.supply_grid(SUPPLY_FE, 16)
-        em.do_field_emission_planar(i, N_sup, mh_batch)
+        em.do_field_emission_planar(i, N_sup, bool(mh_batch))
         st.step(p)
         if i > n_steps // 2:
             Qo += st.s.ramo_current[1] * dt
@@ -302,9 +355,10 @@ def test_tip_system_reference_test(orc):
 
 
 @gpu
-def test_thermo_field_system(orc):
+@pytest.mark.parametrize("mh_batch", [False, 2])
+def test_thermo_field_system(orc, mh_batch):
     w = ((2.0, 2.5), (2.5, 2.0))
-    sim, p, st, em = _planar_pair(orc, 99, w=w, mode=9, T=1000.0, V=2000.0, d=1000 * NM, dt=1e-16)
+    sim, p, st, em = _planar_pair(orc, 99, w=w, mode=9, T=1000.0, V=2000.0, d=1000 * NM, dt=1e-16, mh_batch=mh_batch)
     n_steps = 60
     with sim:
         for i in range(1, n_steps + 1):

@@ -252,6 +252,35 @@ def test_planar_field_batch_vs_oracle(orc, ic, nic, M):
     assert relerr(one[None], want[:1]) < TOL
 
 
+@pytest.mark.parametrize("ic,nic", [(False, 0), (True, 0), (True, 1), (True, 2), (True, 4)])
+@pytest.mark.parametrize("M,n", [(1, 0), (1, 1), (5, 127), (33, 2000), (300, 129), (2000, 5000)])
+def test_surface_field_z_vs_oracle(orc, ic, nic, M, n):
+    """rb2_field_surface_z: E_z on the cathode plane from the mirror-antisymmetric form of the image series
+    equals the z component of Calc_Field_at (mod_verlet.F90:1466) evaluated there, to the FP64 gate."""
+    cfg, p = planar(orc, ic=ic, nic=nic)
+    pos, q, m, sp = cloud(max(n, 1), 7)
+    pos, q, m, sp = pos[:n], q[:n], m[:n], sp[:n]
+    rng = np.random.default_rng(17 + M)
+    pts = np.stack([rng.uniform(-500, 500, M), rng.uniform(-500, 500, M), np.zeros(M)], axis=1) * NM
+    with rb.HotPath(cfg) as hp:
+        if n:
+            hp.upload(pos, q, m, species=sp)
+        ez = hp.field_surface_z(pts)
+        full = hp.Calc_Field_at_Batch(pts)
+        bad = pts.copy()
+        bad[-1, 2] = 1.0 * NM
+        with pytest.raises(rb.Rb2Error):
+            hp.field_surface_z(bad)
+    if n == 0:
+        assert np.all(ez == cfg.E_z)
+        return
+    want = np.array([orc.calc_field_at(p, pos, q, pts[k], sp, ld=True)[2] for k in range(min(M, 300))])
+    assert np.max(np.abs(ez[:len(want)] - want) / np.abs(want)) < TOL
+    assert np.max(np.abs(ez - full[:, 2]) / np.abs(ez)) < TOL
+    if ic:  # the lateral components the general kernel returns there are rounding noise
+        assert np.max(np.abs(full[:, :2])) < 1e-9 * np.max(np.abs(full[:, 2]))
+
+
 def test_reference_planar_batch_case(orc):
     """mod_tests.F90:1554-1603 (N_ic_max = 1, 3 particles, 4 points; vacuum check)."""
     d, V = 100 * NM, 2.0
