@@ -56,6 +56,13 @@ module mod_b200_bridge
     integer(c_int) :: emit, sec, id
   end type rb2_event
 
+  type, bind(C) :: rb2_mh_config
+    integer(c_int) :: kind, ndim, ndim_first, image_charge, y_num, x_num
+    real(c_double) :: emit_pos(2), emit_dim(2)
+    real(c_double) :: T_temp
+    real(c_double) :: init_std, target_rate, std_gain, std_min, std_max
+  end type rb2_mh_config
+
   type, bind(C) :: rb2_step_result
     real(c_double) :: ramo_current(4)
     real(c_double) :: avg_part_vel(3), avg_elec_vel(3), avg_ion_vel(3)
@@ -127,6 +134,22 @@ module mod_b200_bridge
       integer(c_int), value :: M
       real(c_double), intent(in)  :: pos_in(3, *)
       real(c_double), intent(out) :: field_out(3, *)
+    end function
+    integer(c_int) function rb2_field_surface_z(M, pos_in, Ez_out) bind(C, name='rb2_field_surface_z')
+      import :: c_int, c_double
+      integer(c_int), value :: M
+      real(c_double), intent(in)  :: pos_in(3, *)
+      real(c_double), intent(out) :: Ez_out(*)
+    end function
+    integer(c_int) function rb2_mh_planar(cfg, w_theta, M, seed, df_out, F_out, pos_out, a_rate_io, mh_std_io) &
+        bind(C, name='rb2_mh_planar')
+      import :: c_int, c_double, c_long_long, rb2_mh_config
+      type(rb2_mh_config), intent(in) :: cfg
+      real(c_double), intent(in) :: w_theta(*)          ! transpose(w_theta_arr): rows of the `work` file
+      integer(c_int), value :: M
+      integer(c_long_long), value :: seed
+      real(c_double), intent(out) :: df_out(*), F_out(*), pos_out(3, *)
+      real(c_double), intent(inout) :: a_rate_io, mh_std_io
     end function
     integer(c_int) function rb2_field_window_open() bind(C, name='rb2_field_window_open')
       import :: c_int
