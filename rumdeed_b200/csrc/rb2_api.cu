@@ -465,6 +465,8 @@ int rb2_mark_remove(int k, const int *index, const int *reason)
     if (k < 0) return rb2_fail(RB2_ERR_ARG, "k < 0");
     if (k == 0) return RB2_OK;
     if (!index || !reason) return rb2_fail(RB2_ERR_ARG, "index and reason are required");
+    for (int t = 0; t < k; ++t)
+        if (index[t] < 0 || index[t] >= c.n) return rb2_fail(RB2_ERR_ARG, "rb2_mark_remove: index %d outside 0..%d", index[t], c.n - 1);
     int rc = rb2_ensure_stage(c, 0, (size_t)2 * k);
     if (rc) return rc;
     RB2_CUDA(cudaMemcpyAsync(c.d_stage_i, index, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, c.stream));

@@ -251,8 +251,10 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (wb < 1) wb = 1;
     if (wb > (size_t)g.nsb) wb = (size_t)g.nsb;
     const int Wb = (int)wb;
-    // group size: enough CTAs to fill 4 CTAs/SM for ~8 waves
-    const double want_ctas = (double)ctx.sm_count * 4 * ctx.sym_waves;
+    // group size: enough CTAs to fill 4 CTAs/SM for sym_waves waves ON EACH RANK (the CTAs of a band are dealt
+    // round-robin to the ranks; with fewer waves per rank the tail of every band launch shows -- 83 % vs 96 %
+    // of the ideal split at 8 ranks, tools/sym_rank_sweep.py)
+    const double want_ctas = (double)ctx.sm_count * 4 * ctx.sym_waves * g.world;
     int G = (int)((double)g.nsb * Wb / want_ctas);
     if (G < 1) G = 1;
     if (G > Wb) G = Wb;

@@ -554,3 +554,57 @@ def test_large_cloud_properties(orc):
         a0 = hp.download(("acc",))["acc"]
         f = a0 * m[:, None]
         assert np.linalg.norm(f.sum(axis=0)) < 1e-9 * np.abs(f).sum()
+
+
+# --------------------------------------------------------------------------------------------------
+def test_empty_and_overflowing_store(orc):
+    """Edge cases the reference guards: an empty system steps to nothing (mod_verlet.F90:123-162 with
+    nrPart = 0), zero field points are a no-op (:1658), Add_Particle beyond MAX_PARTICLES drops the particle
+    and counts it (mod_pair.F90:37-43), and bad indices are refused instead of touching memory."""
+    d = 100 * NM
+    cfg = rb.planar_config(2.0, d, (100 * NM, 100 * NM, d), 0.25e-15, True, 1, capacity=4)
+    with rb.HotPath(cfg) as hp:
+        r = hp.Update_Position(1)
+        assert r.counts.nrPart == 0 and r.n_events == 0 and list(r.ramo_current) == [0.0] * 4
+        assert hp.Remove_Particles(1).nrPart == 0
+        hp.Calculate_Acceleration_Particles()
+        assert hp.Calc_Field_at_Batch(np.zeros((0, 3))).shape == (0, 3)
+        assert hp.field_surface_z(np.zeros((0, 3))).shape == (0,)
+        assert hp.download(("pos",))["pos"].shape == (0, 3)
+        pos = np.array([[0.0, 0.0, 10.0 * (k + 1)] for k in range(6)]) * NM
+        hp.Add_Particles(pos, np.zeros((6, 3)), np.ones(6, dtype=np.int32), 1)
+        k = hp.counts()
+        assert (k.nrPart, k.nrElec, k.nrPart_dropped) == (4, 4, 2)
+        got = hp.download(("pos",))["pos"]
+        assert np.array_equal(got, pos[:4])
+        for bad in (-1, 4, 1000):
+            with pytest.raises(rb.Rb2Error):
+                hp.Mark_Particles_Remove(bad, REMOVE_TOP)
+        hp.Update_Position(2)          # the full store still steps
+        assert hp.counts().nrPart == 4
+        hp.Mark_Particles_Remove(0, REMOVE_TOP)
+        assert hp.Remove_Particles(2).nrPart == 3
+        hp.Add_Particle(pos[5], [0, 0, 0], SPECIES_ELEC, 3, 1)   # room again
+        k = hp.counts()
+        assert (k.nrPart, k.nrPart_dropped) == (4, 2)
+
+
+def test_many_field_points_and_determinism(orc):
+    """M far above one wave of CTAs; repeated evaluation is bit-identical (fixed summation order)."""
+    cfg, p = planar(orc, ic=True, nic=1)
+    pos, q, m, sp = cloud(3000, 11)
+    rng = np.random.default_rng(3)
+    M = 70000
+    pts = np.stack([rng.uniform(-500, 500, M), rng.uniform(-500, 500, M), rng.uniform(0, 900, M)], axis=1) * NM
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        a = hp.Calc_Field_at_Batch(pts)
+        b = hp.Calc_Field_at_Batch(pts)
+        hp.Calculate_Acceleration_Particles()
+        acc1 = hp.download(("acc",))["acc"]
+        hp.Calculate_Acceleration_Particles()
+        acc2 = hp.download(("acc",))["acc"]
+    assert np.array_equal(a, b) and np.array_equal(acc1, acc2)
+    idx = rng.choice(M, 64, replace=False)
+    want = np.stack([orc.calc_field_at(p, pos, q, pts[k], sp, ld=True) for k in idx])
+    assert relerr(a[idx], want) < TOL
