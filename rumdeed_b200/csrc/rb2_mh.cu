@@ -3,7 +3,8 @@
 // Replaces the host loop of Metropolis_Hastings_rectangle_J_batch (reference
 // src/mod_field_emission_v2.F90:1284-1458): M chains advance together.  ONE persistent cooperative kernel
 // runs the search for favourable start spots and all jump iterations; per iteration
-//   phase A  every CTA takes (tile of 32 chains) x (chunk of particles) work units: the proposals
+//   phase A  the sequence of (tile of 32 chains) x (128-particle sub-tile) work items is cut into one equal
+//            contiguous range per CTA (even finish before the barrier, no work queue): the proposals
 //            (Marsaglia polar normals, reflection at the emitter edges :1466-1516) are recomputed from the
 //            counter-based generator wherever they are needed, and the surface field sum runs over the
 //            particle records staged in shared memory;
@@ -151,11 +152,20 @@ struct MhState {
     int *cnt;                                  // [2 * (ndim + 1)] accepted / rejected per iteration
     int *bad;                                  // [max_init] chains still without a favourable spot per round
     const SurfRec *recs;                       // [n]
+    const long long *wstart;                   // [G + 1] first work item of every CTA (host-computed W*g/G)
+    const int *tfirst;                         // [G] tile of that work item
+    const int *kfirst;                         // [G] how many CTAs contribute to that tile before this one
+    const int *tcount;                         // [n_tiles] contributions per tile
     double *df_out, *F_out, *pos_out, *scal_out;
 };
 
 struct MhPlan {
     int M, n, n_tiles, nsplit, j_chunk, units, max_init;
+    // persistent sampler: the sequence of (tile, 128-record sub-tile) work items, S per tile, W in total, is cut
+    // into gridDim.x equal contiguous ranges; a CTA writes one partial sum per tile its range touches, into
+    // partial[tile][k][32] with k = its rank among the tile's contributors (maxslots = most contributors)
+    int S, maxslots;
+    long long W;
     unsigned long long seed;
     double two_d, E_vac, fac, mh_std0, a_rate0;
     int nic;
@@ -241,8 +251,9 @@ __device__ __forceinline__ void propose(const MhParams &P, const MhState &S, con
 }
 
 // One work unit: 32 surface points (one per lane, the same in all four warps) against the particle records
-// [j0, j1).  The CTA stages 128-record sub-tiles in shared memory (double buffered), warp w takes records
-// 32w .. 32w+31 of each, and the four warp sums are joined in a fixed order.  The result is valid in warp 0.
+// [j0, j1).  Of every 128 records warp w stages records 32w .. 32w+31 in its own slice of shared memory
+// (double buffered, register prefetch) and reads them back as broadcasts; the four warp sums are joined in a
+// fixed order.  The result is valid in warp 0.
 template <int NIC>
 __device__ __forceinline__ double surf_unit_sum(const SurfRec *__restrict__ g_recs, int j0, int j1, double px, double py,
                                                 const MhPlan &L, SurfRec (*recs)[MHB], double (*red)[32])
@@ -257,13 +268,16 @@ __device__ __forceinline__ double surf_unit_sum(const SurfRec *__restrict__ g_re
     };
     fetch(0);
     double acc = 0.0;
+    // each warp stages and consumes its own 32 records: only warp-level synchronisation inside the loop, so
+    // the four warps of a CTA drift apart freely (a CTA barrier per sub-tile cost ~25 % in stalls)
     for (int t = 0; t < nsub; ++t) {
         recs[t & 1][tid] = nxt;
-        __syncthreads();
+        __syncwarp();
         if (t + 1 < nsub) fetch(t + 1);
         const SurfRec *rr = &recs[t & 1][warp * 32];
 #pragma unroll 4
         for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+        __syncwarp();
     }
     red[warp][lane] = acc;
     __syncthreads();
@@ -278,14 +292,20 @@ __device__ __forceinline__ void phase_field(const MhParams &P, const MhState &S,
                                             SurfRec (*recs)[MHB], double (*red)[32])
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int u = blockIdx.x; u < L.units; u += gridDim.x) {
-        const int tile = u / L.nsplit, s = u - tile * L.nsplit;
+    if (L.W == 0) return;
+    const long long w0 = S.wstart[blockIdx.x], w1 = S.wstart[blockIdx.x + 1];
+    const int tile_first = S.tfirst[blockIdx.x];
+    for (long long w = w0; w < w1;) {
+        const int tile = (int)(w / L.S), s0 = (int)(w - (long long)tile * L.S);
+        const int s1 = (int)min((long long)L.S, (long long)s0 + (w1 - w));
         const int c = tile * 32 + lane;
         double px = 0.0, py = 0.0;
         if (c < L.M) propose(P, S, L, iter, c, mh_std, px, py);
-        const int j0 = s * L.j_chunk, j1 = min(L.n, j0 + L.j_chunk);
-        const double sum = surf_unit_sum<NIC>(S.recs, j0, j1, px, py, L, recs, red);
-        if (warp == 0 && c < L.M) S.partial[(size_t)s * L.M + c] = sum;
+        const double sum = surf_unit_sum<NIC>(S.recs, s0 * MHB, min(L.n, s1 * MHB), px, py, L, recs, red);
+        // contribution index within the tile: only the first tile of a range can have earlier contributors
+        const int k = (tile == tile_first) ? S.kfirst[blockIdx.x] : 0;
+        if (warp == 0) S.partial[((size_t)tile * L.maxslots + k) * 32 + lane] = sum;
+        w += s1 - s0;
     }
 }
 
@@ -327,7 +347,12 @@ __device__ __forceinline__ void phase_accept(const MhParams &P, const MhState &S
     int n_acc = 0, n_rej = 0, n_bad = 0;
     for (int c = gwarp; c < L.M; c += nwarps) {
         double sum = 0.0;
-        for (int s = lane; s < L.nsplit; s += 32) sum += __ldcg(&S.partial[(size_t)s * L.M + c]);
+        if (L.W > 0) {  // the contributions to this chain's tile, in ascending CTA order (fixed-shape join)
+            const int t = c >> 5, nk = S.tcount[t];
+            const double *pp = S.partial + ((size_t)t * L.maxslots) * 32 + (c & 31);
+#pragma unroll 4
+            for (int k = lane; k < nk; k += 32) sum += __ldcg(pp + (size_t)k * 32);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane != 0) continue;
@@ -484,14 +509,31 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     if (occ < 1) return rb2_fail(RB2_ERR_CUDA, "sampler kernel does not fit on an SM");
     const int G_max = occ * ctx.sm_count;
     MhPlan L = make_plan(ctx, M, G_max);
-    const int warps_needed = (M + 3) / 4;  // CTAs so that phase B has one warp per chain
-    const int G = std::max(1, std::min(G_max, std::max(L.units, warps_needed)));
+    L.S = (n + MHB - 1) / MHB;
+    L.W = (long long)L.n_tiles * L.S;
+    const long long warps_needed = (M + 3) / 4;  // CTAs so that phase B has one warp per chain
+    const int G = (int)std::max<long long>(1, std::min<long long>(G_max, std::max<long long>(L.W, warps_needed)));
+    // the even split and, per tile, who contributes in which order
+    std::vector<long long> h_wstart((size_t)G + 1);
+    std::vector<int> h_tab((size_t)2 * G + L.n_tiles, 0);  // tfirst[G], kfirst[G], tcount[n_tiles]
+    int *h_tfirst = h_tab.data(), *h_kfirst = h_tfirst + G, *h_tcount = h_kfirst + G;
+    for (int g = 0; g <= G; ++g) h_wstart[g] = L.W * g / G;
+    L.maxslots = 1;
+    for (int g = 0; g < G; ++g) {
+        const long long a = h_wstart[g], b = h_wstart[g + 1];
+        if (b <= a) continue;
+        const int t0 = (int)(a / L.S), t1 = (int)((b - 1) / L.S);
+        h_tfirst[g] = t0;
+        h_kfirst[g] = h_tcount[t0];
+        for (int t = t0; t <= t1; ++t) L.maxslots = std::max(L.maxslots, ++h_tcount[t]);
+    }
+    const size_t n_partial = (size_t)L.n_tiles * L.maxslots * 32;
     L.max_init = max_init;
     L.seed = seed;
     L.mh_std0 = *mh_std_io; L.a_rate0 = *a_rate_io;
-    // scratch (doubles): 4M state + nsplit*M partial + 5M outputs + table + 2 scalars + 8n records
-    const size_t nd = (size_t)9 * M + (size_t)L.nsplit * M + nw + 4 + (size_t)8 * n + 2;
-    const size_t ni = (size_t)M + 2 * ((size_t)cfg->ndim + 1) + max_init;
+    // scratch (doubles): 4M state + partial sums + 5M outputs + table + 2 scalars + 8n records
+    const size_t nd = (size_t)9 * M + n_partial + nw + 4 + (size_t)8 * n + 2 + (size_t)G + 1;
+    const size_t ni = (size_t)M + 2 * ((size_t)cfg->ndim + 1) + max_init + h_tab.size();
     int rc = rb2_ensure_stage(ctx, nd, ni);
     if (rc) return rc;
     cudaStream_t st = ctx.stream;
@@ -500,15 +542,19 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     S.cur_x = d; S.cur_y = d + M; S.sup_cur = d + 2 * (size_t)M; S.F_cur = d + 3 * (size_t)M;
     S.df_out = d + 4 * (size_t)M; S.F_out = d + 5 * (size_t)M; S.pos_out = d + 6 * (size_t)M;
     S.partial = d + 9 * (size_t)M;
-    double *d_w = S.partial + (size_t)L.nsplit * M;
+    double *d_w = S.partial + n_partial;
     S.scal_out = d_w + nw;
-    size_t off = (size_t)(S.scal_out + 2 - d);
+    long long *d_wstart = reinterpret_cast<long long *>(S.scal_out + 2);
+    S.wstart = d_wstart;
+    size_t off = (size_t)(S.scal_out + 2 - d) + (size_t)G + 1;
     off = (off + 1) & ~(size_t)1;  // 16-byte alignment for the records
     SurfRec *d_recs = reinterpret_cast<SurfRec *>(d + off);
     S.recs = d_recs;
     S.ok = ctx.d_stage_i;
     S.cnt = ctx.d_stage_i + M;
     S.bad = S.cnt + 2 * ((size_t)cfg->ndim + 1);
+    int *d_tab = S.bad + max_init;
+    S.tfirst = d_tab; S.kfirst = d_tab + G; S.tcount = d_tab + 2 * (size_t)G;
     MhParams P;
     P.c = *cfg;
     P.w_theta = d_w;
@@ -518,6 +564,8 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     RB2_CUDA(cudaMemcpyAsync(d_w, w_theta_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice, st));
     RB2_CUDA(cudaMemsetAsync(ctx.d_stage_i, 0, ni * sizeof(int), st));
     RB2_CUDA(cudaMemsetAsync(d, 0, (size_t)4 * M * sizeof(double), st));
+    RB2_CUDA(cudaMemcpyAsync(d_wstart, h_wstart.data(), ((size_t)G + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemcpyAsync(d_tab, h_tab.data(), h_tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     int launches = 1;
     if (n > 0) {
         k_surf_pack<<<(n + 255) / 256, 256, 0, st>>>(ctx.a.pq, n, L.two_d, gc.image_charge ? gc.N_ic_max : 0, d_recs);
