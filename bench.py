@@ -193,7 +193,7 @@ def workload_config(args, world):
             "n_particles": args.n, "N_ic_max": args.nic, "image_charge": True,
             "flops_per_pair": flops_per_pair(True, args.nic),
             "parallelism": (f"pair work units x{world}" + (" + NCCL all-reduce of the partial pair sums" if world > 1 else ""))
-            if (getattr(args, "pair_mode", "auto") == "sym" or (getattr(args, "pair_mode", "auto") == "auto" and args.n >= 16384))
+            if (getattr(args, "pair_mode", "auto") == "sym" or (getattr(args, "pair_mode", "auto") == "auto" and args.n >= 3500))
             else (f"i-partition x{world}" + (" + NCCL all-gather of accelerations" if world > 1 else "")),
             "l2": "256 MiB L2-flush write between timed steps (outside the per-step CUDA-event pairs)"}
 
@@ -225,8 +225,8 @@ def run_ours(args):
                            capacity=cap, device=local)
     hp = rb.HotPath(cfg)
     hp.upload(pos, q, m)
-    # pair kernel: "sym" = each unordered pair once (default from 16384 particles on), "gather" = ordered pairs
-    sym = (args.pair_mode == "sym") or (args.pair_mode == "auto" and n >= 16384)
+    # pair kernel: "sym" = each unordered pair once (default from 3500 particles on), "gather" = ordered pairs
+    sym = (args.pair_mode == "sym") or (args.pair_mode == "auto" and n >= 3500)
     hp.set_option("pair_mode", 2 if sym else 1)
     if sym:
         hp.set_pair_rank(rank, world)   # (target superblock, source group) work units dealt round-robin
@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pair-mode", default="auto", choices=["auto", "sym", "gather"],
-                    help="pair kernel: sym = each unordered pair once (default for N >= 16384), gather = ordered pairs")
+                    help="pair kernel: sym = each unordered pair once (default for N >= 3500), gather = ordered pairs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

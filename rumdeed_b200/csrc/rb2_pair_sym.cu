@@ -29,7 +29,7 @@
 namespace {
 
 #ifndef RB2_SYM_UNROLL
-#define RB2_SYM_UNROLL 2
+#define RB2_SYM_UNROLL 4
 #endif
 #ifndef RB2_SYM_LDSVIS
 #define RB2_SYM_LDSVIS 1
@@ -41,16 +41,22 @@ constexpr int SB = 128;  // particles per superblock = threads per CTA
 constexpr int SYM_UNROLL = RB2_SYM_UNROLL;
 
 struct SymGeom {
-    int n, nsb, n_pad;
-    int band_start, band_len;  // source superblocks [band_start, band_start + band_len)
-    int G, ngroups;            // source superblocks per CTA group, groups in this band
+    int n, nsb, n_pad;         // nsb: 128-particle source tiles; n_pad: multiple of the target superblock size
+    int nIb;                   // target superblocks (T * 128 particles each)
+    int band_start, band_len;  // source tiles [band_start, band_start + band_len)
+    int G, ngroups;            // source tiles per CTA group, groups in this band
     int rank, world;           // CTA (I, grp) is owned by rank (I + grp) % world
 };
 
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
 
-template <int NIC>
-__global__ void __launch_bounds__(SB, RB2_SYM_MINB)
+// T targets per lane: the CTA's target superblock I holds the T source tiles T*I .. T*I+T-1 (sub-set s of the
+// targets = tile T*I + s, one particle of each sub-set per thread).  Against source tile J a sub-set is evaluated
+// symmetrically when its tile index is < J (then i < j for every pair), in the gather form when it IS tile J, and
+// not at all when its tile index is > J (those pairs belong to the sweep of the other sub-set).  T = 2 halves the
+// shared-memory reads, the shuffles and the partial-sum traffic per pair and doubles the independent work per warp.
+template <int NIC, int T>
+__global__ void __launch_bounds__(SB, T == 1 ? RB2_SYM_MINB : 2)
 k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
 {
     const int I = blockIdx.x;
@@ -58,82 +64,95 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
     if (((I + grp) % g.world) != g.rank) return;
     const int J0 = g.band_start + grp * g.G;
     const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
-    const int Jbeg = max(J0, I);
+    const int Jbeg = max(J0, T * I);
     if (Jbeg >= J1) return;
 
-    __shared__ double xs[SB], ys[SB], zs[SB], qs[SB];
-    __shared__ double jacc[3][SB];
+    // source tile, double buffered (one CTA barrier per tile), and the visitors' reaction sums: one private copy per
+    // warp (warp w meets each 32-particle block of the tile exactly once, so it just stores), again double buffered
+    // because the sums of tile J are read after the barrier while the sweep of tile J+1 has started
+    __shared__ double xs[2][SB], ys[2][SB], zs[2][SB], qs[2][SB];
+    __shared__ double jacc[2][4][3][SB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = I * SB + tid;
     const int last = g.n - 1;
-    double xi, yi, zi, qi;
-    {
+    double xi[T], yi[T], zi[T], qi[T], ax[T], ay[T], az[T];
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+        const int i = (I * T + s) * SB + tid;
         const double4 p = pq[i < g.n ? i : last];
-        xi = p.x; yi = p.y; zi = p.z;
-        qi = (i < g.n) ? p.w : 0.0;  // padding lanes: charge 0, any finite position
+        xi[s] = p.x; yi[s] = p.y; zi[s] = p.z;
+        qi[s] = (i < g.n) ? p.w : 0.0;  // padding lanes: charge 0, any finite position
+        ax[s] = 0.0; ay[s] = 0.0; az[s] = 0.0;
     }
-    double ax = 0.0, ay = 0.0, az = 0.0;
     const int src_lane = (lane + 1) & 31;
 
     double4 pj_next;
     {
         const int j = Jbeg * SB + tid;
-        pj_next = pq[j < g.n ? j : last];
+        const double4 pj = pq[j < g.n ? j : last];
+        xs[0][tid] = pj.x; ys[0][tid] = pj.y; zs[0][tid] = pj.z;
+        qs[0][tid] = (j < g.n) ? pj.w : 0.0;
+        const int jn = j + SB;
+        pj_next = pq[jn < g.n ? jn : last];
     }
-    for (int J = Jbeg; J < J1; ++J) {
-        const int j = J * SB + tid;
-        const double4 pj = pj_next;
-        if (J + 1 < J1) {  // software prefetch of the next source superblock: the load flies during this tile
-            const int jn = j + SB;
-            pj_next = pq[jn < g.n ? jn : last];
-        }
-        __syncthreads();  // everybody is done with the previous tile's shared memory
-        xs[tid] = pj.x; ys[tid] = pj.y; zs[tid] = pj.z;
-        qs[tid] = (j < g.n) ? pj.w : 0.0;
-        jacc[0][tid] = 0.0; jacc[1][tid] = 0.0; jacc[2][tid] = 0.0;
-        __syncthreads();
-
-        if (J == I) {
-            // diagonal tile: ordered evaluation of this superblock against itself
-            Acc4 a = {0.0, 0.0, 0.0, 0.0};
-            for (int jj = 0; jj < SB; ++jj) {
-                const double4 s = make_double4(xs[jj], ys[jj], zs[jj], qs[jj]);
-                const double qe = (jj == tid) ? 0.0 : s.w;
-                const double qsg = (jj > tid) ? qe : -qe;
-                planar_term<NIC>(xi, yi, zi, s, qe, qsg, P, a);
+    __syncthreads();
+    int cur = 0;
+    for (int J = Jbeg; J < J1; ++J, cur ^= 1) {
+        const double *__restrict__ X = xs[cur], *__restrict__ Y = ys[cur], *__restrict__ Z = zs[cur], *__restrict__ Q = qs[cur];
+        const int rel = J - T * I;  // >= 0; sub-set s is symmetric iff s < rel, diagonal iff s == rel
+        if (rel < T) {
+            // gather form of tile J against itself (ordered pairs, per-element self mask and role sign)
+#pragma unroll
+            for (int s = 0; s < T; ++s) {
+                if (s != rel) continue;
+                Acc4 a = {0.0, 0.0, 0.0, 0.0};
+                for (int jj = 0; jj < SB; ++jj) {
+                    const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
+                    const double qe = (jj == tid) ? 0.0 : sj.w;
+                    const double qsg = (jj > tid) ? qe : -qe;
+                    planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a);
+                }
+                ax[s] += a.x; ay[s] += a.y; az[s] += a.z + a.t;
             }
-            ax += a.x; ay += a.y; az += a.z + a.t;
-        } else {
+        }
+        if (rel >= 1) {
+            double qe[T];  // a sub-set that is not symmetric against this tile neither pushes nor collects
+#pragma unroll
+            for (int s = 0; s < T; ++s) qe[s] = (s < rel) ? qi[s] : 0.0;
             for (int r = 0; r < 4; ++r) {
-                const int home = ((warp + r) & 3) * 32 + lane;
                 const int wb0 = ((warp + r) & 3) * 32;
-                double vx = xs[home], vy = ys[home], vz = zs[home], vq = qs[home];
+                const int home = wb0 + lane;
+                double vx = X[home], vy = Y[home], vz = Z[home], vq = Q[home];
                 double bx = 0.0, by = 0.0, bz = 0.0;   // reaction on the visitor, travels with it
-                double tx = 0.0, ty = 0.0, tz = 0.0;   // force on my particle from this round
+                double tx[T], ty[T], tz[T];            // force on my particles from this round
+#pragma unroll
+                for (int s = 0; s < T; ++s) { tx[s] = 0.0; ty[s] = 0.0; tz[s] = 0.0; }
 #pragma unroll SYM_UNROLL
                 for (int k = 0; k < 32; ++k) {
 #if RB2_SYM_LDSVIS
                     // visitor coordinates straight from shared memory (conflict-free rotated index);
                     // only the travelling accumulators go through the shuffle unit
                     const int vi = wb0 + ((lane + k) & 31);
-                    vx = xs[vi]; vy = ys[vi]; vz = zs[vi]; vq = qs[vi];
+                    vx = X[vi]; vy = Y[vi]; vz = Z[vi]; vq = Q[vi];
 #endif
-                    const PairW w = planar_weights<NIC>(xi, yi, zi, vx, vy, vz, P);
-                    // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
-                    const double ti = vq * w.U, tj = qi * w.U;
-                    tx = fma(w.dx, ti, tx);
-                    ty = fma(w.dy, ti, ty);
-                    bx = fma(-w.dx, tj, bx);
-                    by = fma(-w.dy, tj, by);
-                    if (NIC < 0) {
-                        tz = fma(w.dz, ti, tz);
-                        bz = fma(-w.dz, tj, bz);
-                    } else {
-                        const double czz = w.dz * w.wc;
-                        const double icz = w.Zsame - w.Zopp;
-                        tz = fma(vq, icz + czz, tz);
-                        bz = fma(qi, icz - czz, bz);
+#pragma unroll
+                    for (int s = 0; s < T; ++s) {
+                        const PairW w = planar_weights<NIC>(xi[s], yi[s], zi[s], vx, vy, vz, P);
+                        // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
+                        const double ti = vq * w.U, tj = qe[s] * w.U;
+                        tx[s] = fma(w.dx, ti, tx[s]);
+                        ty[s] = fma(w.dy, ti, ty[s]);
+                        bx = fma(-w.dx, tj, bx);
+                        by = fma(-w.dy, tj, by);
+                        if (NIC < 0) {
+                            tz[s] = fma(w.dz, ti, tz[s]);
+                            bz = fma(-w.dz, tj, bz);
+                        } else {
+                            const double czz = w.dz * w.wc;
+                            const double icz = w.Zsame - w.Zopp;
+                            tz[s] = fma(vq, icz + czz, tz[s]);
+                            bz = fma(qe[s], icz - czz, bz);
+                        }
                     }
 #if !RB2_SYM_LDSVIS
                     vx = rot1(vx, src_lane); vy = rot1(vy, src_lane); vz = rot1(vz, src_lane); vq = rot1(vq, src_lane);
@@ -141,49 +160,70 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
                     bx = rot1(bx, src_lane); by = rot1(by, src_lane); bz = rot1(bz, src_lane);
                 }
                 // 32 rotations by one lane: every visitor is back at its home lane
-                ax += tx; ay += ty; az += tz;
-                jacc[0][home] += bx; jacc[1][home] += by; jacc[2][home] += bz;
-                __syncthreads();  // the next round's owner of this warp-block sees the sums
+#pragma unroll
+                for (int s = 0; s < T; ++s)
+                    if (s < rel) { ax[s] += tx[s]; ay[s] += ty[s]; az[s] += tz[s]; }
+                jacc[cur][warp][0][home] = bx; jacc[cur][warp][1][home] = by; jacc[cur][warp][2][home] = bz;
             }
-            const size_t base = (((size_t)(J - g.band_start) * g.nsb + I) * 3) * SB + tid;
-            bufJ[base] = jacc[0][tid];
-            bufJ[base + SB] = jacc[1][tid];
-            bufJ[base + 2 * SB] = jacc[2][tid];
+        }
+        // stage the next tile into the other buffer (its last readers passed the previous barrier)
+        if (J + 1 < J1) {
+            const int jn = (J + 1) * SB + tid;
+            xs[cur ^ 1][tid] = pj_next.x; ys[cur ^ 1][tid] = pj_next.y; zs[cur ^ 1][tid] = pj_next.z;
+            qs[cur ^ 1][tid] = (jn < g.n) ? pj_next.w : 0.0;
+            const int jnn = jn + SB;
+            if (J + 2 < J1) pj_next = pq[jnn < g.n ? jnn : last];
+        }
+        __syncthreads();
+        if (rel >= 1) {
+            // block b of the tile was met by warp (b - r) & 3 in round r: add in round order
+            const int b = warp;
+            const size_t base = (((size_t)(J - g.band_start) * g.nIb + I) * 3) * SB + tid;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                bufJ[base + c * SB] = ((jacc[cur][b][c][tid] + jacc[cur][(b + 3) & 3][c][tid]) + jacc[cur][(b + 2) & 3][c][tid]) +
+                                      jacc[cur][(b + 1) & 3][c][tid];
         }
     }
-    const size_t ib = (size_t)grp * 3 * g.n_pad + i;
-    bufI[ib] = ax;
-    bufI[ib + g.n_pad] = ay;
-    bufI[ib + 2 * (size_t)g.n_pad] = az;
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+        const size_t ib = (size_t)grp * 3 * g.n_pad + (size_t)(I * T + s) * SB + tid;
+        bufI[ib] = ax[s];
+        bufI[ib + g.n_pad] = ay[s];
+        bufI[ib + 2 * (size_t)g.n_pad] = az[s];
+    }
 }
 
-// raw[c][p] += (sum over this band's groups of the target sums) + (sum over I < J(p) of the source sums),
-// both in ascending order; only slots written by this rank are read.
+// raw[c][p] += (sum over this band's groups of the target sums) + (sum over the target superblocks that met
+// tile J(p) symmetrically of the source sums), both in ascending order; only slots written by this rank are read.
+template <int T>
 __global__ void __launch_bounds__(SB)
 k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restrict__ bufJ, double *__restrict__ raw)
 {
-    const int Jp = blockIdx.x;  // superblock of this particle
+    const int Jp = blockIdx.x;  // 128-particle tile of this particle
+    const int It = Jp / T;      // its target superblock
     const int tid = threadIdx.x;
     const int p = Jp * SB + tid;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    // as a target (I = Jp)
+    // as a target (superblock It)
     for (int grp = 0; grp < g.ngroups; ++grp) {
         const int J0 = g.band_start + grp * g.G;
         const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
-        if (max(J0, Jp) >= J1) continue;
-        if (((Jp + grp) % g.world) != g.rank) continue;
+        if (max(J0, T * It) >= J1) continue;
+        if (((It + grp) % g.world) != g.rank) continue;
         const size_t ib = (size_t)grp * 3 * g.n_pad + p;
         s0 += bufI[ib];
         s1 += bufI[ib + g.n_pad];
         s2 += bufI[ib + 2 * (size_t)g.n_pad];
     }
-    // as a source (J = Jp), when Jp lies in this band
+    // as a source (tile Jp), when Jp lies in this band: target superblocks I with T*I < Jp
     if (Jp >= g.band_start && Jp < g.band_start + g.band_len) {
         const int grp = (Jp - g.band_start) / g.G;
-        const size_t col = (size_t)(Jp - g.band_start) * g.nsb;
+        const size_t col = (size_t)(Jp - g.band_start) * g.nIb;
+        const int Iend = (Jp + T - 1) / T;
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll 4
-        for (int I = 0; I < Jp; ++I) {
+        for (int I = 0; I < Iend; ++I) {
             if (((I + grp) % g.world) != g.rank) continue;
             const size_t base = ((col + I) * 3) * SB + tid;
             t0 += bufJ[base];
@@ -231,14 +271,18 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (n < 1) return RB2_OK;
     const rb2_config &c = ctx.cfg;
     if (c.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "the pair-symmetric kernel implements the planar geometry only");
+    // targets per lane: two from 16384 particles on (tools/sym_crossover.py: 800 vs 812 us there, 2.90 vs 3.08 ms at
+    // 32768, 5.5 % at 1e6), one below (half as many, twice as long CTAs do not fill the machine at small N)
+    const int T = ctx.sym_tpl == 1 ? 1 : (ctx.sym_tpl == 2 ? 2 : (n >= 16384 ? 2 : 1));
     SymGeom g{};
     g.n = n;
     g.nsb = (n + SB - 1) / SB;
-    g.n_pad = g.nsb * SB;
+    g.nIb = (g.nsb + T - 1) / T;
+    g.n_pad = g.nIb * T * SB;
     g.rank = ctx.pair_rank;
     g.world = ctx.pair_world < 1 ? 1 : ctx.pair_world;
-    // band width from the scratch budget (3 KB per (source, target) superblock pair)
-    const size_t col_bytes = (size_t)g.nsb * 3 * SB * sizeof(double);
+    // band width from the scratch budget (3 KB per (source tile, target superblock) pair)
+    const size_t col_bytes = (size_t)g.nIb * 3 * SB * sizeof(double);
     size_t budget = ctx.sym_budget_bytes;
     {
         size_t fr = 0, tot = 0;  // never ask for more than half of what is free (plus what we already hold)
@@ -251,11 +295,11 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (wb < 1) wb = 1;
     if (wb > (size_t)g.nsb) wb = (size_t)g.nsb;
     const int Wb = (int)wb;
-    // group size: enough CTAs to fill 4 CTAs/SM for sym_waves waves ON EACH RANK (the CTAs of a band are dealt
-    // round-robin to the ranks; with fewer waves per rank the tail of every band launch shows -- 83 % vs 96 %
+    // group size: enough CTAs to fill the resident CTA slots for sym_waves waves ON EACH RANK (the CTAs of a band are
+    // dealt round-robin to the ranks; with fewer waves per rank the tail of every band launch shows -- 83 % vs 96 %
     // of the ideal split at 8 ranks, tools/sym_rank_sweep.py)
-    const double want_ctas = (double)ctx.sm_count * 4 * ctx.sym_waves * g.world;
-    int G = (int)((double)g.nsb * Wb / want_ctas);
+    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world;
+    int G = (int)((double)g.nIb * Wb / want_ctas);
     if (G < 1) G = 1;
     if (G > Wb) G = Wb;
     const int ngroups_max = (Wb + G - 1) / G;
@@ -276,16 +320,21 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         g.band_len = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
         g.G = G;
         g.ngroups = (g.band_len + G - 1) / G;
-        const int nI = b0 + g.band_len;  // targets I <= last source superblock of the band
+        const int nI = (b0 + g.band_len - 1) / T + 1;  // target superblocks that start at or below the band's last tile
         dim3 grid(nI, g.ngroups), block(SB);
-#define RB2_GO(N) k_pair_sym<N><<<grid, block, 0, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ)
+#define RB2_GO(N)                                                                                      \
+    do {                                                                                               \
+        if (T == 1) k_pair_sym<N, 1><<<grid, block, 0, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ); \
+        else k_pair_sym<N, 2><<<grid, block, 0, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);        \
+    } while (0)
         if (!c.image_charge) RB2_GO(-1);
         else if (c.N_ic_max == 0) RB2_GO(0);
         else if (c.N_ic_max == 1) RB2_GO(1);
         else RB2_GO(2);
 #undef RB2_GO
         RB2_CUDA(cudaGetLastError());
-        k_sym_reduce<<<g.nsb, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw);
+        if (T == 1) k_sym_reduce<1><<<g.nsb, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw);
+        else k_sym_reduce<2><<<g.nIb * 2, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw);
         RB2_CUDA(cudaGetLastError());
         launches += 2;
     }

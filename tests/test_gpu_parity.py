@@ -64,16 +64,20 @@ def test_planar_acceleration_vs_oracle(orc, ic, nic, n):
 
 
 @pytest.mark.parametrize("ic,nic", [(False, 0), (True, 0), (True, 1), (True, 2)])
-@pytest.mark.parametrize("n,budget_mb", [(1, 2048), (2, 2048), (33, 2048), (127, 2048), (128, 2048), (129, 0.01), (300, 0.01),
-                                          (1000, 0.02), (2500, 0.05), (2500, 2048), (6000, 0.2)])
-def test_pair_symmetric_kernel_vs_oracle(orc, ic, nic, n, budget_mb):
+@pytest.mark.parametrize("tpl", [1, 2])
+@pytest.mark.parametrize("n,budget_mb", [(1, 2048), (2, 2048), (33, 2048), (127, 2048), (128, 2048), (129, 0.01), (255, 2048),
+                                          (256, 0.01), (257, 2048), (300, 0.01), (385, 0.01), (1000, 0.02), (2500, 0.05),
+                                          (2500, 2048), (6000, 0.2)])
+def test_pair_symmetric_kernel_vs_oracle(orc, ic, nic, n, budget_mb, tpl):
     """The pair-symmetric kernel (each unordered pair once, like the reference's CPU loop
     mod_verlet.F90:763-884) against the long-double oracle, with small scratch budgets to force
-    several bands / groups, sizes around the 32- and 128-particle tile edges, and ions mixed in."""
+    several bands / groups, sizes around the 32-, 128- and 256-particle tile edges, ions mixed in, and one or
+    two targets per lane (sym_tpl)."""
     cfg, p = planar(orc, ic=ic, nic=nic)
     pos, q, m, sp = cloud(n, 777 + n)
     with rb.HotPath(cfg) as hp:
         hp.set_option("pair_mode", 2)
+        hp.set_option("sym_tpl", tpl)
         hp.set_option("sym_budget_mb", budget_mb)
         hp.upload(pos, q, m, species=sp)
         hp.Calculate_Acceleration_Particles()
@@ -89,13 +93,15 @@ def test_pair_symmetric_kernel_vs_oracle(orc, ic, nic, n, budget_mb):
     assert relerr(acc, gather) < 1e-12
 
 
-def test_pair_symmetric_split_over_two_ranks(orc):
+@pytest.mark.parametrize("tpl", [1, 2])
+def test_pair_symmetric_split_over_two_ranks(orc, tpl):
     """Work units dealt to two 'processes' (run one after the other here) and summed give the full result."""
     cfg, p = planar(orc, ic=True, nic=1)
     pos, q, m, sp = cloud(3000, 4242)
     raws = []
     with rb.HotPath(cfg) as hp:
         hp.set_option("pair_mode", 2)
+        hp.set_option("sym_tpl", tpl)
         hp.set_option("sym_budget_mb", 0.1)
         hp.upload(pos, q, m, species=sp)
         hp.Calculate_Acceleration_Particles()

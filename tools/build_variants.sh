@@ -9,14 +9,10 @@ build() { # name, extra flags
   out=../../tools/variants/$name
   mkdir -p $out
   make -s OUT=$out EXTRA="$*" >/dev/null
-  echo "built $name: $(cuobjdump -res-usage $out/_obj/rb2_pair_sym.o 2>/dev/null | grep -A1 'pair_symILi1E' | grep -o 'REG:[0-9]*')"
+  echo "built $name: $(cuobjdump -res-usage $out/_obj/rb2_pair_sym.o 2>/dev/null | grep -A1 'pair_symILi1ELi2' | grep -o 'REG:[0-9]*')"
 }
 build base
 build u1 -DRB2_SYM_UNROLL=1
 build u4 -DRB2_SYM_UNROLL=4
-build lds -DRB2_SYM_LDSVIS=1
-build lds_u4 -DRB2_SYM_LDSVIS=1 -DRB2_SYM_UNROLL=4
-build lds_u1 -DRB2_SYM_LDSVIS=1 -DRB2_SYM_UNROLL=1
-build minb3 -DRB2_SYM_MINB=3
-build lds_minb3 -DRB2_SYM_LDSVIS=1 -DRB2_SYM_MINB=3
-build lds_minb5 -DRB2_SYM_LDSVIS=1 -DRB2_SYM_MINB=5
+build shfl -DRB2_SYM_LDSVIS=0
+build shfl_u1 -DRB2_SYM_LDSVIS=0 -DRB2_SYM_UNROLL=1
