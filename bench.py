@@ -52,54 +52,77 @@ def flops_per_pair(image_charge, nic):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), read
+    in-process through NVML from a sampling thread.  (Spawning `nvidia-smi -lms` instead stalls the GPUs for tens
+    of milliseconds at start-up and per query once peer mappings exist -- measured: 13.3 -> 18-22 ms per step at
+    N = 1e5 on 2 GPUs -- so it is only the fallback when NVML cannot be loaded.)"""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, period_s=0.1):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.period = period_s
+        self.samples = []
+        self.reasons = set()
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.handle = None
+        self.mx = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: match by PCI bus id
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
+                dom = getattr(torch.cuda.get_device_properties(gpu_index), "pci_domain_id", 0)
+                dev = torch.cuda.get_device_properties(gpu_index).pci_device_id
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0")
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, pw))
+                for name, bit in self.REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.nvml is None:
+            return
+        self.samples.clear()
+        self.reasons.clear()
+        self.stop_flag.clear()
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": "NVML, in-process sampling thread"}
+        if self.thread is None:
+            out["how"] = "NVML unavailable"
             return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, mx, pw, reasons = [], [], [], set()
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
-                       reasons=sorted(reasons), samples=len(sm))
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        if self.samples:
+            sm = [x[0] for x in self.samples]
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=self.mx, power_w_max=float(max(x[1] for x in self.samples)),
+                       reasons=sorted(self.reasons), samples=len(sm))
         return out
 
 
@@ -192,7 +215,8 @@ def workload_config(args, world):
                         f"N_ic_max={args.nic}, dt=1e-4ps (BASELINE.json configs[4])",
             "n_particles": args.n, "N_ic_max": args.nic, "image_charge": True,
             "flops_per_pair": flops_per_pair(True, args.nic),
-            "parallelism": (f"pair work units x{world}" + (" + NCCL all-reduce of the partial pair sums" if world > 1 else ""))
+            "parallelism": (f"pair work units x{world}" + ((" + peer-memory (NVLink) exchange of the partial pair sums fused into the finalise kernel"
+                                                            if getattr(args, "exchange", "p2p") == "p2p" else " + NCCL all-reduce of the partial pair sums") if world > 1 else ""))
             if (getattr(args, "pair_mode", "auto") == "sym" or (getattr(args, "pair_mode", "auto") == "auto" and args.n >= 3500))
             else (f"i-partition x{world}" + (" + NCCL all-gather of accelerations" if world > 1 else "")),
             "l2": "256 MiB L2-flush write between timed steps (outside the per-step CUDA-event pairs)"}
@@ -228,8 +252,15 @@ def run_ours(args):
     # pair kernel: "sym" = each unordered pair once (default from 3500 particles on), "gather" = ordered pairs
     sym = (args.pair_mode == "sym") or (args.pair_mode == "auto" and n >= 3500)
     hp.set_option("pair_mode", 2 if sym else 1)
+    p2p = sym and world > 1 and args.exchange == "p2p"
     if sym:
         hp.set_pair_rank(rank, world)   # (target superblock, source group) work units dealt round-robin
+        if p2p:
+            # the one exchange step over NVLink peer memory, fused into the finalise kernel (rb2_p2p.cu): every rank
+            # exports its exchange block as a CUDA IPC handle, the handles are gathered once, every rank maps them
+            handles = [None] * world
+            dist.all_gather_object(handles, hp.p2p_export(n))
+            hp.p2p_attach(world, rank, handles)
     else:
         hp.set_partition(i0, i1)        # contiguous i-rows per rank
     ext = torch.cuda.ExternalStream(hp.stream(), device=local)
@@ -254,7 +285,7 @@ def run_ours(args):
                 dist.all_gather_into_tensor(t[: 3 * cap], t[3 * i0: 3 * (i0 + chunk)])
 
     def one_step(step):
-        if world == 1:
+        if world == 1 or p2p:
             return hp.Update_Position(step)
         hp.Update_Particle_Position(step)
         if sym:
@@ -280,14 +311,15 @@ def run_ours(args):
     barrier()
     hp.launch_count(reset=True)
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     accel_ms = []
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.zero_()                      # L2 flush on torch's stream ...
+        if not args.no_flush:
+            flush.zero_()                  # L2 flush on torch's stream ...
         torch.cuda.current_stream().synchronize()
         ev[k][0].record(ext)               # ... timed region on the library's launching stream
         one_step(args.warmup + k + 1)
@@ -297,7 +329,8 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     launches = hp.launch_count()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms_list = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(step_ms_list)
     info = hp.last_accel_info()
 
     # end to end through the C ABI with HOST buffers: pinned pos/q/m in, accelerations out
@@ -310,6 +343,11 @@ def run_ours(args):
         if world == 1 or not sym:
             # stateless C-ABI call: host pos/q/m in, this rank's acceleration rows out
             hp.accel_host_ptr(n, h_pos.data_ptr(), h_q.data_ptr(), h_m.data_ptr(), h_acc.data_ptr())
+        elif p2p:
+            # split pair work, partial sums exchanged over peer memory inside the finalise kernel
+            hp.upload(h_pos.numpy(), h_q.numpy(), h_m.numpy())
+            hp.Calculate_Acceleration_Particles()
+            h_acc.numpy()[:] = hp.download(("acc",))["acc"]
         else:
             # split pair work: upload, partial sums, all-reduce, finalise, rows back to the host
             hp.upload(h_pos.numpy(), h_q.numpy(), h_m.numpy())
@@ -354,6 +392,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "md_steps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
+            "ms_steps_rank0": [round(x, 4) for x in step_ms_list], "accel_ms_steps_rank0": [round(x, 4) for x in accel_ms],
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "kernel": ("k_pair_sym<N_ic_max=%d> + k_sym_reduce per band, k_sym_finalize (each unordered pair "
@@ -362,8 +401,8 @@ def run_ours(args):
                                     "the executed-flop peak)" % args.nic) if sym
                          else "k_pair<planar, N_ic_max=%d> + k_accel_finalize (ordered pairs)" % args.nic,
                          "kernel_ms": acc_ms, "flops_per_pair": fpp,
-                         "fp64_instr_per_ordered_pair": (40.5 if sym else 74) if args.nic == 1 else None,
-                         "fp64_pipe_util_est": ((40.5 if sym else 74) * 2.0 / fpp) * (achieved / peak) if args.nic == 1 else None,
+                         "fp64_instr_per_ordered_pair": (39.7 if sym else 74) if args.nic == 1 else None,
+                         "fp64_pipe_util_est": ((39.7 if sym else 74) * 2.0 / fpp) * (achieved / peak) if args.nic == 1 else None,
                          "peak_source": "measured in this run: rb2_fp64_peak independent-DFMA-chain kernel "
                                         f"(burst {peak_burst:.2f}, sustained 1.5 s {peak_sust:.2f} TFLOP/s; nominal 37.2); "
                                         "MEASURED_PEAKS.json holds no FP64 figure",
@@ -371,7 +410,8 @@ def run_ours(args):
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 24 * n,
                     "ms_per_step": e2e_ms,
                     "what": "rb2_accel_host: pinned host pos/q/m -> device, pair kernel, accelerations -> host" if (world == 1 or not sym)
-                    else "rb2_upload_particles (host pos/q/m) -> rb2_accel_partial -> NCCL all-reduce -> rb2_accel_finalize -> rb2_download_particles(acc)"},
+                    else ("rb2_upload_particles (host pos/q/m) -> rb2_accel_only (split pair work, peer-memory exchange) -> rb2_download_particles(acc)" if p2p
+                          else "rb2_upload_particles (host pos/q/m) -> rb2_accel_partial -> NCCL all-reduce -> rb2_accel_finalize -> rb2_download_particles(acc)")},
             "pair_kernel": "pair-symmetric" if sym else "gather",
             "gpu_launches": launches, "clocks": clk,
         }
@@ -385,6 +425,9 @@ def run_ours(args):
             except Exception as e:  # the baseline is a reported extra, never the product path
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
+    if p2p:
+        barrier()  # nobody unmaps while a peer may still read
+        hp.p2p_detach()
     hp.close()
     if world > 1:
         dist.destroy_process_group()
@@ -400,6 +443,11 @@ def main():
     ap.add_argument("--nic", type=int, default=1, help="N_ic_max")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostics only: no L2 flush between steps (not a valid bench line)")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostics only: no nvidia-smi sampling")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange of the partial pair sums: p2p = peer-memory loads fused into the finalise kernel "
+                         "(default), nccl = torch.distributed all-reduce between rb2_accel_partial and rb2_accel_finalize")
     ap.add_argument("--pair-mode", default="auto", choices=["auto", "sym", "gather"],
                     help="pair kernel: sym = each unordered pair once (default for N >= 3500), gather = ordered pairs")
     args = ap.parse_args()

@@ -178,7 +178,18 @@ int rb2_set_partition(int i_begin, int i_end);
 int rb2_set_pair_rank(int rank, int world);
 int rb2_accel_partial(void);
 int rb2_accel_finalize(void);
-/* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb". */
+/* The exchange over NVLink peer memory instead of an all-reduce by the host plumbing: every process exports its
+ * exchange block (partial sums for up to n_max particles + flags) as a CUDA IPC handle of RB2_P2P_HANDLE_BYTES
+ * bytes, the host plumbing gathers the `world` handles (rank order, any transport) and every process attaches
+ * them.  From then on rb2_accel_finalize -- and rb2_step / rb2_accel_only, which then accept a split -- waits for
+ * the peers' partial sums, adds them in rank order straight from the peers' memory and finalises, in one kernel;
+ * no host involvement, no other collective.  rb2_p2p_attach also sets the pair rank. */
+#define RB2_P2P_HANDLE_BYTES 64
+int rb2_p2p_export(int n_max, void *handle_out);
+int rb2_p2p_attach(int world, int rank, const void *handles);
+int rb2_p2p_detach(void);
+/* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
+ * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2). */
 int rb2_set_option(const char *name, double value);
 /* Device pointer + byte size of the (3,capacity) acceleration buffer so that the
  * host plumbing (torch.distributed / NCCL) can all-gather the slices in place. */

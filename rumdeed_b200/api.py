@@ -91,6 +91,8 @@ class MhConfig(C.Structure):
                 ("std_min", C.c_double), ("std_max", C.c_double)]
 
 
+P2P_HANDLE_BYTES = 64
+
 _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int)
 
@@ -102,6 +104,7 @@ EXPORTS = (
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_accel_host",
     "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
+    "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
 )
 
@@ -143,6 +146,8 @@ def load_library(path: str | None = None):
     lib.rb2_set_option.argtypes = [C.c_char_p, C.c_double]
     lib.rb2_device_buffer.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.rb2_stream.argtypes = [C.POINTER(C.c_void_p)]
+    lib.rb2_p2p_export.argtypes = [C.c_int, C.c_void_p]
+    lib.rb2_p2p_attach.argtypes = [C.c_int, C.c_int, C.c_void_p]
     lib.rb2_fp64_peak.argtypes = [C.c_double, _PD, C.POINTER(C.c_float)]
     lib.rb2_launch_count.argtypes = [C.POINTER(C.c_longlong), C.c_int]
     lib.rb2_last_accel_info.argtypes = [C.POINTER(C.c_float)] + [_PI] * 4
@@ -438,6 +443,22 @@ class HotPath:
 
     def accel_finalize(self):
         self._check(self.lib.rb2_accel_finalize())
+
+    def p2p_export(self, n_max) -> bytes:
+        """This process's exchange block (partial pair sums + flags) as a CUDA IPC handle."""
+        buf = C.create_string_buffer(P2P_HANDLE_BYTES)
+        self._check(self.lib.rb2_p2p_export(int(n_max), buf))
+        return buf.raw
+
+    def p2p_attach(self, world, rank, handles):
+        """Map every rank's exchange block (handles: the `world` exported handles in rank order).  From here on
+        the acceleration evaluation exchanges the partial sums over peer memory inside its finalise kernel."""
+        blob = b"".join(handles)
+        assert len(blob) == world * P2P_HANDLE_BYTES
+        self._check(self.lib.rb2_p2p_attach(int(world), int(rank), C.c_char_p(blob)))
+
+    def p2p_detach(self):
+        self._check(self.lib.rb2_p2p_detach())
 
     def device_buffer(self, name: str):
         p = C.c_void_p()

@@ -138,8 +138,9 @@ bool use_sym_kernel(const Rb2Ctx &c, int n, int i0, int i1)
 int launch_accel_any(Rb2Ctx &c, const double4 *pq, const double *mass, int n, int i0, int i1, double *acc)
 {
     if (use_sym_kernel(c, n, i0, i1)) {
-        if (c.pair_world > 1)
-            return rb2_fail(RB2_ERR_ARG, "pair work is split over %d processes: use rb2_accel_partial / rb2_accel_finalize", c.pair_world);
+        if (c.pair_world > 1 && c.p2p_world != c.pair_world)  // attached: the finalisation below exchanges over peer memory
+            return rb2_fail(RB2_ERR_ARG, "pair work is split over %d processes: attach the peers (rb2_p2p_attach) or use "
+                                         "rb2_accel_partial / rb2_accel_finalize around your own all-reduce", c.pair_world);
         int rc = rb2_launch_accel_sym_partial(c, pq, n);
         if (rc) return rc;
         c.last_pair_kernel = 2;
@@ -282,6 +283,7 @@ int rb2_finalize(void)
     Rb2Ctx &c = g_rb2;
     if (!c.init) return RB2_OK;
     cudaStreamSynchronize(c.stream);
+    rb2_p2p_release(c);
     free_arrays(c.a);
     free_arrays(c.b);
     cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);
@@ -777,7 +779,7 @@ int rb2_accel_finalize(void)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
-    if (c.n > 0 && (!c.sym_raw || c.sym_n_pad < c.n)) return rb2_fail(RB2_ERR_ARG, "rb2_accel_finalize without rb2_accel_partial");
+    if (c.n > 0 && (!c.sym_raw_cur || c.sym_n_pad < c.n)) return rb2_fail(RB2_ERR_ARG, "rb2_accel_finalize without rb2_accel_partial");
     int rc = rb2_launch_accel_sym_finalize(c, c.a.pq, c.a.mass, c.n, c.a.acc);
     if (rc) return rc;
     c.accel_timed = c.n > 0;
@@ -808,7 +810,7 @@ int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes)
     else if (!strcmp(name, "acc_prev")) { p = c.a.acc_prev; b = 3 * cap * sizeof(double); }
     else if (!strcmp(name, "acc_prev2")) { p = c.a.acc_prev2; b = 3 * cap * sizeof(double); }
     else if (!strcmp(name, "mass")) { p = c.a.mass; b = cap * sizeof(double); }
-    else if (!strcmp(name, "raw")) { p = c.sym_raw; b = (size_t)3 * c.sym_n_pad * sizeof(double); }
+    else if (!strcmp(name, "raw")) { p = c.sym_raw_cur; b = (size_t)3 * c.sym_n_pad * sizeof(double); }
     else return rb2_fail(RB2_ERR_ARG, "unknown buffer '%s'", name);
     *dev_ptr = p;
     if (bytes) *bytes = b;

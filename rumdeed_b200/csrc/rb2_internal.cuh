@@ -74,6 +74,8 @@ struct DevArrays {
     int *species = nullptr, *step = nullptr, *emitter = nullptr, *section = nullptr, *life = nullptr, *id = nullptr;
 };
 
+#define RB2_P2P_MAX 16
+
 struct Rb2Ctx {
     bool         init = false;
     rb2_config   cfg{};
@@ -108,6 +110,12 @@ struct Rb2Ctx {
     double *sym_bufI = nullptr, *sym_bufJ = nullptr, *sym_raw = nullptr;
     size_t sym_bufI_bytes = 0, sym_bufJ_bytes = 0, sym_raw_bytes = 0;
     int    sym_n_pad = 0;
+    double *sym_raw_cur = nullptr;        // partial sums of the current evaluation (sym_raw, or a slot of the exchange block)
+    // peer-memory exchange (rb2_p2p.cu)
+    void  *p2p_local = nullptr;           // this rank's exchange block (exported over CUDA IPC)
+    void  *p2p_peer[RB2_P2P_MAX] = {};    // every rank's block as mapped here ([rank] == p2p_local)
+    int    p2p_world = 0, p2p_npad_max = 0;
+    unsigned long long p2p_epoch = 0;     // evaluations since attach; parity selects the partial-sum slot
     int    last_pair_kernel = 0;          // 1 gather, 2 symmetric
     rb2_event *d_events = nullptr; int ev_cap = 0;
     std::vector<rb2_event> host_events;
@@ -153,6 +161,10 @@ int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra
 int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                          double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez);
+// peer-memory exchange (rb2_p2p.cu)
+double *rb2_p2p_begin_evaluation(Rb2Ctx &ctx, int n_pad);
+int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);
+int rb2_p2p_release(Rb2Ctx &ctx);
 // pair-symmetric kernel (rb2_pair_sym.cu)
 int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n);
 int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);

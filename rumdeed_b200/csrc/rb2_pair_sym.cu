@@ -37,6 +37,9 @@ namespace {
 #ifndef RB2_SYM_MINB
 #define RB2_SYM_MINB 3
 #endif
+#ifndef RB2_SYM_MINB2
+#define RB2_SYM_MINB2 2
+#endif
 constexpr int SB = 128;  // particles per superblock = threads per CTA
 constexpr int SYM_UNROLL = RB2_SYM_UNROLL;
 
@@ -56,7 +59,7 @@ __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_s
 // not at all when its tile index is > J (those pairs belong to the sweep of the other sub-set).  T = 2 halves the
 // shared-memory reads, the shuffles and the partial-sum traffic per pair and doubles the independent work per warp.
 template <int NIC, int T>
-__global__ void __launch_bounds__(SB, T == 1 ? RB2_SYM_MINB : 2)
+__global__ void __launch_bounds__(SB, T == 1 ? RB2_SYM_MINB : RB2_SYM_MINB2)
 k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
 {
     const int I = blockIdx.x;
@@ -307,13 +310,20 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (rc) return rc;
     rc = ensure_bytes(&ctx.sym_bufI, &ctx.sym_bufI_bytes, (size_t)ngroups_max * 3 * g.n_pad * sizeof(double));
     if (rc) return rc;
-    rc = ensure_bytes(&ctx.sym_raw, &ctx.sym_raw_bytes, (size_t)3 * g.n_pad * sizeof(double));
-    if (rc) return rc;
+    if (ctx.p2p_world > 1) {
+        // peers read the partial sums in place: they live in the exported exchange block (rb2_p2p.cu)
+        ctx.sym_raw_cur = rb2_p2p_begin_evaluation(ctx, g.n_pad);
+        if (!ctx.sym_raw_cur) return RB2_ERR_CAPACITY;
+    } else {
+        rc = ensure_bytes(&ctx.sym_raw, &ctx.sym_raw_bytes, (size_t)3 * g.n_pad * sizeof(double));
+        if (rc) return rc;
+        ctx.sym_raw_cur = ctx.sym_raw;
+    }
     ctx.sym_n_pad = g.n_pad;
     cudaStream_t st = ctx.stream;
     const StepParams SP = rb2_make_step_params(c);
     RB2_CUDA(cudaEventRecord(ctx.ev_a0, st));
-    RB2_CUDA(cudaMemsetAsync(ctx.sym_raw, 0, (size_t)3 * g.n_pad * sizeof(double), st));
+    RB2_CUDA(cudaMemsetAsync(ctx.sym_raw_cur, 0, (size_t)3 * g.n_pad * sizeof(double), st));
     int launches = 0;
     for (int b0 = 0; b0 < g.nsb; b0 += Wb) {
         g.band_start = b0;
@@ -333,8 +343,8 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         else RB2_GO(2);
 #undef RB2_GO
         RB2_CUDA(cudaGetLastError());
-        if (T == 1) k_sym_reduce<1><<<g.nsb, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw);
-        else k_sym_reduce<2><<<g.nIb * 2, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw);
+        if (T == 1) k_sym_reduce<1><<<g.nsb, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
+        else k_sym_reduce<2><<<g.nIb * 2, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
         RB2_CUDA(cudaGetLastError());
         launches += 2;
     }
@@ -346,8 +356,9 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
 int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out)
 {
     if (n < 1) return RB2_OK;
+    if (ctx.p2p_world > 1) return rb2_launch_accel_sym_exchange_finalize(ctx, pq, mass, n, acc_out);
     const StepParams SP = rb2_make_step_params(ctx.cfg);
-    k_sym_finalize<<<(n + 255) / 256, 256, 0, ctx.stream>>>(n, ctx.sym_n_pad, ctx.sym_raw, pq, mass, SP.pl, acc_out);
+    k_sym_finalize<<<(n + 255) / 256, 256, 0, ctx.stream>>>(n, ctx.sym_n_pad, ctx.sym_raw_cur, pq, mass, SP.pl, acc_out);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(1);
     RB2_CUDA(cudaEventRecord(ctx.ev_a1, ctx.stream));
