@@ -58,7 +58,7 @@ class ClockSampler:
     N = 1e5 on 2 GPUs -- so it is only the fallback when NVML cannot be loaded.)"""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index=0, period_s=0.1):
+    def __init__(self, gpu_index=0, period_s=0.25):
         self.gpu = gpu_index
         self.period = period_s
         self.samples = []
@@ -82,26 +82,37 @@ class ClockSampler:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            self._sample()  # first use of each query is slow (tens of ms, and it blocks kernel launches): do it now
+            self.samples.clear()
+            self.reasons.clear()
         except Exception:
             self.nvml = None
 
-    def _loop(self):
+    def _sample(self):
         nv = self.nvml
-        while not self.stop_flag.is_set():
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.samples.append((sm, pw))
+        for name, bit in self.REASONS:
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        # a query holds a driver lock that kernel launches also take (a launch-bound step at N = 1e4 stalls for
+        # milliseconds per query), so sample sparsely: the first one half a period in, then every period
+        if self.stop_flag.wait(0.5 * self.period):
+            return
+        while True:
             try:
-                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                try:
-                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                except Exception:
-                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                self.samples.append((sm, pw))
-                for name, bit in self.REASONS:
-                    if bits & bit:
-                        self.reasons.add(name)
+                self._sample()
             except Exception:
                 pass
-            self.stop_flag.wait(self.period)
+            if self.stop_flag.wait(self.period):
+                return
 
     def start(self):
         if self.nvml is None:
@@ -119,6 +130,13 @@ class ClockSampler:
             return out
         self.stop_flag.set()
         self.thread.join(timeout=2)
+        if not self.samples:
+            # region shorter than the sampling period: one sample right behind the last timed step
+            try:
+                self._sample()
+                out["how"] += " (timed region shorter than the sampling period: one sample taken right behind it)"
+            except Exception:
+                pass
         if self.samples:
             sm = [x[0] for x in self.samples]
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=self.mx, power_w_max=float(max(x[1] for x in self.samples)),

@@ -298,10 +298,12 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (wb < 1) wb = 1;
     if (wb > (size_t)g.nsb) wb = (size_t)g.nsb;
     const int Wb = (int)wb;
-    // group size: enough CTAs to fill the resident CTA slots for sym_waves waves ON EACH RANK (the CTAs of a band are
-    // dealt round-robin to the ranks; with fewer waves per rank the tail of every band launch shows -- 83 % vs 96 %
-    // of the ideal split at 8 ranks, tools/sym_rank_sweep.py)
-    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world;
+    // group size: enough CTAs to fill the resident CTA slots for sym_waves waves per band launch, times world^2: the
+    // CTAs of a band are dealt round-robin to the ranks, so each rank needs that many waves of its own (x world), and
+    // the deal (I + grp) % world only balances when there are many more groups than ranks (x world again).
+    // tools/sym_rank_sweep.py at 8 ranks, N = 1e6: 93.6 % of the ideal split with x world, 99.4 % with x world^2;
+    // N = 1e5 at 4 ranks: 36 % vs 98 %.
+    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world * g.world;
     int G = (int)((double)g.nIb * Wb / want_ctas);
     if (G < 1) G = 1;
     if (G > Wb) G = Wb;
