@@ -189,7 +189,8 @@ int rb2_p2p_export(int n_max, void *handle_out);
 int rb2_p2p_attach(int world, int rank, const void *handles);
 int rb2_p2p_detach(void);
 /* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
- * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2). */
+ * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "event_buffer" (initial number of
+ * absorb / plane-crossing records the device buffer holds; it grows on demand). */
 int rb2_set_option(const char *name, double value);
 /* Device pointer + byte size of the (3,capacity) acceleration buffer so that the
  * host plumbing (torch.distributed / NCCL) can all-gather the slices in place. */

@@ -150,7 +150,9 @@ int launch_accel_any(Rb2Ctx &c, const double4 *pq, const double *mass, int n, in
     return rb2_launch_accel(c, pq, mass, n, i0, i1, acc);
 }
 
-// position update + (ordered) event records; leaves the stream busy with nothing pending on the host
+// Queues the position update, the (device-guarded) record passes, the counter copy and -- for the fused step -- the
+// acceleration evaluation.  Nothing here waits for the device: finish_position() reads the results after the
+// caller's stream synchronisation.
 int do_update_position(Rb2Ctx &c, bool overlap_accel, int *rc_accel)
 {
     c.host_events.clear();
@@ -161,25 +163,33 @@ int do_update_position(Rb2Ctx &c, bool overlap_accel, int *rc_accel)
     RB2_CUDA(cudaMemsetAsync(&c.d_counters->n_events, 0, sizeof(int), c.stream));
     int rc = rb2_launch_update_position(c);
     if (rc) return rc;
+    rc = rb2_launch_events(c);  // must see the pre-update velocities: before the velocity update in stream order
+    if (rc) return rc;
     RB2_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, c.stream));
-    RB2_CUDA(cudaEventRecord(c.ev_c, c.stream));
     if (overlap_accel) {
-        // queue the O(N^2) kernel behind the counter copy; the host learns the record count
-        // while it runs
         int i0 = c.part_begin, i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
         if (i0 < 0) i0 = 0;
         *rc_accel = launch_accel_any(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
         if (*rc_accel) return *rc_accel;
         c.accel_timed = true;
     }
-    RB2_CUDA(cudaEventSynchronize(c.ev_c));
+    return RB2_OK;
+}
+
+// After the stream has been synchronised: counters of the position update and its record list on the host.
+int finish_position(Rb2Ctx &c, bool after_velocity_update)
+{
+    if (c.n < 1) return RB2_OK;
     fill_counts_from_device(c);
     const int nev = c.h_counters->n_events;
     if (nev > 0) {
-        rc = rb2_launch_events(c, nev);
-        if (rc) return rc;
+        if (nev > c.ev_cap) {
+            int rc = rb2_rebuild_events(c, nev, after_velocity_update);
+            if (rc) return rc;
+        }
         c.host_events.resize((size_t)nev);
         RB2_CUDA(cudaMemcpyAsync(c.host_events.data(), c.d_events, (size_t)nev * sizeof(rb2_event), cudaMemcpyDeviceToHost, c.stream));
+        RB2_CUDA(cudaStreamSynchronize(c.stream));
     }
     return RB2_OK;
 }
@@ -527,7 +537,7 @@ int rb2_update_position(int step)
     int rc = do_update_position(c, false, nullptr);
     if (rc) return rc;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
-    return RB2_OK;
+    return finish_position(c, false);
 }
 
 int rb2_accel_only(void)
@@ -575,6 +585,8 @@ int rb2_step(int step, rb2_step_result *out)
     RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     RB2_CUDA(cudaEventRecord(c.ev_s1, c.stream));
     RB2_CUDA(cudaStreamSynchronize(c.stream));
+    rc = finish_position(c, true);
+    if (rc) return rc;
     if (out) {
         memset(out, 0, sizeof(*out));
         fill_velocity_result(c, out);
@@ -739,6 +751,12 @@ int rb2_set_option(const char *name, double value)
         c.pair_mode = (int)value;
     } else if (!strcmp(name, "sym_min_n")) {
         c.sym_min_n = (int)value;
+    } else if (!strcmp(name, "event_buffer")) {
+        if (value < 1) return rb2_fail(RB2_ERR_ARG, "event_buffer must be >= 1 record");
+        c.ev_min = (int)value;
+        if (c.d_events) { RB2_CUDA(cudaStreamSynchronize(c.stream)); RB2_CUDA(cudaFree(c.d_events)); }
+        c.d_events = nullptr;
+        c.ev_cap = 0;
     } else if (!strcmp(name, "sym_tpl")) {
         if (value != 0 && value != 1 && value != 2) return rb2_fail(RB2_ERR_ARG, "sym_tpl (targets per lane) must be 0 (auto), 1 or 2");
         c.sym_tpl = (int)value;

@@ -116,10 +116,14 @@ k_update_position(int n, DevArrays A, int *__restrict__ mask, unsigned char *__r
 struct ValEv { const unsigned char *c; __device__ int operator()(int i) const { return c[i]; } };
 struct ValAlive { const int *m; __device__ int operator()(int i) const { return m[i] ? 1 : 0; } };
 
+// `guard`: when given, the pass is skipped while *guard == 0 (the event passes of a step are always queued and
+// usually have nothing to do)
 template <class V>
-__global__ void __launch_bounds__(TPB) k_scan_local(int n, V val, int *__restrict__ prefix, int *__restrict__ blocksum)
+__global__ void __launch_bounds__(TPB) k_scan_local(int n, V val, int *__restrict__ prefix, int *__restrict__ blocksum,
+                                                    const int *__restrict__ guard)
 {
     __shared__ int warp_tot[TPB / 32];
+    if (guard && *guard == 0) return;
     const int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
     int v[4], s = 0;
 #pragma unroll
@@ -139,10 +143,12 @@ __global__ void __launch_bounds__(TPB) k_scan_local(int n, V val, int *__restric
     if (threadIdx.x == TPB - 1) blocksum[blockIdx.x] = woff + inc;
 }
 // single block: exclusive scan of blocksum[0..nb) in place, total to *total
-__global__ void __launch_bounds__(1024) k_scan_sums(int nb, int *__restrict__ blocksum, int *__restrict__ total)
+__global__ void __launch_bounds__(1024) k_scan_sums(int nb, int *__restrict__ blocksum, int *__restrict__ total,
+                                                    const int *__restrict__ guard)
 {
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
+    if (guard && *guard == 0) return;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -169,8 +175,9 @@ __global__ void __launch_bounds__(1024) k_scan_sums(int nb, int *__restrict__ bl
 __global__ void __launch_bounds__(TPB)
 k_events_scatter(int n, DevArrays A, const unsigned char *__restrict__ evcnt, const unsigned short *__restrict__ evbits,
                  const int *__restrict__ prefix, const int *__restrict__ blocksum, rb2_event *__restrict__ out, int cap,
-                 int planes_N)
+                 int planes_N, const double *__restrict__ vel, const int *__restrict__ guard)
 {
+    if (guard && *guard == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (evcnt[i] == 0) return;
@@ -181,7 +188,7 @@ k_events_scatter(int n, DevArrays A, const unsigned char *__restrict__ evcnt, co
     e.index = i;
     e.x = p.x / rb2k::length_scale;
     e.y = p.y / rb2k::length_scale;
-    e.vx = A.vel[3 * i]; e.vy = A.vel[3 * i + 1]; e.vz = A.vel[3 * i + 2];
+    e.vx = vel[3 * i]; e.vy = vel[3 * i + 1]; e.vz = vel[3 * i + 2];
     e.emit = A.emitter[i]; e.sec = A.section[i]; e.id = A.id[i];
     if (bits & 3) {
         e.kind = (bits & 1) ? 1 : 2;
@@ -203,7 +210,8 @@ k_events_scatter(int n, DevArrays A, const unsigned char *__restrict__ evcnt, co
 constexpr int NRED = 13;  // ramo[0..3], part(3), elec(3), ion(3)
 
 __global__ void __launch_bounds__(TPB)
-k_update_velocity(int n, DevArrays A, StepParams P, double *__restrict__ redpart)
+k_update_velocity(int n, DevArrays A, StepParams P, double *__restrict__ redpart, const unsigned char *__restrict__ evcnt,
+                  double *__restrict__ vel_save)
 {
     __shared__ double sm[TPB / 32][NRED];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,9 +222,13 @@ k_update_velocity(int n, DevArrays A, StepParams P, double *__restrict__ redpart
         const int sp = A.species[i];
         if (sp != RB2_SPECIES_ATOM) {
             double v[3];
+            // a particle with records keeps its pre-update velocity (what the records hold) in the spare velocity
+            // array, so the record list can be rebuilt when it did not fit its buffer (rb2_rebuild_events)
+            const bool keep = evcnt[i] != 0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const int e = 3 * i + c;
+                if (keep) vel_save[e] = A.vel[e];
                 // vel + 1/6*(2*a + 5*a_prev - a_prev2)*dt, src/mod_verlet.F90:470-473
                 const double s = sub_(add_(mul_(2.0, A.acc[e]), mul_(5.0, A.acc_prev[e])), A.acc_prev2[e]);
                 v[c] = add_(A.vel[e], mul_(mul_(1.0 / 6.0, s), P.dt));
@@ -402,12 +414,12 @@ __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, doubl
 inline int nblk(int n) { return (n + TPB - 1) / TPB; }
 
 template <class V>
-int run_scan(Rb2Ctx &ctx, int n, V val)
+int run_scan(Rb2Ctx &ctx, int n, V val, const int *guard = nullptr)
 {
     const int nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
-    k_scan_local<V><<<nb, TPB, 0, ctx.stream>>>(n, val, ctx.prefix, ctx.blocksum);
+    k_scan_local<V><<<nb, TPB, 0, ctx.stream>>>(n, val, ctx.prefix, ctx.blocksum, guard);
     RB2_CUDA(cudaGetLastError());
-    k_scan_sums<<<1, 1024, 0, ctx.stream>>>(nb, ctx.blocksum, ctx.d_total);
+    k_scan_sums<<<1, 1024, 0, ctx.stream>>>(nb, ctx.blocksum, ctx.d_total, guard);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(2);
     return RB2_OK;
@@ -442,22 +454,49 @@ int rb2_launch_update_position(Rb2Ctx &ctx)
     return RB2_OK;
 }
 
-// Build the ordered record list of the last position update into ctx.d_events.
-int rb2_launch_events(Rb2Ctx &ctx, int n_events)
+namespace {
+int ensure_events(Rb2Ctx &ctx, int want)
 {
-    if (ctx.n < 1 || n_events < 1) return RB2_OK;
-    if (n_events > ctx.ev_cap) {
+    if (want > ctx.ev_cap) {
         if (ctx.d_events) RB2_CUDA(cudaFree(ctx.d_events));
         ctx.d_events = nullptr;
         ctx.ev_cap = 0;
-        const int want = n_events + n_events / 2 + 1024;
         RB2_CUDA(cudaMalloc(&ctx.d_events, (size_t)want * sizeof(rb2_event)));
         ctx.ev_cap = want;
     }
-    int rc = run_scan(ctx, ctx.n, ValEv{ctx.evcnt});
+    return RB2_OK;
+}
+
+}  // namespace
+
+// Queue the ordered record list of the position update that is in the stream (absorbed electrons, plane crossings,
+// ascending particle index) into ctx.d_events.  The passes read the record count on the device and do nothing when
+// it is zero, so the step never waits for the host; records beyond the buffer are dropped here and rebuilt by
+// rb2_rebuild_events once the host knows the count.
+int rb2_launch_events(Rb2Ctx &ctx)
+{
+    if (ctx.n < 1) return RB2_OK;
+    int rc = ensure_events(ctx, ctx.ev_min);
+    if (rc != RB2_OK) return rc;
+    const int *guard = &ctx.d_counters->n_events;
+    rc = run_scan(ctx, ctx.n, ValEv{ctx.evcnt}, guard);
     if (rc != RB2_OK) return rc;
     k_events_scatter<<<nblk(ctx.n), TPB, 0, ctx.stream>>>(ctx.n, ctx.a, ctx.evcnt, ctx.evbits, ctx.prefix, ctx.blocksum,
-                                                         ctx.d_events, ctx.ev_cap, ctx.cfg.planes_N);
+                                                         ctx.d_events, ctx.ev_cap, ctx.cfg.planes_N, ctx.a.vel, guard);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(1);
+    return RB2_OK;
+}
+
+// The record list did not fit: grow the buffer and scatter again (the scan of the step is still in place).
+// vel: the velocities the records must hold -- the current ones before the velocity update, the saved ones after.
+int rb2_rebuild_events(Rb2Ctx &ctx, int n_events, bool after_velocity_update)
+{
+    int rc = ensure_events(ctx, n_events + n_events / 2 + 1024);
+    if (rc != RB2_OK) return rc;
+    k_events_scatter<<<nblk(ctx.n), TPB, 0, ctx.stream>>>(ctx.n, ctx.a, ctx.evcnt, ctx.evbits, ctx.prefix, ctx.blocksum,
+                                                         ctx.d_events, ctx.ev_cap, ctx.cfg.planes_N,
+                                                         after_velocity_update ? ctx.b.vel : ctx.a.vel, nullptr);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(1);
     return RB2_OK;
@@ -479,7 +518,7 @@ int rb2_launch_update_velocity(Rb2Ctx &ctx)
         return RB2_OK;
     }
     const StepParams P = rb2_make_step_params(ctx.cfg);
-    k_update_velocity<<<nb, TPB, 0, ctx.stream>>>(ctx.n, ctx.a, P, ctx.d_redpart);
+    k_update_velocity<<<nb, TPB, 0, ctx.stream>>>(ctx.n, ctx.a, P, ctx.d_redpart, ctx.evcnt, ctx.b.vel);
     RB2_CUDA(cudaGetLastError());
     k_reduce_final<<<NRED, TPB, 0, ctx.stream>>>(nb, ctx.d_redpart, ctx.d_red);
     RB2_CUDA(cudaGetLastError());

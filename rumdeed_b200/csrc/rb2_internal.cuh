@@ -118,6 +118,7 @@ struct Rb2Ctx {
     unsigned long long p2p_epoch = 0;     // evaluations since attach; parity selects the partial-sum slot
     int    last_pair_kernel = 0;          // 1 gather, 2 symmetric
     rb2_event *d_events = nullptr; int ev_cap = 0;
+    int    ev_min = 65536;                // initial size of the record buffer (option "event_buffer")
     std::vector<rb2_event> host_events;
 
     // staging (grow-only): field points / fields, add/mark arguments, rb2_accel_host
@@ -172,7 +173,8 @@ int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *
 int rb2_launch_pack(Rb2Ctx &ctx, const double *pos3, const double *q, int n, double4 *pq);
 int rb2_launch_unpack(Rb2Ctx &ctx, const double4 *pq, int n, double *pos3, double *q);
 int rb2_launch_update_position(Rb2Ctx &ctx);
-int rb2_launch_events(Rb2Ctx &ctx, int n_events);
+int rb2_launch_events(Rb2Ctx &ctx);
+int rb2_rebuild_events(Rb2Ctx &ctx, int n_events, bool after_velocity_update);
 int rb2_launch_update_velocity(Rb2Ctx &ctx);
 int rb2_launch_compact(Rb2Ctx &ctx, int step);
 int rb2_launch_add(Rb2Ctx &ctx, int k, int slot0, int id0, int step, const double *d_pos, const double *d_vel,

@@ -438,11 +438,13 @@ def test_particle_removal_reference_case(orc):
         assert np.array_equal(s["pos"][0], np.array([5, 6, 50.0]) * NM) and s["id"][0] == 7
 
 
-@pytest.mark.parametrize("geom", ["planar", "tip"])
-def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom):
+@pytest.mark.parametrize("geom,event_buffer", [("planar", None), ("tip", None), ("planar", 1)])
+def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom, event_buffer):
     """Many Beeman steps with absorption at both electrodes, plane crossings, mid-run additions:
     particle order, ids, records and counters must match the oracle exactly; positions and
-    velocities agree to rounding (the accelerations feeding them agree to ~1e-13)."""
+    velocities agree to rounding (the accelerations feeding them agree to ~1e-13).  event_buffer = 1: the
+    record list never fits its device buffer at first, so it is rebuilt after the step from the saved
+    pre-update velocities."""
     rng = np.random.default_rng(5)
     if geom == "planar":
         d = 200 * NM
@@ -467,6 +469,8 @@ def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom):
     species = np.where((np.arange(n0) % 9) == 8, 2, 1).astype(np.int32)
     st = orc.store(2048)
     with rb.HotPath(cfg) as hp:
+        if event_buffer is not None:
+            hp.set_option("event_buffer", event_buffer)
         for i in range(n0):
             st.add(p, pos[i], vel[i], int(species[i]), 0, 1, -1, 1 + (i % 5))
         hp.Add_Particles(pos, vel, species, 0, emit=np.ones(n0, dtype=np.int32), sec=(1 + (np.arange(n0) % 5)).astype(np.int32))
@@ -474,6 +478,8 @@ def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom):
         for step in range(1, 121):
             st.clear_events()
             st.step(p)
+            if event_buffer is not None and step % 2 == 0:
+                hp.set_option("event_buffer", event_buffer)  # shrink again: every other step overflows
             r = hp.Update_Position(step)
             ev_o, ev_g = st.events(), hp.events()
             assert r.n_events == len(ev_o) == len(ev_g)
