@@ -48,6 +48,9 @@ typedef struct rh_state {
     double ramo_integral;       /* sum of I*dt, C */
     double avg_elec_vel[3];
     float  accel_ms, step_ms;
+    double t_dev_step, t_dev_accel;               /* device time (CUDA events) of rb2_step and of its pair kernels, summed */
+    double t_emission, t_md_step, t_remove, t_io; /* wall-clock seconds spent so far in: ptr_Do_Emission, rb2_step,
+                                                     rb2_remove_marked, the text/binary writers */
 } rh_state;
 
 void *rh_create_from_dir(const char *dir, int write_files, unsigned long long seed, int max_particles);

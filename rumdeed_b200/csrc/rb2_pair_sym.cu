@@ -198,18 +198,23 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
 }
 
 // raw[c][p] += (sum over this band's groups of the target sums) + (sum over the target superblocks that met
-// tile J(p) symmetrically of the source sums), both in ascending order; only slots written by this rank are read.
+// tile J(p) symmetrically of the source sums); only slots written by this rank are read.  One CTA per 128-particle
+// tile, RQ threads per particle: thread (q, tid) adds every RQ-th term in ascending order, the RQ sums are joined
+// in ascending q -- a fixed order, and short dependent chains (at N = 1e4 a single thread per particle spent 55 us
+// on ~160 sequential loads next to a 300 us pair kernel).
+constexpr int RQ = 4;
 template <int T>
-__global__ void __launch_bounds__(SB)
+__global__ void __launch_bounds__(SB * RQ)
 k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restrict__ bufJ, double *__restrict__ raw)
 {
+    __shared__ double part[RQ][3][SB];
     const int Jp = blockIdx.x;  // 128-particle tile of this particle
     const int It = Jp / T;      // its target superblock
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (SB - 1), q = threadIdx.x / SB;
     const int p = Jp * SB + tid;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     // as a target (superblock It)
-    for (int grp = 0; grp < g.ngroups; ++grp) {
+    for (int grp = q; grp < g.ngroups; grp += RQ) {
         const int J0 = g.band_start + grp * g.G;
         const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
         if (max(J0, T * It) >= J1) continue;
@@ -226,7 +231,7 @@ k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restric
         const int Iend = (Jp + T - 1) / T;
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll 4
-        for (int I = 0; I < Iend; ++I) {
+        for (int I = q; I < Iend; I += RQ) {
             if (((I + grp) % g.world) != g.rank) continue;
             const size_t base = ((col + I) * 3) * SB + tid;
             t0 += bufJ[base];
@@ -235,9 +240,15 @@ k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restric
         }
         s0 += t0; s1 += t1; s2 += t2;
     }
-    raw[p] += s0;
-    raw[(size_t)g.n_pad + p] += s1;
-    raw[2 * (size_t)g.n_pad + p] += s2;
+    part[q][0][tid] = s0; part[q][1][tid] = s1; part[q][2][tid] = s2;
+    __syncthreads();
+    if (q == 0) {
+#pragma unroll
+        for (int k = 1; k < RQ; ++k) { s0 += part[k][0][tid]; s1 += part[k][1][tid]; s2 += part[k][2][tid]; }
+        raw[p] += s0;
+        raw[(size_t)g.n_pad + p] += s1;
+        raw[2 * (size_t)g.n_pad + p] += s2;
+    }
 }
 
 // a_i = ( q_i/(4 pi eps0) * raw_i + q_i * E_z zhat ) / m_i   (src/mod_verlet.F90:1333-1338)
@@ -254,14 +265,22 @@ __global__ void k_sym_finalize(int n, int n_pad, const double *__restrict__ raw,
     acc[3 * i + 2] = (qd_1 * raw[2 * (size_t)n_pad + i] + q_1 * P.E_z) * im_1;
 }
 
-int ensure_bytes(double **p, size_t *have, size_t want)
+// Grow-only scratch.  The particle count of a real run changes every step (emission, absorption), so grow by half
+// again: with exact sizes a slowly filling diode paid a cudaFree + cudaMalloc (milliseconds) on most steps.
+int ensure_bytes(double **p, size_t *have, size_t want, size_t limit = 0)
 {
     if (want > *have) {
         if (*p) RB2_CUDA(cudaFree(*p));
         *p = nullptr;
         *have = 0;
-        RB2_CUDA(cudaMalloc(p, want));
-        *have = want;
+        size_t ask = want + want / 2;
+        if (limit && ask > limit) ask = limit > want ? limit : want;
+        if (cudaMalloc(p, ask) != cudaSuccess) {
+            cudaGetLastError();
+            ask = want;
+            RB2_CUDA(cudaMalloc(p, ask));
+        }
+        *have = ask;
     }
     return RB2_OK;
 }
@@ -287,8 +306,10 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     // band width from the scratch budget (3 KB per (source tile, target superblock) pair)
     const size_t col_bytes = (size_t)g.nIb * 3 * SB * sizeof(double);
     size_t budget = ctx.sym_budget_bytes;
-    {
-        size_t fr = 0, tot = 0;  // never ask for more than half of what is free (plus what we already hold)
+    if ((size_t)g.nsb * col_bytes > ctx.sym_bufJ_bytes) {
+        // the whole triangle does not fit what we hold: never ask for more than half of what is free (plus what we
+        // already hold).  cudaMemGetInfo costs a fraction of a millisecond, so only look when it can matter.
+        size_t fr = 0, tot = 0;
         if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
             const size_t cap = (fr + ctx.sym_bufJ_bytes) / 2;
             if (budget > cap) budget = cap;
@@ -308,7 +329,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (G < 1) G = 1;
     if (G > Wb) G = Wb;
     const int ngroups_max = (Wb + G - 1) / G;
-    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, (size_t)Wb * col_bytes);
+    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, (size_t)Wb * col_bytes, budget);
     if (rc) return rc;
     rc = ensure_bytes(&ctx.sym_bufI, &ctx.sym_bufI_bytes, (size_t)ngroups_max * 3 * g.n_pad * sizeof(double));
     if (rc) return rc;
@@ -345,8 +366,8 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         else RB2_GO(2);
 #undef RB2_GO
         RB2_CUDA(cudaGetLastError());
-        if (T == 1) k_sym_reduce<1><<<g.nsb, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
-        else k_sym_reduce<2><<<g.nIb * 2, SB, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
+        if (T == 1) k_sym_reduce<1><<<g.nsb, SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
+        else k_sym_reduce<2><<<g.nIb * 2, SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
         RB2_CUDA(cudaGetLastError());
         launches += 2;
     }

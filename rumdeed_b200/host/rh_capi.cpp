@@ -109,6 +109,8 @@ int rh_get_state(void *p, rh_state *o)
     o->ramo_total = s->last.ramo_current[1] + s->last.ramo_current[2] + s->last.ramo_current[3];
     o->ramo_integral = s->ramo_integral;
     o->accel_ms = s->last.accel_ms; o->step_ms = s->last.step_ms;
+    o->t_dev_step = s->t_dev_step; o->t_dev_accel = s->t_dev_accel;
+    o->t_emission = s->t_emission; o->t_md_step = s->t_md_step; o->t_remove = s->t_remove; o->t_io = s->t_io;
     return 0;
 }
 
@@ -204,6 +206,8 @@ int main(int argc, char **argv)
     rh_get_state(sim, &st);
     printf("RUMDEED: Main loop finished: emitted %lld absorbed top %lld bot %lld, %d electrons in the gap\n", st.nrEmitted_total,
            st.nrAbsorbed_top, st.nrAbsorbed_bot, st.nrElec);
+    printf("RUMDEED: wall clock per phase [s]: emission %.3f  MD step %.3f  removal %.3f  writers %.3f  (%d steps); device time of the MD steps %.3f, of their pair kernels %.3f\n",
+           st.t_emission, st.t_md_step, st.t_remove, st.t_io, st.step, st.t_dev_step, st.t_dev_accel);
     rh_destroy(sim);
     printf("RUMDEED: Program finished\n");
     return 0;

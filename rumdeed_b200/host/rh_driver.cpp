@@ -5,6 +5,8 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <chrono>
+
 #include "rh_host.hpp"
 
 namespace rh {
@@ -125,8 +127,13 @@ int Step(Sim &s, int step)
 {
     Globals &g = s.g;
     s.cur_step = step;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = clk::now();
     // ptr_Do_Emission(i)
     if (s.ptr.ptr_Do_Emission(s, step)) return -1;
+    const auto t1 = clk::now();
+    s.t_emission += secs(t0, t1);
     s.nrEmitted_total += s.slog.nrElecEmit;
     s.cur_time = g.time_step * step / time_scale;
     if (s.ud_emit)  // src/mod_field_emission_v2.F90:203: "(E14.6, *(tr8, i6))"
@@ -134,7 +141,12 @@ int Step(Sim &s, int step)
     // Update_Position(i): Set_Voltage + Beeman step on the device
     g.V_d = g.V_s;
     if (s.ud_volt) fprintf(s.ud_volt, "%12.4E  %8d  %18.8E  %18.8E\n", s.cur_time, step, g.V_d, 0.0);
+    const auto t2 = clk::now();
     if (s.check(rb2_step(step, &s.last), "rb2_step")) return -1;
+    const auto t3 = clk::now();
+    s.t_md_step += secs(t2, t3);
+    s.t_dev_step += 1e-3 * s.last.step_ms;
+    s.t_dev_accel += 1e-3 * s.last.accel_ms;
     s.counts = s.last.counts;
     double ramo_cur = 0.0;
     for (int k = 1; k <= 3; ++k) ramo_cur += s.last.ramo_current[k];
@@ -156,7 +168,11 @@ int Step(Sim &s, int step)
     if (s.ud_absorb_top) fprintf(s.ud_absorb_top, "%12.4E  %8d  %8d  %8d  %8d  %8d\n", s.cur_time, step, s.counts.nrPart_remove_top, s.counts.nrElec_remove_top, s.counts.nrIon_remove_top, s.counts.nrElec_remove_top);
     if (s.ud_absorb_bot) fprintf(s.ud_absorb_bot, "%12.4E  %8d  %8d  %8d  %8d\n", s.cur_time, step, s.counts.nrPart_remove_bot, s.counts.nrElec_remove_bot, s.counts.nrIon_remove_bot);
     rb2_counts k{};
+    const auto t4 = clk::now();
     if (s.check(rb2_remove_marked(step, &k), "rb2_remove_marked")) return -1;
+    const auto t5 = clk::now();
+    s.t_remove += secs(t4, t5);
+    s.t_io += secs(t1, t2) + secs(t3, t4);
     s.counts = k;
     return 0;
 }

@@ -137,6 +137,7 @@ struct Sim {
     double residual = 0.0;
     long long nrEmitted_total = 0, nrAbsorbed_top = 0, nrAbsorbed_bot = 0;
     double ramo_integral = 0.0;  // sum over steps of I*dt (Shockley-Ramo charge)
+    double t_emission = 0.0, t_md_step = 0.0, t_remove = 0.0, t_io = 0.0, t_dev_step = 0.0, t_dev_accel = 0.0;  // wall-clock seconds per phase of the main loop
     // tip geometry scalars (src/mod_hyperboloid_tip.f90)
     double d_tip = 0, R_base = 0, h_tip = 0, a_foci = 0, eta_1 = 0, theta_tip = 0, r_tip = 0, max_xi = 0, shift_z = 0;
     double pre_fac_E_tip = 0, pre_fac_E_tip_unit_voltage = 0;

@@ -47,6 +47,8 @@ class State(C.Structure):
         ("F_avg", C.c_double * 3), ("neval", C.c_int), ("fail", C.c_int), ("integral_error", C.c_double),
         ("ramo_current", C.c_double * 4), ("ramo_total", C.c_double), ("ramo_integral", C.c_double),
         ("avg_elec_vel", C.c_double * 3), ("accel_ms", C.c_float), ("step_ms", C.c_float),
+        ("t_dev_step", C.c_double), ("t_dev_accel", C.c_double),
+        ("t_emission", C.c_double), ("t_md_step", C.c_double), ("t_remove", C.c_double), ("t_io", C.c_double),
     ]
 
 
