@@ -207,6 +207,11 @@ int rb2_stream(void **stream_out);
  * (field(3) in src/mod_field_emission_v2.F90:668-745, :1122-1458). */
 int rb2_field_surface_z(int M, const double *pos_in, double *Ez_out);
 
+/* Sample_Elec_Position (src/mod_pair.F90:975-1037), the sweep only: for each of the nrPart particles the distance
+ * to the nearest OTHER electron and its 0-based index (rows that are not electrons: 1000.0 and -1, the reference's
+ * initial value).  Bit-exact with the serial scan (lowest index wins ties).  Either pointer may be NULL. */
+int rb2_nearest_electron(double *dist_out, int *id_out);
+
 /* ---- device-resident emission sampler ------------------------------------------------- */
 /* Lock-step Metropolis-Hastings over the planar emitter: replaces the host loop of
  * Metropolis_Hastings_rectangle_J_batch (src/mod_field_emission_v2.F90:1284-1458; kind 1) and, with

@@ -158,6 +158,7 @@ class Oracle:
         lib.orc_tip_elec_supply.argtypes = [PP, C.c_double, C.c_double, C.c_double]
         lib.orc_tip_elec_supply.restype = C.c_double
         lib.orc_max_threads.restype = C.c_int
+        lib.orc_nearest_elec.argtypes = [C.c_int, _PD, _PI, _PD, _PI]
         self.k = Constants()
         lib.orc_get_constants(C.byref(self.k))
 
@@ -266,6 +267,16 @@ class Oracle:
         out = np.zeros_like(pts)
         self.lib.orc_calc_field_at_batch(C.byref(p), n, _d(pos), _d(q), _i(sp), pts.shape[0], _d(pts), _d(out))
         return out
+
+    def nearest_elec(self, pos, species):
+        """Sample_Elec_Position (mod_pair.F90:975-1037): nearest other electron of every electron."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        sp = np.ascontiguousarray(species, dtype=np.int32)
+        n = pos.shape[0]
+        dist = np.empty(n)
+        idx = np.empty(n, dtype=np.int32)
+        self.lib.orc_nearest_elec(n, _d(pos), _i(sp), _d(dist), _i(idx))
+        return dist, idx
 
     # -- FN helpers ---------------------------------------------------------------
     def fn_v_y(self, p, F, w): return self.lib.orc_fn_v_y(C.byref(p), F, w)

@@ -49,6 +49,26 @@ void orc_get_constants(orc_constants *c)
     c->a_FN = k_aFN(); c->b_FN = k_bFN(); c->l_const = k_lconst();
 }
 
+/* Sample_Elec_Position, src/mod_pair.F90:990-1011 (the per-row scan; the file writer is host-side I/O). */
+void orc_nearest_elec(int n, const double *pos, const int *species, double *dist_out, int *id_out)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        double best = 1000.0; /* particles_nearest_dist = 1000.0d0, :988 */
+        int id = -1;
+        if (species[i] == ORC_SPECIES_ELEC) {
+            for (int j = 0; j < n; ++j) {
+                if (j == i || species[j] != ORC_SPECIES_ELEC) continue;
+                const double dx = pos[3 * i] - pos[3 * j], dy = pos[3 * i + 1] - pos[3 * j + 1], dz = pos[3 * i + 2] - pos[3 * j + 2];
+                const double dist = sqrt(dx * dx + dy * dy + dz * dz); /* norm2, :1002 */
+                if (dist < best) { best = dist; id = j; }
+            }
+        }
+        dist_out[i] = best;
+        id_out[i] = id;
+    }
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -159,6 +159,11 @@ double orc_tip_t_y(const orc_params *p, double F, double w_theta);
 double orc_tip_escape_prob(const orc_params *p, double F, double w_theta);
 double orc_tip_elec_supply(const orc_params *p, double A, double F, double w_theta);
 
+/* Sample_Elec_Position, src/mod_pair.F90:975-1037: for every electron the distance to the nearest OTHER electron
+ * (species test only: electrons already marked for removal still count) and that electron's 0-based index; rows
+ * that are not electrons keep the initial distance 1000.0 and get index -1.  Strict `<` over ascending j: the
+ * lowest index wins a tie.  dist = sqrt(dx*dx + dy*dy + dz*dz), summed left to right without contraction. */
+void orc_nearest_elec(int n, const double *pos, const int *species, double *dist_out, int *id_out);
 int orc_max_threads(void);
 
 #ifdef __cplusplus

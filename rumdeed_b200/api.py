@@ -104,7 +104,7 @@ EXPORTS = (
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_accel_host",
     "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
-    "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach",
+    "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
 )
 
@@ -147,6 +147,7 @@ def load_library(path: str | None = None):
     lib.rb2_device_buffer.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.rb2_stream.argtypes = [C.POINTER(C.c_void_p)]
     lib.rb2_p2p_export.argtypes = [C.c_int, C.c_void_p]
+    lib.rb2_nearest_electron.argtypes = [_PD, _PI]
     lib.rb2_p2p_attach.argtypes = [C.c_int, C.c_int, C.c_void_p]
     lib.rb2_fp64_peak.argtypes = [C.c_double, _PD, C.POINTER(C.c_float)]
     lib.rb2_launch_count.argtypes = [C.POINTER(C.c_longlong), C.c_int]
@@ -443,6 +444,16 @@ class HotPath:
 
     def accel_finalize(self):
         self._check(self.lib.rb2_accel_finalize())
+
+    def Sample_Elec_Position(self):
+        """The sweep of Sample_Elec_Position (mod_pair.F90:975-1037): (nearest distance, 0-based index of the nearest
+        other electron) for every particle; rows that are not electrons hold (1000.0, -1)."""
+        n = self.counts().nrPart
+        dist = np.empty(n)
+        idx = np.empty(n, dtype=np.int32)
+        if n > 0:
+            self._check(self.lib.rb2_nearest_electron(_d(dist), _i(idx)))
+        return dist, idx
 
     def p2p_export(self, n_max) -> bytes:
         """This process's exchange block (partial pair sums + flags) as a CUDA IPC handle."""

@@ -162,6 +162,8 @@ int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra
 int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                          double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez);
+// nearest-electron sweep (rb2_nearest.cu)
+int rb2_launch_nearest(Rb2Ctx &ctx, double *d_dist, int *d_id);
 // peer-memory exchange (rb2_p2p.cu)
 double *rb2_p2p_begin_evaluation(Rb2Ctx &ctx, int n_pad);
 int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);

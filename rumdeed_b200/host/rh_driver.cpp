@@ -77,6 +77,7 @@ int Init(Sim &s)
         s.ud_integrand = open_out(s, "integration.dt", "w");
         s.ud_volt = open_out(s, "volt.dt", "w");
         s.ud_density_emit = open_out(s, "density_emit.bin", "wb");
+        if (g.write_position_file) s.ud_pos = open_out(s, "position.bin", "wb");  // src/main.F90:548
         s.ud_density_absorb_top = open_out(s, "density_absorb_top.bin", "wb");
         s.ud_density_absorb_bot = open_out(s, "density_absorb_bot.bin", "wb");
         for (int k = 0; k < g.planes_N; ++k) {
@@ -122,6 +123,56 @@ static void write_event_files(Sim &s)
     }
 }
 
+// Write_Position, src/mod_pair.F90:841-867: stream of (steps, N_steps) once, then per step (step, nrPart) and per
+// particle x, y, z [m], emitter, section, id.
+static int write_position(Sim &s, int step)
+{
+    if (!s.ud_pos) return 0;
+    const int N_steps = 1;
+    if (step == 1) { const int h[2] = {s.g.steps, N_steps}; fwrite(h, sizeof(int), 2, s.ud_pos); }
+    const int n = s.counts.nrPart;
+    const int h[2] = {step, n};
+    fwrite(h, sizeof(int), 2, s.ud_pos);
+    if (n < 1) return 0;
+    std::vector<double> pos((size_t)3 * n);
+    std::vector<int> emit((size_t)n), sec((size_t)n), id((size_t)n);
+    if (s.check(rb2_download_particles(pos.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                       emit.data(), sec.data(), nullptr, id.data(), nullptr), "rb2_download_particles")) return -1;
+    for (int i = 0; i < n; ++i) {
+        fwrite(&pos[(size_t)3 * i], sizeof(double), 3, s.ud_pos);
+        const int t[3] = {emit[i], sec[i], id[i]};
+        fwrite(t, sizeof(int), 3, s.ud_pos);
+    }
+    return 0;
+}
+
+// Sample_Elec_Position, src/mod_pair.F90:975-1037: every sample_elec_rate steps the nearest-neighbour sweep (on the
+// device, rb2_nearest_electron) and out/elec-<step>.bin with x, y, z, nearest distance [m] of every electron.
+static int sample_elec_position(Sim &s, int step)
+{
+    if (!s.g.sample_elec_file || !s.write_files) return 0;
+    if (step % s.g.sample_elec_rate != 0) return 0;
+    const int n = s.counts.nrPart;
+    std::vector<double> pos((size_t)3 * (n > 0 ? n : 1)), dist((size_t)(n > 0 ? n : 1));
+    std::vector<int> species((size_t)(n > 0 ? n : 1));
+    if (n > 0) {
+        if (s.check(rb2_nearest_electron(dist.data(), nullptr), "rb2_nearest_electron")) return -1;
+        if (s.check(rb2_download_particles(pos.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, species.data(),
+                                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), "rb2_download_particles")) return -1;
+    }
+    char nm[64];
+    snprintf(nm, sizeof(nm), "elec-%d.bin", step);
+    FILE *f = open_out(s, nm, "wb");
+    if (!f) { fprintf(stderr, "RUMDEED: Failed to open the electron position file.\n"); return 0; }
+    for (int i = 0; i < n; ++i) {
+        if (species[i] != species_elec) continue;
+        const double rec[4] = {pos[(size_t)3 * i], pos[(size_t)3 * i + 1], pos[(size_t)3 * i + 2], dist[i]};
+        fwrite(rec, sizeof(double), 4, f);
+    }
+    fclose(f);
+    return 0;
+}
+
 // One iteration of the main loop, src/main.F90:175-219
 int Step(Sim &s, int step)
 {
@@ -161,6 +212,8 @@ int Step(Sim &s, int step)
                 nrm(s.last.avg_elec_vel), nrm(s.last.avg_ion_vel), s.last.ramo_current[1], s.last.ramo_current[2], s.last.ramo_current[3]);
     }
     if (s.write_files) write_event_files(s);
+    if (write_position(s, step)) return -1;        // src/main.F90:191
+    if (sample_elec_position(s, step)) return -1;  // src/main.F90:193
     // Remove_Particles(i): Write_Absorbed (src/mod_pair.F90:790-805) + compaction
     s.nrAbsorbed_top += s.counts.nrElec_remove_top;
     s.nrAbsorbed_bot += s.counts.nrElec_remove_bot;
@@ -182,7 +235,7 @@ int Clean_up(Sim &s)
 {
     if (s.ptr.ptr_Clean_Up) s.ptr.ptr_Clean_Up(s);
     FILE **fs[] = {&s.ud_ramo, &s.ud_emit, &s.ud_absorb, &s.ud_absorb_top, &s.ud_absorb_bot, &s.ud_field, &s.ud_integrand, &s.ud_volt,
-                   &s.ud_density_emit, &s.ud_density_absorb_top, &s.ud_density_absorb_bot};
+                   &s.ud_density_emit, &s.ud_density_absorb_top, &s.ud_density_absorb_bot, &s.ud_pos};
     for (FILE **f : fs) if (*f) { fclose(*f); *f = nullptr; }
     for (int k = 0; k < RB2_PLANES_MAX; ++k) if (s.planes_ud[k]) { fclose(s.planes_ud[k]); s.planes_ud[k] = nullptr; }
     if (s.write_files) {  // Write_Life_Time, src/mod_pair.F90:776-786

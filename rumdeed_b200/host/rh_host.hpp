@@ -70,6 +70,8 @@ struct Globals {
     double planes_z[RB2_PLANES_MAX] = {5.0, 10.0, 25.0, 50.0, 75.0, 100.0, 125.0, 250.0, 500.0, 750.0};
     bool mh_batch = false;
     bool mh_device = false;  // lock-step chains run by rb2_mh_planar (implies mh_batch)
+    bool write_position_file = false;                        // src/mod_global.F90:353
+    bool sample_elec_file = false; int sample_elec_rate = 500;  // src/mod_global.F90:360-361
     int cuba_method = 2;
     double cuba_epsabs = 0.5, cuba_epsrel = 1.0e-3;
     int cuba_mineval = 1000, cuba_maxeval = 5000000;
@@ -144,6 +146,7 @@ struct Sim {
     // output units
     FILE *ud_ramo = nullptr, *ud_emit = nullptr, *ud_absorb = nullptr, *ud_absorb_top = nullptr, *ud_absorb_bot = nullptr;
     FILE *ud_field = nullptr, *ud_integrand = nullptr, *ud_volt = nullptr, *ud_density_emit = nullptr;
+    FILE *ud_pos = nullptr;  // out/position.bin (Write_Position)
     FILE *ud_density_absorb_top = nullptr, *ud_density_absorb_bot = nullptr, *planes_ud[RB2_PLANES_MAX] = {nullptr};
     std::vector<double> scratch_pts, scratch_fld, scratch_ez;
 

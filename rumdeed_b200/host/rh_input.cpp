@@ -148,6 +148,9 @@ int Read_Input_Variables(const std::string &path, Globals &g, std::string &err)
     logical("MH_BATCH", g.mh_batch);
     logical("MH_DEVICE", g.mh_device);  // extension: lock-step chains resident on the GPU (rb2_mh_planar)
     if (g.mh_device) g.mh_batch = true;
+    logical("WRITE_POSITION_FILE", g.write_position_file);
+    logical("SAMPLE_ELEC_FILE", g.sample_elec_file);
+    integer("SAMPLE_ELEC_RATE", g.sample_elec_rate);
     integer("CUBA_METHOD", g.cuba_method);
     dbl("CUBA_EPSABS", g.cuba_epsabs);
     dbl("CUBA_EPSREL", g.cuba_epsrel);
@@ -169,6 +172,7 @@ int Read_Input_Variables(const std::string &path, Globals &g, std::string &err)
     g.time_step2 = g.time_step * g.time_step;
     g.P_abs *= P_ntp;
     if (g.steps <= 0) { err = "ERROR: steps <= 0"; return -1; }
+    if (g.sample_elec_rate < 1) g.sample_elec_rate = 1;
     return 0;
 }
 

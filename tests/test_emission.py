@@ -79,7 +79,8 @@ def test_namelist_reader_fixture(tmp_path):
         "&INPUT\n  V_S = 1.0d3,   ! volts\n  BOX_DIM = 0.0d0, 0.0d0, 500.0d0,\n  TIME_STEP = 0.25d-3,\n  STEPS = 17,\n"
         "  EMISSION_MODE = 10,\n  NREMIT = 1,\n  IMAGE_CHARGE = .True.,\n  N_IC_MAX = 1,\n  MH_BATCH = .true.,\n"
         "  EMITTERS_DIM(1:3, 1) = 100.0d0, 100.0d0, 0.0d0,\n  EMITTERS_POS(1:3, 1) = -50.0d0, -50.0d0, 0.0d0,\n"
-        "  EMITTERS_TYPE(1) = 2,\n  EMITTERS_DELAY(1) = 0,\n  PLANES_N = 2,\n  PLANES_Z = 10.0d0, 250.0d0,\n/\n")
+        "  EMITTERS_TYPE(1) = 2,\n  EMITTERS_DELAY(1) = 0,\n  PLANES_N = 2,\n  PLANES_Z = 10.0d0, 250.0d0,\n"
+        "  WRITE_POSITION_FILE = .true.,\n  SAMPLE_ELEC_FILE = .true.,\n  SAMPLE_ELEC_RATE = 200,\n/\n")
     (tmp_path / "work").write_text("1\n2 2\n4.1 4.2\n4.3 4.4\n")
     s = Simulation(str(tmp_path), init=False)
     assert s.steps_in_input == 17
@@ -413,7 +414,8 @@ def test_driver_executable_writes_reference_format_files(tmp_path):
         "&INPUT\n  V_S = 1.0d3,\n  BOX_DIM = 0.0d0, 0.0d0, 500.0d0,\n  TIME_STEP = 0.25d-3,\n  STEPS = 400,\n  EMISSION_MODE = 10,\n"
         "  NREMIT = 1,\n  IMAGE_CHARGE = .True.,\n  N_IC_MAX = 1,\n  MH_BATCH = .true.,\n"
         "  EMITTERS_DIM(1:3, 1) = 100.0d0, 100.0d0, 0.0d0,\n  EMITTERS_POS(1:3, 1) = -50.0d0, -50.0d0, 0.0d0,\n"
-        "  EMITTERS_TYPE(1) = 2,\n  EMITTERS_DELAY(1) = 0,\n  PLANES_N = 2,\n  PLANES_Z = 10.0d0, 250.0d0,\n/\n")
+        "  EMITTERS_TYPE(1) = 2,\n  EMITTERS_DELAY(1) = 0,\n  PLANES_N = 2,\n  PLANES_Z = 10.0d0, 250.0d0,\n"
+        "  WRITE_POSITION_FILE = .true.,\n  SAMPLE_ELEC_FILE = .true.,\n  SAMPLE_ELEC_RATE = 200,\n/\n")
     (tmp_path / "work").write_text("1\n1 1\n2.00\n")
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rumdeed_b200", "rumdeed_b200_run")
     r = subprocess.run([exe, str(tmp_path), "4242", "0", "50000"], capture_output=True, text=True, timeout=600)
@@ -433,6 +435,24 @@ def test_driver_executable_writes_reference_format_files(tmp_path):
     assert np.all(top["vz"] > 0) and len(pl2) >= len(top)
     emitted = np.loadtxt(out / "emitted.dt")
     assert int(emitted[:, 2].sum()) == len(de)
+    # position.bin (Write_Position) read the way scripts/python_package/rumdeed_io.py does; elec-<step>.bin
+    # (Sample_Elec_Position): x, y, z, nearest distance of every electron
+    pdt = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("emit", "<i4"), ("sec", "<i4"), ("id", "<i4")])
+    with open(out / "position.bin", "rb") as f:
+        assert list(np.fromfile(f, count=2, dtype=np.int32)) == [400, 1]
+        last = None
+        for k in range(1, 401):
+            step_k, nr = np.fromfile(f, count=2, dtype=np.int32)
+            assert step_k == k and nr == int(ramo[k - 1, 4])
+            last = np.fromfile(f, count=nr, dtype=pdt)
+        assert f.read() == b""
+    el = np.fromfile(out / "elec-400.bin", dtype="<f8").reshape(-1, 4)
+    assert len(el) == len(last) and np.array_equal(el[:, 0], last["x"]) and np.array_equal(el[:, 2], last["z"])
+    d = el[:, None, :3] - el[None, :, :3]
+    dd = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2])
+    np.fill_diagonal(dd, np.inf)
+    assert np.array_equal(el[:, 3], dd.min(axis=1))
+    assert (out / "elec-200.bin").exists() and not (out / "elec-100.bin").exists()
     # steady-state current of the reference's test system stays in its band
     I_ss = ramo[250:, 2].mean()
     assert 0.5e-3 < I_ss < 4.0e-3

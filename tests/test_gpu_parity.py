@@ -620,3 +620,30 @@ def test_many_field_points_and_determinism(orc):
     idx = rng.choice(M, 64, replace=False)
     want = np.stack([orc.calc_field_at(p, pos, q, pts[k], sp, ld=True) for k in idx])
     assert relerr(a[idx], want) < TOL
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1000, 5000, 20011])
+def test_nearest_electron_sweep_is_bit_exact(orc, n):
+    """Sample_Elec_Position (mod_pair.F90:975-1037): nearest other electron of every electron -- distance and
+    index identical to the serial scan (ions do not count, electrons marked for removal still do, ties go to the
+    lowest index: duplicated positions and a lattice patch provoke them)."""
+    cfg, p = planar(orc, cap=max(n, 16))
+    pos, q, m, sp = cloud(n, 31 + n)
+    if n >= 1000:
+        pos[10] = pos[3]                      # coincident electrons: distance exactly 0
+        pos[500:520] = pos[400:420]           # more exact ties
+        g = np.arange(64)
+        pos[600:664] = np.stack([(g % 4) * 2.0, ((g // 4) % 4) * 2.0, 300.0 + (g // 16) * 2.0], axis=1) * NM  # lattice: equal distances
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        if n >= 1000:
+            hp.Mark_Particles_Remove(7, REMOVE_TOP)   # still an electron until Remove_Particles
+        dist, idx = hp.Sample_Elec_Position()
+    dist_o, idx_o = orc.nearest_elec(pos, sp)
+    assert np.array_equal(idx, idx_o)
+    assert np.array_equal(dist, dist_o)
+    elec = sp == SPECIES_ELEC
+    assert np.all(dist[~elec] == 1000.0) and np.all(idx[~elec] == -1)
+    if n >= 1000:
+        assert dist[10] == 0.0 and idx[10] == 3 and idx[3] == 10

@@ -351,3 +351,25 @@ def test_fn_functions(orc):
     assert orc.fn_v_y(p_on, -1.0e12, w) == 0.0
     # tip variant (mod_emission_tip.f90:1734) is exp of the same exponent
     assert abs(math.log(orc.tip_escape_prob(p_on, -2.0e9, w)) - (-28.723444978828507)) < 1e-9
+
+
+def test_nearest_electron_oracle_against_numpy(orc):
+    """orc_nearest_elec restates the scan of Sample_Elec_Position (mod_pair.F90:990-1011): checked against a dense
+    numpy evaluation of the same definition (species test only, strict <, lowest index wins)."""
+    rng = np.random.default_rng(3)
+    n = 300
+    pos = rng.uniform(0, 1e-7, (n, 3))
+    pos[17] = pos[5]
+    sp = np.where(np.arange(n) % 7 == 6, 2, 1).astype(np.int32)
+    dist, idx = orc.nearest_elec(pos, sp)
+    d = pos[:, None, :] - pos[None, :, :]
+    d2 = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+    dd = np.sqrt(d2)
+    elec = sp == 1
+    dd[:, ~elec] = np.inf
+    np.fill_diagonal(dd, np.inf)
+    want_idx = np.argmin(dd, axis=1)  # first minimum = lowest index
+    want = dd[np.arange(n), want_idx]
+    assert np.array_equal(idx[elec], want_idx[elec]) and np.array_equal(dist[elec], want[elec])
+    assert np.all(dist[~elec] == 1000.0) and np.all(idx[~elec] == -1)
+    assert dist[17] == 0.0 and idx[17] == 5
