@@ -157,6 +157,25 @@ module mod_b200_bridge
     integer(c_int) function rb2_field_window_close() bind(C, name='rb2_field_window_close')
       import :: c_int
     end function
+    integer(c_int) function rb2_nearest_electron(dist_out, id_out) bind(C, name='rb2_nearest_electron')
+      import :: c_int, c_double
+      real(c_double), intent(out) :: dist_out(*)
+      integer(c_int), intent(out) :: id_out(*)          ! 0-based index of the nearest other electron, -1: none
+    end function
+    ! multi-GPU (one process per GPU): export / gather / attach the exchange blocks, see INTEGRATION.md section 4
+    integer(c_int) function rb2_p2p_export(n_max, handle_out) bind(C, name='rb2_p2p_export')
+      import :: c_int, c_char
+      integer(c_int), value :: n_max
+      character(kind=c_char), intent(out) :: handle_out(64)
+    end function
+    integer(c_int) function rb2_p2p_attach(world, rank, handles) bind(C, name='rb2_p2p_attach')
+      import :: c_int, c_char
+      integer(c_int), value :: world, rank
+      character(kind=c_char), intent(in) :: handles(64, *)   ! handles(:, r+1) = what rank r exported
+    end function
+    integer(c_int) function rb2_p2p_detach() bind(C, name='rb2_p2p_detach')
+      import :: c_int
+    end function
     function rb2_last_error_string() bind(C, name='rb2_last_error_string') result(p)
       import :: c_ptr
       type(c_ptr) :: p
@@ -331,6 +350,17 @@ contains
     call Check(rb2_field_batch(1_c_int, p, f), 'rb2_field_batch')
     field = f(:, 1)
   end function B200_Calc_Field_at
+
+  ! The sweep of Sample_Elec_Position (mod_pair.F90:990-1011); the caller keeps its file writer (:1014-1035).
+  subroutine B200_Sample_Elec_Nearest()
+    integer(c_int), allocatable :: id0(:)
+    allocate(id0(max(nrPart, 1)))
+    particles_nearest_dist = 1000.0d0
+    if (nrPart > 0) then
+      call Check(rb2_nearest_electron(particles_nearest_dist, id0), 'rb2_nearest_electron')
+      where (id0(1:nrPart) >= 0) particles_nearest_id(1:nrPart) = id0(1:nrPart) + 1
+    end if
+  end subroutine B200_Sample_Elec_Nearest
 
   subroutine B200_Particles_To_Device()
     call Check(rb2_field_window_open(), 'rb2_field_window_open')
