@@ -27,6 +27,7 @@ module mod_b200_bridge
   public :: B200_Update_Position, B200_Calculate_Acceleration_Particles
   public :: B200_Calc_Field_at, B200_Calc_Field_at_Batch
   public :: B200_Particles_To_Device, B200_Release_Device_Particles
+  public :: B200_Init_Collisions, B200_Do_Electron_Atom_Collisions
 
   integer, parameter :: RB2_GEOM_PLANAR = 1, RB2_GEOM_TIP = 2
   integer, parameter :: RB2_PLANES_MAX = 10
@@ -63,6 +64,29 @@ module mod_b200_bridge
     real(c_double) :: init_std, target_rate, std_gain, std_min, std_max
   end type rb2_mh_config
 
+  ! collisions (COLLISION_MODE 1, 2): struct rb2_collision_config / _result / records
+  type, bind(C) :: rb2_collision_config
+    integer(c_int) :: collision_mode, ion_life_time
+    real(c_double) :: n_d, cyl_radius
+    integer(c_int) :: n_tot, n_ion
+    type(c_ptr)    :: tot_energy, tot_data, ion_energy, ion_data
+  end type rb2_collision_config
+
+  type, bind(C) :: rb2_recomb_record
+    integer(c_int) :: step, elec_slot, ion_slot, elec_emit, ion_life
+    integer(c_int) :: elec_sec, elec_id, ion_emit, ion_sec, ion_id
+    real(c_double) :: ion_pos(3), elec_pos(3)
+    real(c_double) :: elec_speed, dist, recom_rad, t
+  end type rb2_recomb_record
+
+  type, bind(C) :: rb2_ionization_record
+    integer(c_int) :: step, in_slot, new_id, ion_id, elec_emit, pad
+    real(c_double) :: pos(3)
+    real(c_double) :: in_speed, out_speed, new_speed
+    real(c_double) :: new_vel(3), ejec_pos(3), ejec_vel(3), ion_pos(3)
+    real(c_double) :: E1, collE, ejecE
+  end type rb2_ionization_record
+
   type, bind(C) :: rb2_step_result
     real(c_double) :: ramo_current(4)
     real(c_double) :: avg_part_vel(3), avg_elec_vel(3), avg_ion_vel(3)
@@ -70,6 +94,38 @@ module mod_b200_bridge
     type(rb2_counts) :: counts
     real(c_float)  :: accel_ms, step_ms
   end type rb2_step_result
+
+  type, bind(C) :: rb2_collision_result
+    integer(c_int) :: nrCollisions, nrIonizations, nrRecombinations, nrIonsExpired
+    integer(c_int) :: nrPart_remove_recom, nrElec_remove_recom, nrIon_remove_recom, n_candidates
+    type(rb2_counts) :: counts
+    real(c_float)  :: ms
+  end type rb2_collision_result
+
+  interface
+    integer(c_int) function rb2_collisions_init(cfg) bind(C, name='rb2_collisions_init')
+      import :: c_int, rb2_collision_config
+      type(rb2_collision_config), intent(in) :: cfg
+    end function
+    integer(c_int) function rb2_do_collisions(step, seed, res) bind(C, name='rb2_do_collisions')
+      import :: c_int, c_long_long, rb2_collision_result
+      integer(c_int), value :: step
+      integer(c_long_long), value :: seed
+      type(rb2_collision_result), intent(out) :: res
+    end function
+    integer(c_int) function rb2_get_recombination_records(max_records, recs, n_out) bind(C, name='rb2_get_recombination_records')
+      import :: c_int, rb2_recomb_record
+      integer(c_int), value :: max_records
+      type(rb2_recomb_record), intent(out) :: recs(*)
+      integer(c_int), intent(out) :: n_out
+    end function
+    integer(c_int) function rb2_get_ionization_records(max_records, recs, n_out) bind(C, name='rb2_get_ionization_records')
+      import :: c_int, rb2_ionization_record
+      integer(c_int), value :: max_records
+      type(rb2_ionization_record), intent(out) :: recs(*)
+      integer(c_int), intent(out) :: n_out
+    end function
+  end interface
 
   interface
     integer(c_int) function rb2_init(cfg) bind(C, name='rb2_init')
@@ -369,5 +425,69 @@ contains
   subroutine B200_Release_Device_Particles()
     call Check(rb2_field_window_close(), 'rb2_field_window_close')
   end subroutine B200_Release_Device_Particles
+
+  !-----------------------------------------------------------------------------
+  ! Collisions (mod_collisions.F90).  B200_Init_Collisions is called once after Read_Cross_Section (main.F90:397);
+  ! B200_Do_Electron_Atom_Collisions replaces the body of Do_Electron_Atom_Collisions (mod_collisions.F90:30-76)
+  ! for collision_mode 1 and 2 and feeds the reference's own writers.
+  subroutine B200_Init_Collisions(cross_tot_energy, cross_tot_data, cross_ion_energy, cross_ion_data)
+    double precision, dimension(:), contiguous, target, intent(in) :: cross_tot_energy, cross_tot_data
+    double precision, dimension(:), contiguous, target, intent(in) :: cross_ion_energy, cross_ion_data
+    type(rb2_collision_config) :: c
+    c%collision_mode = collision_mode
+    c%ion_life_time  = ion_life_time
+    c%n_d            = n_d
+    c%cyl_radius     = emitters_dim(1, 1)
+    c%n_tot = size(cross_tot_energy); c%n_ion = size(cross_ion_energy)
+    c%tot_energy = c_loc(cross_tot_energy); c%tot_data = c_loc(cross_tot_data)
+    c%ion_energy = c_loc(cross_ion_energy); c%ion_data = c_loc(cross_ion_data)
+    call Check(rb2_collisions_init(c), 'rb2_collisions_init')
+  end subroutine B200_Init_Collisions
+
+  subroutine B200_Do_Electron_Atom_Collisions(step, nrCollisions, nrIonizations, nrRecombinations)
+    integer, intent(in)  :: step
+    integer, intent(out) :: nrCollisions, nrIonizations, nrRecombinations
+    type(rb2_collision_result) :: r
+    type(rb2_recomb_record), allocatable :: rec(:)
+    type(rb2_ionization_record), allocatable :: ion(:)
+    double precision :: rnd
+    integer(c_long_long) :: seed
+    integer :: k, n, IFAIL
+    call random_number(rnd)                       ! the device generator is keyed by one host draw per step
+    seed = int(rnd*9.0d18, c_long_long)
+    call Check(rb2_do_collisions(step, seed, r), 'rb2_do_collisions')
+    nrCollisions = r%nrCollisions; nrIonizations = r%nrIonizations; nrRecombinations = r%nrRecombinations
+    nrPart = r%counts%nrPart;  nrElec = r%counts%nrElec;  nrIon = r%counts%nrIon;  nrAtom = r%counts%nrAtom
+    nrID = r%counts%nrID
+    nrPart_remove = r%counts%nrPart_remove;  nrElec_remove = r%counts%nrElec_remove
+    nrIon_remove = r%counts%nrIon_remove;    nrAtom_remove = r%counts%nrAtom_remove
+    nrPart_remove_top = r%counts%nrPart_remove_top;  nrIon_remove_top = r%counts%nrIon_remove_top
+    nrPart_remove_recom = r%nrPart_remove_recom
+    nrElec_remove_recom = r%nrElec_remove_recom
+    nrIon_remove_recom  = r%nrIon_remove_recom
+    if (nrIonizations > 0) then
+      allocate(ion(nrIonizations))
+      call Check(rb2_get_ionization_records(nrIonizations, ion, n), 'rb2_get_ionization_records')
+      do k = 1, min(n, nrIonizations)             ! Write_Ionization_Data, mod_pair.F90:930-935
+        write(unit=ud_ionization_data) ion(k)%step, ion(k)%pos, ion(k)%in_speed, ion(k)%out_speed, ion(k)%new_speed, &
+          & 0.0d0, 0.0d0, ion(k)%in_slot + 1, ion(k)%new_id, ion(k)%ion_id, ion(k)%elec_emit
+      end do
+    end if
+    if (nrRecombinations > 0) then
+      allocate(rec(nrRecombinations))
+      call Check(rb2_get_recombination_records(nrRecombinations, rec, n), 'rb2_get_recombination_records')
+      do k = 1, min(n, nrRecombinations)
+        ! what the two Mark_Particles_Remove(.., remove_recom) calls write (mod_pair.F90:265-272, :308-315)
+        write(unit=ud_density_absorb_recom) rec(k)%ion_pos, rec(k)%ion_emit, rec(k)%ion_sec, rec(k)%ion_id, species_ion, &
+          & cur_time/time_step*time_scale
+        write(unit=ud_density_absorb_recom) rec(k)%elec_pos, rec(k)%elec_emit, rec(k)%elec_sec, rec(k)%elec_id, species_elec, &
+          & cur_time/time_step*time_scale
+        ! Write_Recombination_Data, mod_pair.F90:919-926
+        write(unit=ud_recombination_data) rec(k)%step, rec(k)%ion_pos, rec(k)%elec_speed, rec(k)%dist, rec(k)%recom_rad, &
+          & rec(k)%elec_slot + 1, rec(k)%ion_slot + 1, rec(k)%elec_emit, rec(k)%ion_life
+      end do
+    end if
+    write(ud_coll, '(i6,tr2,i6,tr2,i6,tr2,i6)', iostat=IFAIL) step, nrCollisions, nrIonizations, nrRecombinations
+  end subroutine B200_Do_Electron_Atom_Collisions
 
 end module mod_b200_bridge

@@ -236,6 +236,67 @@ typedef struct rb2_mh_config {
 int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed,
                   double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 
+/* ---- electron / N2 collisions (collision_mode 1 and 2) -------------------------
+ * Do_Electron_Atom_Collisions (src/mod_collisions.F90:30-76, called from src/main.F90:202 through
+ * Do_Collisions, src/mod_verlet.F90:164-170), one-time-step variants:
+ *   continuous ionisation  Do_Continuous_Ionization_ots   src/mod_collisions.F90:558-705
+ *   discrete recombination Do_Discrete_Recombination_ots  src/mod_collisions.F90:86-245
+ *                          (O(nrIon x nrElec) sweep with the quartic of src/mod_polynomialroots.F90)
+ * The per-electron collision data of Update_Collision_Data (:2103-2134) is recomputed from the velocities inside
+ * the kernels; rb2_collision_data returns it for inspection.  Discrete ionisation (modes 3, 4: N2 atoms as
+ * particles) is not on the device path: rb2_collisions_init refuses those modes. */
+typedef struct rb2_collision_config {
+    int    collision_mode;    /* 1 continuous ionisation, 2 = 1 + discrete recombination */
+    int    ion_life_time;     /* time steps, src/mod_global.F90:210 */
+    double n_d;               /* N2 number density P/(k_b T), src/main.F90:382-383 */
+    double cyl_radius;        /* emitters_dim(1,1): collisions only inside this radius (:594) */
+    int    n_tot, n_ion;      /* rows of N2-tot-cross.txt / N2-ion-cross.txt (Read_Cross_Section, :1909-1983) */
+    const double *tot_energy, *tot_data, *ion_energy, *ion_data;  /* eV, 1e-20 m^2 */
+} rb2_collision_config;
+
+/* One recombination: the arguments of Write_Recombination_Data (src/mod_pair.F90:919-926) plus what the two
+ * Mark_Particles_Remove(.., remove_recom) calls write to density_absorb_recom.bin (:265-272, :308-315).
+ * Slots are 0-based; ion_life = step - particles_step(ion). */
+typedef struct rb2_recomb_record {
+    int    step, elec_slot, ion_slot, elec_emit, ion_life;
+    int    elec_sec, elec_id, ion_emit, ion_sec, ion_id;
+    double ion_pos[3], elec_pos[3];
+    double elec_speed, dist, recom_rad, t;
+} rb2_recomb_record;
+
+/* One ionisation: the arguments of Write_Ionization_Data (src/mod_pair.F90:930-935) plus the state of the three
+ * particles involved.  in_slot is 0-based; new_id / ion_id are the particle ids given to the ejected electron and
+ * the ion (-1 when the store was full and the particle was dropped). */
+typedef struct rb2_ionization_record {
+    int    step, in_slot, new_id, ion_id, elec_emit, pad;
+    double pos[3];
+    double in_speed, out_speed, new_speed;
+    double new_vel[3], ejec_pos[3], ejec_vel[3], ion_pos[3];
+    double E1, collE, ejecE;
+} rb2_ionization_record;
+
+typedef struct rb2_collision_result {
+    int nrCollisions, nrIonizations, nrRecombinations;   /* the three columns of collisions.dt (:74-75) */
+    int nrIonsExpired;                                    /* ions removed for their age (:121-124) */
+    int nrPart_remove_recom, nrElec_remove_recom, nrIon_remove_recom; /* since the last Remove_Particles */
+    int n_candidates;         /* (ion, electron) pairs that reached the quartic test (diagnostic) */
+    rb2_counts counts;
+    float ms;                 /* device time of the call, CUDA events */
+} rb2_collision_result;
+
+int rb2_collisions_init(const rb2_collision_config *cfg);
+/* Update_Collision_Data_All_ots (:2155-2169).  out (may be NULL) receives 5 doubles per particle slot:
+ * cur_energy, ion_cross_sec, ion_cross_rad, recom_cross_rad, tot_cross_sec (zeros for non-electrons). */
+int rb2_collision_data(double *out);
+int rb2_continuous_ionization(int step, unsigned long long seed, rb2_collision_result *out);
+int rb2_discrete_recombination(int step, rb2_collision_result *out);
+/* Do_Electron_Atom_Collisions(step): ionisation, then (mode 2) recombination; nrCollisions includes the
+ * recombinations like the reference's collisions.dt line. */
+int rb2_do_collisions(int step, unsigned long long seed, rb2_collision_result *out);
+/* Records of the last call, in the order the serial reference writes them (ascending ion / electron slot). */
+int rb2_get_recombination_records(int max_records, rb2_recomb_record *out, int *n_out);
+int rb2_get_ionization_records(int max_records, rb2_ionization_record *out, int *n_out);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* Independent-DFMA-chain micro-benchmark: measured FP64 peak of this GPU in TFLOP/s
  * (FMA = 2 flops) over about `ms_target` milliseconds. */

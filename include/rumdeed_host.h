@@ -51,6 +51,8 @@ typedef struct rh_state {
     double t_dev_step, t_dev_accel;               /* device time (CUDA events) of rb2_step and of its pair kernels, summed */
     double t_emission, t_md_step, t_remove, t_io; /* wall-clock seconds spent so far in: ptr_Do_Emission, rb2_step,
                                                      rb2_remove_marked, the text/binary writers */
+    long long nrIonizations_total, nrRecombinations_total; /* collisions (COLLISION_MODE 1, 2) */
+    double t_collisions, t_dev_collisions;        /* wall clock / device time of Do_Collisions, summed */
 } rh_state;
 
 void *rh_create_from_dir(const char *dir, int write_files, unsigned long long seed, int max_particles);

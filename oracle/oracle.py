@@ -88,7 +88,8 @@ def build(force: bool = False, march: str | None = None, out_dir: str | None = N
                          and os.path.exists(os.path.join(out, "liboracle_fast.so")))
     if not need:
         src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in (
-            "rumdeed_oracle.c", "rumdeed_oracle.h", "rumdeed_oracle_emission.c", "rumdeed_oracle_emission.h"))
+            "rumdeed_oracle.c", "rumdeed_oracle.h", "rumdeed_oracle_emission.c", "rumdeed_oracle_emission.h",
+            "rumdeed_oracle_collisions.c", "rumdeed_oracle_collisions.h"))
         need = src_m > min(os.path.getmtime(os.path.join(out, f)) for f in ("liboracle.so", "liboracle_fast.so"))
     if need:
         cmd = ["make", "-C", _HERE, "-B", f"OUT={out}"]

@@ -91,6 +91,37 @@ class MhConfig(C.Structure):
                 ("std_min", C.c_double), ("std_max", C.c_double)]
 
 
+class CollisionConfig(C.Structure):
+    """rb2_collision_config."""
+    _fields_ = [("collision_mode", C.c_int), ("ion_life_time", C.c_int), ("n_d", C.c_double), ("cyl_radius", C.c_double),
+                ("n_tot", C.c_int), ("n_ion", C.c_int),
+                ("tot_energy", C.POINTER(C.c_double)), ("tot_data", C.POINTER(C.c_double)),
+                ("ion_energy", C.POINTER(C.c_double)), ("ion_data", C.POINTER(C.c_double))]
+
+
+class RecombRecord(C.Structure):
+    """rb2_recomb_record."""
+    _fields_ = [(n, C.c_int) for n in ("step", "elec_slot", "ion_slot", "elec_emit", "ion_life",
+                                      "elec_sec", "elec_id", "ion_emit", "ion_sec", "ion_id")] + \
+               [("ion_pos", C.c_double * 3), ("elec_pos", C.c_double * 3),
+                ("elec_speed", C.c_double), ("dist", C.c_double), ("recom_rad", C.c_double), ("t", C.c_double)]
+
+
+class IonizationRecord(C.Structure):
+    """rb2_ionization_record."""
+    _fields_ = [(n, C.c_int) for n in ("step", "in_slot", "new_id", "ion_id", "elec_emit", "pad")] + \
+               [("pos", C.c_double * 3), ("in_speed", C.c_double), ("out_speed", C.c_double), ("new_speed", C.c_double),
+                ("new_vel", C.c_double * 3), ("ejec_pos", C.c_double * 3), ("ejec_vel", C.c_double * 3),
+                ("ion_pos", C.c_double * 3), ("E1", C.c_double), ("collE", C.c_double), ("ejecE", C.c_double)]
+
+
+class CollisionResult(C.Structure):
+    """rb2_collision_result."""
+    _fields_ = [(n, C.c_int) for n in ("nrCollisions", "nrIonizations", "nrRecombinations", "nrIonsExpired",
+                                      "nrPart_remove_recom", "nrElec_remove_recom", "nrIon_remove_recom",
+                                      "n_candidates")] + [("counts", Counts), ("ms", C.c_float)]
+
+
 P2P_HANDLE_BYTES = 64
 
 _PD = C.POINTER(C.c_double)
@@ -105,6 +136,8 @@ EXPORTS = (
     "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
+    "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
+    "rb2_do_collisions", "rb2_get_recombination_records", "rb2_get_ionization_records",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
 )
 
@@ -149,6 +182,13 @@ def load_library(path: str | None = None):
     lib.rb2_p2p_export.argtypes = [C.c_int, C.c_void_p]
     lib.rb2_nearest_electron.argtypes = [_PD, _PI]
     lib.rb2_p2p_attach.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    lib.rb2_collisions_init.argtypes = [C.POINTER(CollisionConfig)]
+    lib.rb2_collision_data.argtypes = [_PD]
+    lib.rb2_continuous_ionization.argtypes = [C.c_int, C.c_ulonglong, C.POINTER(CollisionResult)]
+    lib.rb2_discrete_recombination.argtypes = [C.c_int, C.POINTER(CollisionResult)]
+    lib.rb2_do_collisions.argtypes = [C.c_int, C.c_ulonglong, C.POINTER(CollisionResult)]
+    lib.rb2_get_recombination_records.argtypes = [C.c_int, C.POINTER(RecombRecord), _PI]
+    lib.rb2_get_ionization_records.argtypes = [C.c_int, C.POINTER(IonizationRecord), _PI]
     lib.rb2_fp64_peak.argtypes = [C.c_double, _PD, C.POINTER(C.c_float)]
     lib.rb2_launch_count.argtypes = [C.POINTER(C.c_longlong), C.c_int]
     lib.rb2_last_accel_info.argtypes = [C.POINTER(C.c_float)] + [_PI] * 4
@@ -454,6 +494,55 @@ class HotPath:
         if n > 0:
             self._check(self.lib.rb2_nearest_electron(_d(dist), _i(idx)))
         return dist, idx
+
+    # -- mod_collisions ------------------------------------------------------------------------------
+    def Init_Collisions(self, collision_mode, tot_energy, tot_data, ion_energy, ion_data, n_d, cyl_radius,
+                        ion_life_time=100000000):
+        """Read_Cross_Section + the namelist values Do_Electron_Atom_Collisions reads (src/mod_collisions.F90)."""
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (tot_energy, tot_data, ion_energy, ion_data)]
+        c = CollisionConfig()
+        c.collision_mode, c.ion_life_time, c.n_d, c.cyl_radius = int(collision_mode), int(ion_life_time), n_d, cyl_radius
+        c.n_tot, c.n_ion = len(keep[0]), len(keep[2])
+        c.tot_energy, c.tot_data, c.ion_energy, c.ion_data = (_d(a) for a in keep)
+        self._check(self.lib.rb2_collisions_init(C.byref(c)))
+
+    def Update_Collision_Data_All(self):
+        """src/mod_collisions.F90:2155: (n, 5) = energy, ion_cross_sec, ion_cross_rad, recom_cross_rad, tot_cross_sec."""
+        n = self.counts().nrPart
+        out = np.zeros((n, 5))
+        if n:
+            self._check(self.lib.rb2_collision_data(_d(out)))
+        return out
+
+    def Do_Continuous_Ionization(self, step, seed) -> CollisionResult:
+        r = CollisionResult()
+        self._check(self.lib.rb2_continuous_ionization(int(step), int(seed), C.byref(r)))
+        return r
+
+    def Do_Discrete_Recombination(self, step) -> CollisionResult:
+        r = CollisionResult()
+        self._check(self.lib.rb2_discrete_recombination(int(step), C.byref(r)))
+        return r
+
+    def Do_Electron_Atom_Collisions(self, step, seed) -> CollisionResult:
+        """src/mod_collisions.F90:30."""
+        r = CollisionResult()
+        self._check(self.lib.rb2_do_collisions(int(step), int(seed), C.byref(r)))
+        return r
+
+    def recombination_records(self):
+        n = C.c_int(0)
+        self._check(self.lib.rb2_get_recombination_records(0, None, C.byref(n)))
+        buf = (RecombRecord * max(n.value, 1))()
+        self._check(self.lib.rb2_get_recombination_records(n.value, buf, C.byref(n)))
+        return [buf[k] for k in range(n.value)]
+
+    def ionization_records(self):
+        n = C.c_int(0)
+        self._check(self.lib.rb2_get_ionization_records(0, None, C.byref(n)))
+        buf = (IonizationRecord * max(n.value, 1))()
+        self._check(self.lib.rb2_get_ionization_records(n.value, buf, C.byref(n)))
+        return [buf[k] for k in range(n.value)]
 
     def p2p_export(self, n_max) -> bytes:
         """This process's exchange block (partial pair sums + flags) as a CUDA IPC handle."""

@@ -196,6 +196,8 @@ int finish_position(Rb2Ctx &c, bool after_velocity_update)
 
 }  // namespace
 
+int rb2_fetch_counters(Rb2Ctx &c) { return fetch_counters(c); }
+
 int rb2_ensure_stage(Rb2Ctx &c, size_t n_doubles, size_t n_ints)
 {
     if (n_doubles > c.stage_d_cap) {
@@ -294,6 +296,7 @@ int rb2_finalize(void)
     if (!c.init) return RB2_OK;
     cudaStreamSynchronize(c.stream);
     rb2_p2p_release(c);
+    rb2_collisions_release(c);
     free_arrays(c.a);
     free_arrays(c.b);
     cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);

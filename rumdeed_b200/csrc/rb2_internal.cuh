@@ -65,6 +65,7 @@ struct DevCounters {  // cumulative since the last rb2_remove_marked
     int mark_part, mark_elec, mark_ion, mark_atom;
     int top_part, bot_part, top_elec, bot_elec, top_ion, bot_ion;
     int n_events, pad;
+    int recom_part, recom_elec, recom_ion, pad2;  // remove_recom marks (collisions)
 };
 
 struct DevArrays {
@@ -162,6 +163,9 @@ int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra
 int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                          double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez);
+// collisions (rb2_collisions.cu)
+void rb2_collisions_release(Rb2Ctx &ctx);
+int rb2_fetch_counters(Rb2Ctx &ctx);  // device counters -> ctx.counts (rb2_api.cu)
 // nearest-electron sweep (rb2_nearest.cu)
 int rb2_launch_nearest(Rb2Ctx &ctx, double *d_dist, int *d_id);
 // peer-memory exchange (rb2_p2p.cu)

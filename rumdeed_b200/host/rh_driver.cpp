@@ -92,6 +92,7 @@ int Init(Sim &s)
             fclose(f);
         }
     }
+    if (Init_Collisions(s)) return -1;  // src/main.F90:397 (Read_Cross_Section_Data), :164-166
     return 0;
 }
 
@@ -220,6 +221,8 @@ int Step(Sim &s, int step)
     if (s.ud_absorb) fprintf(s.ud_absorb, "%12.4E  %8d  %8d  %8d  %8d\n", s.cur_time, step, s.counts.nrPart_remove, s.counts.nrElec_remove, s.counts.nrIon_remove);
     if (s.ud_absorb_top) fprintf(s.ud_absorb_top, "%12.4E  %8d  %8d  %8d  %8d  %8d\n", s.cur_time, step, s.counts.nrPart_remove_top, s.counts.nrElec_remove_top, s.counts.nrIon_remove_top, s.counts.nrElec_remove_top);
     if (s.ud_absorb_bot) fprintf(s.ud_absorb_bot, "%12.4E  %8d  %8d  %8d  %8d\n", s.cur_time, step, s.counts.nrPart_remove_bot, s.counts.nrElec_remove_bot, s.counts.nrIon_remove_bot);
+    if (s.ud_absorb_recom) fprintf(s.ud_absorb_recom, "%12.4E  %8d  %8d  %8d  %8d\n", s.cur_time, step, s.recom_counts[0], s.recom_counts[1], s.recom_counts[2]);
+    s.recom_counts[0] = s.recom_counts[1] = s.recom_counts[2] = 0;
     rb2_counts k{};
     const auto t4 = clk::now();
     if (s.check(rb2_remove_marked(step, &k), "rb2_remove_marked")) return -1;
@@ -227,6 +230,9 @@ int Step(Sim &s, int step)
     s.t_remove += secs(t4, t5);
     s.t_io += secs(t1, t2) + secs(t3, t4);
     s.counts = k;
+    // Do_Collisions(i), src/main.F90:202
+    if (Do_Collisions(s, step)) return -1;
+    s.t_collisions += secs(t5, clk::now());
     return 0;
 }
 
@@ -235,7 +241,8 @@ int Clean_up(Sim &s)
 {
     if (s.ptr.ptr_Clean_Up) s.ptr.ptr_Clean_Up(s);
     FILE **fs[] = {&s.ud_ramo, &s.ud_emit, &s.ud_absorb, &s.ud_absorb_top, &s.ud_absorb_bot, &s.ud_field, &s.ud_integrand, &s.ud_volt,
-                   &s.ud_density_emit, &s.ud_density_absorb_top, &s.ud_density_absorb_bot, &s.ud_pos};
+                   &s.ud_density_emit, &s.ud_density_absorb_top, &s.ud_density_absorb_bot, &s.ud_pos, &s.ud_coll, &s.ud_ionization_data,
+                   &s.ud_recombination_data, &s.ud_density_absorb_recom, &s.ud_absorb_recom};
     for (FILE **f : fs) if (*f) { fclose(*f); *f = nullptr; }
     for (int k = 0; k < RB2_PLANES_MAX; ++k) if (s.planes_ud[k]) { fclose(s.planes_ud[k]); s.planes_ud[k] = nullptr; }
     if (s.write_files) {  // Write_Life_Time, src/mod_pair.F90:776-786

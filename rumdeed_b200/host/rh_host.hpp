@@ -62,7 +62,7 @@ struct Globals {
     int steps = 0, nrEmit = 1, emission_mode = 0;
     bool image_charge = true;
     int N_ic_max = 0;
-    int collision_mode = 0;
+    int collision_mode = 0, collision_delay = 0, ion_life_time = 100000000;  // src/mod_global.F90:207-210
     double T_temp = 293.15, P_abs = 1.0;
     double emitters_pos[3] = {0, 0, 0}, emitters_dim[3] = {0, 0, 0};
     int emitters_type = 0, emitters_delay = 0;
@@ -147,6 +147,11 @@ struct Sim {
     FILE *ud_ramo = nullptr, *ud_emit = nullptr, *ud_absorb = nullptr, *ud_absorb_top = nullptr, *ud_absorb_bot = nullptr;
     FILE *ud_field = nullptr, *ud_integrand = nullptr, *ud_volt = nullptr, *ud_density_emit = nullptr;
     FILE *ud_pos = nullptr;  // out/position.bin (Write_Position)
+    FILE *ud_coll = nullptr, *ud_ionization_data = nullptr, *ud_recombination_data = nullptr, *ud_density_absorb_recom = nullptr,
+         *ud_absorb_recom = nullptr;  // collision outputs (src/main.F90:603-641, :719)
+    long long nrIonizations_total = 0, nrRecombinations_total = 0;
+    int recom_counts[3] = {0, 0, 0};  // nrPart/nrElec/nrIon_remove_recom since the last Remove_Particles
+    double t_collisions = 0.0, t_dev_collisions = 0.0;
     FILE *ud_density_absorb_top = nullptr, *ud_density_absorb_bot = nullptr, *planes_ud[RB2_PLANES_MAX] = {nullptr};
     std::vector<double> scratch_pts, scratch_fld, scratch_ez;
 
@@ -178,6 +183,10 @@ int Init_Field_Emission_v2(Sim &s);
 int Init_Emission_Tip(Sim &s);
 int Init_Field_Thermo_Emission(Sim &s);
 int Init_Photo_Emission(Sim &s);
+
+// ---- collisions (src/mod_collisions.F90; rh_collisions.cpp) --------------------------------------------
+int Init_Collisions(Sim &s);          // Read_Cross_Section + rb2_collisions_init + output files
+int Do_Collisions(Sim &s, int step);  // src/mod_verlet.F90:164-170
 
 // FN helpers (src/mod_field_emission_v2.F90:515-625)
 double v_y(const Sim &s, double F, double w_theta);

@@ -137,6 +137,8 @@ int Read_Input_Variables(const std::string &path, Globals &g, std::string &err)
     logical("IMAGE_CHARGE", g.image_charge);
     integer("N_IC_MAX", g.N_ic_max);
     integer("COLLISION_MODE", g.collision_mode);
+    integer("COLLISION_DELAY", g.collision_delay);
+    integer("ION_LIFE_TIME", g.ion_life_time);
     dbl("T_TEMP", g.T_temp);
     dbl("P_ABS", g.P_abs);
     vec("EMITTERS_DIM", g.emitters_dim, 3);

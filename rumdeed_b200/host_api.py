@@ -49,6 +49,8 @@ class State(C.Structure):
         ("avg_elec_vel", C.c_double * 3), ("accel_ms", C.c_float), ("step_ms", C.c_float),
         ("t_dev_step", C.c_double), ("t_dev_accel", C.c_double),
         ("t_emission", C.c_double), ("t_md_step", C.c_double), ("t_remove", C.c_double), ("t_io", C.c_double),
+        ("nrIonizations_total", C.c_longlong), ("nrRecombinations_total", C.c_longlong),
+        ("t_collisions", C.c_double), ("t_dev_collisions", C.c_double),
     ]
 
 

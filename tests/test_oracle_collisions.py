@@ -1,0 +1,240 @@
+"""Pins the collision part of the CPU oracle (oracle/rumdeed_oracle_collisions.c).
+
+Golden values: the reference's own Test_Collision_Math (src/mod_tests.F90:1742-1786).  The quartic solver
+(src/mod_polynomialroots.F90) has no vector in the reference: it is checked against numpy.roots and against
+polynomials built from known roots; the recombination test is checked against a brute-force time scan.
+"""
+import numpy as np
+import pytest
+
+from oracle.collisions import Collisions
+
+Q_0, M_0 = 1.602176634e-19, 9.1093837015e-31
+
+
+def synthetic_tables():
+    """Smooth stand-ins for N2-tot-cross.txt / N2-ion-cross.txt (energy eV, cross section 1e-20 m^2)."""
+    et = np.concatenate([np.arange(0.1, 1.0, 0.1), np.arange(1.0, 30.0, 1.0), np.arange(30.0, 1001.0, 10.0)])
+    tot = 5.0 + 20.0 * np.exp(-((et - 2.3) / 0.8) ** 2) + 8.0 * np.exp(-et / 80.0)
+    ei = np.concatenate([[0.1], np.arange(16.0, 30.0, 0.5), np.arange(30.0, 1001.0, 10.0)])
+    ion = np.where(ei < 15.6, 0.0, 2.6 * (1 - 15.581 / np.maximum(ei, 15.6)) * np.exp(-ei / 900.0) * (1 + np.log(np.maximum(ei, 15.6) / 15.581)) / 2.2)
+    return et, tot, ei, ion
+
+
+@pytest.fixture(scope="module")
+def col():
+    return Collisions(tables=synthetic_tables())
+
+
+def close(a, b, rel=1e-12):
+    return abs(a - b) <= rel * max(abs(a), abs(b))
+
+
+def test_reference_collision_math_vectors(col):
+    # src/mod_tests.F90:1750-1761
+    assert close(col.normal_dist(0.0, 1.0, 0.0), 0.3989422804014327)
+    assert close(col.normal_dist(5.0, 25.0, 12.5), 0.015255512618420964)
+    assert close(col.folded_normal_dist(5.0, 25.0, 30.0), 0.015667927606195526)
+    assert close(col.folded_normal_dist(12.0, 40.0, 77.0),
+                 col.normal_dist(12.0, 40.0, 77.0) + col.normal_dist(-12.0, 40.0, 77.0))
+    # :1766-1773 the envelope bounds the distribution on [0, 180]
+    fmax = col.folded_normal_max(5.0, 25.0)
+    assert all(col.folded_normal_dist(5.0, 25.0, float(k)) <= fmax * (1 + 1e-12) for k in range(181))
+    # :1777-1782 Kramers cross section
+    assert close(col.kramers(10.0) * 1e26, 3.995353707087291, 1e-9)
+    assert close(col.kramers(100.0) * 1e28, 8.842728751351863, 1e-9)
+    assert col.kramers(10.0) > col.kramers(100.0)
+
+
+def test_constants(col):
+    # src/mod_global.F90:50-68: Rydberg energy 13.6057 eV, Z_eff = sqrt(N_bind N_n^2 / Ryd)
+    assert abs(col.k.Ryd - 13.605693) < 1e-5
+    assert close(col.k.Z_eff ** 2, 15.581 * 4.0 / col.k.Ryd)
+
+
+def test_cross_section_lookup(col):
+    et, tot, ei, ion = synthetic_tables()
+    # fitted branches, src/mod_collisions.F90:1991-1993, :2020-2021
+    for e in (70.5, 200.0, 3000.0):
+        assert close(col.cross_tot(e), (7.98 * np.exp(-0.005845 * e) + 4.628 * np.exp(-0.0007864 * e)) * 1e-20)
+    for e in (180.5, 1000.0, 3000.0):
+        assert close(col.cross_ion(e), (2.251 * np.exp(-0.00311 * e) + 1.04 * np.exp(-0.0003378 * e)) * 1e-20)
+    # tabulated branch = linear interpolation, clamped at both ends
+    for e in (0.05, 0.1, 0.33, 2.5, 17.2, 69.9, 70.0):
+        assert close(col.cross_tot(e), np.interp(e, et, tot) * 1e-20, 1e-10)
+    for e in (0.01, 15.0, 16.25, 100.0, 180.0):
+        assert close(col.cross_ion(e) + 1e-30, np.interp(e, ei, ion) * 1e-20 + 1e-30, 1e-10)
+    assert close(col.cross_tot(5000.0), tot[-1] * 1e-20, 1e-10)  # clamp above the table (> 3000 eV)
+
+
+def test_update_collision_data(col):
+    v = np.array([[0.0, 0.0, 2.0e6], [1.0e6, -2.0e6, 3.0e6], [0.0, 3.0e7, 3.0e7]])
+    out = col.collision_data(v)
+    for r in range(3):
+        e = 0.5 * M_0 * np.dot(v[r], v[r]) / Q_0
+        e_cap = min(e, 5000.0)
+        assert close(out[r, 0], e, 1e-14)                       # energy stored uncapped (:2125)
+        assert close(out[r, 1], col.cross_ion(e_cap), 1e-13)    # cross sections use the 5 keV cap (:2111-2115)
+        assert close(out[r, 2], np.sqrt(out[r, 1] / np.pi), 1e-14)
+        assert close(out[r, 3], np.sqrt(col.kramers(e) / np.pi), 1e-13)
+        assert close(out[r, 4], col.cross_tot(e_cap), 1e-13)
+
+
+def _match_roots(got, want, tol):
+    got, want = list(got), list(want)
+    for w in want:
+        k = int(np.argmin([abs(g - w) for g in got]))
+        assert abs(got[k] - w) <= tol * max(1.0, abs(w)), (got, want)
+        got.pop(k)
+
+
+def test_quartic_solver_against_known_roots(col):
+    rng = np.random.default_rng(7)
+    seen = set()
+    for trial in range(400):
+        kind = trial % 4
+        if kind == 0:    # four real roots
+            roots = list(rng.uniform(-3, 3, 4))
+        elif kind == 1:  # two real + complex pair
+            re, im = rng.uniform(-2, 2), rng.uniform(0.2, 2)
+            roots = list(rng.uniform(-3, 3, 2)) + [complex(re, im), complex(re, -im)]
+        elif kind == 2:  # two complex pairs
+            roots = []
+            for _ in range(2):
+                re, im = rng.uniform(-2, 2), rng.uniform(0.2, 2)
+                roots += [complex(re, im), complex(re, -im)]
+        else:            # real roots of different magnitudes (the closed form loses the small roots of a quartic
+            #                  with a ratio >~ 1e3 between its roots: 1e-14 relative errors of the resolvent
+            #                  cubic become ~1e-5 absolute ones after the cube and square roots)
+            roots = list(rng.uniform(0.3, 1, 4) * rng.choice([-1, 1], 4) * 10.0 ** rng.integers(-1, 1, 4))
+        lead = rng.uniform(0.5, 2.0)
+        co = np.real(np.poly(roots)) * lead
+        code, z = col.solve_polynomial(*co)
+        seen.add(code)
+        if code == 31:
+            assert np.all(np.diff(z[:3].real) >= 0) and np.all(z[:3].imag == 0)   # sorted, real
+            assert np.isnan(z[3].real)                                            # root4 is never assigned (:561)
+            allr = sorted(np.real(roots))
+            _match_roots(z[:3].real, allr[:3], 1e-6)
+        elif code == 42:
+            real = sorted(r.real for r in roots if abs(np.imag(r)) < 1e-12)
+            assert len(real) == 2
+            _match_roots(sorted(z[:2].real), real, 1e-7)
+            cplx = [r for r in roots if abs(np.imag(r)) >= 1e-12]
+            assert abs(z[2].real - cplx[0].real) < 1e-7 and abs(abs(z[2].imag) - abs(cplx[0].imag)) < 1e-7
+        else:
+            assert code in (44, 23)
+            assert all(abs(np.imag(r)) > 1e-12 for r in roots)
+    assert {31, 42, 44} <= seen
+
+
+def test_lower_order_paths(col):
+    code, z = col.solve_polynomial(0.0, 0.0, 1.0, -3.0, 2.0)   # quadratic z^2 - 3 z + 2
+    assert code == 22 and sorted(z[:2].real) == [1.0, 2.0]
+    code, z = col.solve_polynomial(0.0, 0.0, 1.0, 0.0, 4.0)    # z^2 + 4
+    assert code == 23 and abs(z[0] - 2j) < 1e-15 and abs(z[1] + 2j) < 1e-15
+    code, z = col.solve_polynomial(0.0, 0.0, 0.0, 2.0, -3.0)   # linear
+    assert code == 1 and z[0] == 1.5
+    code, z = col.solve_polynomial(0.0, 0.0, 0.0, 0.0, 1.0)
+    assert code == 0
+
+
+def _brute_force_entry(ion, ep, ev, ea, R, dt, n=200001):
+    t = np.linspace(0.0, dt, n)
+    r = (ep - ion)[None, :] + ev[None, :] * t[:, None] + 0.5 * ea[None, :] * t[:, None] ** 2
+    d = np.linalg.norm(r, axis=1)
+    inside = np.nonzero(d <= R)[0]
+    return (t[inside[0]] if len(inside) else None), d.min()
+
+
+def test_recombination_pair_against_time_scan(col):
+    rng = np.random.default_rng(11)
+    dt = 1.0e-16
+    hits = misses = 0
+    for _ in range(300):
+        ion = rng.uniform(-50e-9, 50e-9, 3)
+        speed = 10.0 ** rng.uniform(5.5, 7.3)
+        dirv = rng.normal(size=3); dirv /= np.linalg.norm(dirv)
+        ev = speed * dirv
+        ea = rng.normal(size=3) * 10.0 ** rng.uniform(17, 20)
+        R = 10.0 ** rng.uniform(-12.5, -10.5)
+        # start somewhere behind the ion along the trajectory, with a lateral offset around R
+        off = rng.normal(size=3); off -= off.dot(dirv) * dirv; off /= np.linalg.norm(off)
+        ep = ion - dirv * speed * dt * rng.uniform(-0.2, 1.3) + off * R * rng.uniform(0.0, 2.0)
+        hit, t, dist = col.recombination_pair(ion, ep, ev, ea, R, dt)
+        t_bf, dmin = _brute_force_entry(ion, ep, ev, ea, R, dt)
+        if abs(dmin - R) < 1e-3 * R:
+            continue  # grazing: the scan resolution decides
+        if np.linalg.norm(ep - ion) <= R:
+            assert hit and t == 0.0
+        elif t_bf is not None and t_bf > 2 * dt / 200000:
+            assert hit, (dmin, R)
+            assert abs(t - t_bf) <= 2 * dt / 200000 + 1e-6 * dt
+            assert abs(dist - R) < 1e-3 * R  # the closed-form root is only good to ~1e-5 here
+        elif t_bf is None:
+            assert not hit
+        hits += hit; misses += (not hit)
+    assert hits > 30 and misses > 30
+
+
+def test_discrete_recombination_serial_claims(col):
+    """Two ions reach for the same electron: the lower-indexed ion takes it, the other takes its next candidate."""
+    dt = 1.0e-16
+    R = 5.0e-11
+    pos = np.array([[0, 0, 100e-9], [0, 0, 100e-9 + 2e-11],      # ions 0, 1
+                    [1e-11, 0, 100e-9], [0, 2e-11, 100e-9],       # electrons 2, 3 (both inside R of both ions)
+                    [0, 0, 300e-9], [0, 0, 500e-9]], float)       # ion 4 (expired), electron 5 far away
+    vel = np.zeros((6, 3)); vel[[2, 3, 5], 2] = 1.0e6
+    acc = np.zeros((6, 3)); acc[[2, 3, 5], 2] = 3.5e20
+    species = np.array([2, 2, 1, 1, 2, 1], np.int32)
+    life = np.array([1000, 1000, -1, -1, 7, -1], np.int32)
+    born = np.array([3, 5, 1, 2, 0, 6], np.int32)
+    emitter = np.array([2, 2, 1, 4, 2, 1], np.int32)
+    rr = np.full(6, R)
+    nr, nexp, ev, mask, reason = col.discrete_recombination(pos, vel, acc, species, np.ones(6, np.int32), life, born,
+                                                            emitter, rr, step=10, dt=dt)
+    assert (nr, nexp) == (2, 1)
+    assert [(e.ion_slot, e.elec_slot) for e in ev] == [(0, 2), (1, 3)]
+    assert [e.ion_life for e in ev] == [7, 5] and [e.elec_emit for e in ev] == [1, 4]
+    assert list(mask) == [0, 0, 0, 0, 0, 1]
+    assert list(reason) == [3, 3, 3, 3, 1, 0]
+    assert ev[0].t == 0.0 and abs(ev[0].dist - 1e-11) < 1e-20
+
+
+def test_continuous_ionization_statistics(col):
+    rng = np.random.default_rng(5)
+    n = 20000
+    n_d = 101325.0 / (1.380649e-23 * 293.15)
+    E = rng.uniform(5.0, 400.0, n)
+    speed = np.sqrt(2 * Q_0 * E / M_0)
+    dirv = rng.normal(size=(n, 3)); dirv /= np.linalg.norm(dirv, axis=1)[:, None]
+    vel = dirv * speed[:, None]
+    pos = np.stack([rng.uniform(-100e-9, 100e-9, n), rng.uniform(-100e-9, 100e-9, n), rng.uniform(1e-9, 999e-9, n)], 1)
+    path = 200e-9                                    # long artificial path so that collisions are frequent
+    prev = pos - dirv * path
+    species = np.ones(n, np.int32); species[::50] = 2
+    mask = np.ones(n, np.int32); mask[7::100] = 0
+    emitter = np.ones(n, np.int32)
+    cyl = 120e-9
+    nr, ncoll, ev, vel2, emit2 = col.continuous_ionization(pos, prev, vel, species, mask, emitter, n_d, cyl, step=3)
+    ok = (species == 1) & (mask == 1) & (np.hypot(pos[:, 0], pos[:, 1]) <= cyl) & (E > col.k.N_bind)
+    cd = col.collision_data(vel)
+    p_coll = np.minimum(path * n_d * cd[:, 4], 1.0) * ok
+    p_ion = p_coll * cd[:, 1] / cd[:, 4]
+    for got, p in ((ncoll, p_coll), (nr, p_ion)):
+        mean, sd = p.sum(), np.sqrt((p * (1 - p)).sum())
+        assert abs(got - mean) < 5 * sd + 1, (got, mean, sd)
+    assert nr == len(ev) and nr > 200
+    for e in ev:
+        i = e.in_slot
+        assert ok[i] and emit2[i] == 2 and e.elec_emit == 1
+        assert close(e.collE + e.ejecE, e.E1 - col.k.N_bind, 1e-12)           # energy conservation
+        assert close(0.5 * M_0 * np.dot(vel2[i], vel2[i]) / Q_0, e.collE, 1e-9) or e.collE < 1e-12
+        assert close(e.new_speed, np.sqrt(2 * Q_0 * e.ejecE / M_0), 1e-9)
+        assert np.all(np.abs(np.array(e.ejec_pos) - pos[i]) <= 1e-9) and np.all(np.abs(np.array(e.ion_pos) - pos[i]) <= 1e-9)
+    untouched = np.ones(n, bool); untouched[[e.in_slot for e in ev]] = False
+    assert np.array_equal(vel2[untouched], vel[untouched]) and np.all(emit2[untouched] == 1)
+    # the colliding electron is scattered forward (folded normal, mu = 5 deg, sigma = 25 deg)
+    ang = [np.degrees(np.arccos(np.clip(np.dot(vel2[e.in_slot], vel[e.in_slot]) /
+                                        (np.linalg.norm(vel2[e.in_slot]) * np.linalg.norm(vel[e.in_slot])), -1, 1))) for e in ev]
+    assert 10.0 < np.mean(ang) < 35.0

@@ -21,6 +21,8 @@ except Exception as ex:
 phase = [l for l in log if "wall clock per phase" in l]
 print(f"{name:28s} rc={rc} steps={steps} wall={e-s:7.2f}s  steps/s={steps/(e-s):8.1f}  I(last quarter)={I:.4e} A  nrElec(end)={nel}")
 print("   ", phase[0] if phase else log[-2:])
+for l in log:
+    if "collisions:" in l: print("   ", l)
 PY
   rm -rf $d
 }
@@ -29,5 +31,6 @@ if [ "$WHICH" = all ] || [ "$WHICH" = batch ]; then run "GPU-Planar-FE MH_BATCH"
 if [ "$WHICH" = all ] || [ "$WHICH" = device ]; then run "GPU-Planar-FE MH_DEVICE"  gpu_planar_fe $SP "MH_DEVICE = .True.,"; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = device ]; then run "Planar-FE 4.7eV MH_DEVICE" planar_fe_4p7 $SP "MH_DEVICE = .True.,"; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = tip ]; then run "Tip-FE MH_BATCH"          tip_fe $ST "MH_BATCH = .True.,"; fi
+if [ "$WHICH" = all ] || [ "$WHICH" = ion ]; then run "Ion (collisions) MH_DEVICE" ion $SP "MH_DEVICE = .True.,"; fi
 # (the serial default sampler, MH_BATCH = .False., is a host loop of one M = 1 field call per jump: latency bound at
 #  ~40 us per call, 2.2 steps/s on the 4.7 eV deck; the reference documents MH_BATCH for GPU builds)
