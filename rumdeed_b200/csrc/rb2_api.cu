@@ -763,6 +763,8 @@ int rb2_set_option(const char *name, double value)
     } else if (!strcmp(name, "sym_tpl")) {
         if (value != 0 && value != 1 && value != 2) return rb2_fail(RB2_ERR_ARG, "sym_tpl (targets per lane) must be 0 (auto), 1 or 2");
         c.sym_tpl = (int)value;
+    } else if (!strcmp(name, "mh_small")) {
+        c.mh_small = (value != 0.0) ? 1 : 0;
     } else if (!strcmp(name, "sym_waves")) {
         if (value < 1) return rb2_fail(RB2_ERR_ARG, "sym_waves must be >= 1");
         c.sym_waves = value;

@@ -511,21 +511,29 @@ k_recomb_prepare(int n, DevArrays A, int *__restrict__ mask, DevCounters *__rest
     if (is_i) ions[ki] = i;
 }
 
+// IPT ions per thread: every electron record read from shared memory (two LDS.128) serves IPT distance tests; with one
+// ion per thread the shared-memory pipe, not the FP64 pipe, was the limiter (ncu: LSU wavefronts 77 %, FP64 68 %).
+template <int IPT>
 __global__ void __launch_bounds__(TPB)
 k_recomb_sweep(const double4 *__restrict__ pq, const int *__restrict__ ions, const double4 *__restrict__ erec,
                const int *__restrict__ eidx, int e_chunk, int2 *__restrict__ cand, int cand_cap, CollCounts *__restrict__ K)
 {
     __shared__ double4 tile[ETILE];
     const int n_ion = K->n_ion, n_elec = K->n_elec;
-    if ((int)(blockIdx.x * TPB) >= n_ion) return;
-    const int k = blockIdx.x * TPB + threadIdx.x;
+    if ((int)(blockIdx.x * TPB * IPT) >= n_ion) return;
     const int j0 = blockIdx.y * e_chunk, j1 = min(n_elec, j0 + e_chunk);
-    int ion = -1;
-    double x = 0.0, y = 0.0, z = 0.0;
-    if (k < n_ion) {
-        ion = ions[k];
-        const double4 p = pq[ion];
-        x = p.x; y = p.y; z = p.z;
+    int ion[IPT];
+    double x[IPT], y[IPT], z[IPT];
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) {
+        const int k = (blockIdx.x * IPT + u) * TPB + threadIdx.x;
+        ion[u] = -1;
+        x[u] = y[u] = z[u] = 1.0e30;  // no electron record is within reach of a padding lane
+        if (k < n_ion) {
+            ion[u] = ions[k];
+            const double4 p = pq[ion[u]];
+            x[u] = p.x; y[u] = p.y; z[u] = p.z;
+        }
     }
     for (int t0 = j0; t0 < j1; t0 += ETILE) {
         __syncthreads();
@@ -533,14 +541,19 @@ k_recomb_sweep(const double4 *__restrict__ pq, const int *__restrict__ ions, con
             tile[s] = (t0 + s < j1) ? erec[t0 + s] : make_double4(0.0, 0.0, 0.0, -1.0);
         __syncthreads();
         const int cnt = min(ETILE, j1 - t0);
-#pragma unroll 8
+#pragma unroll 4
         for (int s = 0; s < cnt; ++s) {
             const double4 e = tile[s];
-            const double dx = e.x - x, dy = e.y - y, dz = e.z - z;
-            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            if (d2 <= e.w && ion >= 0) {  // rare
-                const int slot = atomicAdd(&K->n_cand, 1);
-                if (slot < cand_cap) cand[slot] = make_int2(ion, eidx[t0 + s]);
+#pragma unroll
+            for (int u = 0; u < IPT; ++u) {
+                const double dx = e.x - x[u], dy = e.y - y[u], dz = e.z - z[u];
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if (d2 <= e.w) {  // rare (an infinite bound -- electron at rest -- admits every ion, like the reference)
+                    if (ion[u] >= 0) {
+                        const int slot = atomicAdd(&K->n_cand, 1);
+                        if (slot < cand_cap) cand[slot] = make_int2(ion[u], eidx[t0 + s]);
+                    }
+                }
             }
         }
     }
@@ -609,11 +622,19 @@ __device__ __forceinline__ double folded_normal_dist(double mu, double sigma, do
     const double sigma2 = sigma * sigma;
     return sqrt(2.0 / (RB2_PI * sigma2)) * exp(-1.0 * (mu * mu + x * x) / (2.0 * sigma2)) * cosh(mu * x / sigma2);
 }
+// The reference scans a 0.1 degree grid over [0, 180] for the largest value (1801 evaluations).  The folded normal is
+// unimodal on that interval (rising to its mode, then falling; the mode is 0 for mu <= sigma), so the first grid point
+// whose successor is smaller is the grid maximum: 11 bisection steps instead of the scan -- the scan alone made one
+// ionising thread the critical path of the whole kernel (0.7 ms).
 __device__ double folded_normal_max(double mu, double sigma)
 {
-    double best = 0.0;
-    for (int k = 0; k <= 1800; ++k) best = fmax(best, folded_normal_dist(mu, sigma, 180.0 * k / 1800.0));
-    return best;
+    int lo = 0, hi = 1800;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (folded_normal_dist(mu, sigma, 180.0 * (mid + 1) / 1800.0) < folded_normal_dist(mu, sigma, 180.0 * mid / 1800.0)) hi = mid;
+        else lo = mid + 1;
+    }
+    return folded_normal_dist(mu, sigma, 180.0 * lo / 1800.0);
 }
 // The acceptance-rejection loop shared by Get_Injected_Vec (:1452-1517) and Get_Ejected_Vec (:1525-1577)
 __device__ void scatter_direction(Philox &g, double mu, double sigma, double m_factor, const double pv[3], double out[3])
@@ -737,7 +758,8 @@ CollParams make_params(const Rb2Ctx &c, int step, unsigned long long seed)
     P.Z_eff = sqrt(P.N_bind * (P.N_n * P.N_n) / P.Ryd);
     P.n_d = S.n_d; P.cyl_radius = S.cyl_radius; P.dt = c.cfg.time_step;
     P.step = step; P.ion_life_time = S.ion_life_time; P.seed = seed;
-    P.inj_max = host_folded_normal_max(5.0, 25.0);
+    static const double inj_max = host_folded_normal_max(5.0, 25.0);
+    P.inj_max = inj_max;
     return P;
 }
 
@@ -816,7 +838,8 @@ int do_recombination(Rb2Ctx &c, int step)
     S.h_cnt->n_cand = 0;
     if (n_ion > 0 && n_elec > 0) {
         // grid: ion blocks x electron chunks (whole tiles), about 8 CTAs per SM
-        const int iblocks = (n_ion + TPB - 1) / TPB;
+        const int ipt = (n_ion >= 2 * TPB * c.sm_count) ? 2 : 1;  // two ions per thread once that still fills the machine
+        const int iblocks = (n_ion + TPB * ipt - 1) / (TPB * ipt);
         int chunks = (8 * c.sm_count + iblocks - 1) / iblocks;
         const int max_chunks = (n_elec + ETILE - 1) / ETILE;
         if (chunks > max_chunks) chunks = max_chunks;
@@ -825,8 +848,10 @@ int do_recombination(Rb2Ctx &c, int step)
         chunks = (n_elec + e_chunk - 1) / e_chunk;
         for (;;) {
             RB2_CUDA(cudaMemsetAsync(&S.d_cnt->n_cand, 0, 2 * sizeof(int), st));  // n_cand, n_hit
-            k_recomb_sweep<<<dim3(iblocks, chunks), TPB, 0, st>>>(c.a.pq, S.ions, S.erec, S.eidx, e_chunk, S.cand, S.cand_cap,
-                                                                  S.d_cnt);
+            if (ipt == 2)
+                k_recomb_sweep<2><<<dim3(iblocks, chunks), TPB, 0, st>>>(c.a.pq, S.ions, S.erec, S.eidx, e_chunk, S.cand, S.cand_cap, S.d_cnt);
+            else
+                k_recomb_sweep<1><<<dim3(iblocks, chunks), TPB, 0, st>>>(c.a.pq, S.ions, S.erec, S.eidx, e_chunk, S.cand, S.cand_cap, S.d_cnt);
             RB2_CUDA(cudaGetLastError());
             RB2_LAUNCHED(1);
             RB2_CUDA(cudaMemcpyAsync(S.h_cnt, S.d_cnt, sizeof(CollCounts), cudaMemcpyDeviceToHost, st));

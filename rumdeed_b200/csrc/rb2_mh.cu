@@ -205,13 +205,11 @@ __global__ void k_surf_pack(const double4 *__restrict__ pq, int n, double two_d,
 
 // Proposal of chain c at iteration iter: a pure function of (seed, chain, iteration, chain state, step), so any
 // thread that needs it recomputes it.  iter < 0: search rounds for a favourable start (uniform over the emitter).
-__device__ __forceinline__ void propose(const MhParams &P, const MhState &S, const MhPlan &L, int iter, int k, double mh_std,
-                                        double &x, double &y)
+// (x, y) enter as the chain's current position and leave as the proposal.
+__device__ __forceinline__ void propose_from(const MhParams &P, const MhPlan &L, int iter, int k, double mh_std, int ok,
+                                             double &x, double &y)
 {
     const rb2_mh_config &c = P.c;
-    x = __ldcg(&S.cur_x[k]);
-    y = __ldcg(&S.cur_y[k]);
-    const int ok = __ldcg(&S.ok[k]);
     if (iter < 0) {
         if (!ok) {
             double u, v;
@@ -248,6 +246,13 @@ __device__ __forceinline__ void propose(const MhParams &P, const MhState &S, con
         if (x > x_max) x = x_max - (x - x_max); else if (x < x_min) x = (x_min - x) + x_min;
         if (y > y_max) y = y_max - (y - y_max); else if (y < y_min) y = (y_min - y) + y_min;
     }
+}
+__device__ __forceinline__ void propose(const MhParams &P, const MhState &S, const MhPlan &L, int iter, int k, double mh_std,
+                                        double &x, double &y)
+{
+    x = __ldcg(&S.cur_x[k]);
+    y = __ldcg(&S.cur_y[k]);
+    propose_from(P, L, iter, k, mh_std, __ldcg(&S.ok[k]), x, y);
 }
 
 // One work unit: 32 surface points (one per lane, the same in all four warps) against the particle records
@@ -437,6 +442,148 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
     if (blockIdx.x == 0 && threadIdx.x == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
 }
 
+// ---- single-barrier variant for at most 32 chains ---------------------------------------------------------------
+// In the reference's own regime (tens of electrons emitted per step, 1e3 - 1e4 electrons in the gap) an iteration of
+// k_mh_persistent is two cooperative grid barriers and three trips through L2 (partials, chain state, counters) around
+// ~1 us of arithmetic.  With one tile of chains all of that state fits a warp:
+//   * every CTA keeps its share of the particle records RESIDENT in shared memory for the whole call (they do not
+//     change while the chains run) and the state of all chains in the registers of its warps (lane = chain);
+//   * per iteration a CTA sums its records for the 32 proposals, publishes one partial per chain, and crosses ONE
+//     barrier (an arrival counter in global memory: release add by one thread, acquire spin; bounded -- a CTA that
+//     never arrives traps the kernel instead of hanging the GPU);
+//   * behind the barrier warp 0 of EVERY CTA joins the partials in CTA order and does the accept / reject step and
+//     the MH_std update redundantly: same inputs, same instructions, same result everywhere, so no second barrier and
+//     no shared chain state in global memory.  The partials are double buffered by iteration parity (a CTA can only
+//     be one barrier ahead of the slowest one).
+// Proposals, targets and the generator keys are those of k_mh_persistent (propose_from, target_log, rand2).
+struct MhSmall {
+    int G, S, R;            // CTAs, 128-record sub-tiles in total, most sub-tiles a CTA holds
+    double *partial;        // [2][G][32]
+    unsigned *bar;          // arrival counter, zeroed by the host
+};
+
+__device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v, spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
+            if (++spins > (1u << 27)) __trap();  // seconds: a peer CTA is gone
+        }
+    }
+    __syncthreads();
+}
+
+template <int NIC>
+__global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan L, MhSmall Q)
+{
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    SurfRec *mine = reinterpret_cast<SurfRec *>(small_smem);  // [R * MHB], zero-weight padding beyond the particle list
+    __shared__ double red[MHB / 32][32];
+    __shared__ double st_x[32], st_y[32], st_std;
+    __shared__ int st_ok[32], st_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s0 = (int)((long long)Q.S * blockIdx.x / Q.G), s1 = (int)((long long)Q.S * (blockIdx.x + 1) / Q.G);
+    for (int t = s0; t < s1; ++t) {
+        const int j = t * MHB + tid;
+        SurfRec r;
+        if (j < L.n) r = S.recs[j];
+        else { r.x = 0.0; r.y = 0.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
+        mine[(t - s0) * MHB + tid] = r;
+    }
+    __syncthreads();
+    // chain state: lane = chain, identical in every warp of every CTA; the target values live in warp 0 only
+    double cx = 0.0, cy = 0.0, sup = 0.0, Fc = 0.0, mh_std = L.mh_std0, a_rate = L.a_rate0;
+    int ok = 0;
+    unsigned phase = 0;
+    const bool live = lane < L.M;
+    const int n_iter_total = P.c.ndim;
+    int bad = L.M, round = 0, jump = 1;
+    bool searching = true;
+    for (;;) {
+        // rounds of the search for a favourable start (generator iteration -(round + 1), like k_mh_persistent), then the
+        // jump iterations 1 .. ndim
+        if (searching && !(round < L.max_init && bad > 0)) searching = false;
+        if (!searching && jump > n_iter_total) break;
+        const int iter = searching ? -(round + 1) : jump;
+        double px = cx, py = cy;
+        if (live) propose_from(P, L, iter, lane, mh_std, ok, px, py);
+        double acc = 0.0;
+        for (int t = 0; t < s1 - s0; ++t) {
+            const SurfRec *rr = &mine[t * MHB + warp * 32];
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+        }
+        red[warp][lane] = acc;
+        __syncthreads();
+        double *part = Q.partial + (size_t)(phase & 1u) * Q.G * 32;
+        if (warp == 0) part[(size_t)blockIdx.x * 32 + lane] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+        ++phase;
+        small_barrier(Q.bar, phase * (unsigned)Q.G);
+        if (warp == 0) {
+            double sum = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < Q.G; ++k) sum += __ldcg(part + (size_t)k * 32 + lane);
+            const double Fz = L.E_vac - L.fac * sum;
+            bool acc_ = false, rej_ = false, bad_ = false;
+            if (live) {
+                if (iter < 0) {
+                    if (!ok) {
+                        if (Fz < 0.0) { cx = px; cy = py; Fc = Fz; sup = target_log(P, Fz, px, py); ok = 1; }
+                        else bad_ = true;
+                    }
+                } else if (ok) {
+                    const bool unfav = (P.c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
+                    bool accept = false;
+                    if (!unfav) {
+                        const double sup_new = target_log(P, Fz, px, py);
+                        accept = sup_new >= sup;
+                        if (!accept) {
+                            double u, v;
+                            rand2(L.seed, lane, iter, 2, 0, u, v);
+                            accept = log(u) <= sup_new - sup;
+                        }
+                        if (accept) { cx = px; cy = py; sup = sup_new; Fc = Fz; }
+                    }
+                    acc_ = accept; rej_ = !accept;
+                }
+            }
+            const int a = __popc(__ballot_sync(0xffffffffu, acc_)), r = __popc(__ballot_sync(0xffffffffu, rej_));
+            const int nb = __popc(__ballot_sync(0xffffffffu, bad_));
+            if (iter > P.c.ndim_first && a + r > 0) {  // MH_std_update, :603-612
+                a_rate = (double)a / (double)(a + r);
+                mh_std = fmin(fmax(mh_std * exp(P.c.std_gain * (a_rate - P.c.target_rate)), P.c.std_min), P.c.std_max);
+            }
+            st_x[lane] = cx; st_y[lane] = cy; st_ok[lane] = ok;
+            if (lane == 0) { st_std = mh_std; st_bad = nb; }
+        }
+        __syncthreads();
+        cx = st_x[lane]; cy = st_y[lane]; ok = st_ok[lane]; mh_std = st_std;
+        if (searching) { bad = st_bad; ++round; } else ++jump;
+        // (the next write to st_* sits behind the next barrier's __syncthreads)
+    }
+    if (blockIdx.x == 0 && warp == 0) {
+        if (live) {
+            const int k = lane;
+            if (ok) {
+                const double w = w_theta_xy(P, cx, cy), sw = sqrt(w);
+                S.pos_out[3 * k] = cx; S.pos_out[3 * k + 1] = cy; S.pos_out[3 * k + 2] = 0.0;
+                S.F_out[k] = Fc;
+                S.df_out[k] = (P.c.kind == 2) ? 0.0 : P.b_FN * (sw * sw * sw) * v_y(P, Fc, w) / (-1.0 * Fc);
+            } else {
+                S.pos_out[3 * k] = P.c.emit_pos[0]; S.pos_out[3 * k + 1] = P.c.emit_pos[1]; S.pos_out[3 * k + 2] = 0.0;
+                S.F_out[k] = 1.0;
+                S.df_out[k] = HUGE_NEG;
+            }
+        }
+        if (lane == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
+    }
+}
+
 // work units: (tiles of 32 points) x (particle chunks, whole 128-record sub-tiles)
 MhPlan make_plan(const Rb2Ctx &ctx, int M, int G_max)
 {
@@ -493,6 +640,69 @@ int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_
     return RB2_OK;
 }
 
+// At most 32 chains over at most 4 resident 128-record sub-tiles per SM: the single-barrier kernel.
+static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
+                           int NIC, int max_init, double *df_out, double *F_out, double *pos_out, double *a_rate_io,
+                           double *mh_std_io)
+{
+    const rb2_config &gc = ctx.cfg;
+    const int n = ctx.n, nw = cfg->y_num * cfg->x_num;
+    MhSmall Q{};
+    Q.S = (n + MHB - 1) / MHB;
+    Q.G = std::max(1, std::min(Q.S, ctx.sm_count));
+    Q.R = std::max(1, (Q.S + Q.G - 1) / Q.G);
+    MhPlan L{};
+    L.M = M; L.n = n; L.n_tiles = 1; L.max_init = max_init; L.seed = seed;
+    L.two_d = 2.0 * gc.d;
+    L.E_vac = rb2_make_step_params(gc).pl.E_z;
+    L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
+    L.nic = gc.N_ic_max;
+    L.mh_std0 = *mh_std_io; L.a_rate0 = *a_rate_io;
+    // scratch (doubles): 5M outputs + 2 scalars + table + 2 x G x 32 partials + 8n records; (ints): the arrival counter
+    size_t off_part = (size_t)5 * M + 2 + nw;
+    size_t off_recs = (off_part + (size_t)2 * Q.G * 32 + 1) & ~(size_t)1;  // 16-byte alignment
+    int rc = rb2_ensure_stage(ctx, off_recs + (size_t)8 * n + 2, 4);
+    if (rc) return rc;
+    cudaStream_t st = ctx.stream;
+    double *d = ctx.d_stage_d;
+    MhState S{};
+    S.df_out = d; S.F_out = d + M; S.pos_out = d + 2 * (size_t)M; S.scal_out = d + 5 * (size_t)M;
+    double *d_w = S.scal_out + 2;
+    Q.partial = d + off_part;
+    SurfRec *d_recs = reinterpret_cast<SurfRec *>(d + off_recs);
+    S.recs = d_recs;
+    Q.bar = reinterpret_cast<unsigned *>(ctx.d_stage_i);
+    MhParams P;
+    P.c = *cfg;
+    P.w_theta = d_w;
+    const double pi = RB2_PI, h_bar = 6.62607015e-34 / (2.0 * pi);
+    P.b_FN = -4.0 / (3.0 * h_bar) * sqrt(2.0 * rb2k::m_0 * rb2k::q_0);
+    P.l_const = rb2k::q_0 / (4.0 * pi * rb2k::epsilon_0);
+    RB2_CUDA(cudaMemcpyAsync(d_w, w_theta_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice, st));
+    RB2_CUDA(cudaMemsetAsync(ctx.d_stage_i, 0, 4 * sizeof(int), st));
+    int launches = 1;
+    if (n > 0) {
+        k_surf_pack<<<(n + 255) / 256, 256, 0, st>>>(ctx.a.pq, n, L.two_d, gc.image_charge ? gc.N_ic_max : 0, d_recs);
+        launches++;
+    }
+    void *kern = NIC < 0 ? (void *)k_mh_small<-1> : NIC == 0 ? (void *)k_mh_small<0>
+               : NIC == 1 ? (void *)k_mh_small<1> : (void *)k_mh_small<2>;
+    const size_t smem = (size_t)Q.R * MHB * sizeof(SurfRec);  // <= 32 KB
+    void *args[] = {&P, &S, &L, &Q};
+    // cooperative launch: the arrival-counter barrier needs all G <= sm_count CTAs resident
+    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(Q.G), dim3(MHB), args, smem, st));
+    RB2_LAUNCHED(launches);
+    double scal1[2];
+    RB2_CUDA(cudaMemcpyAsync(df_out, S.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(F_out, S.F_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(pos_out, S.pos_out, (size_t)3 * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(scal1, S.scal_out, sizeof(scal1), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    *mh_std_io = scal1[0];
+    *a_rate_io = scal1[1];
+    return RB2_OK;
+}
+
 int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                          double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io)
 {
@@ -502,6 +712,8 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     const rb2_config &gc = ctx.cfg;
     const int n = ctx.n, max_init = 10000;
     const int NIC = !gc.image_charge ? -1 : (gc.N_ic_max >= 2 ? 2 : gc.N_ic_max);
+    if (ctx.mh_small && M <= 32 && (n + MHB - 1) / MHB <= 4 * ctx.sm_count)
+        return launch_mh_small(ctx, cfg, w_theta_host, M, seed, NIC, max_init, df_out, F_out, pos_out, a_rate_io, mh_std_io);
     void *kern = NIC < 0 ? (void *)k_mh_persistent<-1> : NIC == 0 ? (void *)k_mh_persistent<0>
                : NIC == 1 ? (void *)k_mh_persistent<1> : (void *)k_mh_persistent<2>;
     int occ = 0;

@@ -203,6 +203,51 @@ def test_device_resident_fe_sampler(orc):
 
 
 @gpu
+@pytest.mark.parametrize("n_pre,nic,kind", [(0, 1, 1), (120, 1, 1), (700, 0, 1), (2500, 2, 1), (300, 1, 2)])
+def test_device_sampler_single_barrier_kernel(orc, n_pre, nic, kind):
+    """Up to 32 chains run in k_mh_small (records resident in shared memory, chain state in registers, one barrier per
+    jump).  Same generator keys and proposals as k_mh_persistent: for the same seed the chains coincide except where
+    an accept decision sits on a rounding knife edge (the partial sums are joined in a different order)."""
+    w = ((2.0, 2.4), (2.4, 2.0))
+    mode, T = (10, 293.15) if kind == 1 else (9, 1200.0)
+    sim, p, st, em = _planar_pair(orc, 41, nic=nic, w=w, mh_batch=2, mode=mode, T=T)
+    emit = 100 * NM
+    M, calls = 24, 25
+    with sim:
+        if n_pre:
+            _preload(sim, st, p, n_pre, 9)
+        hp = rb.HotPath.attach()
+        args = dict(emit_pos=(-0.5 * emit, -0.5 * emit), emit_dim=(emit, emit), w_theta=w, kind=kind, T_temp=T)
+        small = [hp.mh_planar(M, seed=1000 + k, **args) for k in range(calls)]
+        again = hp.mh_planar(M, seed=1000, **args)
+        one = hp.mh_planar(1, seed=77, **args)
+        full = hp.mh_planar(32, seed=78, **args)
+        hp.set_option("mh_small", 0)
+        big = [hp.mh_planar(M, seed=1000 + k, **args) for k in range(calls)]
+        hp.set_option("mh_small", 1)
+    for a, b in zip(small[0][:3], again[:3]):
+        assert np.array_equal(a, b)                       # reproducible
+    assert small[0][3:] == again[3:]
+    ps = np.concatenate([r[2] for r in small]); pb = np.concatenate([r[2] for r in big])
+    Fs = np.concatenate([r[1] for r in small]); Fb = np.concatenate([r[1] for r in big])
+    assert np.all(Fs < 0) and np.all(np.abs(ps[:, :2]) <= 0.5 * emit) and np.all(ps[:, 2] == 0)
+    assert one[1].shape == (1,) and one[1][0] < 0 and full[1].shape == (32,) and np.all(full[1] < 0)
+    same = np.all(np.abs(ps - pb) <= 1e-9 * emit, axis=1)
+    assert same.mean() > 0.9, same.mean()
+    assert np.allclose(Fs[same], Fb[same], rtol=1e-9)
+    # adaptive step: same trajectory of MH_std when the chains coincide
+    n_same_std = sum(abs(a[4] - b[4]) <= 1e-9 * b[4] for a, b in zip(small, big))
+    assert n_same_std >= 0.6 * calls
+    for k in (0, 1):
+        assert _ks(ps[:, k], pb[:, k]) > 1e-3
+    if kind == 1:
+        assert 0.00005 <= small[0][4] <= 0.125
+        k = 3
+        col, row = int((small[0][2][k, 0] / emit + 0.5) * 2), 1 - int((small[0][2][k, 1] / emit + 0.5) * 2)
+        assert small[0][0][k] == pytest.approx(orc.fn_escape_prob_log(p, small[0][1][k], w[row][col]), rel=1e-12)
+
+
+@gpu
 def test_device_resident_thermo_sampler(orc):
     w = ((2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0), (2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0))
     sim, p, st, em = _planar_pair(orc, 32, w=w, mode=9, T=1000.0, V=2000.0, d=1000 * NM, dt=1e-16, mh_batch=2)
