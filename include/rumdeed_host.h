@@ -53,6 +53,8 @@ typedef struct rh_state {
                                                      rb2_remove_marked, the text/binary writers */
     long long nrIonizations_total, nrRecombinations_total; /* collisions (COLLISION_MODE 1, 2) */
     double t_collisions, t_dev_collisions;        /* wall clock / device time of Do_Collisions, summed */
+    double t_em_quad, t_em_mh, t_em_add;          /* planar field emission: supply quadrature, sampler, accept + insert */
+    long long n_candidates_total;                 /* emission candidates (sum of N_round) */
 } rh_state;
 
 void *rh_create_from_dir(const char *dir, int write_files, unsigned long long seed, int max_particles);

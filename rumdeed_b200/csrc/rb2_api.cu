@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "rb2_internal.cuh"
 
 Rb2Ctx g_rb2;
@@ -287,6 +289,7 @@ int rb2_init(const rb2_config *cfg)
     c.init = true;
     if ((rc = rb2_launch_fill_mask(c, c.cap))) return rc;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
+    if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;  // same as rb2_set_option("mh_small", ..)
     return RB2_OK;
 }
 

@@ -524,10 +524,17 @@ __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan 
         if (warp == 0) part[(size_t)blockIdx.x * 32 + lane] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
         ++phase;
         small_barrier(Q.bar, phase * (unsigned)Q.G);
-        if (warp == 0) {
-            double sum = 0.0;
+        {   // join: warp w adds the partials of CTAs w, w + 4, ... (ascending), then the four strands in warp order.  With
+            // one warp walking all G partials the L2 latency of this loop was ~50 ns per CTA and iteration -- most of
+            // the iteration at G = 148.
+            double strand = 0.0;
 #pragma unroll 8
-            for (int k = 0; k < Q.G; ++k) sum += __ldcg(part + (size_t)k * 32 + lane);
+            for (int k = warp; k < Q.G; k += MHB / 32) strand += __ldcg(part + (size_t)k * 32 + lane);
+            red[warp][lane] = strand;  // (every warp is past its read of red[] above: it sits before the barrier)
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const double sum = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
             const double Fz = L.E_vac - L.fac * sum;
             bool acc_ = false, rej_ = false, bad_ = false;
             if (live) {

@@ -113,6 +113,7 @@ int rh_get_state(void *p, rh_state *o)
     o->t_emission = s->t_emission; o->t_md_step = s->t_md_step; o->t_remove = s->t_remove; o->t_io = s->t_io;
     o->nrIonizations_total = s->nrIonizations_total; o->nrRecombinations_total = s->nrRecombinations_total;
     o->t_collisions = s->t_collisions; o->t_dev_collisions = s->t_dev_collisions;
+    o->t_em_quad = s->t_em_quad; o->t_em_mh = s->t_em_mh; o->t_em_add = s->t_em_add; o->n_candidates_total = s->n_candidates_total;
     return 0;
 }
 
@@ -210,6 +211,9 @@ int main(int argc, char **argv)
            st.nrAbsorbed_top, st.nrAbsorbed_bot, st.nrElec);
     printf("RUMDEED: wall clock per phase [s]: emission %.3f  MD step %.3f  removal %.3f  writers %.3f  (%d steps); device time of the MD steps %.3f, of their pair kernels %.3f\n",
            st.t_emission, st.t_md_step, st.t_remove, st.t_io, st.step, st.t_dev_step, st.t_dev_accel);
+    if (st.n_candidates_total)
+        printf("RUMDEED: emission split [s]: supply quadrature %.3f  sampler %.3f  accept + insert %.3f; %.1f candidates per step\n",
+               st.t_em_quad, st.t_em_mh, st.t_em_add, (double)st.n_candidates_total / (st.step > 0 ? st.step : 1));
     if (st.nrIonizations_total || st.nrRecombinations_total || st.t_collisions > 0.0)
         printf("RUMDEED: collisions: %lld ionisations, %lld recombinations, %d ions in the gap; wall clock %.3f s, device %.3f s\n",
                st.nrIonizations_total, st.nrRecombinations_total, st.nrIon, st.t_collisions, st.t_dev_collisions);

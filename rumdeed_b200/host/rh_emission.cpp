@@ -7,6 +7,8 @@
 
 #include <algorithm>
 
+#include <chrono>
+
 #include "rh_host.hpp"
 
 namespace rh {
@@ -136,6 +138,28 @@ int Sim::Add_Particle(const double par_pos[3], const double par_vel[3], int spec
     counts.nrID += 1;
     counts.nrPart += 1;
     if (species == species_elec) counts.nrElec += 1; else if (species == species_ion) counts.nrIon += 1;
+    return 0;
+}
+// k calls of Add_Particle in one trip to the device (same order, same ids).  Only valid where no field evaluation sits
+// between the individual calls, i.e. behind the lock-step samplers (mh_batch), whose fields are all taken before the
+// first insertion -- one host/device round trip (~40 us) per step instead of one per emitted electron.
+int Sim::Add_Particles(int k, const double *pos, const double *vel, int species, int step, int emit, int life, const int *sec)
+{
+    if (k < 1) return 0;
+    std::vector<int> sp((size_t)k, species), em((size_t)k, emit), lf((size_t)k, life);
+    int rc = check(rb2_add_particles(k, pos, vel, sp.data(), step, em.data(), sec, lf.data()), "rb2_add_particles");
+    if (rc) return rc;
+    for (int i = 0; i < k; ++i) {
+        if (ud_density_emit) {
+            double p3[3] = {pos[3 * i] / length_scale, pos[3 * i + 1] / length_scale, pos[3 * i + 2] / length_scale};
+            int tail[4] = {emit, sec[i], counts.nrID, species};
+            fwrite(p3, sizeof(double), 3, ud_density_emit);
+            fwrite(tail, sizeof(int), 4, ud_density_emit);
+        }
+        counts.nrID += 1;
+        counts.nrPart += 1;
+        if (species == species_elec) counts.nrElec += 1; else if (species == species_ion) counts.nrIon += 1;
+    }
     return 0;
 }
 void Sim::xyz_corr(double xi, double eta, double phi, double out[3]) const
@@ -401,9 +425,14 @@ int Metropolis_Hastings_rectangle_J_batch(Sim &s, int M, int emit, double *df_ou
 static int Do_Field_Emission_Planar_rectangle(Sim &s, int step, int emit)
 {
     const Globals &g = s.g;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = clk::now();
     if (s.check(rb2_field_window_open(), "rb2_field_window_open")) return -1;  // Particles_To_Device
     QuadResult q;
     if (Cuba_Integrate(s, SUPPLY_FE, emit, &q)) return -1;  // Do_Surface_Integration_FE, :635-657
+    const auto t1 = clk::now();
+    s.t_em_quad += secs(t0, t1);
     const double N_sup = q.integral;
     const int N_round = (int)lround(N_sup + s.residual);
     s.residual = N_sup - N_round;
@@ -416,9 +445,14 @@ static int Do_Field_Emission_Planar_rectangle(Sim &s, int step, int emit)
         mh_df.resize(N_round); mh_F.resize(N_round); mh_pos.resize((size_t)3 * N_round);
         if (Metropolis_Hastings_rectangle_J_batch(s, N_round, emit, mh_df.data(), mh_F.data(), mh_pos.data()) == -2) return -1;
     }
+    const auto t2 = clk::now();
+    s.t_em_mh += secs(t1, t2);
+    s.n_candidates_total += N_round;
     if (s.check(rb2_field_window_close(), "rb2_field_window_close")) return -1;  // Release_Device_Particles
     int nrElecEmit = 0;
     double df_avg = 0.0;
+    std::vector<double> add_pos;  // lock-step path: the insertions of this step, made in one call behind the loop
+    std::vector<int> add_sec;
     for (int k = 0; k < N_round; ++k) {
         double D_f, F, par_pos[3];
         if (g.mh_batch) { D_f = mh_df[k]; F = mh_F[k]; memcpy(par_pos, &mh_pos[(size_t)3 * k], sizeof(par_pos)); }
@@ -431,10 +465,16 @@ static int Do_Field_Emission_Planar_rectangle(Sim &s, int step, int emit)
             const double par_vel[3] = {0.0, 0.0, 0.0};
             int sec = 1;
             (void)s.work.w_theta_xy(g, par_pos, &sec);
-            if (s.Add_Particle(par_pos, par_vel, species_elec, step, emit, -1, sec)) return -1;
+            if (g.mh_batch) { add_pos.insert(add_pos.end(), par_pos, par_pos + 3); add_sec.push_back(sec); }
+            else if (s.Add_Particle(par_pos, par_vel, species_elec, step, emit, -1, sec)) return -1;
             nrElecEmit++;
         }
     }
+    if (!add_sec.empty()) {
+        const std::vector<double> zero(add_pos.size(), 0.0);
+        if (s.Add_Particles((int)add_sec.size(), add_pos.data(), zero.data(), species_elec, step, emit, -1, add_sec.data())) return -1;
+    }
+    s.t_em_add += secs(t2, clk::now());
     s.slog.df_avg = (N_sup != 0.0) ? df_avg / N_sup : 0.0;
     s.slog.nrElecEmit += nrElecEmit;
     if (s.ud_field)

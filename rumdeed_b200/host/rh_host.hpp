@@ -152,6 +152,8 @@ struct Sim {
     long long nrIonizations_total = 0, nrRecombinations_total = 0;
     int recom_counts[3] = {0, 0, 0};  // nrPart/nrElec/nrIon_remove_recom since the last Remove_Particles
     double t_collisions = 0.0, t_dev_collisions = 0.0;
+    double t_em_quad = 0.0, t_em_mh = 0.0, t_em_add = 0.0;  // planar field emission: supply quadrature, sampler, accept + insert
+    long long n_candidates_total = 0;                       // sum of N_round
     FILE *ud_density_absorb_top = nullptr, *ud_density_absorb_bot = nullptr, *planes_ud[RB2_PLANES_MAX] = {nullptr};
     std::vector<double> scratch_pts, scratch_fld, scratch_ez;
 
@@ -163,6 +165,7 @@ struct Sim {
     int Calc_Field_at_Batch(int M, const double *pos_in, double *field_out);
     int Calc_Field_at_Surface(int M, const double *pos_in, double *field_out);
     int Add_Particle(const double par_pos[3], const double par_vel[3], int species, int step, int emit, int life, int sec);
+    int Add_Particles(int k, const double *pos, const double *vel, int species, int step, int emit, int life, const int *sec);
     // geometry helpers (src/mod_hyperboloid_tip.f90:25-112, 156-163)
     void xyz_corr(double xi, double eta, double phi, double out[3]) const;
     void surface_normal(const double pos[3], double out[3]) const;

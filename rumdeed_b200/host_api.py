@@ -51,6 +51,7 @@ class State(C.Structure):
         ("t_emission", C.c_double), ("t_md_step", C.c_double), ("t_remove", C.c_double), ("t_io", C.c_double),
         ("nrIonizations_total", C.c_longlong), ("nrRecombinations_total", C.c_longlong),
         ("t_collisions", C.c_double), ("t_dev_collisions", C.c_double),
+        ("t_em_quad", C.c_double), ("t_em_mh", C.c_double), ("t_em_add", C.c_double), ("n_candidates_total", C.c_longlong),
     ]
 
 

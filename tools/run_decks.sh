@@ -22,7 +22,7 @@ phase = [l for l in log if "wall clock per phase" in l]
 print(f"{name:28s} rc={rc} steps={steps} wall={e-s:7.2f}s  steps/s={steps/(e-s):8.1f}  I(last quarter)={I:.4e} A  nrElec(end)={nel}")
 print("   ", phase[0] if phase else log[-2:])
 for l in log:
-    if "collisions:" in l: print("   ", l)
+    if "collisions:" in l or "emission split" in l: print("   ", l)
 PY
   rm -rf $d
 }
