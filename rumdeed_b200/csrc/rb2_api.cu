@@ -289,7 +289,8 @@ int rb2_init(const rb2_config *cfg)
     c.init = true;
     if ((rc = rb2_launch_fill_mask(c, c.cap))) return rc;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
-    if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;  // same as rb2_set_option("mh_small", ..)
+    if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;
+    if (const char *e = getenv("RB2_MH_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 4) c.mh_ctas_per_sm = v; }  // same as rb2_set_option("mh_small", ..)
     return RB2_OK;
 }
 
@@ -766,6 +767,9 @@ int rb2_set_option(const char *name, double value)
     } else if (!strcmp(name, "sym_tpl")) {
         if (value != 0 && value != 1 && value != 2) return rb2_fail(RB2_ERR_ARG, "sym_tpl (targets per lane) must be 0 (auto), 1 or 2");
         c.sym_tpl = (int)value;
+    } else if (!strcmp(name, "mh_ctas_per_sm")) {
+        if (value < 1 || value > 4) return rb2_fail(RB2_ERR_ARG, "mh_ctas_per_sm must be 1..4");
+        c.mh_ctas_per_sm = (int)value;
     } else if (!strcmp(name, "mh_small")) {
         c.mh_small = (value != 0.0) ? 1 : 0;
     } else if (!strcmp(name, "sym_waves")) {

@@ -120,6 +120,7 @@ struct Rb2Ctx {
     int    last_pair_kernel = 0;          // 1 gather, 2 symmetric
     rb2_event *d_events = nullptr; int ev_cap = 0;
     int    ev_min = 65536;                // initial size of the record buffer (option "event_buffer")
+    int    mh_ctas_per_sm = 2;            // sampler: CTAs per SM of the cooperative kernel (option "mh_ctas_per_sm", 1..4)
     int    mh_small = 1;                  // sampler: single-barrier kernel for <= 32 chains (option "mh_small", 0 = off)
     std::vector<rb2_event> host_events;
 

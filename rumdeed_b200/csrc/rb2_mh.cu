@@ -3,16 +3,18 @@
 // Replaces the host loop of Metropolis_Hastings_rectangle_J_batch (reference
 // src/mod_field_emission_v2.F90:1284-1458): M chains advance together.  ONE persistent cooperative kernel
 // runs the search for favourable start spots and all jump iterations; per iteration
-//   phase A  the sequence of (tile of 32 chains) x (128-particle sub-tile) work items is cut into one equal
-//            contiguous range per CTA (even finish before the barrier, no work queue): the proposals
-//            (Marsaglia polar normals, reflection at the emitter edges :1466-1516) are recomputed from the
-//            counter-based generator wherever they are needed, and the surface field sum runs over the
-//            particle records staged in shared memory;
-//   phase B  one warp per chain joins the chunk sums in a fixed order, adds the vacuum field and does the
-//            accept / reject step on the log electron supply (Elec_Supply_log :589, or ln J_GTF for the
-//            thermal-field mode, src/mod_field_thermo_emission.F90:257);
-// with a grid barrier after each phase, after which every thread applies the same MH_std update
-// (:603-612, one per iteration after the warm-up) from the iteration's accept / reject counters.
+//   field sums   the sequence of (tile of 32 chains) x (128-particle sub-tile) work items is cut into one equal
+//                contiguous range per CTA (even finish, no work queue): the proposals (Marsaglia polar normals,
+//                reflection at the emitter edges :1466-1516) are recomputed from the counter-based generator wherever
+//                they are needed, and the surface field sum runs over the particle records staged in shared memory;
+//   accept       the CTA that delivers the LAST partial sum of a tile (per-tile arrival counter, "last block" pattern)
+//                joins the tile's sums in a fixed order, adds the vacuum field and does the accept / reject step of
+//                its 32 chains, one per lane, on the log electron supply (Elec_Supply_log :589, or ln J_GTF for the
+//                thermal-field mode, src/mod_field_thermo_emission.F90:257);
+// then ONE grid barrier (an arrival counter, two CTAs per SM), after which every thread applies the same MH_std update
+// (:603-612, one per iteration after the warm-up) from the iteration's accept / reject counters.  (The first version
+// had a cooperative-groups grid barrier after each of the two phases and up to four CTAs per SM: 20 us per jump at
+// 324 chains x 8.7e3 electrons for 5 us of field sums.)  At most 32 chains: k_mh_small below.
 //
 // Surface field.  The chains live on the cathode plane z = 0, where the image series of
 // src/acc_ic_planar_series.inc is mirror-antisymmetric: the partner of charge q at height h = z_j + 2nd is
@@ -26,9 +28,6 @@
 #include "rb2_internal.cuh"
 
 #include <algorithm>
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -156,6 +155,8 @@ struct MhState {
     const int *tfirst;                         // [G] tile of that work item
     const int *kfirst;                         // [G] how many CTAs contribute to that tile before this one
     const int *tcount;                         // [n_tiles] contributions per tile
+    unsigned *tile_arrive;                     // [n_tiles] partial sums delivered so far (all phases, cumulative)
+    unsigned *bar;                             // arrival counter of the grid barrier
     double *df_out, *F_out, *pos_out, *scal_out;
 };
 
@@ -165,11 +166,31 @@ struct MhPlan {
     // into gridDim.x equal contiguous ranges; a CTA writes one partial sum per tile its range touches, into
     // partial[tile][k][32] with k = its rank among the tile's contributors (maxslots = most contributors)
     int S, maxslots;
+    int resident;  // sub-tiles of records every CTA keeps in shared memory (0: stream them from L2 every iteration)
     long long W;
     unsigned long long seed;
     double two_d, E_vac, fac, mh_std0, a_rate0;
     int nic;
 };
+
+// Grid-wide barrier on an arrival counter in global memory (zeroed by the host): release add by one thread per CTA,
+// acquire spin until `target` arrivals.  Needs all CTAs resident (cooperative launch).  Bounded: a CTA that never
+// arrives traps the kernel instead of hanging the GPU.
+__device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v, spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
+            if (++spins > (1u << 27)) __trap();  // seconds: a peer CTA is gone
+        }
+    }
+    __syncthreads();
+}
 
 // one particle against one surface point: sum of g_n / (rho^2 + h_n^2)^(3/2)
 template <int NIC>
@@ -291,13 +312,79 @@ __device__ __forceinline__ double surf_unit_sum(const SurfRec *__restrict__ g_re
     return sum;
 }
 
-// phase A: partial surface sums of every (chain tile, particle chunk) unit
+// Accept / reject step of one tile of 32 chains (lane = chain), run by the warp that delivered the tile's last partial
+// sum (joined by the caller): finish the field, decide, count.  (x, y) is the lane's proposal.
+__device__ __forceinline__ void tile_accept(const MhParams &P, const MhState &S, const MhPlan &L, int iter, int tile, double x,
+                                            double y, double sum)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = tile * 32 + lane;
+    bool acc = false, rej = false, bad = false;
+    if (c < L.M) {
+        const double Fz = L.E_vac - L.fac * sum;
+        const int ok = __ldcg(&S.ok[c]);
+        if (iter < 0) {
+            if (!ok) {
+                if (Fz < 0.0) {
+                    S.cur_x[c] = x; S.cur_y[c] = y; S.F_cur[c] = Fz;
+                    S.sup_cur[c] = target_log(P, Fz, x, y);
+                    S.ok[c] = 1;
+                } else bad = true;
+            }
+        } else if (ok) {
+            const bool unfav = (P.c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
+            bool accept = false;
+            if (!unfav) {
+                const double sup_new = target_log(P, Fz, x, y), sup_old = __ldcg(&S.sup_cur[c]);
+                accept = sup_new >= sup_old;
+                if (!accept) {
+                    double u, v;
+                    rand2(L.seed, c, iter, 2, 0, u, v);
+                    accept = log(u) <= sup_new - sup_old;
+                }
+                if (accept) { S.cur_x[c] = x; S.cur_y[c] = y; S.sup_cur[c] = sup_new; S.F_cur[c] = Fz; }
+            }
+            acc = accept; rej = !accept;
+        }
+    }
+    const int n_acc = __popc(__ballot_sync(0xffffffffu, acc)), n_rej = __popc(__ballot_sync(0xffffffffu, rej));
+    const int n_bad = __popc(__ballot_sync(0xffffffffu, bad));
+    if (lane == 0) {
+        if (iter < 0) { if (n_bad) atomicAdd(&S.bad[-iter - 1], n_bad); }
+        else {
+            if (n_acc) atomicAdd(&S.cnt[2 * iter], n_acc);
+            if (n_rej) atomicAdd(&S.cnt[2 * iter + 1], n_rej);
+        }
+    }
+}
+
+// The same unit sum over `nsub` sub-tiles that this CTA keeps resident in shared memory (see k_mh_persistent).
 template <int NIC>
-__device__ __forceinline__ void phase_field(const MhParams &P, const MhState &S, const MhPlan &L, int iter, double mh_std,
-                                            SurfRec (*recs)[MHB], double (*red)[32])
+__device__ __forceinline__ double surf_unit_sum_resident(const SurfRec *__restrict__ res, int nsub, double px, double py,
+                                                         const MhPlan &L, double (*red)[32])
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (L.W == 0) return;
+    double acc = 0.0;
+    for (int t = 0; t < nsub; ++t) {
+        const SurfRec *rr = res + (size_t)t * MHB + warp * 32;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    const double sum = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+    __syncthreads();
+    return sum;
+}
+
+// Field sums of this CTA's range of (chain tile, 128-record sub-tile) work items; the CTA that delivers the last
+// partial sum of a tile also runs that tile's accept / reject step.
+template <int NIC>
+__device__ __forceinline__ void phase_field(const MhParams &P, const MhState &S, const MhPlan &L, int iter, double mh_std,
+                                            unsigned phase, const SurfRec *resident, SurfRec (*recs)[MHB], double (*red)[32],
+                                            int *s_last)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long w0 = S.wstart[blockIdx.x], w1 = S.wstart[blockIdx.x + 1];
     const int tile_first = S.tfirst[blockIdx.x];
     for (long long w = w0; w < w1;) {
@@ -306,10 +393,34 @@ __device__ __forceinline__ void phase_field(const MhParams &P, const MhState &S,
         const int c = tile * 32 + lane;
         double px = 0.0, py = 0.0;
         if (c < L.M) propose(P, S, L, iter, c, mh_std, px, py);
-        const double sum = surf_unit_sum<NIC>(S.recs, s0 * MHB, min(L.n, s1 * MHB), px, py, L, recs, red);
+        const double sum = resident ? surf_unit_sum_resident<NIC>(resident + (size_t)(w - w0) * MHB, s1 - s0, px, py, L, red)
+                                    : surf_unit_sum<NIC>(S.recs, s0 * MHB, min(L.n, s1 * MHB), px, py, L, recs, red);
         // contribution index within the tile: only the first tile of a range can have earlier contributors
         const int k = (tile == tile_first) ? S.kfirst[blockIdx.x] : 0;
-        if (warp == 0) S.partial[((size_t)tile * L.maxslots + k) * 32 + lane] = sum;
+        if (warp == 0) {
+            S.partial[((size_t)tile * L.maxslots + k) * 32 + lane] = sum;
+            // "last block" pattern (fence, count, fence): whoever delivers the LAST partial sum of a tile does that tile's
+            // accept / reject step right away -- no grid barrier between the two phases, and the accept work of early
+            // tiles overlaps the field sums of late ones
+            __threadfence();
+            if (lane == 0) *s_last = (atomicAdd(&S.tile_arrive[tile], 1u) + 1u == (unsigned)S.tcount[tile] * (phase + 1u));
+        }
+        __syncthreads();
+        if (*s_last) {
+            // join in a fixed order with all four warps: warp w adds contributions w, w + 4, ... (ascending), then the
+            // four strands in warp order.  (One warp walking all contributions paid the L2 latency ~nk / 8 times.)
+            __threadfence();
+            const int nk = S.tcount[tile];
+            const double *pp = S.partial + ((size_t)tile * L.maxslots) * 32 + lane;
+            double strand = 0.0;
+#pragma unroll 16
+            for (int q = warp; q < nk; q += MHB / 32) strand += __ldcg(pp + (size_t)q * 32);
+            red[warp][lane] = strand;
+            __syncthreads();
+            const double joined = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+            __syncthreads();
+            if (warp == 0) tile_accept(P, S, L, iter, tile, px, py, joined);
+        }
         w += s1 - s0;
     }
 }
@@ -344,81 +455,44 @@ __global__ void k_surface_join(const double *__restrict__ partial, MhPlan L, dou
     if (lane == 0) Ez[c] = L.E_vac - L.fac * sum;
 }
 
-// phase B: one warp per chain -- join the chunk sums, finish the field, accept / reject
-__device__ __forceinline__ void phase_accept(const MhParams &P, const MhState &S, const MhPlan &L, int iter, double mh_std)
-{
-    const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * (MHB / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (MHB / 32);
-    int n_acc = 0, n_rej = 0, n_bad = 0;
-    for (int c = gwarp; c < L.M; c += nwarps) {
-        double sum = 0.0;
-        if (L.W > 0) {  // the contributions to this chain's tile, in ascending CTA order (fixed-shape join)
-            const int t = c >> 5, nk = S.tcount[t];
-            const double *pp = S.partial + ((size_t)t * L.maxslots) * 32 + (c & 31);
-#pragma unroll 4
-            for (int k = lane; k < nk; k += 32) sum += __ldcg(pp + (size_t)k * 32);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane != 0) continue;
-        const double Fz = L.E_vac - L.fac * sum;
-        double x, y;
-        propose(P, S, L, iter, c, mh_std, x, y);
-        const int ok = __ldcg(&S.ok[c]);
-        if (iter < 0) {
-            if (ok) continue;
-            if (Fz < 0.0) {
-                S.cur_x[c] = x; S.cur_y[c] = y; S.F_cur[c] = Fz;
-                S.sup_cur[c] = target_log(P, Fz, x, y);
-                S.ok[c] = 1;
-            } else n_bad++;
-            continue;
-        }
-        if (!ok) continue;
-        const bool unfav = (P.c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
-        bool accept = false;
-        if (!unfav) {
-            const double sup_new = target_log(P, Fz, x, y), sup_old = S.sup_cur[c];
-            accept = sup_new >= sup_old;
-            if (!accept) {
-                double u, v;
-                rand2(L.seed, c, iter, 2, 0, u, v);
-                accept = log(u) <= sup_new - sup_old;
-            }
-            if (accept) { S.cur_x[c] = x; S.cur_y[c] = y; S.sup_cur[c] = sup_new; S.F_cur[c] = Fz; }
-        }
-        if (accept) n_acc++; else n_rej++;
-    }
-    if (lane == 0) {
-        if (iter < 0) { if (n_bad) atomicAdd(&S.bad[-iter - 1], n_bad); }
-        else {
-            if (n_acc) atomicAdd(&S.cnt[2 * iter], n_acc);
-            if (n_rej) atomicAdd(&S.cnt[2 * iter + 1], n_rej);
-        }
-    }
-}
-
 template <int NIC>
 __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S, MhPlan L)
 {
-    cg::grid_group grid = cg::this_grid();
     __shared__ SurfRec recs[2][MHB];
     __shared__ double red[MHB / 32][32];
+    __shared__ int s_last;
+    extern __shared__ __align__(16) unsigned char mh_dyn_smem[];
+    // The work range of a CTA is the same in every iteration and the particle records do not change while the chains
+    // run: when the range is short (L.resident sub-tiles fit every range) the CTA loads its records ONCE and keeps them
+    // in shared memory -- otherwise every unit starts with an exposed L2 round trip (~1 us for ~1 us of arithmetic).
+    const SurfRec *resident = nullptr;
+    if (L.resident > 0) {
+        SurfRec *res = reinterpret_cast<SurfRec *>(mh_dyn_smem);
+        const long long w0 = S.wstart[blockIdx.x], w1 = S.wstart[blockIdx.x + 1];
+        for (long long w = w0; w < w1; ++w) {
+            const int sub = (int)(w % L.S), j = sub * MHB + threadIdx.x;
+            SurfRec r;
+            if (j < L.n) r = S.recs[j];
+            else { r.x = 0.0; r.y = 0.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
+            res[(size_t)(w - w0) * MHB + threadIdx.x] = r;
+        }
+        __syncthreads();
+        resident = res;
+    }
     double mh_std = L.mh_std0, a_rate = L.a_rate0;
+    unsigned phase = 0;  // field phases so far (the same in every CTA)
     // a favourable start for every chain (:1303-1361): rounds of uniform draws until the field is negative
     int bad = L.M;
     for (int r = 0; r < L.max_init && bad > 0; ++r) {
-        phase_field<NIC>(P, S, L, -(r + 1), mh_std, recs, red);
-        grid.sync();
-        phase_accept(P, S, L, -(r + 1), mh_std);
-        grid.sync();
+        phase_field<NIC>(P, S, L, -(r + 1), mh_std, phase, resident, recs, red, &s_last);
+        ++phase;
+        small_barrier(S.bar, phase * gridDim.x);
         bad = __ldcg(&S.bad[r]);
     }
     for (int i = 1; i <= P.c.ndim; ++i) {
-        phase_field<NIC>(P, S, L, i, mh_std, recs, red);
-        grid.sync();
-        phase_accept(P, S, L, i, mh_std);
-        grid.sync();
+        phase_field<NIC>(P, S, L, i, mh_std, phase, resident, recs, red, &s_last);
+        ++phase;
+        small_barrier(S.bar, phase * gridDim.x);
         const int a = __ldcg(&S.cnt[2 * i]), r = __ldcg(&S.cnt[2 * i + 1]);
         if (i > P.c.ndim_first && a + r > 0) {  // MH_std_update, :603-612 -- identical in every thread
             a_rate = (double)a / (double)(a + r);
@@ -461,22 +535,6 @@ struct MhSmall {
     double *partial;        // [2][G][32]
     unsigned *bar;          // arrival counter, zeroed by the host
 };
-
-__device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v, spins = 0;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-            if (v >= target) break;
-            if (++spins > (1u << 27)) __trap();  // seconds: a peer CTA is gone
-        }
-    }
-    __syncthreads();
-}
 
 template <int NIC>
 __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan L, MhSmall Q)
@@ -728,10 +786,10 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     if (occ < 1) return rb2_fail(RB2_ERR_CUDA, "sampler kernel does not fit on an SM");
     const int G_max = occ * ctx.sm_count;
     MhPlan L = make_plan(ctx, M, G_max);
-    L.S = (n + MHB - 1) / MHB;
+    L.S = std::max(1, (n + MHB - 1) / MHB);  // an empty store still has one (empty) sub-tile per tile: its owner runs the accept step
     L.W = (long long)L.n_tiles * L.S;
-    const long long warps_needed = (M + 3) / 4;  // CTAs so that phase B has one warp per chain
-    const int G = (int)std::max<long long>(1, std::min<long long>(G_max, std::max<long long>(L.W, warps_needed)));
+    // the barrier costs grow with the number of CTAs and the field sums are throughput bound anyway: two CTAs per SM
+    const int G = (int)std::max<long long>(1, std::min<long long>(std::min(G_max, ctx.mh_ctas_per_sm * ctx.sm_count), L.W));
     // the even split and, per tile, who contributes in which order
     std::vector<long long> h_wstart((size_t)G + 1);
     std::vector<int> h_tab((size_t)2 * G + L.n_tiles, 0);  // tfirst[G], kfirst[G], tcount[n_tiles]
@@ -747,12 +805,23 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
         for (int t = t0; t <= t1; ++t) L.maxslots = std::max(L.maxslots, ++h_tcount[t]);
     }
     const size_t n_partial = (size_t)L.n_tiles * L.maxslots * 32;
+    // records resident in shared memory when every range is at most 6 sub-tiles (48 KB per CTA, two CTAs per SM)
+    const long long max_range = (L.W + G - 1) / G;
+    L.resident = (max_range <= 6) ? (int)max_range : 0;
+    const size_t dyn_smem = (size_t)L.resident * MHB * sizeof(SurfRec);
+    if (dyn_smem > 0) {
+        RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        int occ2 = 0;
+        RB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern, MHB, dyn_smem));
+        if ((long long)occ2 * ctx.sm_count < G) L.resident = 0;  // would not be co-resident: stream instead
+    }
+    const size_t dyn_smem_used = (size_t)L.resident * MHB * sizeof(SurfRec);
     L.max_init = max_init;
     L.seed = seed;
     L.mh_std0 = *mh_std_io; L.a_rate0 = *a_rate_io;
     // scratch (doubles): 4M state + partial sums + 5M outputs + table + 2 scalars + 8n records
     const size_t nd = (size_t)9 * M + n_partial + nw + 4 + (size_t)8 * n + 2 + (size_t)G + 1;
-    const size_t ni = (size_t)M + 2 * ((size_t)cfg->ndim + 1) + max_init + h_tab.size();
+    const size_t ni = (size_t)M + 2 * ((size_t)cfg->ndim + 1) + max_init + h_tab.size() + (size_t)L.n_tiles + 1;
     int rc = rb2_ensure_stage(ctx, nd, ni);
     if (rc) return rc;
     cudaStream_t st = ctx.stream;
@@ -774,6 +843,8 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     S.bad = S.cnt + 2 * ((size_t)cfg->ndim + 1);
     int *d_tab = S.bad + max_init;
     S.tfirst = d_tab; S.kfirst = d_tab + G; S.tcount = d_tab + 2 * (size_t)G;
+    S.tile_arrive = reinterpret_cast<unsigned *>(d_tab + h_tab.size());  // zeroed with the rest of the int scratch below
+    S.bar = S.tile_arrive + L.n_tiles;
     MhParams P;
     P.c = *cfg;
     P.w_theta = d_w;
@@ -791,7 +862,7 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
         launches++;
     }
     void *args[] = {&P, &S, &L};
-    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(MHB), args, 0, st));
+    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(MHB), args, dyn_smem_used, st));
     RB2_LAUNCHED(launches);
     double scal1[2];
     RB2_CUDA(cudaMemcpyAsync(df_out, S.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));

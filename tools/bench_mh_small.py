@@ -22,7 +22,7 @@ for N in [int(float(a)) for a in sys.argv[1:]] or (0, 1000, 5000, 10000, 19000, 
                             rng.uniform(1 * NM, 0.9 * d, N)], axis=1)
             hp.upload(pos, np.full(N, -Q_0), np.full(N, M_0))
         args = dict(emit_pos=(-0.5 * emit, -0.5 * emit), emit_dim=(emit, emit), w_theta=((4.7,),))
-        for M in (1, 10, 32):
+        for M in [int(m) for m in os.environ.get("MH_M", "1,10,32").split(",")]:
             out = {"N": N, "M": M}
             for small in (1, 0):
                 hp.set_option("mh_small", small)
