@@ -516,22 +516,25 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
     if (blockIdx.x == 0 && threadIdx.x == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
 }
 
-// ---- single-barrier variant for at most 32 chains ---------------------------------------------------------------
-// In the reference's own regime (tens of electrons emitted per step, 1e3 - 1e4 electrons in the gap) an iteration of
-// k_mh_persistent is two cooperative grid barriers and three trips through L2 (partials, chain state, counters) around
-// ~1 us of arithmetic.  With one tile of chains all of that state fits a warp:
-//   * every CTA keeps its share of the particle records RESIDENT in shared memory for the whole call (they do not
-//     change while the chains run) and the state of all chains in the registers of its warps (lane = chain);
-//   * per iteration a CTA sums its records for the 32 proposals, publishes one partial per chain, and crosses ONE
-//     barrier (an arrival counter in global memory: release add by one thread, acquire spin; bounded -- a CTA that
-//     never arrives traps the kernel instead of hanging the GPU);
-//   * behind the barrier warp 0 of EVERY CTA joins the partials in CTA order and does the accept / reject step and
-//     the MH_std update redundantly: same inputs, same instructions, same result everywhere, so no second barrier and
-//     no shared chain state in global memory.  The partials are double buffered by iteration parity (a CTA can only
-//     be one barrier ahead of the slowest one).
+// ---- single-barrier variant for at most 128 chains ---------------------------------------------------------------
+// In the reference's own regime (1e3 - 1e4 electrons in the gap, ~100 emission candidates per step) an iteration of
+// k_mh_persistent is a chain of global-memory round trips (chain state, partial sums, arrival counters, accept
+// counters, barrier: ~8 us even with no particles at all) around ~1 us of arithmetic.  With at most four tiles of
+// chains all of that state fits one CTA:
+//   * CTA b works for ONE tile t_b = b / Gs on its own share of the particle records, which stays RESIDENT in shared
+//     memory for the whole call (the records do not change while the chains run);
+//   * every CTA keeps the state of ALL chains in registers: warp w holds tile w (lane = chain).  Per iteration warp t_b
+//     computes the tile's 32 proposals and hands them to the other warps through shared memory, the four warps sum the
+//     resident records (32 each per sub-tile), and the CTA publishes one partial sum per chain of its tile;
+//   * ONE barrier (arrival counter in global memory);
+//   * behind it EVERY CTA joins the partial sums of every tile (all four warps, fixed order) and warp w does the
+//     accept / reject step of tile w -- redundantly: same inputs, same instructions, same result in every CTA, so no
+//     chain state, no accept counters and no second barrier in global memory.  The MH_std update uses the counts of
+//     the (at most four) warps, exchanged through shared memory.  The partial sums are double buffered by iteration
+//     parity (a CTA can only be one barrier ahead of the slowest one).
 // Proposals, targets and the generator keys are those of k_mh_persistent (propose_from, target_log, rand2).
 struct MhSmall {
-    int G, S, R;            // CTAs, 128-record sub-tiles in total, most sub-tiles a CTA holds
+    int T, Gs, G, S;        // tiles, CTAs per tile, CTAs = T * Gs, 128-record sub-tiles in total
     double *partial;        // [2][G][32]
     unsigned *bar;          // arrival counter, zeroed by the host
 };
@@ -540,12 +543,14 @@ template <int NIC>
 __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan L, MhSmall Q)
 {
     extern __shared__ __align__(16) unsigned char small_smem[];
-    SurfRec *mine = reinterpret_cast<SurfRec *>(small_smem);  // [R * MHB], zero-weight padding beyond the particle list
+    SurfRec *mine = reinterpret_cast<SurfRec *>(small_smem);  // resident sub-tiles, zero-weight padding beyond the particle list
     __shared__ double red[MHB / 32][32];
-    __shared__ double st_x[32], st_y[32], st_std;
-    __shared__ int st_ok[32], st_bad;
+    __shared__ double strands[4][MHB / 32][32];  // [tile][warp][lane]
+    __shared__ double sp_x[32], sp_y[32];
+    __shared__ int s_acc[4], s_rej[4], s_bad[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int s0 = (int)((long long)Q.S * blockIdx.x / Q.G), s1 = (int)((long long)Q.S * (blockIdx.x + 1) / Q.G);
+    const int t_b = blockIdx.x / Q.Gs, g_b = blockIdx.x - t_b * Q.Gs;
+    const int s0 = (int)((long long)Q.S * g_b / Q.Gs), s1 = (int)((long long)Q.S * (g_b + 1) / Q.Gs);
     for (int t = s0; t < s1; ++t) {
         const int j = t * MHB + tid;
         SurfRec r;
@@ -553,23 +558,29 @@ __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan 
         else { r.x = 0.0; r.y = 0.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
         mine[(t - s0) * MHB + tid] = r;
     }
+    if (tid < 4) { s_acc[tid] = 0; s_rej[tid] = 0; s_bad[tid] = 0; }
     __syncthreads();
-    // chain state: lane = chain, identical in every warp of every CTA; the target values live in warp 0 only
+    // chain state of tile `warp` (meaningful for warp < T): lane = chain, identical in every CTA
+    const int chain = warp * 32 + lane;
+    const bool live = (warp < Q.T) && (chain < L.M);
     double cx = 0.0, cy = 0.0, sup = 0.0, Fc = 0.0, mh_std = L.mh_std0, a_rate = L.a_rate0;
     int ok = 0;
     unsigned phase = 0;
-    const bool live = lane < L.M;
-    const int n_iter_total = P.c.ndim;
     int bad = L.M, round = 0, jump = 1;
     bool searching = true;
     for (;;) {
         // rounds of the search for a favourable start (generator iteration -(round + 1), like k_mh_persistent), then the
         // jump iterations 1 .. ndim
         if (searching && !(round < L.max_init && bad > 0)) searching = false;
-        if (!searching && jump > n_iter_total) break;
+        if (!searching && jump > P.c.ndim) break;
         const int iter = searching ? -(round + 1) : jump;
-        double px = cx, py = cy;
-        if (live) propose_from(P, L, iter, lane, mh_std, ok, px, py);
+        // proposals of every tile by the warp that holds it (kept: the accept step below needs them); the tile this CTA
+        // sums for goes through shared memory to the other warps
+        double qx = cx, qy = cy;
+        if (live) propose_from(P, L, iter, chain, mh_std, ok, qx, qy);
+        if (warp == t_b) { sp_x[lane] = qx; sp_y[lane] = qy; }
+        __syncthreads();
+        const double px = sp_x[lane], py = sp_y[lane];
         double acc = 0.0;
         for (int t = 0; t < s1 - s0; ++t) {
             const SurfRec *rr = &mine[t * MHB + warp * 32];
@@ -582,58 +593,65 @@ __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan 
         if (warp == 0) part[(size_t)blockIdx.x * 32 + lane] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
         ++phase;
         small_barrier(Q.bar, phase * (unsigned)Q.G);
-        {   // join: warp w adds the partials of CTAs w, w + 4, ... (ascending), then the four strands in warp order.  With
-            // one warp walking all G partials the L2 latency of this loop was ~50 ns per CTA and iteration -- most of
-            // the iteration at G = 148.
-            double strand = 0.0;
+        // join: for every tile, warp w adds the partial sums of that tile's CTAs w, w + 4, ... (ascending); the four
+        // strands are added in warp order by the warp that owns the tile
+        {   // (the loads of all tiles are issued together: tile after tile, each join paid its own L2 round trip)
+            double st[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *pt = part + lane;
+            const int T = Q.T, Gs = Q.Gs;
 #pragma unroll 8
-            for (int k = warp; k < Q.G; k += MHB / 32) strand += __ldcg(part + (size_t)k * 32 + lane);
-            red[warp][lane] = strand;  // (every warp is past its read of red[] above: it sits before the barrier)
+            for (int k = warp; k < Gs; k += MHB / 32) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t < T) st[t] += __ldcg(pt + ((size_t)t * Gs + k) * 32);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) strands[t][warp][lane] = st[t];
         }
         __syncthreads();
-        if (warp == 0) {
-            const double sum = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+        bool acc_ = false, rej_ = false, bad_ = false;
+        if (warp < Q.T) {
+            const double sum = ((strands[warp][0][lane] + strands[warp][1][lane]) + strands[warp][2][lane]) + strands[warp][3][lane];
             const double Fz = L.E_vac - L.fac * sum;
-            bool acc_ = false, rej_ = false, bad_ = false;
             if (live) {
                 if (iter < 0) {
                     if (!ok) {
-                        if (Fz < 0.0) { cx = px; cy = py; Fc = Fz; sup = target_log(P, Fz, px, py); ok = 1; }
+                        if (Fz < 0.0) { cx = qx; cy = qy; Fc = Fz; sup = target_log(P, Fz, qx, qy); ok = 1; }
                         else bad_ = true;
                     }
                 } else if (ok) {
                     const bool unfav = (P.c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
                     bool accept = false;
                     if (!unfav) {
-                        const double sup_new = target_log(P, Fz, px, py);
+                        const double sup_new = target_log(P, Fz, qx, qy);
                         accept = sup_new >= sup;
                         if (!accept) {
                             double u, v;
-                            rand2(L.seed, lane, iter, 2, 0, u, v);
+                            rand2(L.seed, chain, iter, 2, 0, u, v);
                             accept = log(u) <= sup_new - sup;
                         }
-                        if (accept) { cx = px; cy = py; sup = sup_new; Fc = Fz; }
+                        if (accept) { cx = qx; cy = qy; sup = sup_new; Fc = Fz; }
                     }
                     acc_ = accept; rej_ = !accept;
                 }
             }
-            const int a = __popc(__ballot_sync(0xffffffffu, acc_)), r = __popc(__ballot_sync(0xffffffffu, rej_));
+            const int na = __popc(__ballot_sync(0xffffffffu, acc_)), nr = __popc(__ballot_sync(0xffffffffu, rej_));
             const int nb = __popc(__ballot_sync(0xffffffffu, bad_));
+            if (lane == 0) { s_acc[warp] = na; s_rej[warp] = nr; s_bad[warp] = nb; }
+        }
+        __syncthreads();
+        {   // every thread: the same counts, the same update (the next write to s_* sits behind two more barriers)
+            const int a = ((s_acc[0] + s_acc[1]) + s_acc[2]) + s_acc[3], r = ((s_rej[0] + s_rej[1]) + s_rej[2]) + s_rej[3];
             if (iter > P.c.ndim_first && a + r > 0) {  // MH_std_update, :603-612
                 a_rate = (double)a / (double)(a + r);
                 mh_std = fmin(fmax(mh_std * exp(P.c.std_gain * (a_rate - P.c.target_rate)), P.c.std_min), P.c.std_max);
             }
-            st_x[lane] = cx; st_y[lane] = cy; st_ok[lane] = ok;
-            if (lane == 0) { st_std = mh_std; st_bad = nb; }
+            if (searching) { bad = ((s_bad[0] + s_bad[1]) + s_bad[2]) + s_bad[3]; ++round; } else ++jump;
         }
-        __syncthreads();
-        cx = st_x[lane]; cy = st_y[lane]; ok = st_ok[lane]; mh_std = st_std;
-        if (searching) { bad = st_bad; ++round; } else ++jump;
-        // (the next write to st_* sits behind the next barrier's __syncthreads)
     }
-    if (blockIdx.x == 0 && warp == 0) {
+    if (blockIdx.x == 0) {
         if (live) {
-            const int k = lane;
+            const int k = chain;
             if (ok) {
                 const double w = w_theta_xy(P, cx, cy), sw = sqrt(w);
                 S.pos_out[3 * k] = cx; S.pos_out[3 * k + 1] = cy; S.pos_out[3 * k + 2] = 0.0;
@@ -645,7 +663,7 @@ __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan 
                 S.df_out[k] = HUGE_NEG;
             }
         }
-        if (lane == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
+        if (tid == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
     }
 }
 
@@ -705,7 +723,8 @@ int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_
     return RB2_OK;
 }
 
-// At most 32 chains over at most 4 resident 128-record sub-tiles per SM: the single-barrier kernel.
+// At most 128 chains (T <= 4 tiles) over at most 4 resident 128-record sub-tiles per CTA: the single-barrier kernel.
+// Returns RB2_ERR_ARG - 1000 ("does not apply") when the problem is too large for it.
 static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                            int NIC, int max_init, double *df_out, double *F_out, double *pos_out, double *a_rate_io,
                            double *mh_std_io)
@@ -713,11 +732,14 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     const rb2_config &gc = ctx.cfg;
     const int n = ctx.n, nw = cfg->y_num * cfg->x_num;
     MhSmall Q{};
+    Q.T = (M + 31) / 32;
     Q.S = (n + MHB - 1) / MHB;
-    Q.G = std::max(1, std::min(Q.S, ctx.sm_count));
-    Q.R = std::max(1, (Q.S + Q.G - 1) / Q.G);
+    Q.Gs = std::max(1, std::min(Q.S, (2 * ctx.sm_count) / Q.T));  // two CTAs per SM at most
+    Q.G = Q.T * Q.Gs;
+    const int R = std::max(1, (Q.S + Q.Gs - 1) / Q.Gs);
+    if (Q.T > 4 || R > 4) return RB2_ERR_ARG - 1000;
     MhPlan L{};
-    L.M = M; L.n = n; L.n_tiles = 1; L.max_init = max_init; L.seed = seed;
+    L.M = M; L.n = n; L.n_tiles = Q.T; L.max_init = max_init; L.seed = seed;
     L.two_d = 2.0 * gc.d;
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
@@ -752,9 +774,9 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     }
     void *kern = NIC < 0 ? (void *)k_mh_small<-1> : NIC == 0 ? (void *)k_mh_small<0>
                : NIC == 1 ? (void *)k_mh_small<1> : (void *)k_mh_small<2>;
-    const size_t smem = (size_t)Q.R * MHB * sizeof(SurfRec);  // <= 32 KB
+    const size_t smem = (size_t)R * MHB * sizeof(SurfRec);  // <= 32 KB
     void *args[] = {&P, &S, &L, &Q};
-    // cooperative launch: the arrival-counter barrier needs all G <= sm_count CTAs resident
+    // cooperative launch: the arrival-counter barrier needs all G <= 2 x sm_count CTAs resident
     RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(Q.G), dim3(MHB), args, smem, st));
     RB2_LAUNCHED(launches);
     double scal1[2];
@@ -777,8 +799,10 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     const rb2_config &gc = ctx.cfg;
     const int n = ctx.n, max_init = 10000;
     const int NIC = !gc.image_charge ? -1 : (gc.N_ic_max >= 2 ? 2 : gc.N_ic_max);
-    if (ctx.mh_small && M <= 32 && (n + MHB - 1) / MHB <= 4 * ctx.sm_count)
-        return launch_mh_small(ctx, cfg, w_theta_host, M, seed, NIC, max_init, df_out, F_out, pos_out, a_rate_io, mh_std_io);
+    if (ctx.mh_small && M <= 128) {
+        const int rc_small = launch_mh_small(ctx, cfg, w_theta_host, M, seed, NIC, max_init, df_out, F_out, pos_out, a_rate_io, mh_std_io);
+        if (rc_small != RB2_ERR_ARG - 1000) return rc_small;  // else: too many particles for the resident scheme
+    }
     void *kern = NIC < 0 ? (void *)k_mh_persistent<-1> : NIC == 0 ? (void *)k_mh_persistent<0>
                : NIC == 1 ? (void *)k_mh_persistent<1> : (void *)k_mh_persistent<2>;
     int occ = 0;

@@ -203,16 +203,17 @@ def test_device_resident_fe_sampler(orc):
 
 
 @gpu
-@pytest.mark.parametrize("n_pre,nic,kind", [(0, 1, 1), (120, 1, 1), (700, 0, 1), (2500, 2, 1), (300, 1, 2)])
-def test_device_sampler_single_barrier_kernel(orc, n_pre, nic, kind):
-    """Up to 32 chains run in k_mh_small (records resident in shared memory, chain state in registers, one barrier per
+@pytest.mark.parametrize("n_pre,nic,kind,M", [(0, 1, 1, 24), (120, 1, 1, 24), (700, 0, 1, 24), (2500, 2, 1, 24), (300, 1, 2, 24),
+                                              (0, 1, 1, 33), (120, 1, 1, 100), (2500, 1, 1, 128), (300, 1, 2, 70)])
+def test_device_sampler_single_barrier_kernel(orc, n_pre, nic, kind, M):
+    """Up to 128 chains run in k_mh_small (records resident in shared memory, chain state in registers, one barrier per
     jump).  Same generator keys and proposals as k_mh_persistent: for the same seed the chains coincide except where
     an accept decision sits on a rounding knife edge (the partial sums are joined in a different order)."""
     w = ((2.0, 2.4), (2.4, 2.0))
     mode, T = (10, 293.15) if kind == 1 else (9, 1200.0)
     sim, p, st, em = _planar_pair(orc, 41, nic=nic, w=w, mh_batch=2, mode=mode, T=T)
     emit = 100 * NM
-    M, calls = 24, 25
+    calls = 25 if M <= 32 else 8
     with sim:
         if n_pre:
             _preload(sim, st, p, n_pre, 9)
