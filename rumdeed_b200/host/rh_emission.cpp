@@ -773,23 +773,30 @@ int Tip_Supply_Grid(Sim &s, int nr_xi, int nr_phi, double *n_s_out, double *F_av
 {
     const double len_phi = 2.0 * pi / nr_phi, len_xi = (s.max_xi - 1.0) / nr_xi;
     const int M = nr_xi * nr_phi;
-    s.scratch_pts.resize((size_t)3 * M);
-    s.scratch_fld.resize((size_t)3 * M);
-    for (int i = 1; i <= nr_xi; ++i)
-        for (int j = 1; j <= nr_phi; ++j)
-            s.xyz_corr(1.0 + (i - 0.5) * len_xi, s.eta_1, (j - 0.5) * len_phi, &s.scratch_pts[(size_t)3 * ((i - 1) * nr_phi + (j - 1))]);
-    if (s.Calc_Field_at_Batch(M, s.scratch_pts.data(), s.scratch_fld.data())) return -1;
-    double n_s = 0.0, F_avg = 0.0;
-    for (int i = 1; i <= nr_xi; ++i)
-        for (int j = 1; j <= nr_phi; ++j) {
-            const size_t o = (size_t)3 * ((i - 1) * nr_phi + (j - 1));
-            const double F = s.Field_normal(&s.scratch_pts[o], &s.scratch_fld[o]);
-            F_avg += F;
-            if (F < 0.0) {
-                const double A_f = s.Tip_Area(1.0 + (i - 1.0) * len_xi, 1.0 + (i + 0.0) * len_xi, (j - 1.0) * len_phi, (j + 0.0) * len_phi);
-                n_s += Elec_Supply(s, A_f, F);
+    // The grid lives on the tip surface: mid points, surface normals and patch areas depend on the geometry only, so
+    // they are computed once (1e4 points x ~10 sqrt / log / sin / cos calls were 3-4 ms of every time step).
+    if (s.tip_grid_key[0] != nr_xi || s.tip_grid_key[1] != nr_phi || s.tip_grid_geom[0] != s.max_xi || s.tip_grid_geom[1] != s.eta_1 ||
+        s.tip_grid_geom[2] != s.a_foci || s.tip_grid_geom[3] != s.shift_z) {
+        s.tip_grid_pts.resize((size_t)3 * M); s.tip_grid_nrm.resize((size_t)3 * M); s.tip_grid_area.resize((size_t)M);
+        for (int i = 1; i <= nr_xi; ++i)
+            for (int j = 1; j <= nr_phi; ++j) {
+                const size_t k = (size_t)(i - 1) * nr_phi + (j - 1);
+                s.xyz_corr(1.0 + (i - 0.5) * len_xi, s.eta_1, (j - 0.5) * len_phi, &s.tip_grid_pts[3 * k]);
+                s.surface_normal(&s.tip_grid_pts[3 * k], &s.tip_grid_nrm[3 * k]);
+                s.tip_grid_area[k] = s.Tip_Area(1.0 + (i - 1.0) * len_xi, 1.0 + (i + 0.0) * len_xi, (j - 1.0) * len_phi, (j + 0.0) * len_phi);
             }
-        }
+        s.tip_grid_key[0] = nr_xi; s.tip_grid_key[1] = nr_phi;
+        s.tip_grid_geom[0] = s.max_xi; s.tip_grid_geom[1] = s.eta_1; s.tip_grid_geom[2] = s.a_foci; s.tip_grid_geom[3] = s.shift_z;
+    }
+    s.scratch_fld.resize((size_t)3 * M);
+    if (s.Calc_Field_at_Batch(M, s.tip_grid_pts.data(), s.scratch_fld.data())) return -1;
+    double n_s = 0.0, F_avg = 0.0;
+    for (int k = 0; k < M; ++k) {  // same order as the reference's double loop (i outer, j inner)
+        const double *u = &s.tip_grid_nrm[(size_t)3 * k], *f = &s.scratch_fld[(size_t)3 * k];
+        const double F = u[0] * f[0] + u[1] * f[1] + u[2] * f[2];  // Field_normal
+        F_avg += F;
+        if (F < 0.0) n_s += Elec_Supply(s, s.tip_grid_area[k], F);
+    }
     *n_s_out = n_s;
     if (F_avg_out) *F_avg_out = F_avg / ((double)nr_phi * nr_xi);
     return 0;
@@ -948,7 +955,12 @@ static int Do_Emission_Tip(Sim &s, int step)
     s.slog = StepLog{};
     if (s.g.emitters_type != 1) return s.fail("RUMDEED: tip emitter type != 1 (field emission) is not on the device path");
     double n_s = 0.0, F_avg = 0.0;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = clk::now();
     if (Tip_Supply_Grid(s, 100, 100, &n_s, &F_avg)) return -1;
+    const auto t1 = clk::now();
+    s.t_em_quad += secs(t0, t1);
     s.slog.N_sup = n_s;
     s.slog.F_avg[2] = F_avg;
     const int n_r = (int)lround(n_s);
@@ -961,6 +973,9 @@ static int Do_Emission_Tip(Sim &s, int step)
         b_F.resize(n_r); b_D.resize(n_r); b_pos.resize((size_t)3 * n_r);
         if (Metro_algo_tip_v3_batch(s, n_r, 80, b_F.data(), b_D.data(), b_pos.data()) == -2) return -1;
     }
+    const auto t2 = clk::now();
+    s.t_em_mh += secs(t1, t2);
+    s.n_candidates_total += n_r;
     for (int k = 0; k < n_r; ++k) {
         double xi, phi, F, D_f, par_pos[3];
         if (s.g.mh_batch) { F = b_F[k]; D_f = b_D[k]; memcpy(par_pos, &b_pos[(size_t)3 * k], sizeof(par_pos)); }
@@ -975,6 +990,7 @@ static int Do_Emission_Tip(Sim &s, int step)
         }
     }
     s.slog.nrElecEmit = nrElecEmit;
+    s.t_em_add += secs(t2, clk::now());
     return 0;
 }
 

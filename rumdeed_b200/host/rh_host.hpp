@@ -156,6 +156,10 @@ struct Sim {
     long long n_candidates_total = 0;                       // sum of N_round
     FILE *ud_density_absorb_top = nullptr, *ud_density_absorb_bot = nullptr, *planes_ud[RB2_PLANES_MAX] = {nullptr};
     std::vector<double> scratch_pts, scratch_fld, scratch_ez;
+    // tip supply grid (Tip_Supply_Grid): geometry-only quantities, computed once
+    std::vector<double> tip_grid_pts, tip_grid_nrm, tip_grid_area;
+    int tip_grid_key[2] = {0, 0};
+    double tip_grid_geom[4] = {0, 0, 0, 0};
 
     int fail(const std::string &m) { err = m; return -1; }
     int check(int rc, const char *where);

@@ -569,6 +569,41 @@ def test_large_cloud_properties(orc):
 
 
 # --------------------------------------------------------------------------------------------------
+def test_full_size_cloud_properties(orc):
+    """BASELINE.json's largest configuration (N = 1e6, planar image charges, N_ic_max = 1), where the oracle cannot
+    evaluate every row: rows sampled against the long-double oracle (1e-11), bit-identical repetition (fixed summation
+    order, no atomics), Newton's third law on the Coulomb-only variant, and Add / Mark / Remove bookkeeping at scale."""
+    n = 1_000_000
+    cfg, p = planar(orc, ic=True, nic=1, cap=n + 16)
+    pos, q, m, sp = cloud(n, 20261017, ions=True)
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        assert np.all(np.isfinite(acc))
+        for i in [0, 127, 128, 16383, 16384, 500_000, 777_777, n - 129, n - 1]:
+            truth = orc.accel_gather_ld(p, pos, q, m, i, i + 1)
+            assert relerr(acc[i:i + 1], truth) < TOL, i
+        hp.Calculate_Acceleration_Particles()
+        assert np.array_equal(hp.download(("acc",))["acc"], acc)
+        # stable compaction at scale: remove every 7th particle, the survivors keep their order and ids
+        kill = np.arange(3, n, 7, dtype=np.int32)
+        hp.Mark_Particles_Remove(kill, REMOVE_TOP)
+        k = hp.Remove_Particles(1)
+        keep = np.ones(n, bool); keep[kill] = False
+        assert k.nrPart == int(keep.sum())
+        st = hp.download(("pos", "id", "charge"))
+        assert np.array_equal(st["id"], np.arange(n, dtype=np.int32)[keep])
+        assert np.array_equal(st["pos"], pos[keep]) and np.array_equal(st["charge"], q[keep])
+        # Coulomb only, no vacuum field: sum_i m_i a_i = 0
+        cfg0 = rb.planar_config(0.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1e-16, False, 0, capacity=n + 16)
+        hp.update_config(cfg0)
+        hp.Calculate_Acceleration_Particles()
+        f = hp.download(("acc",))["acc"] * m[keep][:, None]
+        assert np.linalg.norm(f.sum(axis=0)) < 1e-9 * np.abs(f).sum()
+
+
+# --------------------------------------------------------------------------------------------------
 def test_empty_and_overflowing_store(orc):
     """Edge cases the reference guards: an empty system steps to nothing (mod_verlet.F90:123-162 with
     nrPart = 0), zero field points are a no-op (:1658), Add_Particle beyond MAX_PARTICLES drops the particle

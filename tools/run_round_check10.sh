@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "full_size" 2>&1 | tail -15 > gpurun_out/c10_fullsize.log; tail -3 gpurun_out/c10_fullsize.log
+timeout 600 python -m pytest tests/test_emission.py -m gpu -q -x -k "tip" 2>&1 | tail -15 > gpurun_out/c10_tip.log; tail -3 gpurun_out/c10_tip.log
+DECK_TIMEOUT=200 timeout 400 tools/run_decks.sh 2000 5000 tip > gpurun_out/deck_tip10.log 2>&1; cat gpurun_out/deck_tip10.log
