@@ -236,6 +236,16 @@ typedef struct rb2_mh_config {
 int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed,
                   double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 
+/* Lock-step chains on the hyperboloid tip: Metro_algo_tip_v3 (src/mod_emission_tip.f90:1241-1390) for the M candidates
+ * of a time step together -- (xi, phi) proposals with reflection in xi and wrap in phi, target ln S + 1/2 ln(xi^2 - eta_1^2)
+ * on the NORMAL field component, shared adaptive step (one update per jump after the warm-up quarter).  Every jump is
+ * queued on the device (proposals, the tip field kernel of rb2_field_batch, accept / reject); the host is blocked only
+ * for the start-spot rounds and once for the result.  Outputs (host): normal surface field eta_f_out[M] (1.0 marks a chain
+ * that found no favourable spot), escape probability df_out[M] (Escape_Prob_Tip :1734-1760; 0 for failed chains) and
+ * positions pos_out[3M] on the tip surface.  a_rate_io / mh_std_io: a_rate / MH_std of the reference module (:50). */
+int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
+               double *a_rate_io, double *mh_std_io);
+
 /* ---- electron / N2 collisions (collision_mode 1 and 2) -------------------------
  * Do_Electron_Atom_Collisions (src/mod_collisions.F90:30-76, called from src/main.F90:202 through
  * Do_Collisions, src/mod_verlet.F90:164-170), one-time-step variants:

@@ -133,7 +133,7 @@ EXPORTS = (
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
     "rb2_add_particles", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_accel_host",
-    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar",
+    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_tip",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
@@ -174,6 +174,7 @@ def load_library(path: str | None = None):
     lib.rb2_field_batch_delta.argtypes = [C.c_int, _PD, C.c_int, _PD, _PD, _PD]
     lib.rb2_field_surface_z.argtypes = [C.c_int, _PD, _PD]
     lib.rb2_mh_planar.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
+    lib.rb2_mh_tip.argtypes = [C.c_int, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
     lib.rb2_set_partition.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_pair_rank.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_option.argtypes = [C.c_char_p, C.c_double]
@@ -462,6 +463,14 @@ class HotPath:
         ar, sd = C.c_double(a_rate), C.c_double(MH_std)
         self._check(self.lib.rb2_mh_planar(C.byref(c), _d(w), M, seed, _d(df), _d(F), _d(pos), C.byref(ar), C.byref(sd)))
         return df, F, pos, ar.value, sd.value
+
+    def mh_tip(self, M, seed, ndim=80, a_rate=0.5, MH_std=1.0):
+        """Device-resident lock-step tip chains (Metro_algo_tip_v3, src/mod_emission_tip.f90:1241-1390).
+        Returns (eta_f, df, pos, a_rate, MH_std)."""
+        ef, df, pos = np.zeros(M), np.zeros(M), np.zeros((M, 3))
+        ar, sd = C.c_double(a_rate), C.c_double(MH_std)
+        self._check(self.lib.rb2_mh_tip(M, ndim, seed, _d(ef), _d(df), _d(pos), C.byref(ar), C.byref(sd)))
+        return ef, df, pos, ar.value, sd.value
 
     def Particles_To_Device(self):
         self._check(self.lib.rb2_field_window_open())

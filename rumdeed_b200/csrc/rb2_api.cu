@@ -745,6 +745,16 @@ int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsign
     return rb2_launch_mh_planar(c, cfg, w_theta, M, seed, df_out, F_out, pos_out, a_rate_io, mh_std_io);
 }
 
+int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out, double *a_rate_io,
+               double *mh_std_io)
+{
+    RB2_REQUIRE_INIT();
+    if (M < 0) return rb2_fail(RB2_ERR_ARG, "M < 0");
+    if (M == 0) return RB2_OK;
+    if (!eta_f_out || !df_out || !pos_out || !a_rate_io || !mh_std_io) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    return rb2_launch_mh_tip(g_rb2, M, ndim, seed, eta_f_out, df_out, pos_out, a_rate_io, mh_std_io);
+}
+
 int rb2_field_window_open(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 int rb2_field_window_close(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 
@@ -770,6 +780,8 @@ int rb2_set_option(const char *name, double value)
     } else if (!strcmp(name, "mh_ctas_per_sm")) {
         if (value < 1 || value > 4) return rb2_fail(RB2_ERR_ARG, "mh_ctas_per_sm must be 1..4");
         c.mh_ctas_per_sm = (int)value;
+    } else if (!strcmp(name, "tip_field_small")) {
+        c.tip_field_small = (value != 0.0) ? 1 : 0;
     } else if (!strcmp(name, "mh_small")) {
         c.mh_small = (value != 0.0) ? 1 : 0;
     } else if (!strcmp(name, "sym_waves")) {

@@ -121,6 +121,7 @@ struct Rb2Ctx {
     rb2_event *d_events = nullptr; int ev_cap = 0;
     int    ev_min = 65536;                // initial size of the record buffer (option "event_buffer")
     int    mh_ctas_per_sm = 2;            // sampler: CTAs per SM of the cooperative kernel (option "mh_ctas_per_sm", 1..4)
+    int    tip_field_small = 1;           // tip field: CTA-per-point kernel for small batches (option "tip_field_small")
     int    mh_small = 1;                  // sampler: single-barrier kernel for <= 32 chains (option "mh_small", 0 = off)
     std::vector<rb2_event> host_events;
 
@@ -165,6 +166,8 @@ int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra
 int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                          double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez);
+int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
+                      double *a_rate_io, double *mh_std_io);
 // collisions (rb2_collisions.cu)
 void rb2_collisions_release(Rb2Ctx &ctx);
 int rb2_fetch_counters(Rb2Ctx &ctx);  // device counters -> ctx.counts (rb2_api.cu)

@@ -723,6 +723,223 @@ int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_
     return RB2_OK;
 }
 
+// ---- lock-step chains on the hyperboloid tip ----------------------------------------------------------------------
+// Metro_algo_tip_v3 (src/mod_emission_tip.f90:1241-1390) for all candidates of a time step together, the scheme of
+// Metropolis_Hastings_rectangle_J_batch applied to the tip's (xi, phi) chains (the host mirror's
+// Metro_algo_tip_v3_batch).  A jump is three launches queued back to back -- proposals -> the tip field kernel of
+// rb2_field_batch (k_pair<tip, field> + finalise, device pointers) -> accept / reject + MH_std update -- and all
+// `ndim` jumps are queued without a host wait in between; only the rounds of the search for a favourable start are
+// host-stepped (one or two per call).  The host loop paid one rb2_field_batch round trip (~70 us) and ~60 us of host
+// math per jump.  One CTA runs the proposal / accept kernels (a few hundred chains; the shared step needs the
+// accept counts of all chains anyway).
+struct TipMh {
+    int M, ndim_first;
+    unsigned long long seed;
+    double max_xi, eta_1, a_foci, shift_z;
+    double sup_fac;              // (time_step / q_0) * a_FN / w_theta
+    double esc_fac;              // b_FN * w_theta^(3/2)
+    double *xi, *phi, *eta_f, *sup, *cur;   // chain state: [M], [M], [M], [M], [3M]
+    double *w_xi, *w_phi;                  // proposals
+    double *pts, *fld;                     // [3M] field points / fields of the current jump
+    double *scal;                          // [0] MH_std, [1] a_rate
+    int *ok, *valid, *bad;                 // [M], [M], [1]
+    double *df_out;                        // [M]
+};
+constexpr double TIP_W = 4.7;  // w_theta of the tip, src/mod_emission_tip.f90:45
+constexpr int TIPB = 256;
+
+__device__ __forceinline__ void tip_xyz(const TipMh &T, double xi, double phi, double *out)  // xyz_corr, src/mod_hyperboloid_tip.f90:78-89
+{
+    const double xy = T.a_foci * sqrt((xi * xi - 1.0) * (1.0 - T.eta_1 * T.eta_1));
+    out[0] = xy * cos(phi);
+    out[1] = xy * sin(phi);
+    out[2] = T.a_foci * xi * T.eta_1 + T.shift_z;
+}
+__device__ __forceinline__ double tip_field_normal(const TipMh &T, const double *pos, const double *f)  // :156-163, :25-34
+{
+    const double eta_fac = T.eta_1 / sqrt(1 - T.eta_1 * T.eta_1);
+    const double div_fac = -1.0 / sqrt(pos[0] * pos[0] + pos[1] * pos[1] + (T.a_foci * T.a_foci) * (1 - T.eta_1 * T.eta_1));
+    const double nx = eta_fac * pos[0] * div_fac, ny = eta_fac * pos[1] * div_fac, nz = 1.0;
+    const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
+    return (nx / nrm) * f[0] + (ny / nrm) * f[1] + (nz / nrm) * f[2];
+}
+__device__ __forceinline__ double tip_target_log(const MhParams &P, const TipMh &T, double eta_f, double xi)  // Tip_fe_target_log, :1213-1219
+{
+    const double t = t_y(P, eta_f, TIP_W);
+    const double sup = T.sup_fac / (t * t) * (eta_f * eta_f);
+    return log(fmax(sup, TINY)) + 0.5 * log(xi * xi - T.eta_1 * T.eta_1);
+}
+
+// iter < 0: search round -iter (uniform over the surface for chains without a start); iter >= 1: jump iter
+__global__ void __launch_bounds__(TIPB) k_tip_propose(MhParams P, TipMh T, int iter)
+{
+    const double two_pi = 2.0 * RB2_PI;
+    for (int c = threadIdx.x; c < T.M; c += TIPB) {
+        const int ok = T.ok[c];
+        int valid = 0;
+        double nxi = T.xi[c], nphi = T.phi[c];
+        if (iter < 0) {
+            if (!ok) {
+                double u, v;
+                rand2(T.seed, c, iter, 0, 0, u, v);
+                nxi = 1.0 + (T.max_xi - 1.0) * u;
+                nphi = two_pi * v;
+                valid = 1;
+            }
+        } else if (ok) {
+            const double frac = (iter > T.ndim_first) ? T.scal[0] : 0.10;
+            double g0 = 0.0, g1 = 0.0;
+            for (int attempt = 0; attempt < 64; ++attempt) {  // box_muller = Marsaglia polar, src/mod_global.F90:578-595
+                double u, v;
+                rand2(T.seed, c, iter, 1, attempt, u, v);
+                const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
+                if (w < 1.0 && w > 0.0) {
+                    const double f = sqrt((-2.0 * log(w)) / w);
+                    g0 = a * f; g1 = b * f;
+                    break;
+                }
+            }
+            nxi = nxi + g0 * ((T.max_xi - 1.0) * frac);
+            nphi = fmod(nphi + g1 * (two_pi * frac), two_pi);
+            if (nphi < 0.0) nphi += two_pi;                 // Fortran modulo()
+            if (nxi > T.max_xi) nxi = 2.0 * T.max_xi - nxi;  // reflection, :1300-1310
+            if (nxi < 1.0) nxi = 2.0 - nxi;
+            valid = !(nxi < 1.0 || nxi > T.max_xi);
+        }
+        T.valid[c] = valid;
+        T.w_xi[c] = nxi; T.w_phi[c] = nphi;
+        if (valid) tip_xyz(T, nxi, nphi, &T.pts[3 * c]);
+        else { T.pts[3 * c] = T.cur[3 * c]; T.pts[3 * c + 1] = T.cur[3 * c + 1]; T.pts[3 * c + 2] = T.cur[3 * c + 2]; }
+    }
+}
+
+__global__ void __launch_bounds__(TIPB) k_tip_accept(MhParams P, TipMh T, int iter)
+{
+    __shared__ int s_acc, s_rej, s_bad;
+    if (threadIdx.x == 0) { s_acc = 0; s_rej = 0; s_bad = 0; }
+    __syncthreads();
+    int n_acc = 0, n_rej = 0, n_bad = 0;
+    for (int c = threadIdx.x; c < T.M; c += TIPB) {
+        const int ok = T.ok[c], valid = T.valid[c];
+        if (iter < 0) {
+            if (ok) continue;
+            const double ef = tip_field_normal(T, &T.pts[3 * c], &T.fld[3 * c]);
+            if (ef < 0.0) {
+                T.xi[c] = T.w_xi[c]; T.phi[c] = T.w_phi[c]; T.eta_f[c] = ef; T.ok[c] = 1;
+                for (int k = 0; k < 3; ++k) T.cur[3 * c + k] = T.pts[3 * c + k];
+                T.sup[c] = tip_target_log(P, T, ef, T.w_xi[c]);
+            } else n_bad++;
+            continue;
+        }
+        if (!ok) continue;
+        if (!valid) { n_rej++; continue; }
+        const double ef = tip_field_normal(T, &T.pts[3 * c], &T.fld[3 * c]);
+        if (ef >= 0.0) { n_rej++; continue; }
+        const double sup_new = tip_target_log(P, T, ef, T.w_xi[c]), sup_old = T.sup[c];
+        bool accept = sup_new >= sup_old;
+        if (!accept) {
+            double u, v;
+            rand2(T.seed, c, iter, 2, 0, u, v);
+            accept = log(u) <= sup_new - sup_old;
+        }
+        if (accept) {
+            T.xi[c] = T.w_xi[c]; T.phi[c] = T.w_phi[c]; T.eta_f[c] = ef; T.sup[c] = sup_new;
+            for (int k = 0; k < 3; ++k) T.cur[3 * c + k] = T.pts[3 * c + k];
+            n_acc++;
+        } else n_rej++;
+    }
+    if (n_acc) atomicAdd(&s_acc, n_acc);
+    if (n_rej) atomicAdd(&s_rej, n_rej);
+    if (n_bad) atomicAdd(&s_bad, n_bad);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (iter < 0) *T.bad = s_bad;
+        else if (iter > T.ndim_first && s_acc + s_rej > 0) {  // :1370-1380
+            const double a_rate = (double)s_acc / (double)(s_acc + s_rej);
+            T.scal[1] = a_rate;
+            T.scal[0] = fmin(fmax(T.scal[0] * exp(0.025 * (a_rate - 0.35)), 0.0005), 0.125);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TIPB) k_tip_finish(MhParams P, TipMh T)
+{
+    for (int c = threadIdx.x; c < T.M; c += TIPB) {
+        if (T.ok[c]) {
+            const double F = T.eta_f[c];
+            T.df_out[c] = exp(T.esc_fac * v_y(P, F, TIP_W) / fabs(F));  // Escape_Prob_Tip, :1734-1760
+        } else {  // no favourable spot: defined outputs, no emission
+            tip_xyz(T, 1.0, 0.0, &T.cur[3 * c]);
+            T.eta_f[c] = 1.0;
+            T.df_out[c] = 0.0;
+        }
+    }
+}
+
+int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
+                      double *a_rate_io, double *mh_std_io)
+{
+    if (M < 1) return RB2_OK;
+    const rb2_config &gc = ctx.cfg;
+    if (gc.geometry != RB2_GEOM_TIP) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_mh_tip: hyperboloid-tip geometry only");
+    if (ndim < 1) return rb2_fail(RB2_ERR_ARG, "ndim < 1");
+    const double pi = RB2_PI, h_bar = 6.62607015e-34 / (2.0 * pi);
+    MhParams P{};
+    P.c.image_charge = gc.image_charge;
+    P.l_const = rb2k::q_0 / (4.0 * pi * rb2k::epsilon_0);
+    P.b_FN = -4.0 / (3.0 * h_bar) * sqrt(2.0 * rb2k::m_0 * rb2k::q_0);
+    const double a_FN = (rb2k::q_0 * rb2k::q_0) / (16.0 * (pi * pi) * h_bar);
+    TipMh T{};
+    T.M = M; T.ndim_first = (int)lround(ndim * 0.25); T.seed = seed;
+    T.max_xi = gc.max_xi; T.eta_1 = gc.eta_1; T.a_foci = gc.a_foci; T.shift_z = gc.shift_z;
+    T.sup_fac = (gc.time_step / rb2k::q_0) * a_FN / TIP_W;
+    { const double sw = sqrt(TIP_W); T.esc_fac = P.b_FN * (sw * sw * sw); }
+    // scratch: 17 M doubles + 2 scalars, 2 M + 1 ints
+    int rc = rb2_ensure_stage(ctx, (size_t)18 * M + 4, (size_t)2 * M + 4);
+    if (rc) return rc;
+    double *d = ctx.d_stage_d;
+    T.xi = d; T.phi = d + M; T.eta_f = d + 2 * (size_t)M; T.sup = d + 3 * (size_t)M; T.cur = d + 4 * (size_t)M;
+    T.w_xi = d + 7 * (size_t)M; T.w_phi = d + 8 * (size_t)M; T.pts = d + 9 * (size_t)M; T.fld = d + 12 * (size_t)M;
+    T.df_out = d + 15 * (size_t)M; T.scal = d + 16 * (size_t)M;
+    T.ok = ctx.d_stage_i; T.valid = T.ok + M; T.bad = T.valid + M;
+    cudaStream_t st = ctx.stream;
+    double scal[2] = {fmin(fmax(*mh_std_io, 0.0005), 0.125), *a_rate_io};  // the clamp of :1250-1254 at entry
+    RB2_CUDA(cudaMemsetAsync(d, 0, (size_t)16 * M * sizeof(double), st));
+    RB2_CUDA(cudaMemsetAsync(ctx.d_stage_i, 0, ((size_t)2 * M + 4) * sizeof(int), st));
+    RB2_CUDA(cudaMemcpyAsync(T.scal, scal, sizeof(scal), cudaMemcpyHostToDevice, st));
+    // search for favourable starts: host-stepped rounds (one or two in practice, 10000 at most like the reference)
+    int bad = M;
+    for (int r = 0; r < 10000 && bad > 0; ++r) {
+        k_tip_propose<<<1, TIPB, 0, st>>>(P, T, -(r + 1));
+        rc = rb2_launch_field(ctx, ctx.a.pq, ctx.n, nullptr, 0, T.pts, M, T.fld);
+        if (rc) return rc;
+        k_tip_accept<<<1, TIPB, 0, st>>>(P, T, -(r + 1));
+        RB2_CUDA(cudaGetLastError());
+        RB2_LAUNCHED(2);
+        RB2_CUDA(cudaMemcpyAsync(&bad, T.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB2_CUDA(cudaStreamSynchronize(st));
+    }
+    // the jumps: queued back to back, no host wait
+    for (int i = 1; i <= ndim; ++i) {
+        k_tip_propose<<<1, TIPB, 0, st>>>(P, T, i);
+        rc = rb2_launch_field(ctx, ctx.a.pq, ctx.n, nullptr, 0, T.pts, M, T.fld);
+        if (rc) return rc;
+        k_tip_accept<<<1, TIPB, 0, st>>>(P, T, i);
+        RB2_LAUNCHED(2);
+    }
+    k_tip_finish<<<1, TIPB, 0, st>>>(P, T);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(1);
+    RB2_CUDA(cudaMemcpyAsync(eta_f_out, T.eta_f, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(df_out, T.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(pos_out, T.cur, (size_t)3 * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(scal, T.scal, sizeof(scal), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    *mh_std_io = scal[0];
+    *a_rate_io = scal[1];
+    return RB2_OK;
+}
+
 // At most 128 chains (T <= 4 tiles) over at most 4 resident 128-record sub-tiles per CTA: the single-barrier kernel.
 // Returns RB2_ERR_ARG - 1000 ("does not apply") when the problem is too large for it.
 static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,

@@ -406,10 +406,65 @@ int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, 
 }
 
 // Calc_Field_at_Batch: M points in d_pts (3,M) -> d_fld (3,M); sources pq[0..n) plus extra[0..n_extra).
+// Tip geometry, few points against few particles (the tip sampler: ~200 proposals x ~1e3 electrons per jump): the tiled
+// kernel above has one thread per point and at most n / 128 source chunks -- 16 CTAs of 128 sequential heavy (IEEE sqrt /
+// divide) pair evaluations each, ~90 us.  Here a CTA owns ONE point, its 128 threads stride over the sources, and the
+// sums are joined in a fixed order (shuffle tree, then the four warps): M CTAs, a few us.  Same arithmetic per pair.
+__global__ void __launch_bounds__(128) k_tip_field_point(const double4 *__restrict__ src, int n, const double *__restrict__ pts,
+                                                          int do_ic, TipParams T, double *__restrict__ fld)
+{
+    __shared__ double sh[3][4];
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double xi = pts[3 * k], yi = pts[3 * k + 1], zi = pts[3 * k + 2];
+    TipImage im_i{};
+    if (do_ic) im_i = tip_image_point(T, xi, yi, zi);
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int j = tid; j < n; j += 128) {
+        const double4 pj = src[j];
+        const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;  // Coulomb, src/mod_verlet.F90:1511-1518
+        const double r = sqrt(dx * dx + dy * dy + dz * dz) + rb2k::soft;
+        const double inv_r3 = 1.0 / (r * r * r);
+        double fx = inv_r3 * dx, fy = inv_r3 * dy, fz = inv_r3 * dz;
+        if (do_ic) {  // Sphere_IC_field(p, r_j): the field point is imaged (:1520)
+            double ic_x, ic_y, ic_z;
+            tip_ic_force(T, im_i, xi, yi, zi, pj.x, pj.y, pj.z, ic_x, ic_y, ic_z);
+            fx += ic_x; fy += ic_y; fz += ic_z;
+        }
+        ax = fma(pj.w, fx, ax);
+        ay = fma(pj.w, fy, ay);
+        az = fma(pj.w, fz, az);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
+    if (lane == 0) { sh[0][warp] = ax; sh[1][warp] = ay; sh[2][warp] = az; }
+    __syncthreads();
+    if (tid == 0) {
+        const double sx = ((sh[0][0] + sh[0][1]) + sh[0][2]) + sh[0][3];
+        const double sy = ((sh[1][0] + sh[1][1]) + sh[1][2]) + sh[1][3];
+        const double sz = ((sh[2][0] + sh[2][1]) + sh[2][2]) + sh[2][3];
+        double fE_x, fE_y, fE_z;
+        rb2_tip_field_E(T, xi, yi, zi, fE_x, fE_y, fE_z);
+        fld[3 * k] = fE_x + rb2k::div_fac_c * sx;
+        fld[3 * k + 1] = fE_y + rb2k::div_fac_c * sy;
+        fld[3 * k + 2] = fE_z + rb2k::div_fac_c * sz;
+    }
+}
+
 int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra, int n_extra, const double *d_pts, int M,
                      double *d_fld)
 {
     if (M < 1) return RB2_OK;
+    if (ctx.cfg.geometry == RB2_GEOM_TIP && ctx.tip_field_small && n_extra == 0 && n >= 1 && n <= 8192 && M <= 2048) {
+        const StepParams P = rb2_make_step_params(ctx.cfg);
+        k_tip_field_point<<<M, 128, 0, ctx.stream>>>(pq, n, d_pts, P.tip.do_ic, P.tip, d_fld);
+        RB2_CUDA(cudaGetLastError());
+        RB2_LAUNCHED(1);
+        return RB2_OK;
+    }
     Split sp{}, spx{};
     int nslots = 0;
     if (n > 0) { sp = choose_split(M, n, ctx.sm_count); nslots += sp.nsplit; }

@@ -869,6 +869,11 @@ int Metro_algo_tip_v3(Sim &s, int ndim, double *xi_out, double *phi_out, double 
 // step); like the planar pair the two agree statistically, not run for run.
 int Metro_algo_tip_v3_batch(Sim &s, int M, int ndim, double *eta_f_out, double *df_out, double *pos_out)
 {
+    if (s.g.mh_device) {  // the same lock-step chains with every jump queued on the GPU (rb2_mh_tip)
+        if (M < 1) return 0;
+        if (s.check(rb2_mh_tip(M, ndim, s.rng.next(), eta_f_out, df_out, pos_out, &s.a_rate_tip, &s.MH_std_tip), "rb2_mh_tip")) return -2;
+        return 0;
+    }
     const int ndim_first = (int)lround(ndim * 0.25);
     if (s.MH_std_tip > 0.125) s.MH_std_tip = 0.125; else if (s.MH_std_tip < 0.0005) s.MH_std_tip = 0.0005;
     std::vector<int> act(M), ok(M, 0);

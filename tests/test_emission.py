@@ -10,6 +10,8 @@ helpers (work function, GTF, FN, namelist reader) to golden values.
 import math
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -320,6 +322,42 @@ def test_tip_supply_and_sampler_match_oracle(orc):
     assert _ks(eta_f_b, b[:, 2]) > 1e-3 and _ks(df_b, b[:, 3]) > 1e-3
 
 
+@gpu
+def test_device_resident_tip_sampler(orc):
+    """rb2_mh_tip: the lock-step tip chains with every jump queued on the device (proposal kernel, the tip field kernel
+    of rb2_field_batch, accept kernel).  Same distributions as the oracle's serial chains and as the host lock-step
+    variant, reproducible for a seed, positions on the tip surface, escape probability consistent with the field."""
+    sim, p, st, em = _tip_pair(orc, 43, mh_batch=True)
+    with sim:
+        rng = np.random.default_rng(2)
+        pos = np.stack([rng.uniform(-30, 30, 60), rng.uniform(-30, 30, 60), rng.uniform(503, 700, 60)], axis=1) * NM
+        hp = rb.HotPath.attach()
+        hp.Add_Particles(pos, np.zeros((60, 3)), np.ones(60, dtype=np.int32), 0)
+        for r in pos:
+            st.add(p, r, [0, 0, 0], 1, 0, 1)
+        b = np.array([em.metro_algo_tip_v3(80)[1:5] for _ in range(300)])         # xi, phi, eta_f, df
+        eta_h, df_h, pos_h = sim.Metro_algo_tip_v3_batch(600, 80)                 # host lock-step loop
+        eta_d, df_d, pos_d, a_rate, mh_std = hp.mh_tip(600, seed=12345)
+        again = hp.mh_tip(600, seed=12345)
+        other = hp.mh_tip(600, seed=6)
+        few = hp.mh_tip(3, seed=1)
+    assert np.all(eta_d < 0) and np.all((df_d > 0) & (df_d <= 1))
+    assert _ks(eta_d, b[:, 2]) > 1e-3 and _ks(df_d, b[:, 3]) > 1e-3              # against the oracle's serial chains
+    assert _ks(eta_d, eta_h) > 1e-3 and _ks(df_d, df_h) > 1e-3                    # against the host lock-step loop
+    assert _ks(np.hypot(pos_d[:, 0], pos_d[:, 1]), np.hypot(pos_h[:, 0], pos_h[:, 1])) > 1e-3
+    for x, y in zip(again[:3], (eta_d, df_d, pos_d)):
+        assert np.array_equal(x, y)
+    assert again[3:] == (a_rate, mh_std) and not np.array_equal(other[2], pos_d)
+    assert 0.0 < a_rate <= 1.0 and 0.0005 <= mh_std <= 0.125
+    assert few[0].shape == (3,) and np.all(few[0] < 0)
+    # positions lie on the hyperboloid eta = eta_1 (src/mod_hyperboloid_tip.f90:36-76) and the escape probability is
+    # Escape_Prob_Tip of the returned field
+    for k in (0, 17, 599):
+        eta = orc.lib.orc_eta_coor(C.byref(p), pos_d[k, 0], pos_d[k, 1], pos_d[k, 2])
+        assert eta == pytest.approx(p.eta_1, rel=1e-9)
+        assert df_d[k] == pytest.approx(orc.tip_escape_prob(p, eta_d[k], 4.7), rel=1e-10)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # GPU: whole-system runs
 @gpu
@@ -365,14 +403,15 @@ def test_planar_system_reference_test(orc, mh_batch):
 
 
 @gpu
-def test_tip_system_reference_test(orc):
+@pytest.mark.parametrize("mh_batch", [True, 2])
+def test_tip_system_reference_test(orc, mh_batch):
     """mod_tests.F90:2131-2219 (Test_Tip_System) shape: emission from the tip reaches the anode and the
     bookkeeping closes; the emitted count tracks the oracle's."""
     # d = 1000 nm gap, tip 900/100/100 nm, 800 V, dt = 0.25 fs, 350 steps -- the reference's own numbers
     # (the lock-step sampler is used for the 350 steps: the serial one costs ~500 x 81 single-point field
     # calls per step here; their equivalence is covered by test_tip_supply_and_sampler_match_oracle)
     sim, p, st, em = _tip_pair(orc, 777, V=800.0, dt=0.25e-15, dims=(900 * NM, 100 * NM, 100 * NM), box_z=1000 * NM,
-                               mh_batch=True)
+                               mh_batch=mh_batch)
     n_steps = 350
     q0 = rb.api.Q_0
     with sim:

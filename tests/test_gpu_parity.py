@@ -368,12 +368,15 @@ def test_tip_cloud_vs_oracle(orc, n):
         hp.upload(pos, q, m, species=np.where(ion, 2, 1).astype(np.int32))
         hp.Calculate_Acceleration_Particles()
         acc = hp.download(("acc",))["acc"]
-        fld = hp.Calc_Field_at_Batch(pts)
-        vac_only = None
+        fld = hp.Calc_Field_at_Batch(pts)               # small batch: the CTA-per-point tip kernel
+        hp.set_option("tip_field_small", 0)
+        fld_tiled = hp.Calc_Field_at_Batch(pts)         # the tiled pair kernel
+        hp.set_option("tip_field_small", 1)
     assert relerr(acc, orc.accel_gather_ld(p, pos, q, m)) < TOL
     assert relerr(acc, orc.accel_gather(p, pos, q, m)) < TOL
     want = np.stack([orc.calc_field_at(p, pos, q, pts[k], ld=True) for k in range(40)])
-    assert relerr(fld, want) < TOL
+    assert relerr(fld, want) < TOL and relerr(fld_tiled, want) < TOL
+    assert relerr(fld, fld_tiled) < 1e-12
 
 
 # --------------------------------------------------------------------------------------------------
