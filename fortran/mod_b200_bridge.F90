@@ -213,6 +213,14 @@ module mod_b200_bridge
     integer(c_int) function rb2_field_window_close() bind(C, name='rb2_field_window_close')
       import :: c_int
     end function
+    ! lock-step tip chains of a time step on the device (replaces the per-candidate Metro_algo_tip_v3 calls)
+    integer(c_int) function rb2_mh_tip(M, ndim, seed, eta_f_out, df_out, pos_out, a_rate_io, mh_std_io) bind(C, name='rb2_mh_tip')
+      import :: c_int, c_long_long, c_double
+      integer(c_int), value :: M, ndim
+      integer(c_long_long), value :: seed
+      real(c_double), intent(out) :: eta_f_out(*), df_out(*), pos_out(3, *)
+      real(c_double), intent(inout) :: a_rate_io, mh_std_io
+    end function
     integer(c_int) function rb2_nearest_electron(dist_out, id_out) bind(C, name='rb2_nearest_electron')
       import :: c_int, c_double
       real(c_double), intent(out) :: dist_out(*)

@@ -341,6 +341,9 @@ def test_device_resident_tip_sampler(orc):
         again = hp.mh_tip(600, seed=12345)
         other = hp.mh_tip(600, seed=6)
         few = hp.mh_tip(3, seed=1)
+        # a sharper look at the means than KS on 600 samples gives: 4000 chains each way
+        eta_h4, df_h4, _ = sim.Metro_algo_tip_v3_batch(4000, 80)
+        eta_d4, df_d4, _, _, _ = hp.mh_tip(4000, seed=99)
     assert np.all(eta_d < 0) and np.all((df_d > 0) & (df_d <= 1))
     assert _ks(eta_d, b[:, 2]) > 1e-3 and _ks(df_d, b[:, 3]) > 1e-3              # against the oracle's serial chains
     assert _ks(eta_d, eta_h) > 1e-3 and _ks(df_d, df_h) > 1e-3                    # against the host lock-step loop
@@ -350,6 +353,9 @@ def test_device_resident_tip_sampler(orc):
     assert again[3:] == (a_rate, mh_std) and not np.array_equal(other[2], pos_d)
     assert 0.0 < a_rate <= 1.0 and 0.0005 <= mh_std <= 0.125
     assert few[0].shape == (3,) and np.all(few[0] < 0)
+    for a4, b4 in ((eta_d4, eta_h4), (df_d4, df_h4)):
+        se = math.sqrt(a4.var() / a4.size + b4.var() / b4.size)
+        assert abs(a4.mean() - b4.mean()) < 4.5 * se, (a4.mean(), b4.mean(), se)
     # positions lie on the hyperboloid eta = eta_1 (src/mod_hyperboloid_tip.f90:36-76) and the escape probability is
     # Escape_Prob_Tip of the returned field
     for k in (0, 17, 599):
