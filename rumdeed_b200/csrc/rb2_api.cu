@@ -290,6 +290,7 @@ int rb2_init(const rb2_config *cfg)
     if ((rc = rb2_launch_fill_mask(c, c.cap))) return rc;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;
+    if (const char *e = getenv("RB2_MH_SMALL_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c.mh_small_max = v; }
     if (const char *e = getenv("RB2_MH_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 4) c.mh_ctas_per_sm = v; }  // same as rb2_set_option("mh_small", ..)
     return RB2_OK;
 }
@@ -782,6 +783,9 @@ int rb2_set_option(const char *name, double value)
         c.mh_ctas_per_sm = (int)value;
     } else if (!strcmp(name, "tip_field_small")) {
         c.tip_field_small = (value != 0.0) ? 1 : 0;
+    } else if (!strcmp(name, "mh_small_max")) {
+        if (value < 1 || value > 512) return rb2_fail(RB2_ERR_ARG, "mh_small_max must be 1..512");
+        c.mh_small_max = (int)value;
     } else if (!strcmp(name, "mh_small")) {
         c.mh_small = (value != 0.0) ? 1 : 0;
     } else if (!strcmp(name, "sym_waves")) {

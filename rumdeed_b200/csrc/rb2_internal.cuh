@@ -122,7 +122,8 @@ struct Rb2Ctx {
     int    ev_min = 65536;                // initial size of the record buffer (option "event_buffer")
     int    mh_ctas_per_sm = 2;            // sampler: CTAs per SM of the cooperative kernel (option "mh_ctas_per_sm", 1..4)
     int    tip_field_small = 1;           // tip field: CTA-per-point kernel for small batches (option "tip_field_small")
-    int    mh_small = 1;                  // sampler: single-barrier kernel for <= 32 chains (option "mh_small", 0 = off)
+    int    mh_small = 1;                  // sampler: single-barrier kernel for few chains (option "mh_small", 0 = off)
+    int    mh_small_max = 512;            // ... up to this many chains (option "mh_small_max", <= 512)
     std::vector<rb2_event> host_events;
 
     // staging (grow-only): field points / fields, add/mark arguments, rb2_accel_host

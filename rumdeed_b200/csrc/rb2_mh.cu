@@ -534,31 +534,35 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
 //     parity (a CTA can only be one barrier ahead of the slowest one).
 // Proposals, targets and the generator keys are those of k_mh_persistent (propose_from, target_log, rand2).
 struct MhSmall {
-    int T, Gs, G, S;        // tiles, CTAs per tile, CTAs = T * Gs, 128-record sub-tiles in total
+    int T, Gs, G, S, R;     // tiles, CTAs per tile, CTAs = T * Gs, 128-record sub-tiles in total, most sub-tiles per CTA
     double *partial;        // [2][G][32]
     unsigned *bar;          // arrival counter, zeroed by the host
 };
 
-template <int NIC>
-__global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan L, MhSmall Q)
+// WPB warps per CTA: 4 (up to 4 tiles = 128 chains) or 16 (up to 16 tiles = 512 chains, one CTA per SM).  A sub-tile is
+// always MHB = 128 records; warp w sums records w * (128 / WPB) ... of every resident sub-tile.
+template <int NIC, int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, MhPlan L, MhSmall Q)
 {
+    constexpr int NT = WPB * 32, RPW = MHB / WPB;
     extern __shared__ __align__(16) unsigned char small_smem[];
-    SurfRec *mine = reinterpret_cast<SurfRec *>(small_smem);  // resident sub-tiles, zero-weight padding beyond the particle list
-    __shared__ double red[MHB / 32][32];
-    __shared__ double strands[4][MHB / 32][32];  // [tile][warp][lane]
+    // dynamic shared memory: resident sub-tiles (zero-weight padding beyond the particle list), then the join strands
+    SurfRec *mine = reinterpret_cast<SurfRec *>(small_smem);
+    double *strands = reinterpret_cast<double *>(small_smem + (size_t)Q.R * MHB * sizeof(SurfRec));  // [T][WPB][32]
+    __shared__ double red[WPB][32];
     __shared__ double sp_x[32], sp_y[32];
-    __shared__ int s_acc[4], s_rej[4], s_bad[4];
+    __shared__ int s_acc[WPB], s_rej[WPB], s_bad[WPB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t_b = blockIdx.x / Q.Gs, g_b = blockIdx.x - t_b * Q.Gs;
     const int s0 = (int)((long long)Q.S * g_b / Q.Gs), s1 = (int)((long long)Q.S * (g_b + 1) / Q.Gs);
-    for (int t = s0; t < s1; ++t) {
-        const int j = t * MHB + tid;
+    for (int q = tid; q < (s1 - s0) * MHB; q += NT) {
+        const int j = s0 * MHB + q;
         SurfRec r;
         if (j < L.n) r = S.recs[j];
         else { r.x = 0.0; r.y = 0.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
-        mine[(t - s0) * MHB + tid] = r;
+        mine[q] = r;
     }
-    if (tid < 4) { s_acc[tid] = 0; s_rej[tid] = 0; s_bad[tid] = 0; }
+    if (tid < WPB) { s_acc[tid] = 0; s_rej[tid] = 0; s_bad[tid] = 0; }
     __syncthreads();
     // chain state of tile `warp` (meaningful for warp < T): lane = chain, identical in every CTA
     const int chain = warp * 32 + lane;
@@ -583,35 +587,47 @@ __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan 
         const double px = sp_x[lane], py = sp_y[lane];
         double acc = 0.0;
         for (int t = 0; t < s1 - s0; ++t) {
-            const SurfRec *rr = &mine[t * MHB + warp * 32];
+            const SurfRec *rr = &mine[t * MHB + warp * RPW];
 #pragma unroll 4
-            for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+            for (int k = 0; k < RPW; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
         }
         red[warp][lane] = acc;
         __syncthreads();
         double *part = Q.partial + (size_t)(phase & 1u) * Q.G * 32;
-        if (warp == 0) part[(size_t)blockIdx.x * 32 + lane] = ((red[0][lane] + red[1][lane]) + red[2][lane]) + red[3][lane];
+        if (warp == 0) {
+            double sum = red[0][lane];
+#pragma unroll
+            for (int w = 1; w < WPB; ++w) sum += red[w][lane];
+            part[(size_t)blockIdx.x * 32 + lane] = sum;
+        }
         ++phase;
         small_barrier(Q.bar, phase * (unsigned)Q.G);
-        // join: for every tile, warp w adds the partial sums of that tile's CTAs w, w + 4, ... (ascending); the four
-        // strands are added in warp order by the warp that owns the tile
-        {   // (the loads of all tiles are issued together: tile after tile, each join paid its own L2 round trip)
-            double st[4] = {0.0, 0.0, 0.0, 0.0};
+        // join: for every tile, warp w adds the partial sums of that tile's CTAs w, w + WPB, ... (ascending); the WPB
+        // strands are added in warp order by the warp that owns the tile.  The loads of four tiles are issued together:
+        // tile after tile, each join paid its own L2 round trip.
+        {
             const double *pt = part + lane;
             const int T = Q.T, Gs = Q.Gs;
+            for (int t0 = 0; t0 < T; t0 += 4) {
+                double st[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
-            for (int k = warp; k < Gs; k += MHB / 32) {
+                for (int k = warp; k < Gs; k += WPB) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (t < T) st[t] += __ldcg(pt + ((size_t)t * Gs + k) * 32);
+                    for (int u = 0; u < 4; ++u)
+                        if (t0 + u < T) st[u] += __ldcg(pt + ((size_t)(t0 + u) * Gs + k) * 32);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (t0 + u < T) strands[((size_t)(t0 + u) * WPB + warp) * 32 + lane] = st[u];
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) strands[t][warp][lane] = st[t];
         }
         __syncthreads();
         bool acc_ = false, rej_ = false, bad_ = false;
         if (warp < Q.T) {
-            const double sum = ((strands[warp][0][lane] + strands[warp][1][lane]) + strands[warp][2][lane]) + strands[warp][3][lane];
+            const double *sw = strands + (size_t)warp * WPB * 32 + lane;
+            double sum = sw[0];
+#pragma unroll
+            for (int w = 1; w < WPB; ++w) sum += sw[(size_t)w * 32];
             const double Fz = L.E_vac - L.fac * sum;
             if (live) {
                 if (iter < 0) {
@@ -641,12 +657,14 @@ __global__ void __launch_bounds__(MHB) k_mh_small(MhParams P, MhState S, MhPlan 
         }
         __syncthreads();
         {   // every thread: the same counts, the same update (the next write to s_* sits behind two more barriers)
-            const int a = ((s_acc[0] + s_acc[1]) + s_acc[2]) + s_acc[3], r = ((s_rej[0] + s_rej[1]) + s_rej[2]) + s_rej[3];
+            int a = 0, r = 0, nb = 0;
+#pragma unroll
+            for (int w = 0; w < WPB; ++w) { a += s_acc[w]; r += s_rej[w]; nb += s_bad[w]; }
             if (iter > P.c.ndim_first && a + r > 0) {  // MH_std_update, :603-612
                 a_rate = (double)a / (double)(a + r);
                 mh_std = fmin(fmax(mh_std * exp(P.c.std_gain * (a_rate - P.c.target_rate)), P.c.std_min), P.c.std_max);
             }
-            if (searching) { bad = ((s_bad[0] + s_bad[1]) + s_bad[2]) + s_bad[3]; ++round; } else ++jump;
+            if (searching) { bad = nb; ++round; } else ++jump;
         }
     }
     if (blockIdx.x == 0) {
@@ -940,7 +958,8 @@ int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, dou
     return RB2_OK;
 }
 
-// At most 128 chains (T <= 4 tiles) over at most 4 resident 128-record sub-tiles per CTA: the single-barrier kernel.
+// At most 512 chains (T <= 16 tiles) over at most 6 resident 128-record sub-tiles per CTA: the single-barrier kernel, with
+// 4 warps per CTA (two CTAs per SM) up to 4 tiles and 16 warps (one CTA per SM) beyond.
 // Returns RB2_ERR_ARG - 1000 ("does not apply") when the problem is too large for it.
 static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                            int NIC, int max_init, double *df_out, double *F_out, double *pos_out, double *a_rate_io,
@@ -950,11 +969,14 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     const int n = ctx.n, nw = cfg->y_num * cfg->x_num;
     MhSmall Q{};
     Q.T = (M + 31) / 32;
+    if (Q.T > 16) return RB2_ERR_ARG - 1000;
+    const int WPB = Q.T <= 4 ? 4 : 16;
+    const int max_ctas = (WPB == 4 ? 2 : 1) * ctx.sm_count;
     Q.S = (n + MHB - 1) / MHB;
-    Q.Gs = std::max(1, std::min(Q.S, (2 * ctx.sm_count) / Q.T));  // two CTAs per SM at most
+    Q.Gs = std::max(1, std::min(Q.S, max_ctas / Q.T));
     Q.G = Q.T * Q.Gs;
-    const int R = std::max(1, (Q.S + Q.Gs - 1) / Q.Gs);
-    if (Q.T > 4 || R > 4) return RB2_ERR_ARG - 1000;
+    Q.R = std::max(1, (Q.S + Q.Gs - 1) / Q.Gs);
+    if (Q.R > (WPB == 4 ? 4 : 6)) return RB2_ERR_ARG - 1000;
     MhPlan L{};
     L.M = M; L.n = n; L.n_tiles = Q.T; L.max_init = max_init; L.seed = seed;
     L.two_d = 2.0 * gc.d;
@@ -989,12 +1011,21 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
         k_surf_pack<<<(n + 255) / 256, 256, 0, st>>>(ctx.a.pq, n, L.two_d, gc.image_charge ? gc.N_ic_max : 0, d_recs);
         launches++;
     }
-    void *kern = NIC < 0 ? (void *)k_mh_small<-1> : NIC == 0 ? (void *)k_mh_small<0>
-               : NIC == 1 ? (void *)k_mh_small<1> : (void *)k_mh_small<2>;
-    const size_t smem = (size_t)R * MHB * sizeof(SurfRec);  // <= 32 KB
+    void *kern = WPB == 4 ? (NIC < 0 ? (void *)k_mh_small<-1, 4> : NIC == 0 ? (void *)k_mh_small<0, 4>
+                             : NIC == 1 ? (void *)k_mh_small<1, 4> : (void *)k_mh_small<2, 4>)
+                          : (NIC < 0 ? (void *)k_mh_small<-1, 16> : NIC == 0 ? (void *)k_mh_small<0, 16>
+                             : NIC == 1 ? (void *)k_mh_small<1, 16> : (void *)k_mh_small<2, 16>);
+    // resident records + join strands [T][WPB][32]
+    const size_t smem = (size_t)Q.R * MHB * sizeof(SurfRec) + (size_t)Q.T * WPB * 32 * sizeof(double);
+    if (smem > 48 * 1024) RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        int occ = 0;
+        RB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem));
+        if ((long long)occ * ctx.sm_count < Q.G) return RB2_ERR_ARG - 1000;  // not co-resident: the many-chain kernel takes it
+    }
     void *args[] = {&P, &S, &L, &Q};
     // cooperative launch: the arrival-counter barrier needs all G <= 2 x sm_count CTAs resident
-    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(Q.G), dim3(MHB), args, smem, st));
+    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(Q.G), dim3(WPB * 32), args, smem, st));
     RB2_LAUNCHED(launches);
     double scal1[2];
     RB2_CUDA(cudaMemcpyAsync(df_out, S.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1016,7 +1047,7 @@ int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_
     const rb2_config &gc = ctx.cfg;
     const int n = ctx.n, max_init = 10000;
     const int NIC = !gc.image_charge ? -1 : (gc.N_ic_max >= 2 ? 2 : gc.N_ic_max);
-    if (ctx.mh_small && M <= 128) {
+    if (ctx.mh_small && M <= ctx.mh_small_max) {
         const int rc_small = launch_mh_small(ctx, cfg, w_theta_host, M, seed, NIC, max_init, df_out, F_out, pos_out, a_rate_io, mh_std_io);
         if (rc_small != RB2_ERR_ARG - 1000) return rc_small;  // else: too many particles for the resident scheme
     }

@@ -206,10 +206,11 @@ def test_device_resident_fe_sampler(orc):
 
 @gpu
 @pytest.mark.parametrize("n_pre,nic,kind,M", [(0, 1, 1, 24), (120, 1, 1, 24), (700, 0, 1, 24), (2500, 2, 1, 24), (300, 1, 2, 24),
-                                              (0, 1, 1, 33), (120, 1, 1, 100), (2500, 1, 1, 128), (300, 1, 2, 70)])
+                                              (0, 1, 1, 33), (120, 1, 1, 100), (2500, 1, 1, 128), (300, 1, 2, 70),
+                                              (0, 1, 1, 129), (2500, 1, 1, 324), (700, 0, 1, 512), (300, 1, 2, 400), (9000, 2, 1, 200)])
 def test_device_sampler_single_barrier_kernel(orc, n_pre, nic, kind, M):
-    """Up to 128 chains run in k_mh_small (records resident in shared memory, chain state in registers, one barrier per
-    jump).  Same generator keys and proposals as k_mh_persistent: for the same seed the chains coincide except where
+    """Up to 512 chains run in k_mh_small (records resident in shared memory, chain state in registers, one barrier per
+    jump; 4 warps per CTA up to 128 chains, 16 beyond).  Same generator keys and proposals as k_mh_persistent: for the same seed the chains coincide except where
     an accept decision sits on a rounding knife edge (the partial sums are joined in a different order)."""
     w = ((2.0, 2.4), (2.4, 2.0))
     mode, T = (10, 293.15) if kind == 1 else (9, 1200.0)
