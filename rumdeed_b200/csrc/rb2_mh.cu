@@ -176,12 +176,17 @@ struct MhPlan {
 // Grid-wide barrier on an arrival counter in global memory (zeroed by the host): release add by one thread per CTA,
 // acquire spin until `target` arrivals.  Needs all CTAs resident (cooperative launch).  Bounded: a CTA that never
 // arrives traps the kernel instead of hanging the GPU.
-__device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
+__device__ __forceinline__ void small_barrier_arrive(unsigned *bar)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
+    }
+}
+__device__ __forceinline__ void small_barrier_wait(unsigned *bar, unsigned target)
+{
+    if (threadIdx.x == 0) {
         unsigned v, spins = 0;
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
@@ -190,6 +195,11 @@ __device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
         }
     }
     __syncthreads();
+}
+__device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
+{
+    small_barrier_arrive(bar);
+    small_barrier_wait(bar, target);
 }
 
 // one particle against one surface point: sum of g_n / (rho^2 + h_n^2)^(3/2)
@@ -226,6 +236,23 @@ __global__ void k_surf_pack(const double4 *__restrict__ pq, int n, double two_d,
 
 // Proposal of chain c at iteration iter: a pure function of (seed, chain, iteration, chain state, step), so any
 // thread that needs it recomputes it.  iter < 0: search rounds for a favourable start (uniform over the emitter).
+// The two standard normals of chain k's jump `iter`: a function of (seed, chain, iteration) only, so they can be drawn
+// ahead of time (k_mh_small draws the next jump's while it waits at the barrier).
+__device__ __forceinline__ void draw_jump_normals(const MhPlan &L, int iter, int k, double &g0, double &g1)
+{
+    g0 = 0.0; g1 = 0.0;
+    for (int attempt = 0; attempt < 64; ++attempt) {  // Marsaglia polar method, src/mod_global.F90:578-595
+        double u, v;
+        rand2(L.seed, k, iter, 1, attempt, u, v);
+        const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
+        if (w < 1.0 && w > 0.0) {
+            const double f = sqrt((-2.0 * log(w)) / w);
+            g0 = a * f; g1 = b * f;
+            break;
+        }
+    }
+}
+__device__ __forceinline__ void propose_apply(const MhParams &P, int iter, double mh_std, double g0, double g1, double &x, double &y);
 // (x, y) enter as the chain's current position and leave as the proposal.
 __device__ __forceinline__ void propose_from(const MhParams &P, const MhPlan &L, int iter, int k, double mh_std, int ok,
                                              double &x, double &y)
@@ -241,18 +268,14 @@ __device__ __forceinline__ void propose_from(const MhParams &P, const MhPlan &L,
         return;
     }
     if (!ok) return;
+    double g0, g1;
+    draw_jump_normals(L, iter, k, g0, g1);
+    propose_apply(P, iter, mh_std, g0, g1, x, y);
+}
+__device__ __forceinline__ void propose_apply(const MhParams &P, int iter, double mh_std, double g0, double g1, double &x, double &y)
+{
+    const rb2_mh_config &c = P.c;
     const double frac = (iter > c.ndim_first) ? mh_std : c.init_std;
-    double g0 = 0.0, g1 = 0.0;
-    for (int attempt = 0; attempt < 64; ++attempt) {  // Marsaglia polar method, src/mod_global.F90:578-595
-        double u, v;
-        rand2(L.seed, k, iter, 1, attempt, u, v);
-        const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
-        if (w < 1.0 && w > 0.0) {
-            const double f = sqrt((-2.0 * log(w)) / w);
-            g0 = a * f; g1 = b * f;
-            break;
-        }
-    }
     x += g0 * (c.emit_dim[0] * frac);
     y += g1 * (c.emit_dim[1] * frac);
     if (c.kind == 2) {  // src/mod_field_thermo_emission.F90:369-389
@@ -572,6 +595,8 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
     unsigned phase = 0;
     int bad = L.M, round = 0, jump = 1;
     bool searching = true;
+    double ahead_g0 = 0.0, ahead_g1 = 0.0;
+    int ahead_iter = 0;  // jump whose normals are in ahead_g0 / ahead_g1
     for (;;) {
         // rounds of the search for a favourable start (generator iteration -(round + 1), like k_mh_persistent), then the
         // jump iterations 1 .. ndim
@@ -581,7 +606,10 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
         // proposals of every tile by the warp that holds it (kept: the accept step below needs them); the tile this CTA
         // sums for goes through shared memory to the other warps
         double qx = cx, qy = cy;
-        if (live) propose_from(P, L, iter, chain, mh_std, ok, qx, qy);
+        if (live) {
+            if (iter >= 1 && ok && ahead_iter == iter) propose_apply(P, iter, mh_std, ahead_g0, ahead_g1, qx, qy);
+            else propose_from(P, L, iter, chain, mh_std, ok, qx, qy);
+        }
         if (warp == t_b) { sp_x[lane] = qx; sp_y[lane] = qy; }
         __syncthreads();
         const double px = sp_x[lane], py = sp_y[lane];
@@ -601,7 +629,11 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
             part[(size_t)blockIdx.x * 32 + lane] = sum;
         }
         ++phase;
-        small_barrier(Q.bar, phase * (unsigned)Q.G);
+        small_barrier_arrive(Q.bar);
+        // while the other CTAs arrive: the normals of the NEXT jump (Philox + log + sqrt, ~1 us of dependent latency that
+        // would otherwise open the next iteration)
+        if (live && !searching && jump < P.c.ndim) { ahead_iter = jump + 1; draw_jump_normals(L, ahead_iter, chain, ahead_g0, ahead_g1); }
+        small_barrier_wait(Q.bar, phase * (unsigned)Q.G);
         // join: for every tile, warp w adds the partial sums of that tile's CTAs w, w + WPB, ... (ascending); the WPB
         // strands are added in warp order by the warp that owns the tile.  The loads of four tiles are issued together:
         // tile after tile, each join paid its own L2 round trip.
