@@ -548,3 +548,50 @@ def test_driver_executable_writes_reference_format_files(tmp_path):
     # steady-state current of the reference's test system stays in its band
     I_ss = ramo[250:, 2].mean()
     assert 0.5e-3 < I_ss < 4.0e-3
+
+
+@gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rumdeed_b200", "rumdeed_b200_run")),
+                    reason="driver executable not built")
+def test_driver_ion_deck_writes_collision_files(tmp_path):
+    """program RUMDEED on the Ion configuration (tools/decks/ion: planar field emission into N2 at NTP, COLLISION_MODE = 2):
+    collisions.dt, ionization_data.bin and the particle counts are consistent with each other; record layouts of
+    Write_Ionization_Data (src/mod_pair.F90:930-935: i32, 8 f64, 4 i32) and of the collisions.dt line (mod_collisions.F90:74)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in ("input", "work", "N2-tot-cross.txt", "N2-ion-cross.txt"):
+        shutil.copy(os.path.join(root, "tools", "decks", "ion", f), tmp_path / f)
+    txt = (tmp_path / "input").read_text().replace("\n/", "\n  MH_DEVICE = .True.,\n/")
+    (tmp_path / "input").write_text(txt)
+    exe = os.path.join(root, "rumdeed_b200", "rumdeed_b200_run")
+    steps = 600
+    r = subprocess.run([exe, str(tmp_path), "777", str(steps), "200000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = tmp_path / "out"
+    coll = np.loadtxt(out / "collisions.dt", dtype=np.int64)
+    assert coll.shape == (steps, 4) and np.all(coll[:, 0] == np.arange(1, steps + 1))
+    assert np.all(coll[:, 1] >= coll[:, 2] + coll[:, 3])          # collisions >= ionisations + recombinations
+    n_ion = int(coll[:, 2].sum())
+    assert n_ion > 100
+    idt = np.dtype([("step", "<i4"), ("pos", "<f8", 3), ("in_speed", "<f8"), ("out_speed", "<f8"), ("new_speed", "<f8"),
+                    ("ion_dist", "<f8"), ("ion_rad", "<f8"), ("in_id", "<i4"), ("new_id", "<i4"), ("ion_id", "<i4"), ("emit", "<i4")])
+    assert idt.itemsize == 84
+    ev = np.fromfile(out / "ionization_data.bin", dtype=idt)
+    assert len(ev) == n_ion
+    assert np.all(np.diff(ev["step"]) >= 0) and np.all(ev["ion_id"] == ev["new_id"] + 1)
+    assert np.all(ev["in_id"] >= 1) and np.all((ev["emit"] == 1) | (ev["emit"] == 2))
+    # energy balance per event: the two outgoing electrons share E_in - 15.581 eV (src/mod_collisions.F90:626-629)
+    half_m = 0.5 * 9.1093837015e-31 / 1.602176634e-19
+    e_in, e_out, e_new = half_m * ev["in_speed"] ** 2, half_m * ev["out_speed"] ** 2, half_m * ev["new_speed"] ** 2
+    assert np.all(e_in > 15.581) and np.allclose(e_out + e_new, e_in - 15.581, rtol=1e-9, atol=1e-9)
+    assert np.all(ev["pos"][:, 2] > 0) and np.all(np.hypot(ev["pos"][:, 0], ev["pos"][:, 1]) <= 500e-9)
+    # every ion created before the last step is in the gap when the last ramo_current.dt line is written (none leaves or
+    # expires within 600 steps; the line of step k precedes the collisions of step k)
+    ramo = np.loadtxt(out / "ramo_current.dt")
+    if int(coll[:, 3].sum()) == 0:
+        assert int(ramo[-1, 6]) == int(coll[:-1, 2].sum())
+    rec_size = (out / "recombination_data.bin").stat().st_size
+    assert rec_size == 68 * int(coll[:, 3].sum())                  # i32 + 6 f64 + 4 i32 per recombination
+    assert (out / "density_absorb_recom.bin").stat().st_size == 2 * 48 * int(coll[:, 3].sum())
+    assert (out / "absorbed_recom.dt").exists()
