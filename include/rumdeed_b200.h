@@ -190,7 +190,9 @@ int rb2_p2p_attach(int world, int rank, const void *handles);
 int rb2_p2p_detach(void);
 /* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
  * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "event_buffer" (initial number of
- * absorb / plane-crossing records the device buffer holds; it grows on demand). */
+ * absorb / plane-crossing records the device buffer holds; it grows on demand); emission samplers: "mh_small"
+ * (1 / 0: single-barrier kernel for few chains), "mh_small_max" (its chain limit, <= 512), "mh_ctas_per_sm" (1..4,
+ * many-chain kernel), "tip_field_small" (1 / 0: CTA-per-point tip field kernel for small batches). */
 int rb2_set_option(const char *name, double value);
 /* Device pointer + byte size of the (3,capacity) acceleration buffer so that the
  * host plumbing (torch.distributed / NCCL) can all-gather the slices in place. */
