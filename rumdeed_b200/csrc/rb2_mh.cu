@@ -14,7 +14,7 @@
 // then ONE grid barrier (an arrival counter, two CTAs per SM), after which every thread applies the same MH_std update
 // (:603-612, one per iteration after the warm-up) from the iteration's accept / reject counters.  (The first version
 // had a cooperative-groups grid barrier after each of the two phases and up to four CTAs per SM: 20 us per jump at
-// 324 chains x 8.7e3 electrons for 5 us of field sums.)  At most 32 chains: k_mh_small below.
+// 324 chains x 8.7e3 electrons for 5 us of field sums.)  At most 512 chains: k_mh_small below.
 //
 // Surface field.  The chains live on the cathode plane z = 0, where the image series of
 // src/acc_ic_planar_series.inc is mirror-antisymmetric: the partner of charge q at height h = z_j + 2nd is
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
     if (blockIdx.x == 0 && threadIdx.x == 0) { S.scal_out[0] = mh_std; S.scal_out[1] = a_rate; }
 }
 
-// ---- single-barrier variant for at most 128 chains ---------------------------------------------------------------
+// ---- single-barrier variant for at most 512 chains ---------------------------------------------------------------
 // In the reference's own regime (1e3 - 1e4 electrons in the gap, ~100 emission candidates per step) an iteration of
 // k_mh_persistent is a chain of global-memory round trips (chain state, partial sums, arrival counters, accept
 // counters, barrier: ~8 us even with no particles at all) around ~1 us of arithmetic.  With at most four tiles of
@@ -548,12 +548,12 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
 //     memory for the whole call (the records do not change while the chains run);
 //   * every CTA keeps the state of ALL chains in registers: warp w holds tile w (lane = chain).  Per iteration warp t_b
 //     computes the tile's 32 proposals and hands them to the other warps through shared memory, the four warps sum the
-//     resident records (32 each per sub-tile), and the CTA publishes one partial sum per chain of its tile;
+//     resident records (128 / WPB each per sub-tile), and the CTA publishes one partial sum per chain of its tile;
 //   * ONE barrier (arrival counter in global memory);
 //   * behind it EVERY CTA joins the partial sums of every tile (all four warps, fixed order) and warp w does the
 //     accept / reject step of tile w -- redundantly: same inputs, same instructions, same result in every CTA, so no
 //     chain state, no accept counters and no second barrier in global memory.  The MH_std update uses the counts of
-//     the (at most four) warps, exchanged through shared memory.  The partial sums are double buffered by iteration
+//     the warps, exchanged through shared memory.  The partial sums are double buffered by iteration
 //     parity (a CTA can only be one barrier ahead of the slowest one).
 // Proposals, targets and the generator keys are those of k_mh_persistent (propose_from, target_log, rand2).
 struct MhSmall {
