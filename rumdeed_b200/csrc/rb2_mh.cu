@@ -542,15 +542,15 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
 // ---- single-barrier variant for at most 512 chains ---------------------------------------------------------------
 // In the reference's own regime (1e3 - 1e4 electrons in the gap, ~100 emission candidates per step) an iteration of
 // k_mh_persistent is a chain of global-memory round trips (chain state, partial sums, arrival counters, accept
-// counters, barrier: ~8 us even with no particles at all) around ~1 us of arithmetic.  With at most four tiles of
-// chains all of that state fits one CTA:
+// counters, barrier: ~8 us even with no particles at all) around ~1 us of arithmetic.  With at most sixteen tiles
+// of chains (one warp per tile) all of that state fits one CTA:
 //   * CTA b works for ONE tile t_b = b / Gs on its own share of the particle records, which stays RESIDENT in shared
 //     memory for the whole call (the records do not change while the chains run);
 //   * every CTA keeps the state of ALL chains in registers: warp w holds tile w (lane = chain).  Per iteration warp t_b
-//     computes the tile's 32 proposals and hands them to the other warps through shared memory, the four warps sum the
+//     computes the tile's 32 proposals and hands them to the other warps through shared memory, the warps sum the
 //     resident records (128 / WPB each per sub-tile), and the CTA publishes one partial sum per chain of its tile;
 //   * ONE barrier (arrival counter in global memory);
-//   * behind it EVERY CTA joins the partial sums of every tile (all four warps, fixed order) and warp w does the
+//   * behind it EVERY CTA joins the partial sums of every tile (all warps, fixed order) and warp w does the
 //     accept / reject step of tile w -- redundantly: same inputs, same instructions, same result in every CTA, so no
 //     chain state, no accept counters and no second barrier in global memory.  The MH_std update uses the counts of
 //     the warps, exchanged through shared memory.  The partial sums are double buffered by iteration
