@@ -97,9 +97,11 @@ __device__ __forceinline__ void tip_ic_force(const TipParams &T, const TipImage 
     const double sb = (x_b - im.x_im) * (x_b - im.x_im) + (y_b - im.y_im) * (y_b - im.y_im) + (z_b - im.z_im) * (z_b - im.z_im);
     const double tmp_dis_a = sa * sqrt(sa);  // (..)**(3/2)
     const double tmp_dis_b = sb * sqrt(sb);
-    ic_x = pre * ((x_a - x_b) / tmp_dis_a - (T.r_tip * (im.x_im - x_b)) / (im.dis_a * tmp_dis_b));
-    ic_y = pre * ((y_a - y_b) / tmp_dis_a - (T.r_tip * (im.y_im - y_b)) / (im.dis_a * tmp_dis_b));
-    ic_z = pre * ((z_a - z_b) / tmp_dis_a - (T.r_tip * (im.z_im - z_b)) / (im.dis_a * tmp_dis_b));
+    // two IEEE divides instead of the six of the source line by line (same value to rounding: 1e-16, the parity bar is 1e-11)
+    const double wa = 1.0 / tmp_dis_a, wb = T.r_tip / (im.dis_a * tmp_dis_b);
+    ic_x = pre * ((x_a - x_b) * wa - (im.x_im - x_b) * wb);
+    ic_y = pre * ((y_a - y_b) * wa - (im.y_im - y_b) * wb);
+    ic_z = pre * ((z_a - z_b) * wa - (im.z_im - z_b) * wb);
 }
 
 // ---- the tiled pair kernel --------------------------------------------------------------------
