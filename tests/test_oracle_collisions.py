@@ -271,3 +271,76 @@ def test_continuous_ionization_statistics(col):
     ang = [np.degrees(np.arccos(np.clip(np.dot(vel2[e.in_slot], vel[e.in_slot]) /
                                         (np.linalg.norm(vel2[e.in_slot]) * np.linalg.norm(vel[e.in_slot])), -1, 1))) for e in ev]
     assert 10.0 < np.mean(ang) < 35.0
+
+
+def _check_against_numpy(col, coeffs, tol=1e-6, prime=True):
+    """Every root SolvePolynomial assigns must be a root numpy finds (distinct matching).  `prime` first runs a quartic
+    with four real roots so that the module's return code (which CubicRoots does not always set, and which decides how many
+    roots are copied out) is 31, like after a typical call in the recombination loop."""
+    if prime:
+        col.solve_polynomial(*np.poly([-1.0, 0.5, 2.0, 3.0]))
+    code, z = col.solve_polynomial(*coeffs)
+    lead = [c for c in coeffs if c != 0.0]
+    want = list(np.roots(np.trim_zeros(np.array(coeffs, float), "f"))) if len(lead) else []
+    got = [r for r in z if not np.isnan(r.real)]
+    scale = max([1.0] + [abs(w) for w in want])
+    for g in got:
+        k = int(np.argmin([abs(g - w) for w in want]))
+        assert abs(g - want[k]) <= tol * scale, (coeffs, code, got, want)
+        want.pop(k)
+    return code, got
+
+
+def test_polynomial_solver_rare_branches(col):
+    """Branches of src/mod_polynomialroots.F90 that random polynomials do not reach (found with gcov on the oracle):
+    zero constant terms, the d = 0 case of CubicRoots (labels 110 / 130 / 131), QuadraticRoots with a(2) = 0, biquadratics,
+    (nearly) multiple roots.  After this test gcov shows every line of the solver executed except branches that need a
+    NEGATIVE product of the resolvent cubic's roots (label 120 of CubicRoots; `x1 = 0` / label 40 and labels 61 / 80 of
+    QuarticRoots): that product is q^2 / 64 >= 0, so they are rounding artefacts at most.  The device solver
+    (rb2_collisions.cu) is a second transcription of the same source by the same reading, so parity between the two cannot
+    catch a misreading -- this comparison with numpy.roots is the independent check."""
+    # cubic (z + p)^3 + c (z + p): d = r + p t = 0 exactly for dyadic p, c
+    for p, c in ((0.5, 2.0), (0.5, -2.0), (2.0, -1.0), (-0.25, -4.0), (4.0, -0.0625)):
+        a3, a2, a1 = 3 * p, 3 * p * p + c, p ** 3 + c * p
+        code, got = _check_against_numpy(col, (0.0, 1.0, a3, a2, a1), tol=1e-9)
+        assert len(got) == 3
+    # quadratic: a(2) = 0, a(1) = 0, tiny discriminant
+    assert sorted(r.real for r in _check_against_numpy(col, (0, 0, 1.0, 0.0, -4.0), prime=False)[1]) == [-2.0, 2.0]
+    assert sorted(r.real for r in _check_against_numpy(col, (0, 0, 1.0, -3.0, 0.0), prime=False)[1]) == [0.0, 3.0]
+    code, got = _check_against_numpy(col, (0, 0, 1.0, -2.0, 1.0), prime=False)
+    assert code == 22 and got[0] == got[1] == 1.0
+    # zero constant term in the quartic and in the cubic behind it
+    _check_against_numpy(col, np.poly([0.0, 1.0, 2.0, -3.0]))
+    _check_against_numpy(col, np.poly([0.0, 0.0, 2.0, -3.0]))
+    # biquadratics: the resolvent cubic has a zero constant term (q = 0)
+    for c2, e in ((-5.0, 4.0), (5.0, 4.0), (-1.0, -2.0), (0.0, -16.0), (2.0, 5.0)):
+        _check_against_numpy(col, (1.0, 0.0, c2, 0.0, e))
+    # families that steer the resolvent: two complex pairs far apart / close together, one tight real pair + a wide complex
+    # pair, double roots
+    rng = np.random.default_rng(3)
+    codes = set()
+    for trial in range(6000):
+        fam = trial % 6
+        if fam == 0:
+            a, b = rng.uniform(-2, 2, 2); r = [complex(a, rng.uniform(0.01, 3)), complex(b, rng.uniform(0.01, 3))]
+            roots = [r[0], r[0].conjugate(), r[1], r[1].conjugate()]
+        elif fam == 1:
+            a = rng.uniform(-2, 2); im = rng.uniform(0.5, 2)
+            roots = [complex(a, im), complex(a, -im), complex(a + rng.uniform(-1e-3, 1e-3), im * (1 + rng.uniform(-1e-3, 1e-3)))]
+            roots.append(roots[2].conjugate())
+        elif fam == 2:
+            x = rng.uniform(-2, 2); roots = [x, x + rng.uniform(1e-3, 1e-1), complex(rng.uniform(-3, 3), rng.uniform(1, 4))]
+            roots.append(roots[2].conjugate())
+        elif fam == 3:
+            x, y = rng.uniform(-2, 2, 2); roots = [x, x, y, y + rng.uniform(0.5, 2)]
+        elif fam == 4:
+            roots = list(rng.uniform(-1, 1, 4) * np.array([1.0, 1.0, 5.0, 5.0]))
+        else:
+            a = rng.uniform(-1, 1); roots = [complex(a, 1e-2), complex(a, -1e-2), rng.uniform(2, 3), rng.uniform(-3, -2)]
+        co = np.real(np.poly(roots)) * rng.uniform(0.5, 2.0)
+        tol = 2e-3 if fam in (1, 3) else 1e-5          # (nearly) multiple roots: square-root loss of accuracy
+        code, got = _check_against_numpy(col, co, tol=tol, prime=False)
+        codes.add(code)
+    # (label 80 / code 23 of QuarticRoots needs a negative real resolvent root next to a complex pair: the product of the
+    # resolvent's roots is q^2 / 64 >= 0, so that is a rounding artefact at most and no polynomial here produces it)
+    assert {31, 42, 44} <= codes
