@@ -309,6 +309,12 @@ int rb2_do_collisions(int step, unsigned long long seed, rb2_collision_result *o
 int rb2_get_recombination_records(int max_records, rb2_recomb_record *out, int *n_out);
 int rb2_get_ionization_records(int max_records, rb2_ionization_record *out, int *n_out);
 
+/* Test hook: the device transcription of QuarticRoots (src/mod_polynomialroots.F90:336-510, used by the recombination
+ * test) on n polynomials; coeffs = {quartic, cubic, quadratic, linear, constant} each (quartic != 0, else code 0 and NaN
+ * roots).  codes_out[n]: the routine's return code (31, 42, 44, 23; 0 when the constant term is zero, where the reference
+ * leaves its code unset); roots_out[8n]: re, im of z(1..4). */
+int rb2_probe_quartic_roots(int n, const double *coeffs, int *codes_out, double *roots_out);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* Independent-DFMA-chain micro-benchmark: measured FP64 peak of this GPU in TFLOP/s
  * (FMA = 2 flops) over about `ms_target` milliseconds. */

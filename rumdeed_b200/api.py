@@ -137,7 +137,7 @@ EXPORTS = (
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
-    "rb2_do_collisions", "rb2_get_recombination_records", "rb2_get_ionization_records",
+    "rb2_do_collisions", "rb2_get_recombination_records", "rb2_get_ionization_records", "rb2_probe_quartic_roots",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
 )
 
@@ -190,6 +190,7 @@ def load_library(path: str | None = None):
     lib.rb2_do_collisions.argtypes = [C.c_int, C.c_ulonglong, C.POINTER(CollisionResult)]
     lib.rb2_get_recombination_records.argtypes = [C.c_int, C.POINTER(RecombRecord), _PI]
     lib.rb2_get_ionization_records.argtypes = [C.c_int, C.POINTER(IonizationRecord), _PI]
+    lib.rb2_probe_quartic_roots.argtypes = [C.c_int, _PD, _PI, _PD]
     lib.rb2_fp64_peak.argtypes = [C.c_double, _PD, C.POINTER(C.c_float)]
     lib.rb2_launch_count.argtypes = [C.POINTER(C.c_longlong), C.c_int]
     lib.rb2_last_accel_info.argtypes = [C.POINTER(C.c_float)] + [_PI] * 4
@@ -552,6 +553,15 @@ class HotPath:
         buf = (IonizationRecord * max(n.value, 1))()
         self._check(self.lib.rb2_get_ionization_records(n.value, buf, C.byref(n)))
         return [buf[k] for k in range(n.value)]
+
+    def probe_quartic_roots(self, coeffs):
+        """Device QuarticRoots on rows {quartic, cubic, quadratic, linear, constant}: (codes[n], roots[n, 4] complex)."""
+        co = np.ascontiguousarray(coeffs, dtype=np.float64).reshape(-1, 5)
+        n = co.shape[0]
+        codes = np.zeros(n, dtype=np.int32)
+        roots = np.zeros((n, 8))
+        self._check(self.lib.rb2_probe_quartic_roots(n, _d(co), _i(codes), _d(roots)))
+        return codes, roots[:, 0::2] + 1j * roots[:, 1::2]
 
     def p2p_export(self, n_max) -> bytes:
         """This process's exchange block (partial pair sums + flags) as a CUDA IPC handle."""

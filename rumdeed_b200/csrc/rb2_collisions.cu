@@ -463,6 +463,22 @@ __device__ bool recomb_pair(const double ion[3], const double ep[3], const doubl
     return true;
 }
 
+// Test hook: QuarticRoots on the device for a list of polynomials (the solver is otherwise only reachable through the
+// recombination test).  coeffs = {quartic, cubic, quadratic, linear, constant} per polynomial, like SolvePolynomial.
+__global__ void k_quartic_probe(int n, const double *__restrict__ coeffs, int *__restrict__ codes, double *__restrict__ roots)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a[5] = {coeffs[5 * i + 4], coeffs[5 * i + 3], coeffs[5 * i + 2], coeffs[5 * i + 1], coeffs[5 * i]};
+    Cx z[5];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = 0; k < 5; ++k) z[k] = {nan, nan};
+    int code = 0;
+    if (a[4] != 0.0) quartic_roots(a, z, code);
+    codes[i] = code;
+    for (int k = 0; k < 4; ++k) { roots[8 * i + 2 * k] = z[k].re; roots[8 * i + 2 * k + 1] = z[k].im; }
+}
+
 // ---- recombination kernels -------------------------------------------------------------------------------------------
 __device__ __forceinline__ int warp_append(int *counter, bool want)
 {
@@ -1055,6 +1071,25 @@ int rb2_do_collisions(int step, unsigned long long seed, rb2_collision_result *o
     int rc = require_ready();
     if (rc) return rc;
     return run_timed(step, seed, g_coll.mode == 2 ? 3 : 1, out);
+}
+
+int rb2_probe_quartic_roots(int n, const double *coeffs, int *codes_out, double *roots_out)
+{
+    RB2_REQUIRE_INIT();
+    if (n < 1) return RB2_OK;
+    if (!coeffs || !codes_out || !roots_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    Rb2Ctx &c = g_rb2;
+    int rc = rb2_ensure_stage(c, (size_t)13 * n, (size_t)n);
+    if (rc) return rc;
+    double *d_co = c.d_stage_d, *d_roots = d_co + (size_t)5 * n;
+    RB2_CUDA(cudaMemcpyAsync(d_co, coeffs, (size_t)5 * n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    k_quartic_probe<<<(n + 127) / 128, 128, 0, c.stream>>>(n, d_co, c.d_stage_i, d_roots);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(1);
+    RB2_CUDA(cudaMemcpyAsync(codes_out, c.d_stage_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(cudaMemcpyAsync(roots_out, d_roots, (size_t)8 * n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    return RB2_OK;
 }
 
 int rb2_get_recombination_records(int max_records, rb2_recomb_record *out, int *n_out)

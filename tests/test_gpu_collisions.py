@@ -339,3 +339,76 @@ def test_collisions_require_init_and_reject_discrete_modes():
         hp.Init_Collisions(2, *synthetic_tables(), n_d=N_D, cyl_radius=1e-7)
         res = hp.Do_Electron_Atom_Collisions(1, 1)      # empty store
         assert (res.nrCollisions, res.nrIonizations, res.nrRecombinations) == (0, 0, 0)
+
+
+def _poly_families(rng, n_per_family):
+    """(coefficients, family): random quartics of the families used to pin the oracle's solver (test_oracle_collisions)."""
+    out = []
+    for fam in range(8):
+        for _ in range(n_per_family):
+            if fam == 0:
+                roots = list(rng.uniform(-3, 3, 4))
+            elif fam == 1:
+                re, im = rng.uniform(-2, 2), rng.uniform(0.2, 2)
+                roots = list(rng.uniform(-3, 3, 2)) + [complex(re, im), complex(re, -im)]
+            elif fam == 2:
+                roots = []
+                for _k in range(2):
+                    re, im = rng.uniform(-2, 2), rng.uniform(0.2, 2)
+                    roots += [complex(re, im), complex(re, -im)]
+            elif fam == 3:
+                roots = list(rng.uniform(0.3, 1, 4) * rng.choice([-1, 1], 4) * 10.0 ** rng.integers(-1, 1, 4))
+            elif fam == 4:      # zero constant term
+                roots = [0.0] + list(rng.uniform(-3, 3, 3))
+            elif fam == 5:      # biquadratic
+                c2, e = rng.uniform(-5, 5), rng.uniform(-5, 5)
+                out.append((np.array([1.0, 0.0, c2, 0.0, e]) * rng.uniform(0.5, 2.0), fam))
+                continue
+            elif fam == 6:      # tight real pair + wide complex pair
+                x = rng.uniform(-2, 2)
+                roots = [x, x + rng.uniform(1e-3, 1e-1), complex(rng.uniform(-3, 3), rng.uniform(1, 4))]
+                roots.append(roots[2].conjugate())
+            else:               # double roots
+                x, y = rng.uniform(-2, 2, 2)
+                roots = [x, x, y, y + rng.uniform(0.5, 2)]
+            out.append((np.real(np.poly(roots)) * rng.uniform(0.5, 2.0), fam))
+    return out
+
+
+def test_device_quartic_solver_against_numpy_and_oracle(col):
+    """The device transcription of QuarticRoots (rb2_probe_quartic_roots) root by root: every root SolvePolynomial would
+    hand to the recombination test (root1..root3 by return code, src/mod_polynomialroots.F90:557-561) is a root numpy
+    finds, on the families that reach every branch of the solver; return codes agree with the oracle's."""
+    rng = np.random.default_rng(17)
+    polys = _poly_families(rng, 400)
+    co = np.array([p for p, _ in polys])
+    fam = np.array([f for _, f in polys])
+    box = (1000 * NM, 1000 * NM, 1000 * NM)
+    with rb.HotPath(rb.planar_config(2000.0, 1000 * NM, box, DT, True, 1, capacity=1024)) as hp:
+        codes, z = hp.probe_quartic_roots(co)
+    same_code = 0
+    seen = set()
+    for k in range(len(co)):
+        want = list(np.roots(co[k]))
+        code = int(codes[k])
+        seen.add(code)
+        if code == 0:
+            assert fam[k] == 4                     # zero constant term: code left unset, z(1) = 0 and the cubic's roots
+            got = list(z[k])
+        else:
+            got = list(z[k][:3] if code > 23 else z[k][:2])
+        assert not any(np.isnan(g.real) for g in got)
+        tol = 2e-3 if fam[k] in (6, 7) else 1e-5   # (nearly) multiple roots: square-root loss of accuracy
+        scale = max([1.0] + [abs(w) for w in want])
+        for g in got:
+            j = int(np.argmin([abs(g - w) for w in want]))
+            assert abs(g - want[j]) <= tol * scale, (k, fam[k], code, got, want)
+            want.pop(j)
+        if fam[k] in (0, 1, 2, 3, 5):              # (with (nearly) multiple roots the real / complex verdict is rounding noise)
+            code_o, z_o = col.solve_polynomial(*co[k])
+            same_code += (code_o == code)
+            if code_o == code and fam[k] in (0, 1, 2, 3):
+                n_as = 3 if code > 23 else 2
+                assert np.allclose(z[k][:n_as], z_o[:n_as], rtol=1e-9, atol=1e-9 * scale)
+    assert {0, 31, 42, 44} <= seen
+    assert same_code >= 0.99 * np.sum(np.isin(fam, (0, 1, 2, 3, 5))), same_code
