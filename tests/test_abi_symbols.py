@@ -49,9 +49,9 @@ def test_struct_sizes_match_header():
 #include <stdio.h>
 #include "rumdeed_b200.h"
 #include "rumdeed_host.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rb2_config), sizeof(rb2_counts), sizeof(rb2_event),
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rb2_config), sizeof(rb2_counts), sizeof(rb2_event),
                        sizeof(rb2_step_result), sizeof(rb2_mh_config), sizeof(rb2_collision_config), sizeof(rb2_recomb_record),
-                       sizeof(rb2_ionization_record), sizeof(rb2_collision_result), sizeof(rh_state)); return 0; }
+                       sizeof(rb2_ionization_record), sizeof(rb2_collision_result), sizeof(rh_state), sizeof(rh_setup)); return 0; }
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -64,7 +64,7 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rb2_c
     from rumdeed_b200 import api, host_api
     assert sizes == [C.sizeof(rb.Config), C.sizeof(rb.Counts), C.sizeof(rb.Event), C.sizeof(rb.StepResult), C.sizeof(api.MhConfig),
                      C.sizeof(api.CollisionConfig), C.sizeof(api.RecombRecord), C.sizeof(api.IonizationRecord),
-                     C.sizeof(api.CollisionResult), C.sizeof(host_api.State)]
+                     C.sizeof(api.CollisionResult), C.sizeof(host_api.State), C.sizeof(host_api.Setup)]
 
 
 def test_fails_loudly_without_gpu():
