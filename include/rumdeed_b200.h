@@ -132,6 +132,9 @@ int rb2_get_counts(rb2_counts *out);
  * in nrPart_dropped, like the reference. */
 int rb2_add_particles(int k, const double *pos, const double *vel, const int *species,
                       int step, const int *emit, const int *sec, const int *life);
+/* MAX_PARTICLES - nrPart: how many of the next rb2_add_particles calls' particles the store still accepts (the rest
+ * is dropped and counted, src/mod_pair.F90:36-43).  Host-side state only: no device synchronisation. */
+int rb2_capacity_left(int *out);
 /* Mark_Particles_Remove (src/mod_pair.F90:169-339) for k host-chosen particles. */
 int rb2_mark_remove(int k, const int *index, const int *reason);
 /* Remove_Particles (src/mod_pair.F90:352-562): stable compaction, counters reset. */
@@ -149,6 +152,12 @@ int rb2_update_position(int step);                 /* src/mod_verlet.F90:197-232
 int rb2_accel_only(void);                          /* Calculate_Acceleration_Particles, :597 (overwrites) */
 int rb2_update_velocity(rb2_step_result *out);     /* src/mod_verlet.F90:449-509 */
 int rb2_get_events(int max_events, rb2_event *out, int *n_out);
+/* ramo_current_emit(1:n_sec, 1:n_emit) of the last velocity update (src/mod_verlet.F90:489-492, written by
+ * Write_Ramo_Current when write_ramo_sec is set, src/mod_pair.F90:822-826): the Ramo current of the particles that
+ * carry section sec of emitter emit, Fortran layout out[(emit-1)*n_sec + sec-1].  Accumulated by rb2_step /
+ * rb2_update_velocity once rb2_set_option("ramo_sections", S) (and "ramo_emitters", default 1) has switched it on;
+ * a keyed sum in a fixed order (bit-identical from run to run).  Entries beyond the configured S are 0. */
+int rb2_get_ramo_sections(int n_sec, int n_emit, double *out);
 /* Stateless form of the reference's OpenACC call (upload positions, run the
  * kernel, copy the accelerations out: src/mod_verlet.F90:1254-1340) with HOST
  * buffers; used for the end-to-end measurement. */
@@ -189,7 +198,8 @@ int rb2_p2p_export(int n_max, void *handle_out);
 int rb2_p2p_attach(int world, int rank, const void *handles);
 int rb2_p2p_detach(void);
 /* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
- * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "event_buffer" (initial number of
+ * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "ramo_sections" / "ramo_emitters" (size
+ * of the per-section Ramo table, 0 sections = off), "event_buffer" (initial number of
  * absorb / plane-crossing records the device buffer holds; it grows on demand); emission samplers: "mh_small"
  * (1 / 0: single-barrier kernel for few chains), "mh_small_max" (its chain limit, <= 512), "mh_ctas_per_sm" (1..4,
  * many-chain kernel), "tip_field_small" (1 / 0: CTA-per-point tip field kernel for small batches). */

@@ -32,6 +32,7 @@ typedef struct rh_setup {
     double laser_energy, laser_variation, gauss_center, gauss_width, gauss_amplitude;
     int    max_particles;
     unsigned long long seed;
+    int    ramo_sections;      /* > 0: keep ramo_current_emit(1:ramo_sections, 1) per step (write_ramo_sec, src/mod_global.F90:352) */
 } rh_setup;
 
 typedef struct rh_state {
@@ -64,6 +65,8 @@ int   rh_step(void *sim, int step);
 int   rh_run(void *sim, int first_step, int n_steps);
 int   rh_get_state(void *sim, rh_state *out);
 int   rh_steps_in_input(void *sim);
+/* ramo_current_emit(1:n_sec, 1) of the last step (needs WRITE_RAMO_SEC in the deck or rh_setup.ramo_sections > 0) */
+int   rh_get_ramo_sections(void *sim, int n_sec, double *out);
 void  rh_destroy(void *sim);
 const char *rh_last_error(void *sim);
 

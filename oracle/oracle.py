@@ -78,6 +78,7 @@ class StoreStruct(C.Structure):
         ("ramo_current", C.c_double * 4),
         ("avg_part_vel", C.c_double * 3), ("avg_elec_vel", C.c_double * 3), ("avg_ion_vel", C.c_double * 3),
         ("events", C.POINTER(Event)), ("n_events", C.c_int), ("cap_events", C.c_int),
+        ("ramo_current_emit", _PD),
     ]
 
 
@@ -375,6 +376,10 @@ class Store:
 
     def life_time(self, lt, species):
         return int(self.s.life_time[lt][species])
+
+    def ramo_current_emit(self, n_sec=96 * 96):
+        """ramo_current_emit(1:n_sec, 1) of the last velocity update (src/mod_verlet.F90:489-492)."""
+        return np.ctypeslib.as_array(self.s.ramo_current_emit, shape=(96 * 96,))[:n_sec].copy()
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -769,6 +769,7 @@ orc_store *orc_store_new(int capacity)
     for (i = 0; i < capacity; ++i) s->mask[i] = 1;
     s->cap_events = 64;
     s->events = (orc_event *)calloc((size_t)s->cap_events, sizeof(orc_event));
+    s->ramo_current_emit = (double *)calloc((size_t)ORC_MAX_SECTIONS * ORC_MAX_EMITTERS, sizeof(double));
     return s;
 }
 
@@ -777,7 +778,7 @@ void orc_store_free(orc_store *s)
     if (!s) return;
     free(s->pos); free(s->prev_pos); free(s->vel); free(s->acc); free(s->acc_prev); free(s->acc_prev2);
     free(s->charge); free(s->mass); free(s->species); free(s->step); free(s->emitter); free(s->section);
-    free(s->life); free(s->id); free(s->mask); free(s->events);
+    free(s->life); free(s->id); free(s->mask); free(s->events); free(s->ramo_current_emit);
     free(s);
 }
 
@@ -969,6 +970,7 @@ void orc_update_velocity(orc_store *s, const orc_params *p)
     const double dt = p->time_step;
     int i, c;
     for (c = 0; c < 4; ++c) s->ramo_current[c] = 0.0;
+    for (i = 0; i < ORC_MAX_SECTIONS * ORC_MAX_EMITTERS; ++i) s->ramo_current_emit[i] = 0.0; /* src/mod_verlet.F90:155 */
     for (c = 0; c < 3; ++c) { s->avg_part_vel[c] = 0.0; s->avg_elec_vel[c] = 0.0; s->avg_ion_vel[c] = 0.0; }
     for (i = 0; i < s->nrPart; ++i) {
         double E_zu[3], EzV, qq;
@@ -982,6 +984,14 @@ void orc_update_velocity(orc_store *s, const orc_params *p)
         orc_E_zunit(p, &s->pos[3 * i], E_zu);
         EzV = s->vel[3 * i] * E_zu[0] + s->vel[3 * i + 1] * E_zu[1] + s->vel[3 * i + 2] * E_zu[2];
         if (sp >= 0 && sp < 4) s->ramo_current[sp] = s->ramo_current[sp] + qq * EzV;
+        {   /* ramo_current_emit(sec, emit), src/mod_verlet.F90:489-492 (an index outside the array is undefined
+             * behaviour in the reference; such particles are skipped here) */
+            int sec = s->section[i], emit = s->emitter[i];
+            if (sec >= 1 && sec <= ORC_MAX_SECTIONS && emit >= 1 && emit <= ORC_MAX_EMITTERS) {
+                double *r = &s->ramo_current_emit[(size_t)(emit - 1) * ORC_MAX_SECTIONS + (sec - 1)];
+                *r = *r + qq * EzV;
+            }
+        }
         for (c = 0; c < 3; ++c) {
             if (sp == ORC_SPECIES_ELEC) s->avg_elec_vel[c] = s->avg_elec_vel[c] + s->vel[3 * i + c];
             else if (sp == ORC_SPECIES_ION) s->avg_ion_vel[c] = s->avg_ion_vel[c] + s->vel[3 * i + c];

@@ -27,6 +27,8 @@ enum { ORC_GEOM_OTHER = 0, ORC_GEOM_PLANAR = 1, ORC_GEOM_TIP = 2 };  /* src/mod_
 
 #define ORC_PLANES_MAX 10        /* src/mod_global.F90:337 */
 #define ORC_MAX_LIFE_TIME 1000   /* src/mod_global.F90:280 */
+#define ORC_MAX_SECTIONS  (96 * 96) /* src/mod_global.F90:100 */
+#define ORC_MAX_EMITTERS  1       /* src/mod_global.F90:99 */
 
 /* Physical constants, src/mod_global.F90:26-75,333 */
 typedef struct {
@@ -126,6 +128,9 @@ typedef struct {
     double ramo_current[4];                          /* per species (1-based like Fortran) */
     double avg_part_vel[3], avg_elec_vel[3], avg_ion_vel[3];
     orc_event *events; int n_events, cap_events;
+    /* ramo_current_emit(1:MAX_SECTIONS, 1:MAX_EMITTERS), column-major like Fortran: [(emit-1)*MAX_SECTIONS + sec-1]
+     * (src/mod_global.F90:272, zeroed per step src/mod_verlet.F90:155, accumulated :489-492) */
+    double *ramo_current_emit;
 } orc_store;
 
 orc_store *orc_store_new(int capacity);

@@ -131,8 +131,8 @@ _PI = C.POINTER(C.c_int)
 EXPORTS = (
     "rb2_init", "rb2_finalize", "rb2_update_config", "rb2_last_error_string", "rb2_device_available",
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
-    "rb2_add_particles", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
-    "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_accel_host",
+    "rb2_add_particles", "rb2_capacity_left", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
+    "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_get_ramo_sections", "rb2_accel_host",
     "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_tip",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
@@ -162,6 +162,7 @@ def load_library(path: str | None = None):
     lib.rb2_download_particles.argtypes = [_PD] * 8 + [_PI] * 7
     lib.rb2_get_counts.argtypes = [C.POINTER(Counts)]
     lib.rb2_add_particles.argtypes = [C.c_int, _PD, _PD, _PI, C.c_int, _PI, _PI, _PI]
+    lib.rb2_capacity_left.argtypes = [_PI]
     lib.rb2_mark_remove.argtypes = [C.c_int, _PI, _PI]
     lib.rb2_remove_marked.argtypes = [C.c_int, C.POINTER(Counts)]
     lib.rb2_get_life_time.argtypes = [C.POINTER(C.c_longlong)]
@@ -169,6 +170,7 @@ def load_library(path: str | None = None):
     lib.rb2_update_position.argtypes = [C.c_int]
     lib.rb2_update_velocity.argtypes = [C.POINTER(StepResult)]
     lib.rb2_get_events.argtypes = [C.c_int, C.POINTER(Event), _PI]
+    lib.rb2_get_ramo_sections.argtypes = [C.c_int, C.c_int, _PD]
     lib.rb2_accel_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rb2_field_batch.argtypes = [C.c_int, _PD, _PD]
     lib.rb2_field_batch_delta.argtypes = [C.c_int, _PD, C.c_int, _PD, _PD, _PD]
@@ -396,6 +398,13 @@ class HotPath:
         self._check(self.lib.rb2_get_events(n.value, buf, C.byref(n)))
         return [dict(kind=e.kind, plane=e.plane, index=e.index, x=e.x, y=e.y, vx=e.vx, vy=e.vy, vz=e.vz,
                      emit=e.emit, sec=e.sec, id=e.id) for e in buf]
+
+    def ramo_current_emit(self, n_sec, n_emit=1):
+        """ramo_current_emit(1:n_sec, 1:n_emit) of the last velocity update (src/mod_verlet.F90:489-492);
+        needs set_option("ramo_sections", S) beforehand."""
+        out = np.zeros((n_emit, n_sec))
+        self._check(self.lib.rb2_get_ramo_sections(int(n_sec), int(n_emit), _d(out)))
+        return out[0] if n_emit == 1 else out
 
     def accel_host(self, pos, charge, mass, out=None):
         """Stateless host-buffer form (upload, kernel, copy-out), src/mod_verlet.F90:1254-1340."""

@@ -306,6 +306,7 @@ int rb2_finalize(void)
     free_arrays(c.b);
     cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);
     cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
+    cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec); cudaFreeHost(c.h_ramo_sec);
     cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw);
     cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
     cudaFreeHost(c.h_counters); cudaFreeHost(c.h_red); cudaFreeHost(c.h_total); cudaFreeHost(c.h_pts); cudaFreeHost(c.h_fld);
@@ -478,6 +479,14 @@ int rb2_add_particles(int k, const double *pos, const double *vel, const int *sp
     return RB2_OK;
 }
 
+int rb2_capacity_left(int *out)
+{
+    RB2_REQUIRE_INIT();
+    if (!out) return rb2_fail(RB2_ERR_ARG, "out is NULL");
+    *out = g_rb2.cap - g_rb2.n;
+    return RB2_OK;
+}
+
 int rb2_mark_remove(int k, const int *index, const int *reason)
 {
     RB2_REQUIRE_INIT();
@@ -567,6 +576,7 @@ int rb2_update_velocity(rb2_step_result *out)
     Rb2Ctx &c = g_rb2;
     int rc = rb2_launch_update_velocity(c);
     if (rc) return rc;
+    if ((rc = rb2_launch_ramo_sections(c))) return rc;
     RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     if (out) {
@@ -590,6 +600,7 @@ int rb2_step(int step, rb2_step_result *out)
     if (rc) return rc;
     rc = rb2_launch_update_velocity(c);
     if (rc) return rc;
+    if ((rc = rb2_launch_ramo_sections(c))) return rc;
     RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     RB2_CUDA(cudaEventRecord(c.ev_s1, c.stream));
     RB2_CUDA(cudaStreamSynchronize(c.stream));
@@ -603,6 +614,19 @@ int rb2_step(int step, rb2_step_result *out)
         if (c.accel_timed) RB2_CUDA(cudaEventElapsedTime(&out->accel_ms, c.ev_a0, c.ev_a1));
         RB2_CUDA(cudaEventElapsedTime(&out->step_ms, c.ev_s0, c.ev_s1));
     }
+    return RB2_OK;
+}
+
+int rb2_get_ramo_sections(int n_sec, int n_emit, double *out)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (!out || n_sec < 1 || n_emit < 1) return rb2_fail(RB2_ERR_ARG, "rb2_get_ramo_sections: bad arguments");
+    if (c.ramo_n_sec < 1) return rb2_fail(RB2_ERR_ARG, "per-section Ramo current is off: rb2_set_option(\"ramo_sections\", n) first");
+    RB2_CUDA(cudaStreamSynchronize(c.stream));
+    for (int e = 0; e < n_emit; ++e)
+        for (int s = 0; s < n_sec; ++s)
+            out[(size_t)e * n_sec + s] = (c.h_ramo_sec && e < c.ramo_n_emit && s < c.ramo_n_sec) ? c.h_ramo_sec[(size_t)e * c.ramo_n_sec + s] : 0.0;
     return RB2_OK;
 }
 
@@ -775,6 +799,15 @@ int rb2_set_option(const char *name, double value)
         if (c.d_events) { RB2_CUDA(cudaStreamSynchronize(c.stream)); RB2_CUDA(cudaFree(c.d_events)); }
         c.d_events = nullptr;
         c.ev_cap = 0;
+    } else if (!strcmp(name, "ramo_sections") || !strcmp(name, "ramo_emitters")) {
+        const bool sec = !strcmp(name, "ramo_sections");
+        if (value < (sec ? 0 : 1) || value > (sec ? 96 * 96 : 8)) return rb2_fail(RB2_ERR_ARG, "%s out of range", name);
+        const int ns = sec ? (int)value : c.ramo_n_sec, ne = sec ? c.ramo_n_emit : (int)value;
+        if ((size_t)ns * ne * sizeof(double) > 200 * 1024) return rb2_fail(RB2_ERR_ARG, "ramo_sections x ramo_emitters exceeds the shared-memory table (25600 entries)");
+        RB2_CUDA(cudaStreamSynchronize(c.stream));
+        cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec); cudaFreeHost(c.h_ramo_sec);
+        c.d_ramo_part = c.d_ramo_sec = c.h_ramo_sec = nullptr;
+        c.ramo_n_sec = ns; c.ramo_n_emit = ne;
     } else if (!strcmp(name, "sym_tpl")) {
         if (value != 0 && value != 1 && value != 2) return rb2_fail(RB2_ERR_ARG, "sym_tpl (targets per lane) must be 0 (auto), 1 or 2");
         c.sym_tpl = (int)value;

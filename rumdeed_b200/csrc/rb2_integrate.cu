@@ -209,6 +209,22 @@ k_events_scatter(int n, DevArrays A, const unsigned char *__restrict__ evcnt, co
 // ---- Beeman velocity update + Ramo current + velocity sums -----------------------------------
 constexpr int NRED = 13;  // ramo[0..3], part(3), elec(3), ion(3)
 
+// q * (v . E_zunit(pos)): the Shockley-Ramo term of one particle, src/mod_verlet.F90:481-488
+__device__ __forceinline__ double ramo_term(const StepParams &P, const double4 &p, const double v[3])
+{
+    double ex = 0.0, ey = 0.0, ez;
+    if (P.geometry == RB2_GEOM_TIP) {  // E_zunit_tip, src/mod_emission_tip.f90:133-141
+        rb2_tip_field_E(P.tip, p.x, p.y, p.z, ex, ey, ez);
+        ex = ex * P.tip.unit_scale_num / P.tip.unit_scale_den;
+        ey = ey * P.tip.unit_scale_num / P.tip.unit_scale_den;
+        ez = ez * P.tip.unit_scale_num / P.tip.unit_scale_den;
+    } else {  // E_zunit_planar, src/mod_field_emission_v2.F90:158-166
+        ez = -1.0 / P.d;
+    }
+    const double EzV = v[0] * ex + v[1] * ey + v[2] * ez;
+    return p.w * EzV;
+}
+
 __global__ void __launch_bounds__(TPB)
 k_update_velocity(int n, DevArrays A, StepParams P, double *__restrict__ redpart, const unsigned char *__restrict__ evcnt,
                   double *__restrict__ vel_save)
@@ -235,17 +251,7 @@ k_update_velocity(int n, DevArrays A, StepParams P, double *__restrict__ redpart
                 A.vel[e] = v[c];
             }
             const double4 p = A.pq[i];
-            double ex = 0.0, ey = 0.0, ez;
-            if (P.geometry == RB2_GEOM_TIP) {  // E_zunit_tip, src/mod_emission_tip.f90:133-141
-                rb2_tip_field_E(P.tip, p.x, p.y, p.z, ex, ey, ez);
-                ex = ex * P.tip.unit_scale_num / P.tip.unit_scale_den;
-                ey = ey * P.tip.unit_scale_num / P.tip.unit_scale_den;
-                ez = ez * P.tip.unit_scale_num / P.tip.unit_scale_den;
-            } else {  // E_zunit_planar, src/mod_field_emission_v2.F90:158-166
-                ez = -1.0 / P.d;
-            }
-            const double EzV = v[0] * ex + v[1] * ey + v[2] * ez;
-            if (sp >= 0 && sp < 4) r[sp] = p.w * EzV;
+            if (sp >= 0 && sp < 4) r[sp] = ramo_term(P, p, v);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 r[4 + c] = v[c];
@@ -283,6 +289,59 @@ __global__ void __launch_bounds__(TPB) k_reduce_final(int nblocks, const double 
         __syncthreads();
     }
     if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+
+// ---- per-section Ramo current: ramo_current_emit(sec, emit), src/mod_verlet.F90:489-492 -------------------------
+// A keyed sum with a FIXED order (bit-identical from run to run and on every replica): block b owns a contiguous
+// range of particles and walks it tile by tile; inside a tile a warp groups its lanes by key (match.any), the lowest
+// lane of each group adds the group's terms in ascending lane order, and the warps fold their group sums into the
+// block's shared-memory table one warp after the other.  The per-block tables are added in block order by
+// k_ramo_sections_final.  nkeys = n_sec * n_emit doubles of dynamic shared memory (<= 72 KB at MAX_SECTIONS = 9216).
+__global__ void __launch_bounds__(TPB)
+k_ramo_sections(int n, int per_block, DevArrays A, StepParams P, int n_sec, int n_emit, double *__restrict__ part)
+{
+    extern __shared__ double tab[];
+    const int nkeys = n_sec * n_emit;
+    for (int k = threadIdx.x; k < nkeys; k += TPB) tab[k] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * per_block;
+    const int i1 = min(n, i0 + per_block);
+    for (int base = i0; base < i1; base += TPB) {  // block-uniform trip count
+        const int i = base + threadIdx.x;
+        int key = -1;
+        double x = 0.0;
+        if (i < i1) {
+            const int sp = A.species[i];
+            const int sec = A.section[i], emit = A.emitter[i];
+            if (sp != RB2_SPECIES_ATOM && sec >= 1 && sec <= n_sec && emit >= 1 && emit <= n_emit) {
+                key = (emit - 1) * n_sec + (sec - 1);
+                const double v[3] = {A.vel[3 * i], A.vel[3 * i + 1], A.vel[3 * i + 2]};
+                x = ramo_term(P, A.pq[i], v);
+            }
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const bool leader = (key >= 0) && (lane == __ffs(grp) - 1);
+        double sum = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const double t = __shfl_sync(0xffffffffu, x, l);
+            if ((grp >> l) & 1u) sum += t;
+        }
+        for (int ww = 0; ww < TPB / 32; ++ww) {
+            if (w == ww && leader) tab[key] += sum;
+            __syncthreads();
+        }
+    }
+    for (int k = threadIdx.x; k < nkeys; k += TPB) part[(size_t)blockIdx.x * nkeys + k] = tab[k];
+}
+__global__ void __launch_bounds__(TPB) k_ramo_sections_final(int nblocks, int nkeys, const double *__restrict__ part, double *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    double x = 0.0;
+    for (int b = 0; b < nblocks; ++b) x += part[(size_t)b * nkeys + k];
+    out[k] = x;
 }
 
 // ---- stable compaction ---------------------------------------------------------------------------
@@ -525,6 +584,38 @@ int rb2_launch_update_velocity(Rb2Ctx &ctx)
     k_reduce_final<<<NRED, TPB, 0, ctx.stream>>>(nb, ctx.d_redpart, ctx.d_red);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(2);
+    return RB2_OK;
+}
+
+// ramo_current_emit of the velocities now in the store (queued behind the velocity update); the result is copied to
+// ctx.h_ramo_sec in stream order.
+int rb2_launch_ramo_sections(Rb2Ctx &ctx)
+{
+    const int nkeys = ctx.ramo_n_sec * ctx.ramo_n_emit;
+    if (nkeys < 1) return RB2_OK;
+    if (!ctx.d_ramo_sec) {
+        RB2_CUDA(cudaMalloc(&ctx.d_ramo_sec, (size_t)nkeys * sizeof(double)));
+        RB2_CUDA(cudaMallocHost(&ctx.h_ramo_sec, (size_t)nkeys * sizeof(double)));
+        ctx.ramo_blocks = 2 * ctx.sm_count;
+        RB2_CUDA(cudaMalloc(&ctx.d_ramo_part, (size_t)ctx.ramo_blocks * nkeys * sizeof(double)));
+        RB2_CUDA(cudaFuncSetAttribute(k_ramo_sections, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nkeys * sizeof(double))));
+    }
+    if (ctx.n < 1) {
+        RB2_CUDA(cudaMemsetAsync(ctx.d_ramo_sec, 0, (size_t)nkeys * sizeof(double), ctx.stream));
+    } else {
+        int nb = nblk(ctx.n);
+        if (nb > ctx.ramo_blocks) nb = ctx.ramo_blocks;
+        int per_block = (ctx.n + nb - 1) / nb;
+        per_block = (per_block + TPB - 1) / TPB * TPB;
+        nb = (ctx.n + per_block - 1) / per_block;
+        const StepParams P = rb2_make_step_params(ctx.cfg);
+        k_ramo_sections<<<nb, TPB, (size_t)nkeys * sizeof(double), ctx.stream>>>(ctx.n, per_block, ctx.a, P, ctx.ramo_n_sec, ctx.ramo_n_emit, ctx.d_ramo_part);
+        RB2_CUDA(cudaGetLastError());
+        k_ramo_sections_final<<<(nkeys + TPB - 1) / TPB, TPB, 0, ctx.stream>>>(nb, nkeys, ctx.d_ramo_part, ctx.d_ramo_sec);
+        RB2_CUDA(cudaGetLastError());
+        RB2_LAUNCHED(2);
+    }
+    RB2_CUDA(cudaMemcpyAsync(ctx.h_ramo_sec, ctx.d_ramo_sec, (size_t)nkeys * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
     return RB2_OK;
 }
 

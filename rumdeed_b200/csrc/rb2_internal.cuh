@@ -98,6 +98,9 @@ struct Rb2Ctx {
     DevCounters *d_counters = nullptr, *h_counters = nullptr;  // device / pinned host
     double *d_red = nullptr, *h_red = nullptr;                  // velocity-update reductions (16 doubles)
     double *d_redpart = nullptr; int redpart_blocks = 0;
+    // ramo_current_emit(sec, emit) (options "ramo_sections" / "ramo_emitters"; 0 sections = off)
+    int    ramo_n_sec = 0, ramo_n_emit = 1, ramo_blocks = 0;
+    double *d_ramo_part = nullptr, *d_ramo_sec = nullptr, *h_ramo_sec = nullptr;
     int *d_total = nullptr, *h_total = nullptr;                 // scan totals
 
     double *partial = nullptr; size_t partial_bytes = 0;       // pair-kernel partial sums
@@ -188,6 +191,7 @@ int rb2_launch_update_position(Rb2Ctx &ctx);
 int rb2_launch_events(Rb2Ctx &ctx);
 int rb2_rebuild_events(Rb2Ctx &ctx, int n_events, bool after_velocity_update);
 int rb2_launch_update_velocity(Rb2Ctx &ctx);
+int rb2_launch_ramo_sections(Rb2Ctx &ctx);
 int rb2_launch_compact(Rb2Ctx &ctx, int step);
 int rb2_launch_add(Rb2Ctx &ctx, int k, int slot0, int id0, int step, const double *d_pos, const double *d_vel,
                    const int *d_species, const int *d_emit, const int *d_sec, const int *d_life);

@@ -57,6 +57,7 @@ void *rh_create(const rh_setup *u)
     if (u->cuba_maxeval > 0) g.cuba_maxeval = u->cuba_maxeval;
     if (u->max_particles > 0) g.max_particles = u->max_particles;
     g.seed = u->seed;
+    s->ramo_sections = u->ramo_sections > 0 ? u->ramo_sections : 0;
     if (u->work_w_theta && u->work_y_num > 0 && u->work_x_num > 0) {
         s->work.type = 1;
         s->work.y_num = u->work_y_num;
@@ -118,6 +119,15 @@ int rh_get_state(void *p, rh_state *o)
 }
 
 int rh_steps_in_input(void *p) { Sim *s = (Sim *)p; return s ? s->g.steps : 0; }
+
+int rh_get_ramo_sections(void *p, int n_sec, double *out)
+{
+    Sim *s = (Sim *)p;
+    if (!s || !out || n_sec < 1) return -1;
+    if (s->ramo_sections < 1) { s->err = "per-section Ramo current is off (WRITE_RAMO_SEC / ramo_sections)"; return -1; }
+    for (int k = 0; k < n_sec; ++k) out[k] = k < (int)s->ramo_current_emit.size() ? s->ramo_current_emit[(size_t)k] : 0.0;
+    return 0;
+}
 
 void rh_destroy(void *p)
 {

@@ -76,6 +76,18 @@ int Do_Collisions(Sim &s, int step)
             if (s.check(rb2_get_ionization_records(r.nrIonizations, ev.data(), &n), "rb2_get_ionization_records")) return -1;
             for (int k = 0; k < n && k < r.nrIonizations; ++k) {
                 const rb2_ionization_record &e = ev[(size_t)k];
+                // the two Add_Particle calls of the event (ejected electron, then ion; emitter = ion_emitter = 2, default
+                // section 1, src/mod_collisions.F90:668-685) write their density_emit*.bin records (src/mod_pair.F90:85-123)
+                for (int which = 0; which < 2; ++which) {
+                    const int pid = which == 0 ? e.new_id : e.ion_id;
+                    if (pid < 0) continue;  // dropped at MAX_PARTICLES
+                    const double *pp = which == 0 ? e.ejec_pos : e.ion_pos;
+                    const double p3[3] = {pp[0] / length_scale, pp[1] / length_scale, pp[2] / length_scale};
+                    const int sp = which == 0 ? species_elec : species_ion;
+                    FILE *fs = which == 0 ? s.ud_density_emit_elec : s.ud_density_emit_ion;
+                    if (fs) { const int t2[2] = {2, pid}; fwrite(p3, sizeof(double), 3, fs); fwrite(t2, sizeof(int), 2, fs); }
+                    if (s.ud_density_emit) { const int t4[4] = {2, 1, pid, sp}; fwrite(p3, sizeof(double), 3, s.ud_density_emit); fwrite(t4, sizeof(int), 4, s.ud_density_emit); }
+                }
                 const double d[8] = {e.pos[0], e.pos[1], e.pos[2], e.in_speed, e.out_speed, e.new_speed, 0.0, 0.0};
                 const int t[4] = {e.in_slot + 1, e.new_id, e.ion_id, e.elec_emit};  // inID is the Fortran slot
                 fwrite(&e.step, sizeof(int), 1, s.ud_ionization_data);

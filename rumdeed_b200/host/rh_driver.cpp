@@ -5,6 +5,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
 
 #include "rh_host.hpp"
@@ -77,6 +78,10 @@ int Init(Sim &s)
         s.ud_integrand = open_out(s, "integration.dt", "w");
         s.ud_volt = open_out(s, "volt.dt", "w");
         s.ud_density_emit = open_out(s, "density_emit.bin", "wb");
+        s.ud_density_emit_elec = open_out(s, "density_emit_elec.bin", "wb");  // src/main.F90 Init: one file per species
+        s.ud_density_emit_ion = open_out(s, "density_emit_ion.bin", "wb");
+        s.ud_density_emit_atom = open_out(s, "density_emit_atom.bin", "wb");
+        if (g.write_ramo_sec) s.ud_ramo_sec = open_out(s, "ramo_current.bin", "wb");  // src/main.F90:596
         if (g.write_position_file) s.ud_pos = open_out(s, "position.bin", "wb");  // src/main.F90:548
         s.ud_density_absorb_top = open_out(s, "density_absorb_top.bin", "wb");
         s.ud_density_absorb_bot = open_out(s, "density_absorb_bot.bin", "wb");
@@ -91,6 +96,21 @@ int Init(Sim &s)
                     g.V_s, g.d, g.time_step, g.steps, g.emission_mode, (int)g.image_charge, g.N_ic_max);
             fclose(f);
         }
+        // init.bin, src/main.F90:928-938: epsilon_r, m_eeff, m_ieff, length_scale, time_scale, vel_scale, cur_scale (f64),
+        // MAX_PARTICLES, MAX_EMITTERS, MAX_SECTIONS, MAX_LIFE_TIME (i32) -- 72 bytes
+        if (FILE *f = open_out(s, "init.bin", "wb")) {
+            const double d7[7] = {1.0, 1.0, 1.0, length_scale, time_scale, length_scale / time_scale, cur_scale};
+            const int i4[4] = {MAX_PARTICLES, MAX_EMITTERS, MAX_SECTIONS, RB2_MAX_LIFE_TIME};
+            fwrite(d7, sizeof(double), 7, f);
+            fwrite(i4, sizeof(int), 4, f);
+            fclose(f);
+        }
+    }
+    // ramo_current_emit(sec, emit): the device keeps a table of the sections the work function defines
+    if (g.write_ramo_sec || s.ramo_sections > 0) {
+        if (s.ramo_sections < 1) s.ramo_sections = std::max(1, std::min(MAX_SECTIONS, s.work.y_num * s.work.x_num));
+        if (s.check(rb2_set_option("ramo_sections", (double)s.ramo_sections), "rb2_set_option(ramo_sections)")) return -1;
+        s.ramo_current_emit.assign((size_t)MAX_SECTIONS * MAX_EMITTERS, 0.0);
     }
     if (Init_Collisions(s)) return -1;  // src/main.F90:397 (Read_Cross_Section_Data), :164-166
     return 0;
@@ -212,6 +232,10 @@ int Step(Sim &s, int step)
                 ramo_cur, g.V_d, s.counts.nrPart, s.counts.nrElec, s.counts.nrIon, avg_mob, nrm(s.last.avg_part_vel),
                 nrm(s.last.avg_elec_vel), nrm(s.last.avg_ion_vel), s.last.ramo_current[1], s.last.ramo_current[2], s.last.ramo_current[3]);
     }
+    if (s.ramo_sections > 0) {  // Write_Ramo_Current, src/mod_pair.F90:822-826: the whole (MAX_SECTIONS, MAX_EMITTERS) array
+        if (s.check(rb2_get_ramo_sections(MAX_SECTIONS, MAX_EMITTERS, s.ramo_current_emit.data()), "rb2_get_ramo_sections")) return -1;
+        if (s.ud_ramo_sec) fwrite(s.ramo_current_emit.data(), sizeof(double), s.ramo_current_emit.size(), s.ud_ramo_sec);
+    }
     if (s.write_files) write_event_files(s);
     if (write_position(s, step)) return -1;        // src/main.F90:191
     if (sample_elec_position(s, step)) return -1;  // src/main.F90:193
@@ -241,7 +265,8 @@ int Clean_up(Sim &s)
 {
     if (s.ptr.ptr_Clean_Up) s.ptr.ptr_Clean_Up(s);
     FILE **fs[] = {&s.ud_ramo, &s.ud_emit, &s.ud_absorb, &s.ud_absorb_top, &s.ud_absorb_bot, &s.ud_field, &s.ud_integrand, &s.ud_volt,
-                   &s.ud_density_emit, &s.ud_density_absorb_top, &s.ud_density_absorb_bot, &s.ud_pos, &s.ud_coll, &s.ud_ionization_data,
+                   &s.ud_density_emit, &s.ud_density_emit_elec, &s.ud_density_emit_ion, &s.ud_density_emit_atom, &s.ud_ramo_sec,
+                   &s.ud_density_absorb_top, &s.ud_density_absorb_bot, &s.ud_pos, &s.ud_coll, &s.ud_ionization_data,
                    &s.ud_recombination_data, &s.ud_density_absorb_recom, &s.ud_absorb_recom};
     for (FILE **f : fs) if (*f) { fclose(*f); *f = nullptr; }
     for (int k = 0; k < RB2_PLANES_MAX; ++k) if (s.planes_ud[k]) { fclose(s.planes_ud[k]); s.planes_ud[k] = nullptr; }

@@ -125,40 +125,46 @@ int Sim::Calc_Field_at_Surface(int M, const double *pos_in, double *field_out)
     for (int k = 0; k < M; ++k) { field_out[3 * k] = 0.0; field_out[3 * k + 1] = 0.0; field_out[3 * k + 2] = scratch_ez[k]; }
     return 0;
 }
-int Sim::Add_Particle(const double par_pos[3], const double par_vel[3], int species, int step, int emit, int life, int sec)
+// The part of Add_Particle that the host keeps: the density_emit*.bin records (src/mod_pair.F90:92, :103, :114, :123)
+// and the mirror of nrID / nrPart / nrElec / nrIon.  Only called for particles the store accepted: a particle dropped
+// at MAX_PARTICLES writes nothing and does not advance nrID in the reference (:36-43).
+void Sim::record_added(const double pos[3], int species, int emit, int sec)
 {
-    int rc = check(rb2_add_particles(1, par_pos, par_vel, &species, step, &emit, &sec, &life), "rb2_add_particles");
-    if (rc) return rc;
-    if (ud_density_emit) {  // src/mod_pair.F90:123: pos/length_scale, emit, sec, nrID, species
-        double p3[3] = {par_pos[0] / length_scale, par_pos[1] / length_scale, par_pos[2] / length_scale};
-        int tail[4] = {emit, sec, counts.nrID, species};
+    const double p3[3] = {pos[0] / length_scale, pos[1] / length_scale, pos[2] / length_scale};
+    FILE *fs = species == species_elec ? ud_density_emit_elec : species == species_ion ? ud_density_emit_ion : ud_density_emit_atom;
+    if (fs) {  // pos/length_scale, emit, nrID
+        const int tail[2] = {emit, counts.nrID};
+        fwrite(p3, sizeof(double), 3, fs);
+        fwrite(tail, sizeof(int), 2, fs);
+    }
+    if (ud_density_emit) {  // pos/length_scale, emit, sec, nrID, species
+        const int tail[4] = {emit, sec, counts.nrID, species};
         fwrite(p3, sizeof(double), 3, ud_density_emit);
         fwrite(tail, sizeof(int), 4, ud_density_emit);
     }
     counts.nrID += 1;
     counts.nrPart += 1;
     if (species == species_elec) counts.nrElec += 1; else if (species == species_ion) counts.nrIon += 1;
-    return 0;
 }
-// k calls of Add_Particle in one trip to the device (same order, same ids).  Only valid where no field evaluation sits
-// between the individual calls, i.e. behind the lock-step samplers (mh_batch), whose fields are all taken before the
-// first insertion -- one host/device round trip (~40 us) per step instead of one per emitted electron.
+int Sim::Add_Particle(const double par_pos[3], const double par_vel[3], int species, int step, int emit, int life, int sec)
+{
+    return Add_Particles(1, par_pos, par_vel, species, step, emit, life, &sec);
+}
+// k calls of Add_Particle in one trip to the device (same order, same ids).  With k > 1 only valid where no field
+// evaluation sits between the individual calls, i.e. behind the lock-step samplers (mh_batch), whose fields are all taken
+// before the first insertion -- one host/device round trip (~40 us) per step instead of one per emitted electron.
 int Sim::Add_Particles(int k, const double *pos, const double *vel, int species, int step, int emit, int life, const int *sec)
 {
     if (k < 1) return 0;
+    int room = 0;
+    if (check(rb2_capacity_left(&room), "rb2_capacity_left")) return -1;
     std::vector<int> sp((size_t)k, species), em((size_t)k, emit), lf((size_t)k, life);
     int rc = check(rb2_add_particles(k, pos, vel, sp.data(), step, em.data(), sec, lf.data()), "rb2_add_particles");
     if (rc) return rc;
-    for (int i = 0; i < k; ++i) {
-        if (ud_density_emit) {
-            double p3[3] = {pos[3 * i] / length_scale, pos[3 * i + 1] / length_scale, pos[3 * i + 2] / length_scale};
-            int tail[4] = {emit, sec[i], counts.nrID, species};
-            fwrite(p3, sizeof(double), 3, ud_density_emit);
-            fwrite(tail, sizeof(int), 4, ud_density_emit);
-        }
-        counts.nrID += 1;
-        counts.nrPart += 1;
-        if (species == species_elec) counts.nrElec += 1; else if (species == species_ion) counts.nrIon += 1;
+    const int accepted = k < room ? k : room;  // the rest was dropped and counted in nrPart_dropped
+    for (int i = 0; i < accepted; ++i) {
+        const int s_i = sec[i] > MAX_SECTIONS ? MAX_SECTIONS : sec[i];
+        record_added(&pos[(size_t)3 * i], species, emit, s_i);
     }
     return 0;
 }

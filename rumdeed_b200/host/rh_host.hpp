@@ -70,6 +70,7 @@ struct Globals {
     double planes_z[RB2_PLANES_MAX] = {5.0, 10.0, 25.0, 50.0, 75.0, 100.0, 125.0, 250.0, 500.0, 750.0};
     bool mh_batch = false;
     bool mh_device = false;  // lock-step chains run by rb2_mh_planar (implies mh_batch)
+    bool write_ramo_sec = false;                             // src/mod_global.F90:352: ramo_current.bin per section
     bool write_position_file = false;                        // src/mod_global.F90:353
     bool sample_elec_file = false; int sample_elec_rate = 500;  // src/mod_global.F90:360-361
     int cuba_method = 2;
@@ -147,6 +148,10 @@ struct Sim {
     FILE *ud_ramo = nullptr, *ud_emit = nullptr, *ud_absorb = nullptr, *ud_absorb_top = nullptr, *ud_absorb_bot = nullptr;
     FILE *ud_field = nullptr, *ud_integrand = nullptr, *ud_volt = nullptr, *ud_density_emit = nullptr;
     FILE *ud_pos = nullptr;  // out/position.bin (Write_Position)
+    FILE *ud_ramo_sec = nullptr;  // out/ramo_current.bin (Write_Ramo_Current with write_ramo_sec, src/mod_pair.F90:822-826)
+    FILE *ud_density_emit_elec = nullptr, *ud_density_emit_ion = nullptr, *ud_density_emit_atom = nullptr;  // src/mod_pair.F90:92, :103, :114
+    std::vector<double> ramo_current_emit;  // (MAX_SECTIONS, MAX_EMITTERS) of the last step when write_ramo_sec / sections are on
+    int ramo_sections = 0;                  // size of the device table (work.y_num * work.x_num), 0 = off
     FILE *ud_coll = nullptr, *ud_ionization_data = nullptr, *ud_recombination_data = nullptr, *ud_density_absorb_recom = nullptr,
          *ud_absorb_recom = nullptr;  // collision outputs (src/main.F90:603-641, :719)
     long long nrIonizations_total = 0, nrRecombinations_total = 0;
@@ -170,6 +175,8 @@ struct Sim {
     int Calc_Field_at_Surface(int M, const double *pos_in, double *field_out);
     int Add_Particle(const double par_pos[3], const double par_vel[3], int species, int step, int emit, int life, int sec);
     int Add_Particles(int k, const double *pos, const double *vel, int species, int step, int emit, int life, const int *sec);
+    // the density_emit*.bin records + host counters of one ACCEPTED particle (src/mod_pair.F90:85-123)
+    void record_added(const double pos[3], int species, int emit, int sec);
     // geometry helpers (src/mod_hyperboloid_tip.f90:25-112, 156-163)
     void xyz_corr(double xi, double eta, double phi, double out[3]) const;
     void surface_normal(const double pos[3], double out[3]) const;

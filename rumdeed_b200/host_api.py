@@ -34,7 +34,7 @@ class Setup(C.Structure):
         ("laser_gauss_mode", C.c_int), ("laser_mode", C.c_int), ("photon_mode", C.c_int),
         ("laser_energy", C.c_double), ("laser_variation", C.c_double),
         ("gauss_center", C.c_double), ("gauss_width", C.c_double), ("gauss_amplitude", C.c_double),
-        ("max_particles", C.c_int), ("seed", C.c_ulonglong),
+        ("max_particles", C.c_int), ("seed", C.c_ulonglong), ("ramo_sections", C.c_int),
     ]
 
 
@@ -74,6 +74,7 @@ def load_host_library():
     lib.rh_run.argtypes = [V, C.c_int, C.c_int]
     lib.rh_get_state.argtypes = [V, C.POINTER(State)]
     lib.rh_steps_in_input.argtypes = [V]
+    lib.rh_get_ramo_sections.argtypes = [V, C.c_int, _PD]
     lib.rh_destroy.argtypes = [V]; lib.rh_destroy.restype = None
     lib.rh_last_error.argtypes = [V]; lib.rh_last_error.restype = C.c_char_p
     lib.rh_cuba_integrate.argtypes = [V, C.c_int, _PD, _PD, _PI, _PI]
@@ -136,6 +137,7 @@ class Simulation:
                 u.gauss_center, u.gauss_width, u.gauss_amplitude = laser.get("center", 0.0), laser.get("width", 1.0), laser.get("amplitude", 0.0)
             u.max_particles = setup.get("max_particles", max_particles or 200000)
             u.seed = seed
+            u.ramo_sections = int(setup.get("ramo_sections", 0))
             self.ptr = self.lib.rh_create(C.byref(u))
         if not self.ptr:
             raise Rb2Error("rh_create failed")
@@ -174,6 +176,11 @@ class Simulation:
         st = State()
         self.lib.rh_get_state(self.ptr, C.byref(st))
         return st
+
+    def ramo_current_emit(self, n_sec):
+        out = np.zeros(n_sec)
+        self._check(self.lib.rh_get_ramo_sections(self.ptr, int(n_sec), _d(out)))
+        return out
 
     # -- samplers / quadrature --------------------------------------------------------------------------
     def Cuba_Integrate(self, kind):

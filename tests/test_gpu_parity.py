@@ -474,6 +474,7 @@ def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom, event_buffer):
     with rb.HotPath(cfg) as hp:
         if event_buffer is not None:
             hp.set_option("event_buffer", event_buffer)
+        hp.set_option("ramo_sections", 5)
         for i in range(n0):
             st.add(p, pos[i], vel[i], int(species[i]), 0, 1, -1, 1 + (i % 5))
         hp.Add_Particles(pos, vel, species, 0, emit=np.ones(n0, dtype=np.int32), sec=(1 + (np.arange(n0) % 5)).astype(np.int32))
@@ -497,6 +498,8 @@ def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom, event_buffer):
             assert (k.nrElec_remove_top, k.nrElec_remove_bot) == (st.s.nrElec_remove_top, st.s.nrElec_remove_bot)
             for sp_ in (1, 2):
                 assert r.ramo_current[sp_] == pytest.approx(st.s.ramo_current[sp_], rel=1e-9, abs=1e-30)
+            sec_g, sec_o = hp.ramo_current_emit(5), st.ramo_current_emit(5)
+            assert np.allclose(sec_g, sec_o, rtol=1e-9, atol=1e-9 * np.max(np.abs(sec_o)) + 1e-300)  # src/mod_verlet.F90:489-492
             st.remove(step)
             k = hp.Remove_Particles(step)
             assert (k.nrPart, k.nrElec, k.nrIon) == (st.s.nrPart, st.s.nrElec, st.s.nrIon)
@@ -521,6 +524,62 @@ def test_stepped_trajectory_bit_exact_bookkeeping(orc, geom, event_buffer):
         for sp_ in (1, 2):
             ref = np.array([st.life_time(t, sp_) for t in range(rb.api.MAX_LIFE_TIME + 1)])
             assert np.array_equal(lt[:, sp_], ref)
+
+
+@pytest.mark.parametrize("geom", ["planar", "tip"])
+@pytest.mark.parametrize("board,n", [(2, 3), (2, 1000), (4, 300), (4, 70001), (96, 70001)])
+def test_ramo_current_per_section_vs_oracle(orc, geom, board, n):
+    """ramo_current_emit(sec, emit) (src/mod_verlet.F90:489-492, written by Write_Ramo_Current src/mod_pair.F90:822-826)
+    for a board x board checkerboard of sections: every section against the oracle's serial sum, atoms skipped,
+    sections beyond the table ignored, bit-identical from run to run, and the sections add up to the species totals."""
+    rng = np.random.default_rng(1000 * board + n)
+    nsec = board * board
+    if geom == "planar":
+        d, dt = 1000 * NM, 1.0e-16
+        box = (1000 * NM, 1000 * NM, d)
+        cfg = rb.planar_config(2000.0, d, box, dt, True, 1, capacity=n + 8)
+        p = orc.params_planar(2000.0, d, box, dt, True, 1)
+        pos = np.stack([rng.uniform(-500, 500, n), rng.uniform(-500, 500, n), rng.uniform(1, 999, n)], axis=1) * NM
+    else:
+        box, dt = (100 * NM, 100 * NM, 900 * NM), 1.0e-16
+        cfg = rb.tip_config(500.0, 900 * NM, 100 * NM, 100 * NM, box, dt, True, capacity=n + 8)
+        p = orc.params_tip(500.0, 900 * NM, 100 * NM, 100 * NM, box, dt, True)
+        pos = np.stack([rng.uniform(-40, 40, n), rng.uniform(-40, 40, n), rng.uniform(110, 890, n)], axis=1) * NM
+    vel = np.stack([rng.normal(0, 3e4, n), rng.normal(0, 3e4, n), rng.normal(2e5, 4e5, n)], axis=1)
+    species = np.where((np.arange(n) % 7) == 6, 2, 1).astype(np.int32)
+    if n > 10:
+        species[5] = 3  # an atom: no contribution (src/mod_verlet.F90:463)
+    sec = rng.integers(1, nsec + 1, n).astype(np.int32)
+    acc = np.zeros((n, 3))
+    q = np.where(species == 2, Q_0, np.where(species == 1, -Q_0, 0.0))
+    m = np.where(species == 2, M_N2P, M_0)
+    st = orc.store(n + 8)
+    for i in range(n):
+        st.add(p, pos[i], vel[i], int(species[i]), 0, 1, -1, int(sec[i]))
+    st.acc[:] = 0.0; st.acc_prev[:] = 0.0; st.acc_prev2[:] = 0.0
+    st.update_velocity(p)
+    want = st.ramo_current_emit(nsec)
+    got = []
+    for rep in range(2):
+        with rb.HotPath(cfg) as hp:
+            hp.set_option("ramo_sections", nsec)
+            hp.upload(pos, q, m, vel=vel, acc=acc, acc_prev=acc, acc_prev2=acc, species=species, section=sec)
+            r = hp.Update_Particle_Velocity()
+            got.append(hp.ramo_current_emit(nsec))
+            wide = hp.ramo_current_emit(nsec + 3)
+    assert np.array_equal(got[0], got[1])
+    assert np.array_equal(wide[:nsec], got[0]) and np.all(wide[nsec:] == 0.0)
+    scale = np.max(np.abs(want))
+    assert scale > 0.0
+    assert np.max(np.abs(got[0] - want)) <= 1e-12 * scale * max(1.0, math.sqrt(n / nsec))
+    tot = r.ramo_current[1] + r.ramo_current[2]
+    assert got[0].sum() == pytest.approx(tot, rel=1e-10)
+    with rb.HotPath(cfg) as hp:  # off by default: asking for the table is an error, the step itself is unchanged
+        hp.upload(pos, q, m, vel=vel, acc=acc, acc_prev=acc, acc_prev2=acc, species=species, section=sec)
+        r2 = hp.Update_Particle_Velocity()
+        assert r2.ramo_current[1] == r.ramo_current[1]
+        with pytest.raises(rb.api.Rb2Error):
+            hp.ramo_current_emit(nsec)
 
 
 def test_beeman_update_is_bit_exact_without_pair_forces(orc):
