@@ -49,6 +49,7 @@ module mod_b200_bridge
     integer(c_int) :: nrPart_remove_top, nrPart_remove_bot
     integer(c_int) :: nrElec_remove_top, nrElec_remove_bot
     integer(c_int) :: nrIon_remove_top, nrIon_remove_bot
+    integer(c_int) :: nrPart_remove_ion, nrElec_remove_ion, nrAtom_remove_ion
   end type rb2_counts
 
   type, bind(C) :: rb2_event
@@ -352,6 +353,7 @@ contains
     nrPart_remove_top = 0;  nrPart_remove_bot = 0
     nrElec_remove_top = 0;  nrElec_remove_bot = 0
     nrIon_remove_top = 0;  nrIon_remove_bot = 0
+    nrPart_remove_ion = 0;  nrElec_remove_ion = 0;  nrAtom_remove_ion = 0
   end subroutine B200_Remove_Particles
 
   ! Update_Position(step) (main.F90:190): one fused device step.  Fills ramo_current, the
@@ -370,6 +372,8 @@ contains
     nrPart_remove_top = r%counts%nrPart_remove_top;  nrPart_remove_bot = r%counts%nrPart_remove_bot
     nrElec_remove_top = r%counts%nrElec_remove_top;  nrElec_remove_bot = r%counts%nrElec_remove_bot
     nrIon_remove_top = r%counts%nrIon_remove_top;    nrIon_remove_bot = r%counts%nrIon_remove_bot
+    nrPart_remove_ion = r%counts%nrPart_remove_ion;  nrElec_remove_ion = r%counts%nrElec_remove_ion
+    nrAtom_remove_ion = r%counts%nrAtom_remove_ion
     if (r%n_events > 0) then
       if (.not. allocated(ev_buf)) allocate(ev_buf(max(1024, int(r%n_events))))
       if (size(ev_buf) < r%n_events) then

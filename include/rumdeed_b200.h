@@ -78,6 +78,7 @@ typedef struct rb2_counts {
     int nrPart_remove_top, nrPart_remove_bot;
     int nrElec_remove_top, nrElec_remove_bot;
     int nrIon_remove_top, nrIon_remove_bot;
+    int nrPart_remove_ion, nrElec_remove_ion, nrAtom_remove_ion;  /* reason RB2_REMOVE_ION, src/mod_pair.F90:273-279, :327-333 */
 } rb2_counts;
 
 /* One absorbed-electron or plane-crossing record, in the order the serial
@@ -135,7 +136,11 @@ int rb2_add_particles(int k, const double *pos, const double *vel, const int *sp
 /* MAX_PARTICLES - nrPart: how many of the next rb2_add_particles calls' particles the store still accepts (the rest
  * is dropped and counted, src/mod_pair.F90:36-43).  Host-side state only: no device synchronisation. */
 int rb2_capacity_left(int *out);
-/* Mark_Particles_Remove (src/mod_pair.F90:169-339) for k host-chosen particles. */
+/* Mark_Particles_Remove (src/mod_pair.F90:169-339) for k host-chosen particles.  reason: RB2_REMOVE_TOP / _BOT for any
+ * species, RB2_REMOVE_RECOM for electrons and ions, RB2_REMOVE_ION for electrons and atoms.  A reason outside 1..4 is the reference's
+ * 'Error unknown remove case' and fails with RB2_ERR_ARG before anything is marked; a defined reason on a species the
+ * reference has no case for (e.g. an ion with RB2_REMOVE_ION) marks the particle without a per-reason count, which is
+ * what the reference does after printing its message. */
 int rb2_mark_remove(int k, const int *index, const int *reason);
 /* Remove_Particles (src/mod_pair.F90:352-562): stable compaction, counters reset. */
 int rb2_remove_marked(int step, rb2_counts *out);

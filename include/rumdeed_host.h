@@ -67,6 +67,9 @@ int   rh_get_state(void *sim, rh_state *out);
 int   rh_steps_in_input(void *sim);
 /* ramo_current_emit(1:n_sec, 1) of the last step (needs WRITE_RAMO_SEC in the deck or rh_setup.ramo_sections > 0) */
 int   rh_get_ramo_sections(void *sim, int n_sec, double *out);
+/* Host-side switches: "photo_serial" (1: the photo-emission loop runs attempt by attempt, the reference's literal
+ * sequence; 0: speculative device batches, same decisions), "ramo_sections" (before rh_init). */
+int   rh_set_option(void *sim, const char *name, double value);
 void  rh_destroy(void *sim);
 const char *rh_last_error(void *sim);
 

@@ -139,6 +139,7 @@ class Oracle:
         lib.orc_accel_planar_rows.argtypes = [PP, C.c_int, _PD, _PD, _PD, _PI, _PD, C.c_int, C.c_int, C.c_int]
         lib.orc_accel_planar_rows.restype = C.c_longlong
         lib.orc_accel_gather.argtypes = [PP, C.c_int, _PD, _PD, _PD, _PD]
+        lib.orc_accel_gather_ld_rows.argtypes = [PP, C.c_int, _PD, _PD, _PD, C.c_int, _PI, _PD]
         lib.orc_accel_gather_ld.argtypes = [PP, C.c_int, _PD, _PD, _PD, C.c_int, C.c_int, _PD]
         lib.orc_calc_field_at.argtypes = [PP, C.c_int, _PD, _PD, _PI, _PD, _PD]
         lib.orc_calc_field_at_ld.argtypes = [PP, C.c_int, _PD, _PD, _PI, _PD, _PD]
@@ -252,6 +253,14 @@ class Oracle:
         i1 = n if i1 is None else i1
         acc = np.zeros((i1 - i0, 3))
         self.lib.orc_accel_gather_ld(C.byref(p), n, _d(pos), _d(q), _d(m), i0, i1, _d(acc))
+        return acc
+
+    def accel_gather_ld_rows(self, p, pos, q, m, rows):
+        """Long-double truth for the listed rows (OpenMP over the list)."""
+        n, pos, q, m, _ = self._prep(pos, q, m)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        acc = np.zeros((rows.size, 3))
+        self.lib.orc_accel_gather_ld_rows(C.byref(p), n, _d(pos), _d(q), _d(m), rows.size, _i(rows), _d(acc))
         return acc
 
     # -- fields -------------------------------------------------------------------
@@ -436,6 +445,7 @@ class Emission:
             lib.orc_do_field_thermo_emission_planar.restype = C.c_int
             lib.orc_do_photo_emission_rectangle.argtypes = [PE, PR, C.c_int, C.c_double, C.c_int, C.c_int]
             lib.orc_do_photo_emission_rectangle.restype = C.c_int
+            lib.orc_get_laser_energy.argtypes = [PR, C.c_double, C.c_double]; lib.orc_get_laser_energy.restype = C.c_double
             lib.orc_tip_supply_grid.argtypes = [PE, C.c_int, C.c_int, _PD]; lib.orc_tip_supply_grid.restype = C.c_double
             lib.orc_metro_algo_tip_v3.argtypes = [PE, PR, C.c_int, _PD, _PD, _PD, _PD, _PD]
             lib.orc_metro_algo_tip_v3.restype = C.c_int
@@ -495,6 +505,9 @@ class Emission:
 
     def do_photo_emission_rectangle(self, step, p_eV, photon_mode=1, max_elec_emit=-1):
         return self.orc.lib.orc_do_photo_emission_rectangle(self._E(), self._R(), step, p_eV, photon_mode, max_elec_emit)
+
+    def get_laser_energy(self, laser_energy, laser_variation):
+        return self.orc.lib.orc_get_laser_energy(self._R(), laser_energy, laser_variation)
 
     def tip_supply_grid(self, nr_xi=100, nr_phi=100):
         fa = np.zeros(1)

@@ -620,14 +620,16 @@ static void field_E_hyperboloid_ld(const orc_params *p, const long double pos[3]
     out[2] = pre * xi;
 }
 
-void orc_accel_gather_ld(const orc_params *p, int n, const double *pos, const double *q, const double *m,
-                         int i0, int i1, double *acc_out)
+/* rows == NULL: the contiguous rows i0 .. i0+nrows-1; else the listed rows (any order) */
+static void accel_gather_ld_rows(const orc_params *p, int n, const double *pos, const double *q, const double *m,
+                                 int i0, int nrows, const int *rows, double *acc_out)
 {
     const long double eps0 = 1.0L / ((long double)K_MU0 * ((long double)K_C * (long double)K_C));
     const long double dfc = 1.0L / (4.0L * 3.141592653589793238462643383279502884L * eps0);
-    int i;
+    int r;
 #pragma omp parallel for schedule(dynamic, 4)
-    for (i = i0; i < i1; ++i) {
+    for (r = 0; r < nrows; ++r) {
+        const int i = rows ? rows[r] : i0 + r;
         long double x_1 = pos[3 * i], y_1 = pos[3 * i + 1], z_1 = pos[3 * i + 2];
         long double q_1 = q[i], qd_1 = q_1 * dfc, im_1;
         ksum sx = {0, 0}, sy = {0, 0}, sz = {0, 0};
@@ -663,10 +665,20 @@ void orc_accel_gather_ld(const orc_params *p, int n, const double *pos, const do
             field_E_hyperboloid_ld(p, pt, fE);
             kadd(&sx, q_1 * fE[0]); kadd(&sy, q_1 * fE[1]); kadd(&sz, q_1 * fE[2]);
         }
-        acc_out[3 * (i - i0)] = (double)(kval(&sx) * im_1);
-        acc_out[3 * (i - i0) + 1] = (double)(kval(&sy) * im_1);
-        acc_out[3 * (i - i0) + 2] = (double)(kval(&sz) * im_1);
+        acc_out[3 * r] = (double)(kval(&sx) * im_1);
+        acc_out[3 * r + 1] = (double)(kval(&sy) * im_1);
+        acc_out[3 * r + 2] = (double)(kval(&sz) * im_1);
     }
+}
+void orc_accel_gather_ld(const orc_params *p, int n, const double *pos, const double *q, const double *m,
+                         int i0, int i1, double *acc_out)
+{
+    accel_gather_ld_rows(p, n, pos, q, m, i0, i1 - i0, NULL, acc_out);
+}
+void orc_accel_gather_ld_rows(const orc_params *p, int n, const double *pos, const double *q, const double *m,
+                              int nrows, const int *rows, double *acc_out)
+{
+    accel_gather_ld_rows(p, n, pos, q, m, 0, nrows, rows, acc_out);
 }
 
 /* ---------------------------------------------------------------------------

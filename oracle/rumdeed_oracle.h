@@ -93,6 +93,9 @@ void orc_accel_gather(const orc_params *p, int n, const double *pos, const doubl
  * Rows i0<=i<i1 only (0-based); acc_out has 3*(i1-i0) entries. */
 void orc_accel_gather_ld(const orc_params *p, int n, const double *pos, const double *q, const double *m,
                          int i0, int i1, double *acc_out);
+/* same for a list of rows (OpenMP over the list) */
+void orc_accel_gather_ld_rows(const orc_params *p, int n, const double *pos, const double *q, const double *m,
+                              int nrows, const int *rows, double *acc_out);
 
 /* --- field ------------------------------------------------------------------ */
 /* src/mod_verlet.F90:1466-1529 */

@@ -444,6 +444,17 @@ int orc_do_field_thermo_emission_planar(orc_emission *E, orc_rng *r, int step, d
     return nrElecEmit;
 }
 
+/* Get_Laser_Energy, src/mod_photo_emission.f90:850-866: two Box-Muller pairs, |second value of the second pair| */
+double orc_get_laser_energy(orc_rng *r, double laser_energy, double laser_variation)
+{
+    double mean[2], std[2], a[2], b[2];
+    mean[0] = mean[1] = laser_energy;
+    std[0] = std[1] = laser_variation;
+    orc_box_muller(r, mean, std, a);
+    orc_box_muller(r, mean, std, b);
+    return fabs(b[1]);
+}
+
 /* ---- photo emission: src/mod_photo_emission.f90:603-686 -------------------------------------- */
 int orc_do_photo_emission_rectangle(orc_emission *E, orc_rng *r, int step, double p_eV, int photon_mode, int max_elec_emit)
 {

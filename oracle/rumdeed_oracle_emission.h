@@ -50,6 +50,7 @@ int  orc_do_field_emission_planar(orc_emission *E, orc_rng *r, int step, double 
 int  orc_mh_rectangle_J_thermo(orc_emission *E, orc_rng *r, double pos_out[3]);
 int  orc_do_field_thermo_emission_planar(orc_emission *E, orc_rng *r, int step, double N_sup);
 
+double orc_get_laser_energy(orc_rng *r, double laser_energy, double laser_variation);
 int  orc_do_photo_emission_rectangle(orc_emission *E, orc_rng *r, int step, double p_eV, int photon_mode, int max_elec_emit);
 
 double orc_tip_supply_grid(const orc_emission *E, int nr_xi, int nr_phi, double *F_avg_out);

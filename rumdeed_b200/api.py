@@ -62,7 +62,7 @@ class Counts(C.Structure):
         "nrPart", "nrElec", "nrIon", "nrAtom", "nrID", "nrPart_dropped",
         "nrPart_remove", "nrElec_remove", "nrIon_remove", "nrAtom_remove",
         "nrPart_remove_top", "nrPart_remove_bot", "nrElec_remove_top", "nrElec_remove_bot",
-        "nrIon_remove_top", "nrIon_remove_bot")]
+        "nrIon_remove_top", "nrIon_remove_bot", "nrPart_remove_ion", "nrElec_remove_ion", "nrAtom_remove_ion")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -104,6 +104,9 @@ void fill_counts_from_device(Rb2Ctx &c)
     c.counts.nrElec_remove_bot = h.bot_elec;
     c.counts.nrIon_remove_top = h.top_ion;
     c.counts.nrIon_remove_bot = h.bot_ion;
+    c.counts.nrPart_remove_ion = h.ion_part;
+    c.counts.nrElec_remove_ion = h.ion_elec;
+    c.counts.nrAtom_remove_ion = h.ion_atom;
 }
 
 int fetch_counters(Rb2Ctx &c)
@@ -234,13 +237,37 @@ int rb2_device_available(void)
     return prop.major >= 10 ? 1 : 0;
 }
 
-int rb2_init(const rb2_config *cfg)
+// Frees whatever the context holds (also after a failed rb2_init: every pointer that was allocated is non-null, the
+// rest is null) and resets it.
+static void release_all(Rb2Ctx &c)
 {
-    Rb2Ctx &c = g_rb2;
-    if (c.init) rb2_finalize();
-    int rc = check_config(cfg);
-    if (rc) return rc;
-    if (cfg->capacity < 1) return rb2_fail(RB2_ERR_ARG, "capacity must be >= 1");
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    rb2_p2p_release(c);
+    rb2_collisions_release(c);
+    free_arrays(c.a);
+    free_arrays(c.b);
+    cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);
+    cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
+    cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec);
+    if (c.h_ramo_sec) cudaFreeHost(c.h_ramo_sec);
+    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw);
+    cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
+    if (c.h_counters) cudaFreeHost(c.h_counters);
+    if (c.h_red) cudaFreeHost(c.h_red);
+    if (c.h_total) cudaFreeHost(c.h_total);
+    if (c.h_pts) cudaFreeHost(c.h_pts);
+    if (c.h_fld) cudaFreeHost(c.h_fld);
+    if (c.h_stage) cudaFreeHost(c.h_stage);
+    cudaEvent_t evs[] = {c.ev_a0, c.ev_a1, c.ev_s0, c.ev_s1, c.ev_c};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    cudaGetLastError();
+    c = Rb2Ctx{};
+}
+
+static int init_impl(Rb2Ctx &c, const rb2_config *cfg)
+{
+    int rc = RB2_OK;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
         cudaGetLastError();
@@ -295,26 +322,23 @@ int rb2_init(const rb2_config *cfg)
     return RB2_OK;
 }
 
+int rb2_init(const rb2_config *cfg)
+{
+    Rb2Ctx &c = g_rb2;
+    if (c.init) rb2_finalize();
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (cfg->capacity < 1) return rb2_fail(RB2_ERR_ARG, "capacity must be >= 1");
+    rc = init_impl(c, cfg);
+    if (rc) release_all(c);  // a failed allocation half way leaves nothing behind (the error string is kept)
+    return rc;
+}
+
 int rb2_finalize(void)
 {
     Rb2Ctx &c = g_rb2;
     if (!c.init) return RB2_OK;
-    cudaStreamSynchronize(c.stream);
-    rb2_p2p_release(c);
-    rb2_collisions_release(c);
-    free_arrays(c.a);
-    free_arrays(c.b);
-    cudaFree(c.mask); cudaFree(c.evcnt); cudaFree(c.evbits); cudaFree(c.prefix); cudaFree(c.blocksum); cudaFree(c.life_hist);
-    cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
-    cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec); cudaFreeHost(c.h_ramo_sec);
-    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw);
-    cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
-    cudaFreeHost(c.h_counters); cudaFreeHost(c.h_red); cudaFreeHost(c.h_total); cudaFreeHost(c.h_pts); cudaFreeHost(c.h_fld);
-    cudaFreeHost(c.h_stage);
-    cudaEventDestroy(c.ev_a0); cudaEventDestroy(c.ev_a1); cudaEventDestroy(c.ev_s0); cudaEventDestroy(c.ev_s1);
-    cudaEventDestroy(c.ev_c);
-    cudaStreamDestroy(c.stream);
-    c = Rb2Ctx{};
+    release_all(c);
     return RB2_OK;
 }
 
@@ -496,6 +520,8 @@ int rb2_mark_remove(int k, const int *index, const int *reason)
     if (!index || !reason) return rb2_fail(RB2_ERR_ARG, "index and reason are required");
     for (int t = 0; t < k; ++t)
         if (index[t] < 0 || index[t] >= c.n) return rb2_fail(RB2_ERR_ARG, "rb2_mark_remove: index %d outside 0..%d", index[t], c.n - 1);
+    for (int t = 0; t < k; ++t)  // reference: 'Error unknown remove case' (src/mod_pair.F90:280-282); species-specific cases are checked on the device
+        if (reason[t] < RB2_REMOVE_TOP || reason[t] > RB2_REMOVE_ION) return rb2_fail(RB2_ERR_ARG, "rb2_mark_remove: unknown remove case %d", reason[t]);
     int rc = rb2_ensure_stage(c, 0, (size_t)2 * k);
     if (rc) return rc;
     RB2_CUDA(cudaMemcpyAsync(c.d_stage_i, index, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, c.stream));
@@ -567,7 +593,7 @@ int rb2_accel_only(void)
     if (rc) return rc;
     c.accel_timed = (c.n > 0 && i1 > i0);
     RB2_CUDA(cudaStreamSynchronize(c.stream));
-    return RB2_OK;
+    return rb2_p2p_check(c);
 }
 
 int rb2_update_velocity(rb2_step_result *out)
@@ -593,6 +619,14 @@ int rb2_step(int step, rb2_step_result *out)
     (void)step;
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
+    {   // the fused step integrates EVERY row: with an i-partition in effect only rows [i_begin, i_end) would get an
+        // acceleration and the rest would be integrated with a = 0.  Partitioned runs use the three phases
+        // (rb2_update_position, rb2_accel_only + the caller's exchange of the acceleration slices, rb2_update_velocity).
+        const int i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
+        if (c.n > 0 && (c.part_begin > 0 || i1 < c.n))
+            return rb2_fail(RB2_ERR_ARG, "rb2_step with the i-partition [%d, %d) of %d particles: the fused step has no exchange; use "
+                                         "rb2_update_position / rb2_accel_only + exchange / rb2_update_velocity", c.part_begin, i1, c.n);
+    }
     RB2_CUDA(cudaEventRecord(c.ev_s0, c.stream));
     int rc_accel = RB2_OK;
     c.accel_timed = false;
@@ -604,6 +638,7 @@ int rb2_step(int step, rb2_step_result *out)
     RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     RB2_CUDA(cudaEventRecord(c.ev_s1, c.stream));
     RB2_CUDA(cudaStreamSynchronize(c.stream));
+    if ((rc = rb2_p2p_check(c))) return rc;
     rc = finish_position(c, true);
     if (rc) return rc;
     if (out) {
@@ -670,7 +705,7 @@ int rb2_accel_host(int n, const double *pos, const double *charge, const double 
         RB2_CUDA(cudaMemcpyAsync(acc_out + (size_t)3 * i0, c.b.acc + (size_t)3 * i0, (size_t)(i1 - i0) * 3 * sizeof(double),
                                  cudaMemcpyDeviceToHost, st));
     RB2_CUDA(cudaStreamSynchronize(st));
-    return RB2_OK;
+    return rb2_p2p_check(c);
 }
 
 static int ensure_field_buffers(Rb2Ctx &c, int M)
@@ -863,7 +898,7 @@ int rb2_accel_finalize(void)
     if (rc) return rc;
     c.accel_timed = c.n > 0;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
-    return RB2_OK;
+    return rb2_p2p_check(c);
 }
 
 int rb2_set_partition(int i_begin, int i_end)

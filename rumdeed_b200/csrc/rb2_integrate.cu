@@ -446,6 +446,7 @@ __global__ void k_mark(int k, const int *__restrict__ index, const int *__restri
         if (r == RB2_REMOVE_TOP) { atomicAdd(&C->top_part, 1); atomicAdd(&C->top_elec, 1); }
         else if (r == RB2_REMOVE_BOT) { atomicAdd(&C->bot_part, 1); atomicAdd(&C->bot_elec, 1); }
         else if (r == RB2_REMOVE_RECOM) { atomicAdd(&C->recom_part, 1); atomicAdd(&C->recom_elec, 1); }
+        else if (r == RB2_REMOVE_ION) { atomicAdd(&C->ion_part, 1); atomicAdd(&C->ion_elec, 1); }
     } else if (sp == RB2_SPECIES_ION) {
         atomicAdd(&C->mark_ion, 1);
         if (r == RB2_REMOVE_TOP) { atomicAdd(&C->top_part, 1); atomicAdd(&C->top_ion, 1); }
@@ -453,6 +454,7 @@ __global__ void k_mark(int k, const int *__restrict__ index, const int *__restri
         else if (r == RB2_REMOVE_RECOM) { atomicAdd(&C->recom_part, 1); atomicAdd(&C->recom_ion, 1); }
     } else {
         atomicAdd(&C->mark_atom, 1);
+        if (r == RB2_REMOVE_ION) { atomicAdd(&C->ion_part, 1); atomicAdd(&C->ion_atom, 1); }
     }
 }
 

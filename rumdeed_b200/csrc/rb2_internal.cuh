@@ -66,6 +66,7 @@ struct DevCounters {  // cumulative since the last rb2_remove_marked
     int top_part, bot_part, top_elec, bot_elec, top_ion, bot_ion;
     int n_events, pad;
     int recom_part, recom_elec, recom_ion, pad2;  // remove_recom marks (collisions)
+    int ion_part, ion_elec, ion_atom, pad3;       // remove_ion marks (src/mod_pair.F90:273-279, :327-333)
 };
 
 struct DevArrays {
@@ -120,6 +121,8 @@ struct Rb2Ctx {
     void  *p2p_peer[RB2_P2P_MAX] = {};    // every rank's block as mapped here ([rank] == p2p_local)
     int    p2p_world = 0, p2p_npad_max = 0;
     unsigned long long p2p_epoch = 0;     // evaluations since attach; parity selects the partial-sum slot
+    volatile int *p2p_err = nullptr;      // mapped host word the finalise kernel reports a failed exchange in
+    int   *p2p_err_dev = nullptr;         // ... its device address
     int    last_pair_kernel = 0;          // 1 gather, 2 symmetric
     rb2_event *d_events = nullptr; int ev_cap = 0;
     int    ev_min = 65536;                // initial size of the record buffer (option "event_buffer")
@@ -181,6 +184,7 @@ int rb2_launch_nearest(Rb2Ctx &ctx, double *d_dist, int *d_id);
 double *rb2_p2p_begin_evaluation(Rb2Ctx &ctx, int n_pad);
 int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);
 int rb2_p2p_release(Rb2Ctx &ctx);
+int rb2_p2p_check(Rb2Ctx &ctx);  // after a stream synchronisation: RB2_ERR_CUDA when the last exchange failed
 // pair-symmetric kernel (rb2_pair_sym.cu)
 int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n);
 int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);
@@ -232,6 +236,35 @@ __device__ __forceinline__ double rb2_inv_r3_soft(double s)
     const double c0 = fma(-3.0 * rb2k::soft, y0, 1.0);
     const double p = fma(e, fma(1.875, e, 1.5), c0);
     return (y0 * t) * p;
+}
+
+// The first-order softening above is good to 6 (eps/r)^2: 6e-14 at r = 1e-11 m, but 6e-10 at 1e-13 m.  Pairs whose
+// LATERAL offset is below 1e-11 m -- the only ones in which any of the distances of the pair (direct, or to an image
+// partner when both particles sit at an electrode) can be that short -- are flagged in the fast loops (one compare per
+// pair) and re-evaluated with the reference's own operations: r = sqrt(s) + length_scale**2; 1/(r*r*r)
+// (src/mod_verlet.F90:1302-1303), IEEE square root and divide.
+#define RB2_CLOSE_DXY2 1.0e-22
+#ifndef RB2_CLOSE_INT
+#define RB2_CLOSE_INT 1
+#endif
+__device__ __forceinline__ bool rb2_is_close(double dxy2)
+{
+#if RB2_CLOSE_INT
+    // positive doubles order like their high words; an integer compare keeps the FP64 pipe free
+    return __double2hiint(dxy2) < 0x3B5E392A;  // high word of 1.0e-22 (0x3B5E392010175EE6), rounded up
+#else
+    return dxy2 < RB2_CLOSE_DXY2;
+#endif
+}
+__device__ __forceinline__ double rb2_inv_r3_exact(double s)
+{
+    const double r = __dadd_rn(__dsqrt_rn(s), rb2k::soft);
+    return __ddiv_rn(1.0, __dmul_rn(__dmul_rn(r, r), r));
+}
+template <bool EXACT>
+__device__ __forceinline__ double rb2_inv_r3_sel(double s)
+{
+    return EXACT ? rb2_inv_r3_exact(s) : rb2_inv_r3_soft(s);
 }
 
 // Vacuum field of the hyperboloid tip, src/acc_tip_field_E.inc:13-34 ==

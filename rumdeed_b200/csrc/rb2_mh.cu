@@ -202,24 +202,40 @@ __device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
     small_barrier_wait(bar, target);
 }
 
-// one particle against one surface point: sum of g_n / (rho^2 + h_n^2)^(3/2)
-template <int NIC>
-__device__ __forceinline__ double surf_term(const SurfRec &r, double px, double py, double acc, const MhPlan &L)
+// one particle against one surface point: sum of g_n / (rho^2 + h_n^2)^(3/2).  EXACT: reference sqrt / divide (slow
+// path of laterally close pairs, see rb2_is_close); otherwise `close` collects the flag.
+template <int NIC, bool EXACT>
+__device__ __forceinline__ double surf_term(const SurfRec &r, double px, double py, double acc, const MhPlan &L, bool &close)
 {
     const double dx = px - r.x, dy = py - r.y;
     const double d2 = fma(dy, dy, fma(dx, dx, RB2_S_FLOOR));
-    acc = fma(r.g0, rb2_inv_r3_soft(fma(r.h0, r.h0, d2)), acc);
+    if (!EXACT) close = close || rb2_is_close(d2);
+    acc = fma(r.g0, rb2_inv_r3_sel<EXACT>(fma(r.h0, r.h0, d2)), acc);
     if (NIC == 1) {
-        acc = fma(r.g1, rb2_inv_r3_soft(fma(r.h1, r.h1, d2)), acc);
-        acc = fma(r.g2, rb2_inv_r3_soft(fma(r.h2, r.h2, d2)), acc);
+        acc = fma(r.g1, rb2_inv_r3_sel<EXACT>(fma(r.h1, r.h1, d2)), acc);
+        acc = fma(r.g2, rb2_inv_r3_sel<EXACT>(fma(r.h2, r.h2, d2)), acc);
     } else if (NIC >= 2) {
         for (int n = 1; n <= L.nic; ++n) {
             const double h = L.two_d * (double)n, hm = r.h0 - h, hp = r.h0 + h;
-            acc = fma(r.g1 * hm, rb2_inv_r3_soft(fma(hm, hm, d2)), acc);
-            acc = fma(r.g1 * hp, rb2_inv_r3_soft(fma(hp, hp, d2)), acc);
+            acc = fma(r.g1 * hm, rb2_inv_r3_sel<EXACT>(fma(hm, hm, d2)), acc);
+            acc = fma(r.g1 * hp, rb2_inv_r3_sel<EXACT>(fma(hp, hp, d2)), acc);
         }
     }
     return acc;
+}
+// CNT consecutive records against this lane's point, added to acc as one block sum
+template <int NIC, int CNT>
+__device__ __forceinline__ double surf_block(const SurfRec *rr, double px, double py, double acc, const MhPlan &L)
+{
+    double part = 0.0;
+    bool close = false;
+#pragma unroll 4
+    for (int k = 0; k < CNT; ++k) part = surf_term<NIC, false>(rr[k], px, py, part, L, close);
+    if (close) {
+        part = 0.0;
+        for (int k = 0; k < CNT; ++k) part = surf_term<NIC, true>(rr[k], px, py, part, L, close);
+    }
+    return acc + part;
 }
 
 __global__ void k_surf_pack(const double4 *__restrict__ pq, int n, double two_d, int nic, SurfRec *__restrict__ recs)
@@ -324,8 +340,7 @@ __device__ __forceinline__ double surf_unit_sum(const SurfRec *__restrict__ g_re
         __syncwarp();
         if (t + 1 < nsub) fetch(t + 1);
         const SurfRec *rr = &recs[t & 1][warp * 32];
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+        acc = surf_block<NIC, 32>(rr, px, py, acc, L);
         __syncwarp();
     }
     red[warp][lane] = acc;
@@ -390,8 +405,7 @@ __device__ __forceinline__ double surf_unit_sum_resident(const SurfRec *__restri
     double acc = 0.0;
     for (int t = 0; t < nsub; ++t) {
         const SurfRec *rr = res + (size_t)t * MHB + warp * 32;
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+        acc = surf_block<NIC, 32>(rr, px, py, acc, L);
     }
     red[warp][lane] = acc;
     __syncthreads();
@@ -616,8 +630,7 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
         double acc = 0.0;
         for (int t = 0; t < s1 - s0; ++t) {
             const SurfRec *rr = &mine[t * MHB + warp * RPW];
-#pragma unroll 4
-            for (int k = 0; k < RPW; ++k) acc = surf_term<NIC>(rr[k], px, py, acc, L);
+            acc = surf_block<NIC, RPW>(rr, px, py, acc, L);
         }
         red[warp][lane] = acc;
         __syncthreads();

@@ -14,12 +14,25 @@
 // signals k+1 only behind its reads of evaluation k in stream order.
 //
 // Exchange block (one cudaMalloc, exported with cudaIpcGetMemHandle):
-//   [ 4 KB: flags, one u64 per peer ] [ raw parity 0: 3 * npad_max doubles ] [ raw parity 1: the same ]
+//   [ 4 KB: flags, one u64 per peer; header at byte 2048 ] [ raw parity 0: 3 * npad_max doubles ] [ raw parity 1: the same ]
+// A flag holds (evaluation number << 32 | padded particle count of that evaluation).  The header {magic, npad_max} is
+// checked when the peers are attached (all ranks must have exported for the same n_max: the slot offsets depend on
+// it); the padded count is checked against the reader's own in the finalise kernel.  A peer that does not arrive within
+// 20 s, or arrives with another padded count (the ranks did not make the same sequence of evaluations on the same
+// particle store), is REPORTED: the kernel sets an error word in mapped host memory and returns, the call that waited
+// for it fails with RB2_ERR_CUDA -- the context survives.
+//
+// Every pair-symmetric evaluation on an attached context is COLLECTIVE: rb2_step, rb2_accel_only, rb2_accel_host and
+// rb2_accel_partial / rb2_accel_finalize must be called by all ranks in the same order with the same particle count.
 #include "rb2_internal.cuh"
 
 namespace {
 
 constexpr size_t P2P_FLAG_BYTES = 4096;
+constexpr size_t P2P_HEADER_OFFSET = 2048;
+constexpr unsigned long long P2P_MAGIC = 0x7262325F70327031ull;  // "rb2_p2p1"
+struct P2PHeader { unsigned long long magic, npad_max; };
+enum { P2P_ERR_TIMEOUT = 1, P2P_ERR_MISMATCH = 2 };
 constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // a peer that never signals: trap
 
 struct P2PPeers {
@@ -52,29 +65,37 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 
 // Runs behind this rank's partial-sum kernels in stream order: tell every peer (and myself) that the partial sums
 // of evaluation `epoch` are complete.
-__global__ void k_p2p_signal(P2PPeers pp, int rank, int world, unsigned long long epoch)
+__global__ void k_p2p_signal(P2PPeers pp, int rank, int world, unsigned long long epoch, int n_pad)
 {
     const int p = threadIdx.x;
     if (p < world) {
         __threadfence_system();
-        st_release_sys(pp.flags[p] + rank, epoch);
+        st_release_sys(pp.flags[p] + rank, (epoch << 32) | (unsigned long long)(unsigned)n_pad);
     }
 }
 
 // Two particles per thread (n_pad is even, the rows are 16-byte aligned).
 __global__ void __launch_bounds__(256)
 k_sym_finalize_p2p(int n, int n_pad, P2PPeers pp, int rank, int world, unsigned long long epoch,
-                   const double4 *__restrict__ pq, const double *__restrict__ mass, PlanarParams P, double *__restrict__ acc)
+                   const double4 *__restrict__ pq, const double *__restrict__ mass, PlanarParams P, double *__restrict__ acc,
+                   volatile int *__restrict__ err)
 {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
     if (threadIdx.x < world) {
         const unsigned long long *f = pp.flags[rank] + threadIdx.x;  // local memory, written by peer threadIdx.x
         const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(f) < epoch) {
+        unsigned long long v;
+        while (((v = ld_acquire_sys(f)) >> 32) < epoch) {
+            if (*err != 0) { bad = 1; break; }  // another CTA has already given up
             __nanosleep(200);
-            if (globaltimer_ns() - t0 > P2P_TIMEOUT_NS) __trap();  // fail loudly instead of hanging the GPU
+            if (globaltimer_ns() - t0 > P2P_TIMEOUT_NS) { *err = P2P_ERR_TIMEOUT; bad = 1; break; }
         }
+        if (!bad && ((v >> 32) != epoch || (int)(v & 0xffffffffu) != n_pad)) { *err = P2P_ERR_MISMATCH; bad = 1; }
     }
     __syncthreads();
+    if (bad) return;  // reported by the host side of the call (rb2_p2p_check)
     const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
     double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0;
@@ -111,24 +132,39 @@ double *rb2_p2p_begin_evaluation(Rb2Ctx &ctx, int n_pad)
         rb2_fail(RB2_ERR_CAPACITY, "the peer exchange block holds %d padded particles, %d needed", ctx.p2p_npad_max, n_pad);
         return nullptr;
     }
-    ctx.p2p_epoch += 1;
-    return raw_of(ctx.p2p_local, ctx.p2p_npad_max, (int)(ctx.p2p_epoch & 1));
+    // the evaluation number is only committed when its signal is queued (rb2_launch_accel_sym_exchange_finalize): an
+    // error on the way there leaves the protocol where it was
+    return raw_of(ctx.p2p_local, ctx.p2p_npad_max, (int)((ctx.p2p_epoch + 1) & 1));
+}
+
+// After a stream synchronisation: did the last exchange fail?
+int rb2_p2p_check(Rb2Ctx &ctx)
+{
+    if (!ctx.p2p_err || *ctx.p2p_err == 0) return RB2_OK;
+    const int e = *ctx.p2p_err;
+    *ctx.p2p_err = 0;
+    if (e == P2P_ERR_TIMEOUT)
+        return rb2_fail(RB2_ERR_CUDA, "peer exchange: a rank did not publish its partial sums of evaluation %llu within 20 s "
+                                      "(every pair-symmetric evaluation is collective once the peers are attached)", ctx.p2p_epoch);
+    return rb2_fail(RB2_ERR_CUDA, "peer exchange: a rank published evaluation %llu for a different particle count / sequence "
+                                  "of evaluations than this rank", ctx.p2p_epoch);
 }
 
 int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out)
 {
     if (n < 1) return RB2_OK;
+    ctx.p2p_epoch += 1;
     P2PPeers pp{};
     for (int r = 0; r < ctx.p2p_world; ++r) {
         pp.raw[r] = raw_of(ctx.p2p_peer[r], ctx.p2p_npad_max, (int)(ctx.p2p_epoch & 1));
         pp.flags[r] = static_cast<unsigned long long *>(ctx.p2p_peer[r]);
     }
     const StepParams SP = rb2_make_step_params(ctx.cfg);
-    k_p2p_signal<<<1, 32, 0, ctx.stream>>>(pp, ctx.pair_rank, ctx.p2p_world, ctx.p2p_epoch);
+    k_p2p_signal<<<1, 32, 0, ctx.stream>>>(pp, ctx.pair_rank, ctx.p2p_world, ctx.p2p_epoch, ctx.sym_n_pad);
     RB2_CUDA(cudaGetLastError());
     const int threads = 256, per_block = 2 * threads;
     k_sym_finalize_p2p<<<(n + per_block - 1) / per_block, threads, 0, ctx.stream>>>(
-        n, ctx.sym_n_pad, pp, ctx.pair_rank, ctx.p2p_world, ctx.p2p_epoch, pq, mass, SP.pl, acc_out);
+        n, ctx.sym_n_pad, pp, ctx.pair_rank, ctx.p2p_world, ctx.p2p_epoch, pq, mass, SP.pl, acc_out, ctx.p2p_err_dev);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(2);
     RB2_CUDA(cudaEventRecord(ctx.ev_a1, ctx.stream));
@@ -145,6 +181,9 @@ int rb2_p2p_release(Rb2Ctx &c)
     c.p2p_local = nullptr;
     c.p2p_npad_max = 0;
     c.p2p_epoch = 0;
+    if (c.p2p_err) cudaFreeHost((void *)c.p2p_err);
+    c.p2p_err = nullptr;
+    c.p2p_err_dev = nullptr;
     return RB2_OK;
 }
 
@@ -162,7 +201,12 @@ int rb2_p2p_export(int n_max, void *handle_out)
     const size_t bytes = P2P_FLAG_BYTES + 2 * 3 * (size_t)npad_max * sizeof(double);
     RB2_CUDA(cudaMalloc(&c.p2p_local, bytes));
     RB2_CUDA(cudaMemset(c.p2p_local, 0, bytes));
+    const P2PHeader hdr = {P2P_MAGIC, (unsigned long long)npad_max};
+    RB2_CUDA(cudaMemcpy(static_cast<char *>(c.p2p_local) + P2P_HEADER_OFFSET, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
     c.p2p_npad_max = npad_max;
+    RB2_CUDA(cudaHostAlloc((void **)&c.p2p_err, sizeof(int), cudaHostAllocMapped));
+    *c.p2p_err = 0;
+    RB2_CUDA(cudaHostGetDevicePointer((void **)&c.p2p_err_dev, (void *)c.p2p_err, 0));
     cudaIpcMemHandle_t h;
     RB2_CUDA(cudaIpcGetMemHandle(&h, c.p2p_local));
     memcpy(handle_out, &h, sizeof(h));
@@ -183,6 +227,16 @@ int rb2_p2p_attach(int world, int rank, const void *handles)
         void *p = nullptr;
         RB2_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         c.p2p_peer[r] = p;
+        // the slot offsets inside a block depend on n_max: every rank must have exported for the same one
+        P2PHeader hdr{};
+        RB2_CUDA(cudaMemcpy(&hdr, static_cast<char *>(p) + P2P_HEADER_OFFSET, sizeof(hdr), cudaMemcpyDeviceToHost));
+        if (hdr.magic != P2P_MAGIC || hdr.npad_max != (unsigned long long)c.p2p_npad_max) {
+            const unsigned long long got = hdr.npad_max;
+            c.p2p_world = r + 1;  // so that the release below closes what has been opened
+            rb2_p2p_release(c);
+            return rb2_fail(RB2_ERR_ARG, "rb2_p2p_attach: rank %d exported an exchange block for %llu padded particles, this rank "
+                                         "for another size (rb2_p2p_export must be called with the same n_max everywhere)", r, got);
+        }
     }
     c.p2p_world = world;
     c.pair_rank = rank;

@@ -104,6 +104,26 @@ __device__ __forceinline__ void tip_ic_force(const TipParams &T, const TipImage 
     ic_z = pre * ((z_a - z_b) * wa - (im.z_im - z_b) * wb);
 }
 
+// Slow path of a (target, source tile) whose fast sweep flagged a laterally close pair (rb2_is_close): the whole
+// tile again with the reference's sqrt / divide.  i_self: global index of the target when the tile may hold it or
+// lower-indexed particles (per-element self mask and role sign, j = j0 + jj); below -cnt: plain sources.
+template <int NIC>
+__device__ __noinline__ Acc4 planar_tile_exact(double xi, double yi, double zi, const double4 *tile, int cnt, int j0, int i_self,
+                                               PlanarParams P)
+{
+    Acc4 a = {0.0, 0.0, 0.0, 0.0};
+    bool dummy = false;
+    const bool roles = i_self >= 0;
+    for (int jj = 0; jj < cnt; ++jj) {
+        const double4 pj = tile[jj];
+        const int j = j0 + jj;
+        const double qe = (roles && j == i_self) ? 0.0 : pj.w;
+        const double qs = (!roles || j > i_self) ? qe : -qe;
+        planar_term<NIC, true>(xi, yi, zi, pj, qe, qs, P, a, dummy);
+    }
+    return a;
+}
+
 // ---- the tiled pair kernel --------------------------------------------------------------------
 // GEOM 1 planar / 2 tip.  NIC: -1 image charge off, 0, 1, 2 (= runtime N_ic_max loop); tip uses
 // NIC -1 / 0 for image charge off / on.  FIELD: targets are the M field points (no self
@@ -174,6 +194,7 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
         if (warp_active) {
             Acc4 a = {0.0, 0.0, 0.0, 0.0};
             if (GEOM == 1) {
+                bool close = false;
                 if (!FIELD && (j0 < ie) && (j0 + cnt > ib)) {
                     // tile overlaps this CTA's own particles: per-element self mask and role sign
                     for (int jj = 0; jj < cnt; ++jj) {
@@ -181,15 +202,17 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                         const int j = j0 + jj;
                         const double qe = (j == i) ? 0.0 : pj.w;
                         const double qs = (j > i) ? qe : -qe;
-                        planar_term<NIC>(xi, yi, zi, pj, qe, qs, P, a);
+                        planar_term<NIC>(xi, yi, zi, pj, qe, qs, P, a, close);
                     }
+                    if (close) a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, j0, i, P);
                     az += a.t;
                 } else {
 #pragma unroll UNROLL
                     for (int jj = 0; jj < cnt; ++jj) {
                         const double4 pj = tile[jj];
-                        planar_term<NIC>(xi, yi, zi, pj, pj.w, pj.w, P, a);
+                        planar_term<NIC>(xi, yi, zi, pj, pj.w, pj.w, P, a, close);
                     }
+                    if (close) a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, 0, -1 - cnt, P);
                     const double sg = (FIELD || (j0 >= ie)) ? 1.0 : -1.0;
                     az = fma(sg, a.t, az);
                 }

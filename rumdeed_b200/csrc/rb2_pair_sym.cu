@@ -53,6 +53,53 @@ struct SymGeom {
 
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
 
+// One round of a symmetric tile: this warp's 32 T targets against the 32 visitors of block wb0 (see k_pair_sym).
+template <int NIC, int T, bool EXACT>
+__device__ __forceinline__ void sym_round(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+                                          const double *__restrict__ Q, int wb0, int lane, int src_lane, const double (&xi)[T],
+                                          const double (&yi)[T], const double (&zi)[T], const double (&qe)[T], const PlanarParams &P,
+                                          double (&tx)[T], double (&ty)[T], double (&tz)[T], double &bx, double &by, double &bz,
+                                          bool &close)
+{
+    const int home = wb0 + lane;
+    double vx = X[home], vy = Y[home], vz = Z[home], vq = Q[home];
+    bx = 0.0; by = 0.0; bz = 0.0;
+#pragma unroll
+    for (int s = 0; s < T; ++s) { tx[s] = 0.0; ty[s] = 0.0; tz[s] = 0.0; }
+#pragma unroll (EXACT ? 1 : SYM_UNROLL)
+    for (int k = 0; k < 32; ++k) {
+#if RB2_SYM_LDSVIS
+        // visitor coordinates straight from shared memory (conflict-free rotated index);
+        // only the travelling accumulators go through the shuffle unit
+        const int vi = wb0 + ((lane + k) & 31);
+        vx = X[vi]; vy = Y[vi]; vz = Z[vi]; vq = Q[vi];
+#endif
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const PairW w = planar_weights<NIC, EXACT>(xi[s], yi[s], zi[s], vx, vy, vz, P, close);
+            // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
+            const double ti = vq * w.U, tj = qe[s] * w.U;
+            tx[s] = fma(w.dx, ti, tx[s]);
+            ty[s] = fma(w.dy, ti, ty[s]);
+            bx = fma(-w.dx, tj, bx);
+            by = fma(-w.dy, tj, by);
+            if (NIC < 0) {
+                tz[s] = fma(w.dz, ti, tz[s]);
+                bz = fma(-w.dz, tj, bz);
+            } else {
+                const double czz = w.dz * w.wc;
+                const double icz = w.Zsame - w.Zopp;
+                tz[s] = fma(vq, icz + czz, tz[s]);
+                bz = fma(qe[s], icz - czz, bz);
+            }
+        }
+#if !RB2_SYM_LDSVIS
+        vx = rot1(vx, src_lane); vy = rot1(vy, src_lane); vz = rot1(vz, src_lane); vq = rot1(vq, src_lane);
+#endif
+        bx = rot1(bx, src_lane); by = rot1(by, src_lane); bz = rot1(bz, src_lane);
+    }
+}
+
 // T targets per lane: the CTA's target superblock I holds the T source tiles T*I .. T*I+T-1 (sub-set s of the
 // targets = tile T*I + s, one particle of each sub-set per thread).  Against source tile J a sub-set is evaluated
 // symmetrically when its tile index is < J (then i < j for every pair), in the gather form when it IS tile J, and
@@ -109,11 +156,21 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
             for (int s = 0; s < T; ++s) {
                 if (s != rel) continue;
                 Acc4 a = {0.0, 0.0, 0.0, 0.0};
+                bool close = false;
                 for (int jj = 0; jj < SB; ++jj) {
                     const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
                     const double qe = (jj == tid) ? 0.0 : sj.w;
                     const double qsg = (jj > tid) ? qe : -qe;
-                    planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a);
+                    planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, close);
+                }
+                if (close) {  // a laterally close pair: this thread's row of the tile again, reference arithmetic
+                    a = Acc4{0.0, 0.0, 0.0, 0.0};
+                    for (int jj = 0; jj < SB; ++jj) {
+                        const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
+                        const double qe = (jj == tid) ? 0.0 : sj.w;
+                        const double qsg = (jj > tid) ? qe : -qe;
+                        planar_term<NIC, true>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, close);
+                    }
                 }
                 ax[s] += a.x; ay[s] += a.y; az[s] += a.z + a.t;
             }
@@ -125,43 +182,14 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
             for (int r = 0; r < 4; ++r) {
                 const int wb0 = ((warp + r) & 3) * 32;
                 const int home = wb0 + lane;
-                double vx = X[home], vy = Y[home], vz = Z[home], vq = Q[home];
-                double bx = 0.0, by = 0.0, bz = 0.0;   // reaction on the visitor, travels with it
-                double tx[T], ty[T], tz[T];            // force on my particles from this round
-#pragma unroll
-                for (int s = 0; s < T; ++s) { tx[s] = 0.0; ty[s] = 0.0; tz[s] = 0.0; }
-#pragma unroll SYM_UNROLL
-                for (int k = 0; k < 32; ++k) {
-#if RB2_SYM_LDSVIS
-                    // visitor coordinates straight from shared memory (conflict-free rotated index);
-                    // only the travelling accumulators go through the shuffle unit
-                    const int vi = wb0 + ((lane + k) & 31);
-                    vx = X[vi]; vy = Y[vi]; vz = Z[vi]; vq = Q[vi];
-#endif
-#pragma unroll
-                    for (int s = 0; s < T; ++s) {
-                        const PairW w = planar_weights<NIC>(xi[s], yi[s], zi[s], vx, vy, vz, P);
-                        // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
-                        const double ti = vq * w.U, tj = qe[s] * w.U;
-                        tx[s] = fma(w.dx, ti, tx[s]);
-                        ty[s] = fma(w.dy, ti, ty[s]);
-                        bx = fma(-w.dx, tj, bx);
-                        by = fma(-w.dy, tj, by);
-                        if (NIC < 0) {
-                            tz[s] = fma(w.dz, ti, tz[s]);
-                            bz = fma(-w.dz, tj, bz);
-                        } else {
-                            const double czz = w.dz * w.wc;
-                            const double icz = w.Zsame - w.Zopp;
-                            tz[s] = fma(vq, icz + czz, tz[s]);
-                            bz = fma(qe[s], icz - czz, bz);
-                        }
-                    }
-#if !RB2_SYM_LDSVIS
-                    vx = rot1(vx, src_lane); vy = rot1(vy, src_lane); vz = rot1(vz, src_lane); vq = rot1(vq, src_lane);
-#endif
-                    bx = rot1(bx, src_lane); by = rot1(by, src_lane); bz = rot1(bz, src_lane);
-                }
+                double bx, by, bz;          // reaction on the visitor, travels with it
+                double tx[T], ty[T], tz[T]; // force on my particles from this round
+                bool close = false;
+                sym_round<NIC, T, false>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
+                // a laterally close pair anywhere in this warp's 32 x 32T block: the round again with the reference's
+                // sqrt / divide (warp-uniform branch: the shuffles inside need every lane)
+                if (__any_sync(0xffffffffu, close))
+                    sym_round<NIC, T, true>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
                 // 32 rotations by one lane: every visitor is back at its home lane
 #pragma unroll
                 for (int s = 0; s < T; ++s)

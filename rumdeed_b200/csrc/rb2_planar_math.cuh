@@ -26,17 +26,19 @@ struct PairW {
     double Zsame;  // same-charge partner z-sum (enters with the role sign)
 };
 
-// NIC: -1 image charge off, 0, 1, >= 2 (runtime N_ic_max loop).
-template <int NIC>
+// NIC: -1 image charge off, 0, 1, >= 2 (runtime N_ic_max loop).  EXACT: the reference's sqrt / divide for the inverse
+// cubes (slow path of pairs flagged `close`); otherwise `close` collects "lateral offset below 1e-11 m" over the calls.
+template <int NIC, bool EXACT = false>
 __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi, double xj, double yj, double zj,
-                                                const PlanarParams &P)
+                                                const PlanarParams &P, bool &close)
 {
     PairW w;
     w.dx = xi - xj;
     w.dy = yi - yj;
     w.dz = zi - zj;
     const double dxy2 = fma(w.dy, w.dy, fma(w.dx, w.dx, RB2_S_FLOOR));
-    w.wc = rb2_inv_r3_soft(fma(w.dz, w.dz, dxy2));
+    if (!EXACT) close = close || rb2_is_close(dxy2);
+    w.wc = rb2_inv_r3_sel<EXACT>(fma(w.dz, w.dz, dxy2));
     if (NIC < 0) {
         w.U = w.wc;
         w.Zopp = 0.0;
@@ -44,16 +46,16 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
         return w;
     }
     const double S = zi + zj;
-    const double w0 = rb2_inv_r3_soft(fma(S, S, dxy2));
+    const double w0 = rb2_inv_r3_sel<EXACT>(fma(S, S, dxy2));
     double W = -w0;
     w.Zopp = S * w0;
     w.Zsame = 0.0;
     if (NIC == 1) {
         const double a1 = S - P.two_d, a2 = S + P.two_d, b1 = w.dz - P.two_d, b2 = w.dz + P.two_d;
-        const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
-        const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
-        const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
-        const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
+        const double w1 = rb2_inv_r3_sel<EXACT>(fma(a1, a1, dxy2));
+        const double w2 = rb2_inv_r3_sel<EXACT>(fma(a2, a2, dxy2));
+        const double w3 = rb2_inv_r3_sel<EXACT>(fma(b1, b1, dxy2));
+        const double w4 = rb2_inv_r3_sel<EXACT>(fma(b2, b2, dxy2));
         W = (w3 + w4) - ((w0 + w1) + w2);
         w.Zopp = fma(a2, w2, fma(a1, w1, w.Zopp));
         w.Zsame = fma(b2, w4, b1 * w3);
@@ -61,10 +63,10 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
         for (int n = 1; n <= P.nic; ++n) {
             const double h = P.two_d * (double)n;
             const double a1 = S - h, a2 = S + h, b1 = w.dz - h, b2 = w.dz + h;
-            const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
-            const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
-            const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
-            const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
+            const double w1 = rb2_inv_r3_sel<EXACT>(fma(a1, a1, dxy2));
+            const double w2 = rb2_inv_r3_sel<EXACT>(fma(a2, a2, dxy2));
+            const double w3 = rb2_inv_r3_sel<EXACT>(fma(b1, b1, dxy2));
+            const double w4 = rb2_inv_r3_sel<EXACT>(fma(b2, b2, dxy2));
             W += (w3 + w4) - (w1 + w2);
             w.Zopp = fma(a2, w2, fma(a1, w1, w.Zopp));
             w.Zsame = fma(b2, w4, fma(b1, w3, w.Zsame));
@@ -76,11 +78,11 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
 
 // Gather form: accumulate q_j * field(i <- j) into a (a.t collects the same-charge z-sum with
 // the charge qs, which the caller signs: per tile, or per element through qs itself).
-template <int NIC>
+template <int NIC, bool EXACT = false>
 __device__ __forceinline__ void planar_term(double xi, double yi, double zi, const double4 pj, double qj, double qs,
-                                            const PlanarParams &P, Acc4 &a)
+                                            const PlanarParams &P, Acc4 &a, bool &close)
 {
-    const PairW w = planar_weights<NIC>(xi, yi, zi, pj.x, pj.y, pj.z, P);
+    const PairW w = planar_weights<NIC, EXACT>(xi, yi, zi, pj.x, pj.y, pj.z, P, close);
     const double t = qj * w.U;
     a.x = fma(w.dx, t, a.x);
     a.y = fma(w.dy, t, a.y);

@@ -129,6 +129,16 @@ int rh_get_ramo_sections(void *p, int n_sec, double *out)
     return 0;
 }
 
+int rh_set_option(void *p, const char *name, double value)
+{
+    Sim *s = (Sim *)p;
+    if (!s || !name) return -1;
+    if (!strcmp(name, "photo_serial")) s->photo_serial = value != 0.0;
+    else if (!strcmp(name, "ramo_sections")) s->ramo_sections = value > 0 ? (int)value : 0;
+    else { s->err = std::string("unknown host option ") + name; return -1; }
+    return 0;
+}
+
 void rh_destroy(void *p)
 {
     Sim *s = (Sim *)p;

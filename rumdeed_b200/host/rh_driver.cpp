@@ -51,6 +51,9 @@ int Init(Sim &s)
         if (f) fclose(f);
     }
     s.rng.seed(seed);
+    s.rng_photo.seed(seed ^ 0x9E3779B97F4A7C15ULL);
+    s.photo_cand.clear();
+    s.photo_head = 0;
     int geometry = RB2_GEOM_PLANAR, rc = 0;
     switch (g.emission_mode) {  // src/main.F90:106-144
         case EMISSION_PHOTO: rc = Init_Photo_Emission(s); break;

@@ -653,33 +653,101 @@ int Init_Field_Thermo_Emission(Sim &s)
 }
 
 // ---- photo emission (mode 1), src/mod_photo_emission.f90 ---------------------------------------------------------
-// Do_Photo_Emission_Rectangle, :603-686.  The accept-and-insert loop is inherently serial (each
-// accepted electron changes the field the next attempt sees).  Candidates are evaluated
-// speculatively in device batches of (z = 0, z = 1 nm) probe pairs; the first success is inserted
-// and the remaining candidates -- whose random positions do not depend on the state -- are
-// re-evaluated against the enlarged system, which reproduces the serial decisions exactly.
-static int Do_Photo_Emission_Rectangle(Sim &s, int step, int emit, double p_eV, int maxElecEmit)
+// The candidate spots of Do_Photo_Emission_Rectangle come from their own generator (rng_photo, seeded from the run's
+// seed) through a queue that survives the time step: the (x, y) of the k-th attempt of a run is the k-th pair of that
+// stream no matter how many candidates a batch drew ahead, so the serial loop and the speculative one below make the
+// same attempts in the same order.
+static void photo_candidate(Sim &s, size_t k, double xy[2])
 {
     const Globals &g = s.g;
-    const int MAX_EMISSION_TRY = 100, B = 32;
+    while ((s.photo_cand.size() - s.photo_head) / 2 <= k) {
+        const double u = s.rng_photo.uniform(), v = s.rng_photo.uniform();
+        s.photo_cand.push_back(g.emitters_pos[0] + g.emitters_dim[0] * u);
+        s.photo_cand.push_back(g.emitters_pos[1] + g.emitters_dim[1] * v);
+    }
+    xy[0] = s.photo_cand[s.photo_head + 2 * k];
+    xy[1] = s.photo_cand[s.photo_head + 2 * k + 1];
+}
+static void photo_consume(Sim &s, size_t n)
+{
+    s.photo_head += 2 * n;
+    if (s.photo_head > 4096) { s.photo_cand.erase(s.photo_cand.begin(), s.photo_cand.begin() + (long)s.photo_head); s.photo_head = 0; }
+}
+static double photo_velocity_z(const Sim &s, double p_eV, const double par_pos[3])
+{
+    if (s.laser.photon_mode != 2) return 0.0;
+    return sqrt((2.0 * ((p_eV - s.work.w_theta_xy(s.g, par_pos, nullptr)) * q_0)) / m_0);
+}
+
+// Do_Photo_Emission_Rectangle, :603-686, literally: one attempt at a time, one Calc_Field_at per probe, the accepted
+// electron inserted at once.  Two host/device round trips per attempt plus one per electron: the reference sequence
+// that the speculative loop below must reproduce (option photo_serial; tests).
+static int Do_Photo_Emission_Rectangle_serial(Sim &s, int step, int emit, double p_eV, int maxElecEmit)
+{
+    const Globals &g = s.g;
+    const int MAX_EMISSION_TRY = 100;
     int nrTry = 0, nrElecEmit = 0;
-    std::vector<double> cand;  // candidate (x, y) pairs drawn but not consumed yet
-    size_t head = 0;
-    std::vector<double> pts((size_t)6 * B), fld((size_t)6 * B);
     while (nrTry <= MAX_EMISSION_TRY) {
         if (nrElecEmit >= maxElecEmit && maxElecEmit != -1) break;
         if (s.counts.nrElec >= g.max_particles - 1) { fprintf(stderr, "WARNING: Reached maximum number of electrons!!!\n"); break; }
+        double xy[2], field[3];
+        photo_candidate(s, 0, xy);
+        photo_consume(s, 1);
+        double par_pos[3] = {xy[0], xy[1], 0.0};
+        nrTry++;
+        if (s.work.w_theta_xy(g, par_pos, nullptr) <= p_eV) {
+            if (s.Calc_Field_at(par_pos, field)) return -1;
+            if (field[2] < 0.0) {
+                par_pos[2] = 1.0 * length_scale;
+                if (s.Calc_Field_at(par_pos, field)) return -1;
+                if (field[2] < 0.0) {
+                    const double par_vel[3] = {0.0, 0.0, photo_velocity_z(s, p_eV, par_pos)};
+                    if (s.Add_Particle(par_pos, par_vel, species_elec, step, emit, -1, 1)) return -1;
+                    nrElecEmit++;
+                    nrTry = 0;
+                }
+            }
+        }
+    }
+    s.slog.nrElecEmit += nrElecEmit;
+    return 0;
+}
+
+// The same loop with device batches.  The accept-and-insert loop is inherently serial (each accepted electron changes
+// the field the next attempt sees), but the candidate spots do not depend on the state: up to B upcoming attempts are
+// evaluated speculatively as (z = 0, z = 1 nm) probe pairs in ONE rb2_field_batch_delta call against the store plus the
+// electrons accepted so far in this step (exact by linearity); the first success is accepted and the rest of the batch,
+// which saw a stale field, is evaluated again.  All accepted electrons are inserted behind the loop in one
+// rb2_add_particles call (same order, same ids).  One round trip per accepted electron instead of three.
+static int Do_Photo_Emission_Rectangle(Sim &s, int step, int emit, double p_eV, int maxElecEmit)
+{
+    if (s.photo_serial) return Do_Photo_Emission_Rectangle_serial(s, step, emit, p_eV, maxElecEmit);
+    const Globals &g = s.g;
+    const int MAX_EMISSION_TRY = 100, B = 32;
+    int nrTry = 0, nrElecEmit = 0;
+    std::vector<double> pts((size_t)6 * B), fld((size_t)6 * B);
+    std::vector<double> new_pos, new_vel, new_q;  // accepted in this step, not in the store yet
+    std::vector<int> idx(B);
+    const int PENDING_MAX = 256;
+    auto flush = [&]() -> int {
+        const int k = (int)new_q.size();
+        if (k < 1) return 0;
+        const std::vector<int> sec((size_t)k, 1);
+        if (s.Add_Particles(k, new_pos.data(), new_vel.data(), species_elec, step, emit, -1, sec.data())) return -1;
+        new_pos.clear(); new_vel.clear(); new_q.clear();
+        return 0;
+    };
+    while (nrTry <= MAX_EMISSION_TRY) {
+        if (nrElecEmit >= maxElecEmit && maxElecEmit != -1) break;
+        if (s.counts.nrElec + (int)new_q.size() >= g.max_particles - 1) { fprintf(stderr, "WARNING: Reached maximum number of electrons!!!\n"); break; }
         // a batch never looks further than the attempts left before the loop would stop
         const int want = std::min(B, MAX_EMISSION_TRY + 1 - nrTry);
-        while ((cand.size() - head) / 2 < (size_t)want) {
-            const double u = s.rng.uniform(), v = s.rng.uniform();
-            cand.push_back(g.emitters_pos[0] + g.emitters_dim[0] * u);
-            cand.push_back(g.emitters_pos[1] + g.emitters_dim[1] * v);
-        }
         int m = 0;
-        std::vector<int> idx(want, -1);
         for (int k = 0; k < want; ++k) {
-            const double pos0[3] = {cand[head + 2 * k], cand[head + 2 * k + 1], 0.0};
+            double xy[2];
+            photo_candidate(s, (size_t)k, xy);
+            const double pos0[3] = {xy[0], xy[1], 0.0};
+            idx[k] = -1;
             if (s.work.w_theta_xy(g, pos0, nullptr) <= p_eV) {
                 idx[k] = m;
                 double *p = &pts[(size_t)6 * m];
@@ -688,27 +756,33 @@ static int Do_Photo_Emission_Rectangle(Sim &s, int step, int emit, double p_eV, 
                 m++;
             }
         }
-        if (m > 0 && s.Calc_Field_at_Batch(2 * m, pts.data(), fld.data())) return -1;
+        if (m > 0 && s.check(rb2_field_batch_delta(2 * m, pts.data(), (int)new_q.size(), new_pos.data(), new_q.data(), fld.data()),
+                             "rb2_field_batch_delta")) return -1;
         int consumed = want;
         for (int k = 0; k < want; ++k) {
             nrTry++;
             if (idx[k] < 0) continue;
             const double *f = &fld[(size_t)6 * idx[k]];
             if (f[2] < 0.0 && f[5] < 0.0) {
-                double par_pos[3] = {cand[head + 2 * k], cand[head + 2 * k + 1], 1.0 * length_scale};
-                double par_vel[3] = {0.0, 0.0, 0.0};
-                if (s.laser.photon_mode == 2)
-                    par_vel[2] = sqrt((2.0 * ((p_eV - s.work.w_theta_xy(g, par_pos, nullptr)) * q_0)) / m_0);
-                if (s.Add_Particle(par_pos, par_vel, species_elec, step, emit, -1, 1)) return -1;
+                double xy[2];
+                photo_candidate(s, (size_t)k, xy);
+                const double par_pos[3] = {xy[0], xy[1], 1.0 * length_scale};
+                const double par_vel[3] = {0.0, 0.0, photo_velocity_z(s, p_eV, par_pos)};
+                new_pos.insert(new_pos.end(), par_pos, par_pos + 3);
+                new_vel.insert(new_vel.end(), par_vel, par_vel + 3);
+                new_q.push_back(-1.0 * q_0);
                 nrElecEmit++;
                 nrTry = 0;
                 consumed = k + 1;  // the rest of the batch saw a stale field: evaluate it again
                 break;
             }
         }
-        head += (size_t)2 * consumed;
-        if (head > 4096) { cand.erase(cand.begin(), cand.begin() + (long)head); head = 0; }
+        photo_consume(s, (size_t)consumed);
+        // keep the pending list short (it travels to the device with every batch): flushing it into the store in
+        // order is the reference's immediate Add_Particle, only later
+        if ((int)new_q.size() >= PENDING_MAX && flush()) return -1;
     }
+    if (flush()) return -1;
     s.slog.nrElecEmit += nrElecEmit;
     return 0;
 }

@@ -126,6 +126,10 @@ struct Sim {
     Laser laser;
     Pointers ptr;
     Rng rng;
+    Rng rng_photo;                    // candidate spots of the photo-emission loop (own stream, see rh_emission.cpp)
+    std::vector<double> photo_cand;   // ... drawn but not consumed yet
+    size_t photo_head = 0;
+    bool photo_serial = false;        // run Do_Photo_Emission_Rectangle attempt by attempt (reference sequence; tests)
     rb2_config cfg{};
     rb2_counts counts{};
     rb2_step_result last{};

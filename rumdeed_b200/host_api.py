@@ -75,6 +75,7 @@ def load_host_library():
     lib.rh_get_state.argtypes = [V, C.POINTER(State)]
     lib.rh_steps_in_input.argtypes = [V]
     lib.rh_get_ramo_sections.argtypes = [V, C.c_int, _PD]
+    lib.rh_set_option.argtypes = [V, C.c_char_p, C.c_double]
     lib.rh_destroy.argtypes = [V]; lib.rh_destroy.restype = None
     lib.rh_last_error.argtypes = [V]; lib.rh_last_error.restype = C.c_char_p
     lib.rh_cuba_integrate.argtypes = [V, C.c_int, _PD, _PD, _PI, _PI]
@@ -176,6 +177,9 @@ class Simulation:
         st = State()
         self.lib.rh_get_state(self.ptr, C.byref(st))
         return st
+
+    def set_option(self, name, value):
+        self._check(self.lib.rh_set_option(self.ptr, name.encode(), float(value)))
 
     def ramo_current_emit(self, n_sec):
         out = np.zeros(n_sec)

@@ -496,6 +496,205 @@ def test_photo_emission_space_charge_limit(orc):
 
 
 @gpu
+@pytest.mark.parametrize("w,n_pre", [(((2.5,),), 0), (((2.5, 5.0), (5.0, 2.5)), 400)])
+def test_photo_loop_speculative_batches_equal_serial_loop(orc, w, n_pre):
+    """mod_photo_emission.f90:603-686 is an accept-and-insert loop in which every accepted electron changes the field
+    the next attempt sees.  The device path evaluates batches of upcoming attempts speculatively (rb2_field_batch_delta
+    against store + electrons accepted so far) and re-evaluates what an acceptance made stale; this must make EXACTLY
+    the accept / insert sequence of the literal loop (one Calc_Field_at per probe, immediate Add_Particle) on the same
+    random stream: same counts per step and bit-identical particle arrays after several full time steps."""
+    laser = dict(gauss_mode=2, laser_mode=2, photon_mode=2, energy=4.7, variation=0.02)
+    runs = []
+    for serial in (1, 0):
+        sim, p, st, em = _planar_pair(orc, 77, w=w, mode=1, V=2000.0, d=1000 * NM, emit=100 * NM, dt=1e-16, laser=laser)
+        sim.set_option("photo_serial", serial)
+        with sim:
+            if n_pre:
+                _preload(sim, st, p, n_pre, 5, d=1000 * NM)
+            counts = []
+            for i in range(1, 7):
+                counts.append(sim.step(i).nrElecEmit)
+            s = sim.state()
+            d = rb.HotPath.attach().download(("pos", "vel", "acc", "id", "step", "section"))
+        runs.append((counts, s.nrElec, d))
+    (c1, n1, d1), (c0, n0, d0) = runs
+    assert c1 == c0 and n1 == n0 and c1[0] > 500
+    for key in d1:
+        assert np.array_equal(d1[key], d0[key]), key
+    if len(w) == 2:  # no electron starts above a 5.0 eV cell (photon energy 4.7 eV)
+        new = d1["pos"][d1["step"] > 0]
+        assert np.all((new[:, 0] < 0) == (new[:, 1] < 0))
+
+
+@gpu
+def test_full_store_drops_particles_without_records(orc, tmp_path):
+    """Add_Particle at MAX_PARTICLES (src/mod_pair.F90:36-43): the particle is dropped and counted, nothing is written
+    and nrID does not advance -- density_emit*.bin hold exactly the accepted particles."""
+    d = _deck(tmp_path, "gpu_planar_fe")
+    cap = 400
+    with Simulation(d, write_files=True, seed=3, max_particles=cap) as sim:
+        for i in range(1, 16):
+            s = sim.step(i)
+        assert s.nrPart == cap and s.nrID == cap and s.nrElec == cap
+        k = rb.HotPath.attach().counts()
+        assert k.nrPart_dropped > 0 and k.nrID == cap
+    out = tmp_path / "out"
+    assert (out / "density_emit.bin").stat().st_size == cap * 40
+    assert (out / "density_emit_elec.bin").stat().st_size == cap * 32
+    assert (out / "density_emit_ion.bin").stat().st_size == 0
+    init = np.fromfile(out / "init.bin", dtype=np.dtype([("d", "<f8", 7), ("i", "<i4", 4)]))
+    assert init.nbytes == 72 and list(init["i"][0]) == [5000000, 1, 9216, 1000]
+    assert list(init["d"][0]) == [1.0, 1.0, 1.0, 1e-9, 1e-12, 1e-9 / 1e-12, 1.0]
+
+
+def _deck(tmp_path, name, edits=(), extra=""):
+    """Copy tools/decks/<name> to a scratch dir; edits = (old, new) replacements in `input`, extra = namelist lines."""
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tools", "decks", name)
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path / f)
+    txt = (tmp_path / "input").read_text()
+    for old, new in edits:
+        assert old in txt
+        txt = txt.replace(old, new)
+    if extra:
+        txt = txt.replace("\n/", "\n  " + extra + "\n/")
+    (tmp_path / "input").write_text(txt)
+    return str(tmp_path)
+
+
+def _golden_runs():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deck_oracle_runs.json")) as f:
+        return json.load(f)
+
+
+@gpu
+def test_photo_deck_small_emitter_vs_oracle_run(orc, tmp_path):
+    """tools/decks/photo (= Examples/Photo) with the emitter shrunk to 100 x 100 nm so that the CPU oracle can run the
+    same 200 steps live (3 seeds): the first-step burst (space-charge limit of the bare cathode), the emitted total and
+    the current of the last 50 steps agree within a few per cent; exact electron bookkeeping."""
+    from oracle.oracle import Emission
+    d = _deck(tmp_path, "photo", edits=[("-250.0d0, -250.0d0", "-50.0d0, -50.0d0"), ("500.0d0, 500.0d0, 0.0d0", "100.0d0, 100.0d0, 0.0d0")])
+    steps = 200
+    got = []
+    for seed in (11, 12):
+        with Simulation(d, seed=seed, max_particles=50000) as sim:
+            em0 = sim.step(1).nrElecEmit
+            cur = []
+            for i in range(2, steps + 1):
+                cur.append(sim.step(i).ramo_total)
+            s = sim.state()
+            assert s.nrElec == s.nrEmitted_total - s.nrAbsorbed_top - s.nrAbsorbed_bot
+            got.append((em0, s.nrEmitted_total, float(np.mean(cur[-50:]))))
+    ref = []
+    for seed in (21, 22, 23):
+        box = (100 * NM, 100 * NM, 1000 * NM)
+        p = orc.params_planar(2000.0, 1000 * NM, box, 1e-16, True, 1)
+        st = orc.store(50000)
+        em = Emission(orc, p, st, (-50 * NM, -50 * NM, 0), (100 * NM, 100 * NM, 0), ((2.5,),), seed=seed)
+        tot, cur, first = 0, [], None
+        for i in range(1, steps + 1):
+            n = em.do_photo_emission_rectangle(i, em.get_laser_energy(4.7, 0.02), 2, -1)
+            first = n if first is None else first
+            tot += n
+            st.step(p)
+            cur.append(st.s.ramo_current[1])
+            st.remove(i)
+        ref.append((first, tot, float(np.mean(cur[-50:]))))
+    g, r = np.mean(got, axis=0), np.mean(ref, axis=0)
+    assert abs(g[0] - r[0]) < 0.02 * r[0], (got, ref)
+    assert abs(g[1] - r[1]) < 0.02 * r[1], (got, ref)
+    assert abs(g[2] - r[2]) < 0.05 * abs(r[2]), (got, ref)
+
+
+@gpu
+def test_photo_deck_full_size_vs_oracle_fixture(tmp_path):
+    """tools/decks/photo as shipped (500 x 500 nm emitter: ~45 000 electrons leave in the first step) for 200 steps
+    against the CPU oracle's own run of the same deck (tests/golden/deck_oracle_runs.json, made by
+    tests/golden/make_deck_fixtures.py: ~10 CPU-minutes)."""
+    fx = _golden_runs()["photo_full"][0]
+    d = _deck(tmp_path, "photo")
+    with Simulation(d, seed=31, max_particles=200000) as sim:
+        em, cur = [], []
+        for i in range(1, fx["steps"] + 1):
+            s = sim.step(i)
+            em.append(s.nrElecEmit)
+            cur.append(s.ramo_total)
+        s = sim.state()
+        assert s.nrElec == s.nrEmitted_total - s.nrAbsorbed_top - s.nrAbsorbed_bot
+    # the burst stops at 100 consecutive failures -- a random stopping rule: two oracle seeds differ by 1 % here
+    assert abs(em[0] - fx["emitted"][0]) < 0.03 * fx["emitted"][0], (em[0], fx["emitted"][0])
+    assert abs(sum(em) - sum(fx["emitted"])) < 0.03 * sum(fx["emitted"])
+    for a, b in ((100, 120), (180, 200)):
+        assert np.mean(cur[a:b]) == pytest.approx(np.mean(fx["ramo"][a:b]), rel=0.04)
+    assert s.nrElec == pytest.approx(fx["nrPart"][-1], rel=0.03)
+
+
+@gpu
+def test_checkerboard_tfe_deck_vs_oracle_run(orc, tmp_path):
+    """tools/decks/checkerboard_tfe (= Examples/Checkerboard-TFE) as shipped + WRITE_RAMO_SEC, 700 steps (no electron
+    has crossed the gap yet), 6 seeds, against the CPU oracle's live runs of the same deck (6 seeds): emitted count, current, share of the 16 sections
+    among the electrons (chi-square) and in the per-section Ramo current; per step the sections add up to the total
+    and ramo_current.bin holds (MAX_SECTIONS, MAX_EMITTERS) doubles per step (src/mod_pair.F90:822-826)."""
+    from oracle.oracle import Emission
+    from scipy import stats
+    steps, nseed = 700, 6
+    d = _deck(tmp_path, "checkerboard_tfe", extra="WRITE_RAMO_SEC = .True.,")
+    g_emit, g_cur, g_sec, g_share = [], [], np.zeros(16), np.zeros(16)
+    for seed in range(41, 41 + nseed):
+        with Simulation(d, write_files=(seed == 41), seed=seed, max_particles=50000) as sim:
+            cur = []
+            for i in range(1, steps + 1):
+                s = sim.step(i)
+                cur.append(s.ramo_total)
+                sec_now = sim.ramo_current_emit(16)
+                assert sec_now.sum() == pytest.approx(s.ramo_total, rel=1e-10, abs=1e-30)
+                g_share += sec_now
+            s = sim.state()
+            st_g = rb.HotPath.attach().download(("section", "vel", "charge"))
+            # the table of the last step against the particle arrays (planar: E_zunit = -1/d)
+            want = np.bincount(st_g["section"], weights=st_g["charge"] * st_g["vel"][:, 2] * (-1.0 / (1000 * NM)), minlength=17)[1:17]
+            assert np.allclose(sec_now, want, rtol=1e-11, atol=1e-25)
+            assert s.nrAbsorbed_top == 0
+            g_emit.append(s.nrEmitted_total)
+            g_cur.append(float(np.mean(cur[-200:])))
+            g_sec += np.bincount(st_g["section"], minlength=17)[1:17]
+        if seed == 41:
+            out = tmp_path / "out"
+            assert (out / "ramo_current.bin").stat().st_size == steps * 96 * 96 * 1 * 8
+            last = np.fromfile(out / "ramo_current.bin", dtype="<f8").reshape(steps, 96 * 96)[-1]
+            assert np.array_equal(last[:16], sec_now) and np.all(last[16:] == 0.0)
+    w = ((2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0), (2.0, 2.5, 2.0, 2.5), (2.5, 2.0, 2.5, 2.0))
+    o_emit, o_cur, o_sec, o_share = [], [], np.zeros(16), np.zeros(16)
+    for seed in range(51, 51 + nseed):
+        box = (100 * NM, 100 * NM, 1000 * NM)
+        p = orc.params_planar(2000.0, 1000 * NM, box, 1e-16, True, 1)
+        st = orc.store(50000)
+        em = Emission(orc, p, st, (-50 * NM, -50 * NM, 0), (100 * NM, 100 * NM, 0), w, T_temp=1000.0, seed=seed)
+        cur = []
+        for i in range(1, steps + 1):
+            N_sup, _ = em.supply_grid(SUPPLY_GTF, 16)
+            em.do_field_thermo_emission_planar(i, N_sup)
+            st.step(p)
+            cur.append(st.s.ramo_current[1])
+            o_share += st.ramo_current_emit(16)
+            st.remove(i)
+        o_emit.append(st.s.nrID)
+        o_cur.append(float(np.mean(cur[-200:])))
+        o_sec += np.bincount(st.section, minlength=17)[1:17]
+    ge, oe = sum(g_emit), sum(o_emit)
+    assert abs(ge - oe) < 4.0 * math.sqrt(ge + oe), (g_emit, o_emit)           # Poisson candidates: 4 sigma of the difference
+    assert np.mean(g_cur) == pytest.approx(np.mean(o_cur), rel=0.10), (g_cur, o_cur)
+    chi2, pval, _, _ = stats.chi2_contingency(np.stack([g_sec, o_sec]))
+    assert pval > 1e-3, (g_sec, o_sec, pval)
+    assert np.all(g_sec > 0) and g_sec.sum() == ge
+    gs, os_ = g_share / g_share.sum(), o_share / o_share.sum()
+    assert np.max(np.abs(gs - os_)) < 0.35 * np.max(os_), (gs, os_)
+
+
+@gpu
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rumdeed_b200", "rumdeed_b200_run")),
                     reason="driver executable not built")
 def test_driver_executable_writes_reference_format_files(tmp_path):

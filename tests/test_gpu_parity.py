@@ -210,6 +210,88 @@ def test_coincident_and_marked_particles(orc):
     assert np.all(acc[40] == 0.0) and np.all(acc[41] == 0.0)
 
 
+@pytest.mark.parametrize("mode,tpl", [(1, 0), (2, 1), (2, 2)])
+@pytest.mark.parametrize("n", [300, 4000])
+def test_close_pairs_use_reference_arithmetic(orc, n, mode, tpl):
+    """The fast inverse cube is first order in the 1e-18 m softening: good to 6 (eps/r)^2, i.e. not to 1e-11 below
+    r ~ 1e-12 m.  Pairs whose lateral offset is below 1e-11 m are re-evaluated with the reference's own sqrt / divide
+    (src/mod_verlet.F90:1302-1303): separations from 1e-15 to 1e-11 m, along every axis, in the same tile, across
+    tiles and superblocks, against an image partner at either electrode, both kernels -- all within 1e-11 of the
+    long-double oracle."""
+    d = 1000 * NM
+    cfg, p = planar(orc, ic=True, nic=1, cap=n + 64)
+    pos, q, m, sp = cloud(n, 99 + n, ions=True)
+    rng = np.random.default_rng(n)
+    seps = [1e-15, 3e-15, 1e-14, 1e-13, 3e-13, 1e-12, 5e-12, 1e-11, 3e-11]
+    partners = []
+    k = 0
+    for r in seps:
+        for axis in range(3):
+            # i: a particle somewhere in the array, j: another one far away in index (other tile / superblock) or adjacent
+            i = int(rng.integers(0, n))
+            j = (i + 1) % n if k % 2 == 0 else (i + n // 2 + 17) % n
+            off = np.zeros(3); off[axis] = r
+            if axis < 2:
+                off[2] = 0.3 * r
+            pos[j] = pos[i] + off
+            partners.append((i, j))
+            k += 1
+    # both particles grazing the cathode / the anode, laterally 1e-13 m apart: the n = 0 partner (distance z_i + z_j) and
+    # the 2d - z partner come as close as the direct pair
+    base = n - 8
+    pos[base] = [10 * NM, -20 * NM, 2e-13]; pos[base + 1] = [10 * NM + 1e-13, -20 * NM, 3e-13]
+    pos[base + 2] = [-30 * NM, 5 * NM, d - 2e-13]; pos[base + 3] = [-30 * NM, 5 * NM + 1e-13, d - 1e-13]
+    pos[base + 4] = pos[3]  # exactly coincident: contributes exactly 0 (softened weight times zero offset)
+    touched = sorted({x for ij in partners for x in ij} | set(range(base, base + 5)) | {3})
+    with rb.HotPath(cfg) as hp:
+        hp.set_option("pair_mode", mode)
+        if tpl:
+            hp.set_option("sym_tpl", tpl)
+        hp.upload(pos, q, m, species=sp)
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        pts = np.concatenate([pos[[i for i, _ in partners]] + [0, 0, 2e-14], [[10 * NM, -20 * NM, 0.0], [-30 * NM, 5 * NM, d]]])
+        fld = hp.Calc_Field_at_Batch(pts)
+        ez = hp.field_surface_z(np.array([[10 * NM, -20 * NM, 0.0], [10 * NM + 5e-14, -20 * NM, 0.0]]))
+    assert np.all(np.isfinite(acc))
+    truth = orc.accel_gather_ld(p, pos, q, m)
+    assert relerr(acc, truth) < TOL
+    assert relerr(acc[touched], truth[touched]) < TOL
+    want = np.array([orc.calc_field_at(p, pos, q, pt, sp, ld=True) for pt in pts])
+    assert relerr(fld, want) < TOL
+    wz = np.array([orc.calc_field_at(p, pos, q, pt, sp, ld=True)[2] for pt in ([10 * NM, -20 * NM, 0.0], [10 * NM + 5e-14, -20 * NM, 0.0])])
+    assert np.max(np.abs(ez - wz) / np.abs(wz)) < TOL
+
+
+def test_fused_step_refuses_an_i_partition_and_remove_reasons(orc):
+    """The fused step has no exchange: with an i-partition only the owned rows would get an acceleration and the others
+    would be integrated with a = 0 (silently wrong) -- it must fail instead.  Mark_Particles_Remove: reason 4
+    (remove_ion, src/mod_pair.F90:273-279, :327-333) has its own counters, an unknown reason is an error."""
+    cfg, p = planar(orc, cap=256)
+    pos, q, m, sp = cloud(100, 4, ions=True)
+    sp[7] = 3; q[7] = 0.0
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=sp)
+        hp.set_partition(10, 60)
+        with pytest.raises(rb.api.Rb2Error) as e:
+            hp.Update_Position(1)
+        assert "partition" in str(e.value)
+        assert np.array_equal(hp.download(("pos",))["pos"], pos)  # nothing was integrated
+        hp.Update_Particle_Position(1)                            # the three phases keep working with a partition
+        hp.Calculate_Acceleration_Particles()
+        hp.set_partition(0, -1)
+        hp.Update_Position(2)
+        with pytest.raises(rb.api.Rb2Error):
+            hp.Mark_Particles_Remove([1], 9)
+        assert hp.counts().nrPart_remove == 0
+        hp.Mark_Particles_Remove([0, 7], rb.api.REMOVE_ION)       # an electron and the atom
+        k = hp.counts()
+        assert (k.nrPart_remove, k.nrPart_remove_ion, k.nrElec_remove_ion, k.nrAtom_remove_ion) == (2, 2, 1, 1)
+        assert (k.nrPart_remove_top, k.nrPart_remove_bot) == (0, 0)
+        k = hp.Remove_Particles(3)
+        assert (k.nrPart, k.nrAtom, k.nrPart_remove_ion) == (98, 0, 0)
+
+
 def test_partition_and_host_buffer_paths(orc):
     cfg, p = planar(orc, ic=True, nic=1)
     pos, q, m, sp = cloud(1500, 11)
@@ -617,10 +699,22 @@ def test_large_cloud_properties(orc):
         acc = hp.download(("acc",))["acc"]
         info = hp.last_accel_info()
         assert info["ms"] > 0 and info["grid_x"] * info["grid_y"] >= 148
-        rows = [0, 1, 127, 128, 5000, 49999, 50000, 77777, n - 2, n - 1]
-        for i in rows:
-            truth = orc.accel_gather_ld(p, pos, q, m, i, i + 1)
-            assert relerr(acc[i:i + 1], truth) < TOL, i
+        # 1200 rows against the long-double oracle: fixed ones (tile edges, both target sub-sets of a superblock, the
+        # last partial tile, ions) and a seeded random draw over the whole index range
+        rng = np.random.default_rng(7)
+        rows = np.unique(np.concatenate([[0, 1, 127, 128, 129, 255, 256, 383, 384, 5000, 49999, 50000, 77777, n - 33, n - 2, n - 1],
+                                         np.arange(9, n, 1009), rng.integers(0, n, 1100)])).astype(np.int32)
+        assert rows.size >= 1000 and np.any(sp[rows] == SPECIES_ION)
+        truth = orc.accel_gather_ld_rows(p, pos, q, m, rows)
+        assert relerr(acc[rows], truth) < TOL
+        # every row: the pair-symmetric kernel (default at this size) against the independent gather kernel
+        hp.set_option("pair_mode", 1)
+        hp.Calculate_Acceleration_Particles()
+        acc_g = hp.download(("acc",))["acc"]
+        assert not np.array_equal(acc, acc_g)  # two different kernels (summation orders) did run
+        assert relerr(acc, acc_g) < 1e-12
+        assert relerr(acc_g[rows], truth) < TOL
+        hp.set_option("pair_mode", 0)
         # Coulomb only, no vacuum field: sum_i m_i a_i = 0
         cfg0 = rb.planar_config(0.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1e-16, False, 0, capacity=n)
         hp.update_config(cfg0)
@@ -643,9 +737,14 @@ def test_full_size_cloud_properties(orc):
         hp.Calculate_Acceleration_Particles()
         acc = hp.download(("acc",))["acc"]
         assert np.all(np.isfinite(acc))
-        for i in [0, 127, 128, 16383, 16384, 500_000, 777_777, n - 129, n - 1]:
-            truth = orc.accel_gather_ld(p, pos, q, m, i, i + 1)
-            assert relerr(acc[i:i + 1], truth) < TOL, i
+        # 300 rows against the long-double oracle, spread over the whole index range (every band of source tiles, both
+        # target sub-sets of a superblock, the last partial tile of 64 particles, ions)
+        rng = np.random.default_rng(11)
+        rows = np.unique(np.concatenate([[0, 127, 128, 255, 256, 16383, 16384, 500_000, 777_777, n - 129, n - 65, n - 64, n - 1],
+                                         np.arange(9, n, 5003), rng.integers(0, n, 100)])).astype(np.int32)
+        assert rows.size >= 256 and np.any(sp[rows] == SPECIES_ION)
+        truth = orc.accel_gather_ld_rows(p, pos, q, m, rows)
+        assert relerr(acc[rows], truth) < TOL
         hp.Calculate_Acceleration_Particles()
         assert np.array_equal(hp.download(("acc",))["acc"], acc)
         # stable compaction at scale: remove every 7th particle, the survivors keep their order and ids
