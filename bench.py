@@ -33,6 +33,12 @@ sys.path.insert(0, ROOT)
 
 NM = 1.0e-9
 FLOPS_PER_PAIR = {(-1): 21, 0: 39, 1: 99, 2: 159}  # 21 + ic*(18 + 60*N_ic_max)
+# What the kernels EXECUTE at N_ic_max = 1 (ncu opcode counts, profiles/ncu_opmix_r02_n1e5.txt): FP64-pipe instructions and
+# flops (DFMA = 2, DMUL / DADD / DSETP = 1) per pair evaluation.  The pair-symmetric kernel evaluates an UNORDERED pair
+# once (both ordered interactions), the gather kernel an ordered pair.
+EXECUTED = {"sym": {"fp64_instr": 80.3, "flops": 109.0, "per": "unordered pair"},
+            "gather": {"fp64_instr": 75.0, "flops": 101.0, "per": "ordered pair"}}
+SURFACE_FLOPS_PER_POINT_PARTICLE = 54  # k_surface_field at N_ic_max = 1: 31 FP64 instructions, 23 of them FMAs (+ 1 compare)
 METRIC = "pair_interactions_per_s"
 UNIT = "pair-interactions/s"
 
@@ -164,30 +170,29 @@ def load_fast_oracle():
     return om.Oracle(path=path), "-O3 -march=native -fopenmp (built on this host)"
 
 
-def cpu_sample(orc, p, pos, q, m, target_s=12.0):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_stride(n):
+    """The SAME bounded sample in both CPU legs (cpu_baseline and --impl reference): every row up to N = 2e5 (5.5 s at
+    1e5 on 16 cores), every 64th row of the i<j loop at N = 1e6 (a fixed 1/64 slice, ~9 s on 16 cores)."""
+    return 1 if n <= 200_000 else max(1, int(round(64 * (n / 1.0e6) ** 2)))
+
+
+def cpu_sample(orc, p, pos, q, m):
     """Time a bounded, strided sample of the rows of the reference's CPU pair loop
-    (Calculate_Acceleration_Particles_Planar, i<j scatter).  Returns ordered pair-interactions/s."""
+    (Calculate_Acceleration_Particles_Planar, i<j scatter) on all host cores.  Returns ordered pair-interactions/s."""
     n = pos.shape[0]
-    # calibration: a handful of rows
-    stride = max(1, n // 16)
+    orc.set_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1: say what we use
+    stride = cpu_stride(n)
+    total_pairs = n * (n - 1) / 2
     t0 = time.perf_counter()
     _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
     t = time.perf_counter() - t0
-    total_pairs = n * (n - 1) / 2
-    # grow the sample until it takes about target_s (the first estimates are dominated by the fixed cost of
-    # the per-thread reduction arrays, so the rate is refined from each run)
-    for _ in range(4):
-        if stride == 1 or t >= 0.5 * target_s:
-            break
-        rate = pairs / max(t, 1e-9)
-        want_pairs = min(total_pairs, rate * target_s * (1.0 if t > 0.1 * target_s else 3.0))
-        new_stride = max(1, int(round(total_pairs / want_pairs)))
-        if new_stride >= stride:
-            break
-        stride = new_stride
-        t0 = time.perf_counter()
-        _, pairs = orc.accel_planar_rows(p, pos, q, m, 0, n, stride)
-        t = time.perf_counter() - t0
     frac = pairs / total_pairs
     sample = (f"rows i = 0, {stride}, 2*{stride}, ... of the i<j pair loop at N = {n} "
               f"({pairs} unordered pair evaluations = {100 * frac:.3g}% of a full evaluation, {t:.1f} s)")
@@ -206,13 +211,12 @@ def run_reference(args):
     q = np.full(n, -orc.k.q_0)
     m = np.full(n, orc.k.m_0)
     p = orc.params_planar(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic)
-    cores = orc.max_threads()
-    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     vals, times, sample = [], [], ""
     for it in range(args.warmup + args.steps):
-        v, t, sample = cpu_sample(orc, p, pos, q, m, target_s=per_step)
+        v, t, sample = cpu_sample(orc, p, pos, q, m)
         if it >= args.warmup:
             vals.append(v); times.append(t)
+    cores = orc.max_threads()
     value = float(np.mean(vals))
     ms_full = n * (n - 1) / value * 1e3
     line = {
@@ -324,6 +328,24 @@ def run_ours(args):
     peak_burst, _ = hp.fp64_peak(30.0)
     peak_sust, _ = hp.fp64_peak(1500.0)
 
+    def timed_steps(nsteps, first_step):
+        """nsteps MD steps, each bracketed by CUDA events on the library's stream, L2 flushed in between."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        acc_ms = []
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(nsteps):
+            if not args.no_flush:
+                flush.zero_()                  # L2 flush on torch's stream ...
+            torch.cuda.current_stream().synchronize()
+            ev[k][0].record(ext)               # ... timed region on the library's launching stream
+            one_step(first_step + k)
+            ev[k][1].record(ext)
+            acc_ms.append(hp.last_accel_info()["ms"])
+        barrier()
+        wall = time.perf_counter() - t0
+        return [a.elapsed_time(b) for a, b in ev], acc_ms, wall
+
     for w in range(args.warmup):
         one_step(w + 1)
     barrier()
@@ -331,25 +353,26 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    accel_ms = []
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        if not args.no_flush:
-            flush.zero_()                  # L2 flush on torch's stream ...
-        torch.cuda.current_stream().synchronize()
-        ev[k][0].record(ext)               # ... timed region on the library's launching stream
-        one_step(args.warmup + k + 1)
-        ev[k][1].record(ext)
-        accel_ms.append(hp.last_accel_info()["ms"])
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    step_ms_list, accel_ms, t_wall = timed_steps(args.steps, args.warmup + 1)
     clk = clocks.stop() if rank == 0 else None
     launches = hp.launch_count()
-    step_ms_list = [a.elapsed_time(b) for a, b in ev]
     dev_ms = sum(step_ms_list)
     info = hp.last_accel_info()
+
+    # the accelerations of the last step: a checksum for comparing runs (1 GPU vs 8), and -- the replicas of the O(N)
+    # state are integrated redundantly -- bit-identical on every rank of this run
+    import hashlib
+    acc_last = hp.download(("acc",))["acc"]
+    acc_sha = hashlib.sha256(acc_last.tobytes()).hexdigest()[:16]
+    replicas_identical = None
+    if world > 1:
+        shas = [None] * world
+        dist.all_gather_object(shas, acc_sha)
+        replicas_identical = all(s == shas[0] for s in shas)
+    checksum = {"sum_abs": float(np.abs(acc_last).sum()), "sum": [float(x) for x in acc_last.sum(axis=0)], "sha256_16": acc_sha,
+                "replicas_identical": replicas_identical,
+                "what": "particles_cur_accel after the last timed step; sum_abs agrees between 1 and N GPUs to rounding "
+                        "(the ranks' partial sums are added in rank order), the hash is identical on all ranks of one run"}
 
     # end to end through the C ABI with HOST buffers: pinned pos/q/m in, accelerations out
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -382,6 +405,68 @@ def run_ours(args):
     barrier()
     t_e2e = (time.perf_counter() - t0) / e2e_steps
 
+    kern = "sym" if sym else "gather"
+
+    def contract_and_executed(n_, acc_ms_):
+        """Fractions of the measured FP64 peak for one acceleration evaluation of n_ particles in acc_ms_ (slowest rank's
+        share): the contract figure (99 algorithmic flops per ORDERED pair) and what the kernel executed."""
+        pairs_ = float(n_) * float(n_ - 1) / world
+        pk = peak_sust if acc_ms_ > 200.0 else peak_burst
+        a = flops_per_pair(True, args.nic) * pairs_ / (acc_ms_ * 1e-3) / 1e12
+        ex = EXECUTED[kern]
+        evals = pairs_ / 2.0 if kern == "sym" else pairs_
+        e = ex["flops"] * evals / (acc_ms_ * 1e-3) / 1e12 if args.nic == 1 else None
+        u = ex["fp64_instr"] * evals / (acc_ms_ * 1e-3) / (pk * 1e12 / 2.0) if args.nic == 1 else None
+        return a, pk, e, u
+
+    # ---- field batches through the C ABI with HOST buffers (SURVEY 8d: M points on z = 0 against the N particles) ----
+    field_batch = None
+    if world == 1 and not args.no_sweep:
+        field_batch = []
+        rngp = np.random.default_rng(np.random.PCG64(20261018))
+        for M in (1, 32, 256, 4096, 65536):
+            pts = np.zeros((M, 3))
+            pts[:, 0] = rngp.uniform(-500.0, 500.0, M) * NM
+            pts[:, 1] = rngp.uniform(-500.0, 500.0, M) * NM
+            row = {"M": M, "N": n}
+            for name, fn, fl in (("rb2_field_batch", hp.Calc_Field_at_Batch, flops_per_pair(True, args.nic)),
+                                 ("rb2_field_surface_z", hp.field_surface_z, SURFACE_FLOPS_PER_POINT_PARTICLE)):
+                fn(pts)  # warm (buffers grow on the first call)
+                reps = 3 if M >= 4096 else 10
+                ts = []
+                for _ in range(reps):
+                    flush.zero_(); torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    fn(pts)
+                    ts.append(time.perf_counter() - t0)
+                t = float(np.median(ts))
+                row[name] = {"ms": t * 1e3, "point_interactions_per_s": M * float(n) / t,
+                             "fp64_frac": (fl * M * float(n) / t / 1e12) / peak_burst,
+                             "flops_per_point_particle": fl}
+            field_batch.append(row)
+
+    # ---- the rest of the contract sweep (N = 1e4, 1e5) on the same context, same step, same timing ----
+    sweep = None
+    if not args.no_sweep:
+        sweep = []
+        for n_s, k_s in ((10_000, 30), (100_000, 8)):
+            if n_s >= n:
+                continue
+            pos_s = make_cloud(n_s)
+            hp.upload(pos_s, np.full(n_s, -Q_0), np.full(n_s, M_0))
+            for w in range(3):
+                one_step(w + 1)
+            ms_l, acc_l, _ = timed_steps(k_s, 4)
+            t3 = torch.tensor([float(np.median(ms_l)), float(np.mean(ms_l)), float(np.median(acc_l))], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            med, mean, acc_med = [float(x) for x in t3.tolist()]
+            a, pk, e, u = contract_and_executed(n_s, acc_med)
+            sweep.append({"n_particles": n_s, "steps": k_s, "ms_per_step_median": med, "ms_per_step_mean": mean,
+                          "md_steps_per_s": 1e3 / med, "pair_interactions_per_s": float(n_s) * (n_s - 1) / (med * 1e-3),
+                          "kernel_ms_median": acc_med, "frac": a / pk, "frac_executed": (e / pk) if e else None,
+                          "fp64_pipe_util_est": u})
+
     stats = torch.tensor([dev_ms, t_wall * 1e3, t_e2e * 1e3, float(np.mean(accel_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -396,13 +481,14 @@ def run_ours(args):
         value = pairs / (ms_per_step * 1e-3)
         fpp = flops_per_pair(True, args.nic)
         # algorithmic flops of the slowest rank's share of the N(N-1) ordered pair interactions
-        achieved = fpp * pairs / world / (acc_ms * 1e-3) / 1e12
-        peak = peak_sust if acc_ms > 200.0 else peak_burst
-        traffic = None
+        achieved, peak, executed, pipe_util = contract_and_executed(n, acc_ms)
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"k_pair_n{n}", None)
+                tj = json.load(open(tpath))
+                traffic = tj.get(f"k_pair_n{n}", None)
+                traffic_src = "static: " + tj.get("source", "profiles/ncu_traffic.json") + " (an ncu capture of this kernel, not measured in this run)"
             except Exception:
                 traffic = None
         line = {
@@ -412,15 +498,19 @@ def run_ours(args):
             "md_steps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
             "ms_steps_rank0": [round(x, 4) for x in step_ms_list], "accel_ms_steps_rank0": [round(x, 4) for x in accel_ms],
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic,
+                         "achieved_executed": executed, "frac_executed": (executed / peak) if executed else None,
+                         "executed_note": "frac is the contract figure (99 ALGORITHMIC flops per ordered pair, N(N-1) of them); "
+                                          "frac_executed counts what the kernel ran (%s: %.0f flops per %s)" % (
+                                              kern, EXECUTED[kern]["flops"], EXECUTED[kern]["per"]),
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": ("k_pair_sym<N_ic_max=%d> + k_sym_reduce per band, k_sym_finalize (each unordered pair "
                                     "evaluated once and applied to both particles, like the reference's CPU pair loop; "
                                     "achieved = ALGORITHMIC flops of the N(N-1) ordered interactions, so it can exceed "
                                     "the executed-flop peak)" % args.nic) if sym
                          else "k_pair<planar, N_ic_max=%d> + k_accel_finalize (ordered pairs)" % args.nic,
                          "kernel_ms": acc_ms, "flops_per_pair": fpp,
-                         "fp64_instr_per_ordered_pair": (39.7 if sym else 74) if args.nic == 1 else None,
-                         "fp64_pipe_util_est": ((39.7 if sym else 74) * 2.0 / fpp) * (achieved / peak) if args.nic == 1 else None,
+                         "fp64_instr_per_pair_evaluation": EXECUTED[kern]["fp64_instr"] if args.nic == 1 else None,
+                         "fp64_pipe_util_est": pipe_util,
                          "peak_source": "measured in this run: rb2_fp64_peak independent-DFMA-chain kernel "
                                         f"(burst {peak_burst:.2f}, sustained 1.5 s {peak_sust:.2f} TFLOP/s; nominal 37.2); "
                                         "MEASURED_PEAKS.json holds no FP64 figure",
@@ -432,12 +522,13 @@ def run_ours(args):
                           else "rb2_upload_particles (host pos/q/m) -> rb2_accel_partial -> NCCL all-reduce -> rb2_accel_finalize -> rb2_download_particles(acc)")},
             "pair_kernel": "pair-symmetric" if sym else "gather",
             "gpu_launches": launches, "clocks": clk,
+            "acc_checksum": checksum, "sweep": sweep, "field_batch": field_batch,
         }
         if world == 1 and not args.no_cpu:
             try:
                 orc, how = load_fast_oracle()
                 p = orc.params_planar(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic)
-                v, t, sample = cpu_sample(orc, p, pos, q, m, target_s=12.0)
+                v, t, sample = cpu_sample(orc, p, pos, q, m)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": orc.max_threads(), "kind": "port",
                                         "sample": sample + "; " + how}
             except Exception as e:  # the baseline is a reported extra, never the product path
@@ -461,6 +552,7 @@ def main():
     ap.add_argument("--nic", type=int, default=1, help="N_ic_max")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the N = 1e4 / 1e5 sweep and the field-batch table")
     ap.add_argument("--no-flush", action="store_true", help="diagnostics only: no L2 flush between steps (not a valid bench line)")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostics only: no nvidia-smi sampling")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

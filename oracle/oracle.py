@@ -298,6 +298,9 @@ class Oracle:
     def tip_escape_prob(self, p, F, w): return self.lib.orc_tip_escape_prob(C.byref(p), F, w)
     def tip_elec_supply(self, p, A, F, w): return self.lib.orc_tip_elec_supply(C.byref(p), A, F, w)
 
+    def set_threads(self, n: int) -> None:
+        self.lib.orc_set_threads(int(n))
+
     def max_threads(self) -> int:
         return int(self.lib.orc_max_threads())
 

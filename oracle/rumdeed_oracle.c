@@ -69,6 +69,16 @@ void orc_nearest_elec(int n, const double *pos, const int *species, double *dist
     }
 }
 
+/* bench.py's CPU legs set the OpenMP thread count explicitly (torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

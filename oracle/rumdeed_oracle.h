@@ -173,6 +173,7 @@ double orc_tip_elec_supply(const orc_params *p, double A, double F, double w_the
  * lowest index wins a tie.  dist = sqrt(dx*dx + dy*dy + dz*dz), summed left to right without contraction. */
 void orc_nearest_elec(int n, const double *pos, const int *species, double *dist_out, int *id_out);
 int orc_max_threads(void);
+void orc_set_threads(int n);
 
 #ifdef __cplusplus
 }

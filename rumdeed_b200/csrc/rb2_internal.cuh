@@ -245,11 +245,13 @@ __device__ __forceinline__ double rb2_inv_r3_soft(double s)
 // (src/mod_verlet.F90:1302-1303), IEEE square root and divide.
 #define RB2_CLOSE_DXY2 1.0e-22
 #ifndef RB2_CLOSE_INT
-#define RB2_CLOSE_INT 1
-#endif
+#define RB2_CLOSE_INT 0  // measured at N = 1e6 (tools/build_variants.sh): no flag 2549 ms, FP64 compare 2578 ms (218 registers),
+#endif                   // integer compare of the high word 2586 ms (228 registers)
 __device__ __forceinline__ bool rb2_is_close(double dxy2)
 {
-#if RB2_CLOSE_INT
+#ifdef RB2_CLOSE_OFF  // measurement only (tools/build_variants.sh): the fast path alone
+    return false;
+#elif RB2_CLOSE_INT
     // positive doubles order like their high words; an integer compare keeps the FP64 pipe free
     return __double2hiint(dxy2) < 0x3B5E392A;  // high word of 1.0e-22 (0x3B5E392010175EE6), rounded up
 #else

@@ -521,9 +521,9 @@ def test_photo_loop_speculative_batches_equal_serial_loop(orc, w, n_pre):
     assert c1 == c0 and n1 == n0 and c1[0] > 500
     for key in d1:
         assert np.array_equal(d1[key], d0[key]), key
-    if len(w) == 2:  # no electron starts above a 5.0 eV cell (photon energy 4.7 eV)
+    if len(w) == 2:  # no electron starts above a 5.0 eV cell (photon energy 4.7 eV; the first row of `work` is the top row)
         new = d1["pos"][d1["step"] > 0]
-        assert np.all((new[:, 0] < 0) == (new[:, 1] < 0))
+        assert np.all((new[:, 0] < 0) != (new[:, 1] < 0))
 
 
 @gpu

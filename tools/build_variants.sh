@@ -12,7 +12,6 @@ build() { # name, extra flags
   echo "built $name: $(cuobjdump -res-usage $out/_obj/rb2_pair_sym.o 2>/dev/null | grep -A1 'pair_symILi1ELi2' | grep -o 'REG:[0-9]*')"
 }
 build base
-build m3u1 -DRB2_SYM_MINB2=3 -DRB2_SYM_UNROLL=1
-build m3u2 -DRB2_SYM_MINB2=3 -DRB2_SYM_UNROLL=2
-build m3u4 -DRB2_SYM_MINB2=3 -DRB2_SYM_UNROLL=4
-build u8 -DRB2_SYM_UNROLL=8
+# round 2: cost of the close-pair flag (one compare per pair) -- FP64 compare (base), integer compare of the high word, none
+build closeint -DRB2_CLOSE_INT=1
+build closeoff -DRB2_CLOSE_OFF
