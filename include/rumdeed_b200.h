@@ -203,7 +203,8 @@ int rb2_p2p_export(int n_max, void *handle_out);
 int rb2_p2p_attach(int world, int rank, const void *handles);
 int rb2_p2p_detach(void);
 /* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
- * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "ramo_sections" / "ramo_emitters" (size
+ * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "step_graph" (1 / 0: replay rb2_step as a CUDA graph while
+ * consecutive steps queue identical work), "ramo_sections" / "ramo_emitters" (size
  * of the per-section Ramo table, 0 sections = off), "event_buffer" (initial number of
  * absorb / plane-crossing records the device buffer holds; it grows on demand); emission samplers: "mh_small"
  * (1 / 0: single-barrier kernel for few chains), "mh_small_max" (its chain limit, <= 512), "mh_ctas_per_sm" (1..4,
@@ -336,6 +337,9 @@ int rb2_probe_quartic_roots(int n, const double *coeffs, int *codes_out, double 
 int rb2_fp64_peak(double ms_target, double *tflops_out, float *ms_out);
 /* Launch statistics since init / last reset: kernels launched by this library. */
 int rb2_launch_count(long long *out, int reset);
+/* Named counters: "graph_replays" (rb2_step calls served by replaying the captured CUDA graph), "graph_launches"
+ * (kernels + copies inside that graph), "launches" (same as rb2_launch_count). */
+int rb2_get_stat(const char *name, double *out);
 /* Device time of the last acceleration evaluation (ms), and its launch geometry. */
 int rb2_last_accel_info(float *ms, int *grid_x, int *grid_y, int *block, int *j_split);
 

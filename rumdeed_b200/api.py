@@ -138,7 +138,7 @@ EXPORTS = (
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
     "rb2_do_collisions", "rb2_get_recombination_records", "rb2_get_ionization_records", "rb2_probe_quartic_roots",
-    "rb2_fp64_peak", "rb2_launch_count", "rb2_last_accel_info",
+    "rb2_fp64_peak", "rb2_launch_count", "rb2_get_stat", "rb2_last_accel_info",
 )
 
 _lib = None
@@ -163,6 +163,7 @@ def load_library(path: str | None = None):
     lib.rb2_get_counts.argtypes = [C.POINTER(Counts)]
     lib.rb2_add_particles.argtypes = [C.c_int, _PD, _PD, _PI, C.c_int, _PI, _PI, _PI]
     lib.rb2_capacity_left.argtypes = [_PI]
+    lib.rb2_get_stat.argtypes = [C.c_char_p, _PD]
     lib.rb2_mark_remove.argtypes = [C.c_int, _PI, _PI]
     lib.rb2_remove_marked.argtypes = [C.c_int, C.POINTER(Counts)]
     lib.rb2_get_life_time.argtypes = [C.POINTER(C.c_longlong)]
@@ -611,6 +612,11 @@ class HotPath:
     def launch_count(self, reset=False):
         v = C.c_longlong()
         self._check(self.lib.rb2_launch_count(C.byref(v), int(reset)))
+        return v.value
+
+    def stat(self, name: str) -> float:
+        v = C.c_double()
+        self._check(self.lib.rb2_get_stat(name.encode(), C.byref(v)))
         return v.value
 
     def last_accel_info(self):

@@ -258,6 +258,7 @@ static void release_all(Rb2Ctx &c)
     if (c.h_pts) cudaFreeHost(c.h_pts);
     if (c.h_fld) cudaFreeHost(c.h_fld);
     if (c.h_stage) cudaFreeHost(c.h_stage);
+    if (c.graph_exec) cudaGraphExecDestroy(c.graph_exec);
     cudaEvent_t evs[] = {c.ev_a0, c.ev_a1, c.ev_s0, c.ev_s1, c.ev_c};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -316,6 +317,8 @@ static int init_impl(Rb2Ctx &c, const rb2_config *cfg)
     c.init = true;
     if ((rc = rb2_launch_fill_mask(c, c.cap))) return rc;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
+    if (const char *e = getenv("RB2_NO_GRAPH")) c.use_graph = atoi(e) != 0 ? 0 : 1;       // same as rb2_set_option("step_graph", 0)
+    if (const char *e = getenv("RB2_PAIR_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c.pair_mode = v; }
     if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;
     if (const char *e = getenv("RB2_MH_SMALL_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c.mh_small_max = v; }
     if (const char *e = getenv("RB2_MH_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 4) c.mh_ctas_per_sm = v; }  // same as rb2_set_option("mh_small", ..)
@@ -614,6 +617,53 @@ int rb2_update_velocity(rb2_step_result *out)
     return RB2_OK;
 }
 
+// Everything rb2_step queues on the stream, from the first event record to the last.
+static int queue_step(Rb2Ctx &c)
+{
+    RB2_CUDA(rb2_event_record(c, c.ev_s0));
+    int rc_accel = RB2_OK;
+    c.accel_timed = false;
+    int rc = do_update_position(c, true, &rc_accel);
+    if (rc) return rc;
+    rc = rb2_launch_update_velocity(c);
+    if (rc) return rc;
+    if ((rc = rb2_launch_ramo_sections(c))) return rc;
+    RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    RB2_CUDA(rb2_event_record(c, c.ev_s1));
+    return RB2_OK;
+}
+
+// Identity of the work a step would queue: particle count, every array and scratch pointer a kernel receives, the
+// scalars passed by value and the scheduling options.  (FNV-1a over the bytes.)
+static unsigned long long step_key(const Rb2Ctx &c)
+{
+    struct {
+        int n, cap, pair_mode, sym_min_n, pair_rank, pair_world, sym_tpl, ramo_n_sec, ramo_n_emit, ramo_blocks, ev_cap, redpart_blocks,
+            part_begin, part_end, sm_count, pad;
+        double sym_waves;
+        size_t sym_budget, partial_bytes, bufI_bytes, bufJ_bytes, raw_bytes;
+        const void *p[32];
+        rb2_config cfg;
+    } k;
+    memset(&k, 0, sizeof(k));
+    k.n = c.n; k.cap = c.cap; k.pair_mode = c.pair_mode; k.sym_min_n = c.sym_min_n; k.pair_rank = c.pair_rank; k.pair_world = c.pair_world;
+    k.sym_tpl = c.sym_tpl; k.ramo_n_sec = c.ramo_n_sec; k.ramo_n_emit = c.ramo_n_emit; k.ramo_blocks = c.ramo_blocks; k.ev_cap = c.ev_cap;
+    k.redpart_blocks = c.redpart_blocks; k.part_begin = c.part_begin; k.part_end = c.part_end; k.sm_count = c.sm_count;
+    k.sym_waves = c.sym_waves; k.sym_budget = c.sym_budget_bytes; k.partial_bytes = c.partial_bytes;
+    k.bufI_bytes = c.sym_bufI_bytes; k.bufJ_bytes = c.sym_bufJ_bytes; k.raw_bytes = c.sym_raw_bytes;
+    const void *ptrs[] = {c.a.pq, c.a.prev_pos, c.a.vel, c.a.acc, c.a.acc_prev, c.a.acc_prev2, c.a.mass, c.a.species, c.a.step, c.a.emitter,
+                          c.a.section, c.a.life, c.a.id, c.b.vel, c.mask, c.evcnt, c.evbits, c.prefix, c.blocksum, c.d_counters, c.d_red,
+                          c.d_redpart, c.d_total, c.d_events, c.partial, c.sym_bufI, c.sym_bufJ, c.sym_raw, c.d_ramo_part, c.d_ramo_sec,
+                          c.h_ramo_sec, c.h_red};
+    static_assert(sizeof(ptrs) / sizeof(ptrs[0]) == 32, "pointer table");
+    for (int i = 0; i < 32; ++i) k.p[i] = ptrs[i];
+    k.cfg = c.cfg;
+    unsigned long long h = 1469598103934665603ull;
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(&k);
+    for (size_t i = 0; i < sizeof(k); ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h ? h : 1;
+}
+
 int rb2_step(int step, rb2_step_result *out)
 {
     (void)step;
@@ -627,16 +677,53 @@ int rb2_step(int step, rb2_step_result *out)
             return rb2_fail(RB2_ERR_ARG, "rb2_step with the i-partition [%d, %d) of %d particles: the fused step has no exchange; use "
                                          "rb2_update_position / rb2_accel_only + exchange / rb2_update_velocity", c.part_begin, i1, c.n);
     }
-    RB2_CUDA(cudaEventRecord(c.ev_s0, c.stream));
-    int rc_accel = RB2_OK;
-    c.accel_timed = false;
-    int rc = do_update_position(c, true, &rc_accel);
-    if (rc) return rc;
-    rc = rb2_launch_update_velocity(c);
-    if (rc) return rc;
-    if ((rc = rb2_launch_ramo_sections(c))) return rc;
-    RB2_CUDA(cudaMemcpyAsync(c.h_red, c.d_red, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    RB2_CUDA(cudaEventRecord(c.ev_s1, c.stream));
+    int rc = RB2_OK;
+    // The step is ~12 dependent launches; at a few thousand particles their launch gaps are a third of the step.  When
+    // two consecutive steps would queue exactly the same work (step_key), the second one is captured into a CUDA graph
+    // and replayed from then on.  A run whose particle count changes every step (emission) simply never captures.
+    const bool can_graph = c.use_graph && c.p2p_world <= 1 && c.n > 0;
+    const unsigned long long key = can_graph ? step_key(c) : 0;
+    if (can_graph && c.graph_exec && key == c.graph_key) {
+        c.host_events.clear();
+        c.accel_timed = c.graph_accel_timed;
+        RB2_CUDA(cudaGraphLaunch(c.graph_exec, c.stream));
+        c.launches += c.graph_launches;
+        c.graph_replays += 1;
+    } else if (can_graph && key == c.prev_step_key) {
+        if (c.graph_exec) { cudaGraphExecDestroy(c.graph_exec); c.graph_exec = nullptr; }
+        const long long l0 = c.launches;
+        cudaGraph_t graph = nullptr;
+        RB2_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+        c.capturing = true;
+        rc = queue_step(c);
+        c.capturing = false;
+        const cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+        if (rc || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            c.use_graph = 0;  // something in the step cannot be captured here: plain launches from now on
+            c.launches = l0;
+            if ((rc = queue_step(c))) return rc;
+        } else {
+            const cudaError_t ei = cudaGraphInstantiate(&c.graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) {
+                cudaGetLastError();
+                c.graph_exec = nullptr;
+                c.use_graph = 0;
+                c.launches = l0;
+                if ((rc = queue_step(c))) return rc;
+            } else {
+                c.graph_key = key;
+                c.graph_launches = c.launches - l0;
+                c.graph_accel_timed = c.accel_timed;
+                RB2_CUDA(cudaGraphLaunch(c.graph_exec, c.stream));
+            }
+        }
+    } else {
+        if ((rc = queue_step(c))) return rc;
+    }
+    c.prev_step_key = key;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     if ((rc = rb2_p2p_check(c))) return rc;
     rc = finish_position(c, true);
@@ -843,6 +930,10 @@ int rb2_set_option(const char *name, double value)
         cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec); cudaFreeHost(c.h_ramo_sec);
         c.d_ramo_part = c.d_ramo_sec = c.h_ramo_sec = nullptr;
         c.ramo_n_sec = ns; c.ramo_n_emit = ne;
+    } else if (!strcmp(name, "step_graph")) {
+        c.use_graph = (value != 0.0) ? 1 : 0;
+        if (c.graph_exec) { RB2_CUDA(cudaStreamSynchronize(c.stream)); cudaGraphExecDestroy(c.graph_exec); c.graph_exec = nullptr; }
+        c.graph_key = c.prev_step_key = 0;
     } else if (!strcmp(name, "sym_tpl")) {
         if (value != 0 && value != 1 && value != 2) return rb2_fail(RB2_ERR_ARG, "sym_tpl (targets per lane) must be 0 (auto), 1 or 2");
         c.sym_tpl = (int)value;
@@ -959,6 +1050,17 @@ int rb2_launch_count(long long *out, int reset)
     RB2_REQUIRE_INIT();
     if (out) *out = g_rb2.launches;
     if (reset) g_rb2.launches = 0;
+    return RB2_OK;
+}
+
+int rb2_get_stat(const char *name, double *out)
+{
+    RB2_REQUIRE_INIT();
+    if (!name || !out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    if (!strcmp(name, "graph_replays")) *out = (double)g_rb2.graph_replays;
+    else if (!strcmp(name, "graph_launches")) *out = (double)g_rb2.graph_launches;
+    else if (!strcmp(name, "launches")) *out = (double)g_rb2.launches;
+    else return rb2_fail(RB2_ERR_ARG, "unknown counter '%s'", name);
     return RB2_OK;
 }
 

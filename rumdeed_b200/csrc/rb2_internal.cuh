@@ -140,6 +140,14 @@ struct Rb2Ctx {
     double *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned
 
     cudaEvent_t ev_a0 = nullptr, ev_a1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_c = nullptr;
+    // CUDA graph of the fused step (rb2_step): captured the second time in a row that a step would queue exactly the same
+    // launches (same particle count, arrays, scalars, scratch) and replayed while that stays so (option "step_graph")
+    int   use_graph = 1;
+    bool  capturing = false;
+    unsigned long long graph_key = 0, prev_step_key = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_launches = 0, graph_replays = 0;
+    bool  graph_accel_timed = false;
     bool  accel_timed = false;
     int   last_grid_x = 0, last_grid_y = 0, last_block = 0, last_split = 0;
     long long launches = 0;
@@ -163,6 +171,11 @@ int rb2_fail(int code, const char *fmt, ...);
 #define RB2_LAUNCHED(n_) (g_rb2.launches += (n_))
 
 StepParams rb2_make_step_params(const rb2_config &c);
+// event record that also works while the step is being captured into a graph (a timing event needs an explicit node)
+inline cudaError_t rb2_event_record(Rb2Ctx &c, cudaEvent_t e)
+{
+    return c.capturing ? cudaEventRecordWithFlags(e, c.stream, cudaEventRecordExternal) : cudaEventRecord(e, c.stream);
+}
 int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
 
 // pair / field kernels (rb2_pair.cu)
@@ -245,8 +258,8 @@ __device__ __forceinline__ double rb2_inv_r3_soft(double s)
 // (src/mod_verlet.F90:1302-1303), IEEE square root and divide.
 #define RB2_CLOSE_DXY2 1.0e-22
 #ifndef RB2_CLOSE_INT
-#define RB2_CLOSE_INT 0  // measured at N = 1e6 (tools/build_variants.sh): no flag 2549 ms, FP64 compare 2578 ms (218 registers),
-#endif                   // integer compare of the high word 2586 ms (228 registers)
+#define RB2_CLOSE_INT 1  // measured at N = 1e6 with the slow path out of line (tools/build_variants.sh, two runs): no flag 2552 / 2555 ms,
+#endif                   // integer compare of the high word 2538 / 2541 ms, FP64 compare 2569 / 2572 ms; N = 1e4: 0.315 / 0.315 / 0.319 ms
 __device__ __forceinline__ bool rb2_is_close(double dxy2)
 {
 #ifdef RB2_CLOSE_OFF  // measurement only (tools/build_variants.sh): the fast path alone

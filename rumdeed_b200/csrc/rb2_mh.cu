@@ -329,7 +329,7 @@ __device__ __forceinline__ double surf_unit_sum(const SurfRec *__restrict__ g_re
     auto fetch = [&](int t) {
         const int j = j0 + t * MHB + tid;
         if (j < j1) nxt = g_recs[j];
-        else { nxt.x = 0.0; nxt.y = 0.0; nxt.h0 = 1.0; nxt.g0 = 0.0; nxt.h1 = 1.0; nxt.g1 = 0.0; nxt.h2 = 1.0; nxt.g2 = 0.0; }
+        else { nxt.x = 1.0; nxt.y = 1.0; nxt.h0 = 1.0; nxt.g0 = 0.0; nxt.h1 = 1.0; nxt.g1 = 0.0; nxt.h2 = 1.0; nxt.g2 = 0.0; }
     };
     fetch(0);
     double acc = 0.0;
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
             const int sub = (int)(w % L.S), j = sub * MHB + threadIdx.x;
             SurfRec r;
             if (j < L.n) r = S.recs[j];
-            else { r.x = 0.0; r.y = 0.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
+            else { r.x = 1.0; r.y = 1.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
             res[(size_t)(w - w0) * MHB + threadIdx.x] = r;
         }
         __syncthreads();
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
         const int j = s0 * MHB + q;
         SurfRec r;
         if (j < L.n) r = S.recs[j];
-        else { r.x = 0.0; r.y = 0.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
+        else { r.x = 1.0; r.y = 1.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
         mine[q] = r;
     }
     if (tid < WPB) { s_acc[tid] = 0; s_rej[tid] = 0; s_bad[tid] = 0; }

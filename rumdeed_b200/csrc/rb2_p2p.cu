@@ -167,7 +167,7 @@ int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const
         n, ctx.sym_n_pad, pp, ctx.pair_rank, ctx.p2p_world, ctx.p2p_epoch, pq, mass, SP.pl, acc_out, ctx.p2p_err_dev);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(2);
-    RB2_CUDA(cudaEventRecord(ctx.ev_a1, ctx.stream));
+    RB2_CUDA(rb2_event_record(ctx, ctx.ev_a1));
     return RB2_OK;
 }
 

@@ -109,17 +109,16 @@ __device__ __forceinline__ void tip_ic_force(const TipParams &T, const TipImage 
 // lower-indexed particles (per-element self mask and role sign, j = j0 + jj); below -cnt: plain sources.
 template <int NIC>
 __device__ __noinline__ Acc4 planar_tile_exact(double xi, double yi, double zi, const double4 *tile, int cnt, int j0, int i_self,
-                                               PlanarParams P)
+                                               PlanarParams P)  // i_self < 0: no roles; INT_MAX: every source has the lower index
 {
     Acc4 a = {0.0, 0.0, 0.0, 0.0};
-    bool dummy = false;
     const bool roles = i_self >= 0;
     for (int jj = 0; jj < cnt; ++jj) {
         const double4 pj = tile[jj];
         const int j = j0 + jj;
         const double qe = (roles && j == i_self) ? 0.0 : pj.w;
-        const double qs = (!roles || j > i_self) ? qe : -qe;
-        planar_term<NIC, true>(xi, yi, zi, pj, qe, qs, P, a, dummy);
+        const bool swapped = roles && j < i_self;
+        planar_term_exact<NIC>(xi, yi, zi, pj, qe, swapped ? -qe : qe, P, a, swapped);
     }
     return a;
 }
@@ -155,6 +154,8 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
         const double4 pi = tgt_pq[ii];
         xi = pi.x; yi = pi.y; zi = pi.z;
     }
+
+    if (!active) { xi = 1.0 + (double)tid; yi = 0.0; zi = 1.0; }  // idle lanes: metres away from every source (never "laterally close")
 
     const int j_begin = blockIdx.y * j_chunk;
     const int j_end = min(n_src, j_begin + j_chunk);
@@ -202,7 +203,9 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                         const int j = j0 + jj;
                         const double qe = (j == i) ? 0.0 : pj.w;
                         const double qs = (j > i) ? qe : -qe;
-                        planar_term<NIC>(xi, yi, zi, pj, qe, qs, P, a, close);
+                        bool c1 = false;  // the self pair (offset 0) is not a close pair: it is masked out by qe = 0
+                        planar_term<NIC>(xi, yi, zi, pj, qe, qs, P, a, c1);
+                        close = close || (c1 && j != i);
                     }
                     if (close) a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, j0, i, P);
                     az += a.t;
@@ -212,9 +215,16 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                         const double4 pj = tile[jj];
                         planar_term<NIC>(xi, yi, zi, pj, pj.w, pj.w, P, a, close);
                     }
-                    if (close) a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, 0, -1 - cnt, P);
-                    const double sg = (FIELD || (j0 >= ie)) ? 1.0 : -1.0;
-                    az = fma(sg, a.t, az);
+                    if (close) {
+                        // sources all above (or field points: no roles) / all below this CTA's rows; the slow path
+                        // resolves the roles per element, so its a.t is already signed
+                        const bool above = FIELD || (j0 >= ie);
+                        a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, j0, above ? -1 : 0x7fffffff, P);
+                        az += a.t;
+                    } else {
+                        const double sg = (FIELD || (j0 >= ie)) ? 1.0 : -1.0;
+                        az = fma(sg, a.t, az);
+                    }
                 }
             } else {
                 for (int jj = 0; jj < cnt; ++jj) {
@@ -417,7 +427,7 @@ int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, 
     const Split sp = choose_split(n_tgt, n, ctx.sm_count);
     int rc = ensure_partial(ctx, (size_t)sp.nsplit * 3 * (size_t)n_tgt * sizeof(double));
     if (rc != RB2_OK) return rc;
-    RB2_CUDA(cudaEventRecord(ctx.ev_a0, ctx.stream));
+    RB2_CUDA(rb2_event_record(ctx, ctx.ev_a0));
     rc = launch_pair<false>(ctx, pq, n, pq, nullptr, i_begin, i_end, sp, 0, ctx.partial);
     if (rc != RB2_OK) return rc;
     const StepParams P = rb2_make_step_params(ctx.cfg);
@@ -425,7 +435,7 @@ int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, 
                                                                   ctx.cfg.geometry, P.pl, P.tip, acc_out);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(1);
-    RB2_CUDA(cudaEventRecord(ctx.ev_a1, ctx.stream));
+    RB2_CUDA(rb2_event_record(ctx, ctx.ev_a1));
     ctx.last_grid_x = sp.nblk; ctx.last_grid_y = sp.nsplit; ctx.last_block = BLOCK; ctx.last_split = sp.j_chunk;
     return RB2_OK;
 }

@@ -37,6 +37,9 @@ namespace {
 #ifndef RB2_SYM_MINB
 #define RB2_SYM_MINB 3
 #endif
+#ifndef RB2_EXACT_INLINE
+#define RB2_EXACT_INLINE 0
+#endif
 #ifndef RB2_SYM_MINB2
 #define RB2_SYM_MINB2 2
 #endif
@@ -76,7 +79,8 @@ __device__ __forceinline__ void sym_round(const double *__restrict__ X, const do
 #endif
 #pragma unroll
         for (int s = 0; s < T; ++s) {
-            const PairW w = planar_weights<NIC, EXACT>(xi[s], yi[s], zi[s], vx, vy, vz, P, close);
+            const PairW w = EXACT ? planar_weights_exact<NIC>(xi[s], yi[s], zi[s], vx, vy, vz, P, false)
+                                  : planar_weights<NIC>(xi[s], yi[s], zi[s], vx, vy, vz, P, close);
             // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
             const double ti = vq * w.U, tj = qe[s] * w.U;
             tx[s] = fma(w.dx, ti, tx[s]);
@@ -98,6 +102,36 @@ __device__ __forceinline__ void sym_round(const double *__restrict__ X, const do
 #endif
         bx = rot1(bx, src_lane); by = rot1(by, src_lane); bz = rot1(bz, src_lane);
     }
+}
+
+// a laterally close pair on the diagonal tile: this thread's row of the tile again, reference arithmetic
+template <int NIC>
+__device__ __noinline__ Acc4 sym_diag_exact(const double *X, const double *Y, const double *Z, const double *Q, int tid, double xi,
+                                            double yi, double zi, PlanarParams P)
+{
+    Acc4 a = {0.0, 0.0, 0.0, 0.0};
+    for (int jj = 0; jj < SB; ++jj) {
+        const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
+        const double qe = (jj == tid) ? 0.0 : sj.w;
+        const double qsg = (jj > tid) ? qe : -qe;
+        planar_term_exact<NIC>(xi, yi, zi, sj, qe, qsg, P, a, jj < tid);
+    }
+    return a;
+}
+
+// The slow path of a round (a laterally close pair somewhere in it) out of line, so that the hot loop stays compact:
+// at one CTA per SM (N ~ 1e4) the inlined copy cost 30 % in instruction fetch.  Arguments and results travel by value.
+template <int T>
+struct RoundIO {
+    double xi[T], yi[T], zi[T], qe[T], tx[T], ty[T], tz[T], bx, by, bz;
+};
+template <int NIC, int T>
+__device__ __noinline__ RoundIO<T> sym_round_exact(const double *X, const double *Y, const double *Z, const double *Q, int wb0, int lane,
+                                                   int src_lane, RoundIO<T> io, PlanarParams P)
+{
+    bool dummy = false;
+    sym_round<NIC, T, true>(X, Y, Z, Q, wb0, lane, src_lane, io.xi, io.yi, io.zi, io.qe, P, io.tx, io.ty, io.tz, io.bx, io.by, io.bz, dummy);
+    return io;
 }
 
 // T targets per lane: the CTA's target superblock I holds the T source tiles T*I .. T*I+T-1 (sub-set s of the
@@ -124,12 +158,14 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
     __shared__ double jacc[2][4][3][SB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int last = g.n - 1;
+    // slots beyond the last particle: charge 0 and a position of their own, metres away from everything (at a shared
+    // position -- e.g. the last particle's -- every pair among them would look "laterally close" and take the slow path)
+    auto load = [&](int k) { return k < g.n ? pq[k] : make_double4(1.0 + (double)(k - g.n), 0.0, 1.0, 0.0); };
     double xi[T], yi[T], zi[T], qi[T], ax[T], ay[T], az[T];
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         const int i = (I * T + s) * SB + tid;
-        const double4 p = pq[i < g.n ? i : last];
+        const double4 p = load(i);
         xi[s] = p.x; yi[s] = p.y; zi[s] = p.z;
         qi[s] = (i < g.n) ? p.w : 0.0;  // padding lanes: charge 0, any finite position
         ax[s] = 0.0; ay[s] = 0.0; az[s] = 0.0;
@@ -139,11 +175,11 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
     double4 pj_next;
     {
         const int j = Jbeg * SB + tid;
-        const double4 pj = pq[j < g.n ? j : last];
+        const double4 pj = load(j);
         xs[0][tid] = pj.x; ys[0][tid] = pj.y; zs[0][tid] = pj.z;
         qs[0][tid] = (j < g.n) ? pj.w : 0.0;
         const int jn = j + SB;
-        pj_next = pq[jn < g.n ? jn : last];
+        pj_next = load(jn);
     }
     __syncthreads();
     int cur = 0;
@@ -161,17 +197,11 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
                     const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
                     const double qe = (jj == tid) ? 0.0 : sj.w;
                     const double qsg = (jj > tid) ? qe : -qe;
-                    planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, close);
+                    bool c1 = false;  // the self pair (offset 0) is not a close pair: it is masked out by qe = 0
+                    planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, c1);
+                    close = close || (c1 && jj != tid);
                 }
-                if (close) {  // a laterally close pair: this thread's row of the tile again, reference arithmetic
-                    a = Acc4{0.0, 0.0, 0.0, 0.0};
-                    for (int jj = 0; jj < SB; ++jj) {
-                        const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
-                        const double qe = (jj == tid) ? 0.0 : sj.w;
-                        const double qsg = (jj > tid) ? qe : -qe;
-                        planar_term<NIC, true>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, close);
-                    }
-                }
+                if (close) a = sym_diag_exact<NIC>(X, Y, Z, Q, tid, xi[s], yi[s], zi[s], P);
                 ax[s] += a.x; ay[s] += a.y; az[s] += a.z + a.t;
             }
         }
@@ -188,8 +218,20 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
                 sym_round<NIC, T, false>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
                 // a laterally close pair anywhere in this warp's 32 x 32T block: the round again with the reference's
                 // sqrt / divide (warp-uniform branch: the shuffles inside need every lane)
+#if RB2_EXACT_INLINE
                 if (__any_sync(0xffffffffu, close))
                     sym_round<NIC, T, true>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
+#else
+                if (__any_sync(0xffffffffu, close)) {
+                    RoundIO<T> io;
+#pragma unroll
+                    for (int s = 0; s < T; ++s) { io.xi[s] = xi[s]; io.yi[s] = yi[s]; io.zi[s] = zi[s]; io.qe[s] = qe[s]; }
+                    io = sym_round_exact<NIC, T>(X, Y, Z, Q, wb0, lane, src_lane, io, P);
+#pragma unroll
+                    for (int s = 0; s < T; ++s) { tx[s] = io.tx[s]; ty[s] = io.ty[s]; tz[s] = io.tz[s]; }
+                    bx = io.bx; by = io.by; bz = io.bz;
+                }
+#endif
                 // 32 rotations by one lane: every visitor is back at its home lane
 #pragma unroll
                 for (int s = 0; s < T; ++s)
@@ -203,7 +245,7 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
             xs[cur ^ 1][tid] = pj_next.x; ys[cur ^ 1][tid] = pj_next.y; zs[cur ^ 1][tid] = pj_next.z;
             qs[cur ^ 1][tid] = (jn < g.n) ? pj_next.w : 0.0;
             const int jnn = jn + SB;
-            if (J + 2 < J1) pj_next = pq[jnn < g.n ? jnn : last];
+            if (J + 2 < J1) pj_next = load(jnn);
         }
         __syncthreads();
         if (rel >= 1) {
@@ -373,7 +415,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     ctx.sym_n_pad = g.n_pad;
     cudaStream_t st = ctx.stream;
     const StepParams SP = rb2_make_step_params(c);
-    RB2_CUDA(cudaEventRecord(ctx.ev_a0, st));
+    RB2_CUDA(rb2_event_record(ctx, ctx.ev_a0));
     RB2_CUDA(cudaMemsetAsync(ctx.sym_raw_cur, 0, (size_t)3 * g.n_pad * sizeof(double), st));
     int launches = 0;
     for (int b0 = 0; b0 < g.nsb; b0 += Wb) {
@@ -412,6 +454,6 @@ int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *
     k_sym_finalize<<<(n + 255) / 256, 256, 0, ctx.stream>>>(n, ctx.sym_n_pad, ctx.sym_raw_cur, pq, mass, SP.pl, acc_out);
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(1);
-    RB2_CUDA(cudaEventRecord(ctx.ev_a1, ctx.stream));
+    RB2_CUDA(rb2_event_record(ctx, ctx.ev_a1));
     return RB2_OK;
 }

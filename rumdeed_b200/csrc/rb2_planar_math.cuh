@@ -26,9 +26,9 @@ struct PairW {
     double Zsame;  // same-charge partner z-sum (enters with the role sign)
 };
 
-// NIC: -1 image charge off, 0, 1, >= 2 (runtime N_ic_max loop).  EXACT: the reference's sqrt / divide for the inverse
-// cubes (slow path of pairs flagged `close`); otherwise `close` collects "lateral offset below 1e-11 m" over the calls.
-template <int NIC, bool EXACT = false>
+// NIC: -1 image charge off, 0, 1, >= 2 (runtime N_ic_max loop).  `close` collects "lateral offset below 1e-11 m" over
+// the calls (rb2_is_close).
+template <int NIC>
 __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi, double xj, double yj, double zj,
                                                 const PlanarParams &P, bool &close)
 {
@@ -37,8 +37,8 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
     w.dy = yi - yj;
     w.dz = zi - zj;
     const double dxy2 = fma(w.dy, w.dy, fma(w.dx, w.dx, RB2_S_FLOOR));
-    if (!EXACT) close = close || rb2_is_close(dxy2);
-    w.wc = rb2_inv_r3_sel<EXACT>(fma(w.dz, w.dz, dxy2));
+    close = close || rb2_is_close(dxy2);
+    w.wc = rb2_inv_r3_soft(fma(w.dz, w.dz, dxy2));
     if (NIC < 0) {
         w.U = w.wc;
         w.Zopp = 0.0;
@@ -46,16 +46,16 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
         return w;
     }
     const double S = zi + zj;
-    const double w0 = rb2_inv_r3_sel<EXACT>(fma(S, S, dxy2));
+    const double w0 = rb2_inv_r3_soft(fma(S, S, dxy2));
     double W = -w0;
     w.Zopp = S * w0;
     w.Zsame = 0.0;
     if (NIC == 1) {
         const double a1 = S - P.two_d, a2 = S + P.two_d, b1 = w.dz - P.two_d, b2 = w.dz + P.two_d;
-        const double w1 = rb2_inv_r3_sel<EXACT>(fma(a1, a1, dxy2));
-        const double w2 = rb2_inv_r3_sel<EXACT>(fma(a2, a2, dxy2));
-        const double w3 = rb2_inv_r3_sel<EXACT>(fma(b1, b1, dxy2));
-        const double w4 = rb2_inv_r3_sel<EXACT>(fma(b2, b2, dxy2));
+        const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
+        const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
+        const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
+        const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
         W = (w3 + w4) - ((w0 + w1) + w2);
         w.Zopp = fma(a2, w2, fma(a1, w1, w.Zopp));
         w.Zsame = fma(b2, w4, b1 * w3);
@@ -63,10 +63,10 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
         for (int n = 1; n <= P.nic; ++n) {
             const double h = P.two_d * (double)n;
             const double a1 = S - h, a2 = S + h, b1 = w.dz - h, b2 = w.dz + h;
-            const double w1 = rb2_inv_r3_sel<EXACT>(fma(a1, a1, dxy2));
-            const double w2 = rb2_inv_r3_sel<EXACT>(fma(a2, a2, dxy2));
-            const double w3 = rb2_inv_r3_sel<EXACT>(fma(b1, b1, dxy2));
-            const double w4 = rb2_inv_r3_sel<EXACT>(fma(b2, b2, dxy2));
+            const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
+            const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
+            const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
+            const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
             W += (w3 + w4) - (w1 + w2);
             w.Zopp = fma(a2, w2, fma(a1, w1, w.Zopp));
             w.Zsame = fma(b2, w4, fma(b1, w3, w.Zsame));
@@ -76,13 +76,58 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
     return w;
 }
 
+// The same quantities for a laterally close pair (slow path), with the reference's own operations: every partner
+// height z_ic and offset diff_z = z_a - z_ic formed like src/acc_ic_planar_series.inc:20-63 does -- the shared-S / shared-D
+// shortcuts above round differently by ulp(2d) ~ 4e-22 m, which matters once a partner is within ~1e-10 m -- and the
+// inverse cubes by IEEE sqrt / divide (src/mod_verlet.F90:1302-1303).  `swapped`: the reference's roles for j < i
+// (z_a = z_j, z_b = z_i, src/mod_verlet.F90:1316-1323); the result is returned in the convention of planar_weights
+// (the caller's role sign on Zsame then reproduces the reference's value).
+template <int NIC>
+__device__ __forceinline__ PairW planar_weights_exact(double xi, double yi, double zi, double xj, double yj, double zj,
+                                                      const PlanarParams &P, bool swapped)
+{
+    PairW w;
+    w.dx = xi - xj;
+    w.dy = yi - yj;
+    w.dz = zi - zj;
+    const double dxy2 = fma(w.dy, w.dy, fma(w.dx, w.dx, RB2_S_FLOOR));
+    w.wc = rb2_inv_r3_exact(__dadd_rn(dxy2, __dmul_rn(w.dz, w.dz)));
+    w.U = w.wc;
+    w.Zopp = 0.0;
+    w.Zsame = 0.0;
+    if (NIC < 0) return w;
+    const double z_a = swapped ? zj : zi, z_b = swapped ? zi : zj;
+    double W, zo, zs = 0.0;
+    {
+        const double z_ic = -1.0 * z_b, dz = z_a - z_ic;
+        const double v = rb2_inv_r3_exact(__dadd_rn(dxy2, __dmul_rn(dz, dz)));
+        W = -v;
+        zo = __dmul_rn(dz, v);
+    }
+    const int nmax = (NIC == 0) ? 0 : (NIC == 1 ? 1 : P.nic);
+    for (int n = 1; n <= nmax; ++n) {
+        const double h = P.two_d * (double)n;  // 2.0d0*n*d_loc
+        double z_ic, dz, v;
+        z_ic = h - z_b; dz = z_a - z_ic;
+        v = rb2_inv_r3_exact(__dadd_rn(dxy2, __dmul_rn(dz, dz))); W -= v; zo = __dadd_rn(zo, __dmul_rn(dz, v));
+        z_ic = -h - z_b; dz = z_a - z_ic;
+        v = rb2_inv_r3_exact(__dadd_rn(dxy2, __dmul_rn(dz, dz))); W -= v; zo = __dadd_rn(zo, __dmul_rn(dz, v));
+        z_ic = h + z_b; dz = z_a - z_ic;
+        v = rb2_inv_r3_exact(__dadd_rn(dxy2, __dmul_rn(dz, dz))); W += v; zs = __dadd_rn(zs, __dmul_rn(dz, v));
+        z_ic = -h + z_b; dz = z_a - z_ic;
+        v = rb2_inv_r3_exact(__dadd_rn(dxy2, __dmul_rn(dz, dz))); W += v; zs = __dadd_rn(zs, __dmul_rn(dz, v));
+    }
+    w.U = w.wc + W;
+    w.Zopp = zo;
+    w.Zsame = swapped ? -zs : zs;
+    return w;
+}
+
 // Gather form: accumulate q_j * field(i <- j) into a (a.t collects the same-charge z-sum with
 // the charge qs, which the caller signs: per tile, or per element through qs itself).
-template <int NIC, bool EXACT = false>
-__device__ __forceinline__ void planar_term(double xi, double yi, double zi, const double4 pj, double qj, double qs,
-                                            const PlanarParams &P, Acc4 &a, bool &close)
+template <int NIC>
+__device__ __forceinline__ void planar_apply(const PairW &w, double qj, double qs, Acc4 &a)
 {
-    const PairW w = planar_weights<NIC, EXACT>(xi, yi, zi, pj.x, pj.y, pj.z, P, close);
     const double t = qj * w.U;
     a.x = fma(w.dx, t, a.x);
     a.y = fma(w.dy, t, a.y);
@@ -92,4 +137,17 @@ __device__ __forceinline__ void planar_term(double xi, double yi, double zi, con
     }
     a.z = fma(qj, fma(w.dz, w.wc, -w.Zopp), a.z);
     a.t = fma(qs, w.Zsame, a.t);
+}
+template <int NIC>
+__device__ __forceinline__ void planar_term(double xi, double yi, double zi, const double4 pj, double qj, double qs,
+                                            const PlanarParams &P, Acc4 &a, bool &close)
+{
+    planar_apply<NIC>(planar_weights<NIC>(xi, yi, zi, pj.x, pj.y, pj.z, P, close), qj, qs, a);
+}
+// slow path of a laterally close pair; swapped: the source has the lower index (qs then carries the minus sign)
+template <int NIC>
+__device__ __forceinline__ void planar_term_exact(double xi, double yi, double zi, const double4 pj, double qj, double qs,
+                                                  const PlanarParams &P, Acc4 &a, bool swapped)
+{
+    planar_apply<NIC>(planar_weights_exact<NIC>(xi, yi, zi, pj.x, pj.y, pj.z, P, swapped), qj, qs, a);
 }

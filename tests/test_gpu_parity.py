@@ -664,6 +664,38 @@ def test_ramo_current_per_section_vs_oracle(orc, geom, board, n):
             hp.ramo_current_emit(nsec)
 
 
+@pytest.mark.parametrize("n", [700, 5000, 20000])
+def test_step_graph_replay_is_bit_identical(orc, n):
+    """rb2_step replayed as a CUDA graph (captured once two consecutive steps queue identical work) against plain
+    launches: bit-identical trajectories, records and Ramo currents; a change of the particle count or of a scalar
+    drops the graph and the next pair of identical steps captures a new one."""
+    out = []
+    for graph in (1, 0):
+        cfg, p = planar(orc, cap=n + 64, planes=(300 * NM, 600 * NM))
+        pos, q, m, sp = cloud(n, 31 + n, ions=True, zmin=5.0)
+        vel = np.zeros((n, 3)); vel[:, 2] = np.linspace(-3e6, 3e6, n)
+        with rb.HotPath(cfg) as hp:
+            hp.set_option("step_graph", graph)
+            hp.set_option("ramo_sections", 3)
+            hp.upload(pos, q, m, vel=vel, species=sp, section=(1 + np.arange(n) % 3).astype(np.int32))
+            log = []
+            for step in range(1, 13):
+                r = hp.Update_Position(step)
+                log.append((r.n_events, tuple(r.ramo_current), tuple(hp.ramo_current_emit(3)), tuple(sorted((e["index"], e["kind"], e["plane"]) for e in hp.events()))))
+                if step == 6:   # absorbed particles leave: another particle count, the graph of steps 3-6 is dropped
+                    hp.Remove_Particles(step)
+                if step == 9:   # a scalar passed by value changes
+                    cfg.E_z *= 1.5
+                    hp.update_config(cfg)
+            out.append((log, hp.download(("pos", "vel", "acc", "acc_prev", "acc_prev2", "charge")), hp.stat("graph_replays")))
+    (lg, dg, rg), (l0, d0, r0) = out
+    assert rg >= 3 and r0 == 0
+    assert lg == l0
+    for key in dg:
+        assert np.array_equal(dg[key], d0[key]), key
+    assert sum(x[0] for x in lg) > 0  # plane crossings / absorptions did happen
+
+
 def test_beeman_update_is_bit_exact_without_pair_forces(orc):
     """With the pair forces off (single species far apart is not needed: use q = 0 atoms-free
     trick: one particle per run) the position/velocity arithmetic itself is bit-identical."""

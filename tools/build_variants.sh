@@ -12,6 +12,7 @@ build() { # name, extra flags
   echo "built $name: $(cuobjdump -res-usage $out/_obj/rb2_pair_sym.o 2>/dev/null | grep -A1 'pair_symILi1ELi2' | grep -o 'REG:[0-9]*')"
 }
 build base
-# round 2: cost of the close-pair flag (one compare per pair) -- FP64 compare (base), integer compare of the high word, none
-build closeint -DRB2_CLOSE_INT=1
+# round 2: cost of the close-pair flag (one compare per pair) -- integer compare of the high word (base), FP64 compare, none; slow path inlined
+build closefp -DRB2_CLOSE_INT=0
+build exinline -DRB2_EXACT_INLINE=1
 build closeoff -DRB2_CLOSE_OFF
