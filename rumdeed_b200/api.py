@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librumdeed_b200.so")
+LIB_PATH = os.environ.get("RB2_LIB_PATH") or os.path.join(_HERE, "librumdeed_b200.so")  # RB2_LIB_PATH: kernel-variant builds (tools/build_variants.sh)
 
 GEOM_PLANAR, GEOM_TIP = 1, 2
 SPECIES_ELEC, SPECIES_ION, SPECIES_ATOM = 1, 2, 3

@@ -649,6 +649,7 @@ static unsigned long long step_key(const Rb2Ctx &c)
     k.n = c.n; k.cap = c.cap; k.pair_mode = c.pair_mode; k.sym_min_n = c.sym_min_n; k.pair_rank = c.pair_rank; k.pair_world = c.pair_world;
     k.sym_tpl = c.sym_tpl; k.ramo_n_sec = c.ramo_n_sec; k.ramo_n_emit = c.ramo_n_emit; k.ramo_blocks = c.ramo_blocks; k.ev_cap = c.ev_cap;
     k.redpart_blocks = c.redpart_blocks; k.part_begin = c.part_begin; k.part_end = c.part_end; k.sm_count = c.sm_count;
+    k.pad = c.sym_kmax * 64 + c.sym_gmax;
     k.sym_waves = c.sym_waves; k.sym_budget = c.sym_budget_bytes; k.partial_bytes = c.partial_bytes;
     k.bufI_bytes = c.sym_bufI_bytes; k.bufJ_bytes = c.sym_bufJ_bytes; k.raw_bytes = c.sym_raw_bytes;
     const void *ptrs[] = {c.a.pq, c.a.prev_pos, c.a.vel, c.a.acc, c.a.acc_prev, c.a.acc_prev2, c.a.mass, c.a.species, c.a.step, c.a.emitter,
@@ -947,6 +948,12 @@ int rb2_set_option(const char *name, double value)
         c.mh_small_max = (int)value;
     } else if (!strcmp(name, "mh_small")) {
         c.mh_small = (value != 0.0) ? 1 : 0;
+    } else if (!strcmp(name, "sym_kmax")) {
+        if (value < 1 || value > 4096) return rb2_fail(RB2_ERR_ARG, "sym_kmax must be 1..4096");
+        c.sym_kmax = (int)value;
+    } else if (!strcmp(name, "sym_gmax")) {
+        if (value < 1 || value > 24) return rb2_fail(RB2_ERR_ARG, "sym_gmax must be 1..24");
+        c.sym_gmax = (int)value;
     } else if (!strcmp(name, "sym_waves")) {
         if (value < 1) return rb2_fail(RB2_ERR_ARG, "sym_waves must be >= 1");
         c.sym_waves = value;

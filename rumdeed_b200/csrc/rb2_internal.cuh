@@ -109,8 +109,9 @@ struct Rb2Ctx {
     int    pair_mode = 0;                 // 0 auto, 1 gather, 2 pair-symmetric
     int    sym_min_n = 3500;              // auto: use the symmetric kernel from this N on (tools/sym_crossover.py)
     int    pair_rank = 0, pair_world = 1; // ownership of (target, group) CTAs across processes
-    size_t sym_budget_bytes = (size_t)8192 << 20;  // scratch for the (source, target) partial sums
+    size_t sym_budget_bytes = (size_t)2048 << 20;  // scratch for the (set, source tile) / (group, target) partial sums
     int    sym_tpl = 0;                   // targets per lane of the pair-symmetric kernel: 0 auto, 1, 2
+    int    sym_kmax = 12, sym_gmax = 24;  // caps of the work-unit shape (options "sym_kmax", "sym_gmax"; tools/sym_unit_sweep.py)
     double sym_waves = 16.0;              // CTA groups are sized for about this many waves per band launch
     double *sym_bufI = nullptr, *sym_bufJ = nullptr, *sym_raw = nullptr;
     size_t sym_bufI_bytes = 0, sym_bufJ_bytes = 0, sym_raw_bytes = 0;

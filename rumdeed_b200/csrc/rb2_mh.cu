@@ -26,6 +26,7 @@
 // Random numbers: Philox4x32-10 keyed by (seed, chain), counter = (iteration, purpose, attempt): the
 // reference's RANDOM_NUMBER is compiler specific, so parity is statistical (tests/test_emission.py).
 #include "rb2_internal.cuh"
+#include "rb2_tip_math.cuh"
 
 #include <algorithm>
 
@@ -132,12 +133,15 @@ __device__ double kevin_jgtf_v2(double F, double T, double Phi)
     }
     return (Arld * Nns(nft, sft) * (T * T)) * 1.0e4;
 }
-// log of the chain target at a favourable field F < 0
-__device__ __forceinline__ double target_log(const MhParams &P, double F, double x, double y)
+// log of the chain target at a favourable field F < 0, work function w at the spot
+__device__ __forceinline__ double target_log_w(const MhParams &P, double F, double w)
 {
-    const double w = w_theta_xy(P, x, y);
     if (P.c.kind == 2) return log(fmax(kevin_jgtf_v2(F, P.c.T_temp, w), TINY));
     return 2.0 * log(-1.0 * F) - 2.0 * log(t_y(P, F, w)) - log(w);  // Elec_Supply_log
+}
+__device__ __forceinline__ double target_log(const MhParams &P, double F, double x, double y)
+{
+    return target_log_w(P, F, w_theta_xy(P, x, y));
 }
 
 struct __align__(16) SurfRec {
@@ -645,6 +649,16 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
         small_barrier_arrive(Q.bar);
         // while the other CTAs arrive: the normals of the NEXT jump (Philox + log + sqrt, ~1 us of dependent latency that
         // would otherwise open the next iteration)
+        // ... and what the accept step needs besides the field sum: the work function at the proposal, log(u) of the test
+        double w_q = 0.0, log_u = 0.0;
+        if (live) {
+            w_q = w_theta_xy(P, qx, qy);
+            if (iter >= 1 && ok) {
+                double u, v;
+                rand2(L.seed, chain, iter, 2, 0, u, v);
+                log_u = log(u);
+            }
+        }
         if (live && !searching && jump < P.c.ndim) { ahead_iter = jump + 1; draw_jump_normals(L, ahead_iter, chain, ahead_g0, ahead_g1); }
         small_barrier_wait(Q.bar, phase * (unsigned)Q.G);
         // join: for every tile, warp w adds the partial sums of that tile's CTAs w, w + WPB, ... (ascending); the WPB
@@ -677,20 +691,15 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
             if (live) {
                 if (iter < 0) {
                     if (!ok) {
-                        if (Fz < 0.0) { cx = qx; cy = qy; Fc = Fz; sup = target_log(P, Fz, qx, qy); ok = 1; }
+                        if (Fz < 0.0) { cx = qx; cy = qy; Fc = Fz; sup = target_log_w(P, Fz, w_q); ok = 1; }
                         else bad_ = true;
                     }
                 } else if (ok) {
                     const bool unfav = (P.c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
                     bool accept = false;
                     if (!unfav) {
-                        const double sup_new = target_log(P, Fz, qx, qy);
-                        accept = sup_new >= sup;
-                        if (!accept) {
-                            double u, v;
-                            rand2(L.seed, chain, iter, 2, 0, u, v);
-                            accept = log(u) <= sup_new - sup;
-                        }
+                        const double sup_new = target_log_w(P, Fz, w_q);
+                        accept = (sup_new >= sup) || (log_u <= sup_new - sup);
                         if (accept) { cx = qx; cy = qy; sup = sup_new; Fc = Fz; }
                     }
                     acc_ = accept; rej_ = !accept;
@@ -809,6 +818,7 @@ struct TipMh {
     double *df_out;                        // [M]
 };
 constexpr double TIP_W = 4.7;  // w_theta of the tip, src/mod_emission_tip.f90:45
+constexpr int TSUB = 32;       // particles per sub-tile of the persistent tip kernel (few particles: spread them over many CTAs)
 constexpr int TIPB = 256;
 
 __device__ __forceinline__ void tip_xyz(const TipMh &T, double xi, double phi, double *out)  // xyz_corr, src/mod_hyperboloid_tip.f90:78-89
@@ -817,6 +827,14 @@ __device__ __forceinline__ void tip_xyz(const TipMh &T, double xi, double phi, d
     out[0] = xy * cos(phi);
     out[1] = xy * sin(phi);
     out[2] = T.a_foci * xi * T.eta_1 + T.shift_z;
+}
+__device__ __forceinline__ void tip_surface_normal(const TipMh &T, double x, double y, double *n)  // surface_normal, :25-34
+{
+    const double eta_fac = T.eta_1 / sqrt(1 - T.eta_1 * T.eta_1);
+    const double div_fac = -1.0 / sqrt(x * x + y * y + (T.a_foci * T.a_foci) * (1 - T.eta_1 * T.eta_1));
+    const double nx = eta_fac * x * div_fac, ny = eta_fac * y * div_fac, nz = 1.0;
+    const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
+    n[0] = nx / nrm; n[1] = ny / nrm; n[2] = nz / nrm;
 }
 __device__ __forceinline__ double tip_field_normal(const TipMh &T, const double *pos, const double *f)  // :156-163, :25-34
 {
@@ -939,6 +957,281 @@ __global__ void __launch_bounds__(TIPB) k_tip_finish(MhParams P, TipMh T)
     }
 }
 
+// ---- the tip chains as ONE persistent kernel (at most 512 chains, a few thousand particles) -------------------------
+// The scheme of k_mh_small applied to the tip: CTA b works for tile t_b = b / Gs of 32 chains on its own share of the
+// particles, resident in shared memory; every CTA keeps the state of all chains in registers (warp w holds tile w) and
+// does every accept step redundantly behind the single barrier of a jump.  Three field components per chain instead of
+// one; the pair arithmetic is tip_point_field (the same as k_tip_field_point / k_pair<tip, field>), the vacuum field
+// and the normal component are added by the warp that owns the tile.  Proposals, targets and generator keys are those
+// of k_tip_propose / k_tip_accept, so for one seed the two paths run the same chains up to rounding in the field sums.
+struct TipSmall {
+    int T, Gs, G, S, R;   // tiles, CTAs per tile, CTAs, 128-particle sub-tiles in total, most sub-tiles per CTA
+    int n, ndim, max_init, do_ic;
+    double mh_std0, a_rate0;
+    double *partial;      // [2][G][3][32]
+    unsigned *bar;
+    double *eta_f_out, *df_out, *pos_out, *scal_out;
+};
+
+__device__ __forceinline__ void tip_normals(unsigned long long seed, int iter, int k, double &g0, double &g1)
+{
+    g0 = 0.0; g1 = 0.0;
+    for (int attempt = 0; attempt < 64; ++attempt) {  // box_muller = Marsaglia polar, src/mod_global.F90:578-595
+        double u, v;
+        rand2(seed, k, iter, 1, attempt, u, v);
+        const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
+        if (w < 1.0 && w > 0.0) {
+            const double f = sqrt((-2.0 * log(w)) / w);
+            g0 = a * f; g1 = b * f;
+            break;
+        }
+    }
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_mh_tip_small(MhParams P, TipMh T, TipParams TP, TipSmall Q, const double4 *__restrict__ pq)
+{
+    constexpr int NT = WPB * 32, RPW = TSUB / WPB;
+    extern __shared__ __align__(16) unsigned char tip_smem[];
+    double4 *mine = reinterpret_cast<double4 *>(tip_smem);                                                // [R][TSUB]
+    double *strands = reinterpret_cast<double *>(tip_smem + (size_t)Q.R * TSUB * sizeof(double4));      // [T][WPB][3][32]
+    __shared__ double red[WPB][3][32];
+    __shared__ double sp[3][32];
+    __shared__ int s_acc[WPB], s_rej[WPB], s_bad[WPB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t_b = blockIdx.x / Q.Gs, g_b = blockIdx.x - t_b * Q.Gs;
+    const int s0 = (int)((long long)Q.S * g_b / Q.Gs), s1 = (int)((long long)Q.S * (g_b + 1) / Q.Gs);
+    for (int q = tid; q < (s1 - s0) * TSUB; q += NT) {
+        const int j = s0 * TSUB + q;
+        mine[q] = (j < Q.n) ? pq[j] : make_double4(1.0 + (double)q, 1.0, 1.0, 0.0);  // padding: charge 0, metres away
+    }
+    if (tid < WPB) { s_acc[tid] = 0; s_rej[tid] = 0; s_bad[tid] = 0; }
+    __syncthreads();
+    const double two_pi = 2.0 * RB2_PI;
+    const int chain = warp * 32 + lane;
+    const bool live = (warp < Q.T) && (chain < T.M);
+    double xi = 1.0, phi = 0.0, eta_f = 1.0, sup = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    double mh_std = Q.mh_std0, a_rate = Q.a_rate0;
+    int ok = 0;
+    if (live) { double c3[3]; tip_xyz(T, 1.0, 0.0, c3); cx = c3[0]; cy = c3[1]; cz = c3[2]; }
+    unsigned phase = 0;
+    int bad = T.M, round = 0, jump = 1;
+    bool searching = true;
+    double ahead_g0 = 0.0, ahead_g1 = 0.0;
+    int ahead_iter = 0;
+    for (;;) {
+        if (searching && !(round < Q.max_init && bad > 0)) searching = false;
+        if (!searching && jump > Q.ndim) break;
+        const int iter = searching ? -(round + 1) : jump;
+        // proposal of my chain (k_tip_propose)
+        double nxi = xi, nphi = phi, qx = cx, qy = cy, qz = cz;
+        int valid = 0;
+        if (live) {
+            if (iter < 0) {
+                if (!ok) {
+                    double u, v;
+                    rand2(T.seed, chain, iter, 0, 0, u, v);
+                    nxi = 1.0 + (T.max_xi - 1.0) * u;
+                    nphi = two_pi * v;
+                    valid = 1;
+                }
+            } else if (ok) {
+                const double frac = (iter > T.ndim_first) ? mh_std : 0.10;
+                double g0, g1;
+                if (ahead_iter == iter) { g0 = ahead_g0; g1 = ahead_g1; }
+                else tip_normals(T.seed, iter, chain, g0, g1);
+                nxi = nxi + g0 * ((T.max_xi - 1.0) * frac);
+                nphi = fmod(nphi + g1 * (two_pi * frac), two_pi);
+                if (nphi < 0.0) nphi += two_pi;                 // Fortran modulo()
+                if (nxi > T.max_xi) nxi = 2.0 * T.max_xi - nxi;  // reflection, :1300-1310
+                if (nxi < 1.0) nxi = 2.0 - nxi;
+                valid = !(nxi < 1.0 || nxi > T.max_xi);
+            }
+            if (valid) { double c3[3]; tip_xyz(T, nxi, nphi, c3); qx = c3[0]; qy = c3[1]; qz = c3[2]; }
+        }
+        if (warp == t_b) { sp[0][lane] = qx; sp[1][lane] = qy; sp[2][lane] = qz; }
+        __syncthreads();
+        const double px = sp[0][lane], py = sp[1][lane], pz = sp[2][lane];
+        TipImage im_i{};
+        if (Q.do_ic) im_i = tip_image_point(TP, px, py, pz);
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int t = 0; t < s1 - s0; ++t) {
+            const double4 *rr = &mine[t * TSUB + warp * RPW];
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const double4 pj = rr[k];
+                double fx, fy, fz;
+                tip_point_field(TP, im_i, Q.do_ic != 0, px, py, pz, pj, fx, fy, fz);
+                ax = fma(pj.w, fx, ax); ay = fma(pj.w, fy, ay); az = fma(pj.w, fz, az);
+            }
+        }
+        red[warp][0][lane] = ax; red[warp][1][lane] = ay; red[warp][2][lane] = az;
+        __syncthreads();
+        double *part = Q.partial + (size_t)(phase & 1u) * Q.G * 96;
+        if (warp < 3) {
+            double sum = red[0][warp][lane];
+#pragma unroll
+            for (int w = 1; w < WPB; ++w) sum += red[w][warp][lane];
+            part[((size_t)blockIdx.x * 3 + warp) * 32 + lane] = sum;
+        }
+        ++phase;
+        small_barrier_arrive(Q.bar);
+        // while the other CTAs arrive: everything of the accept step that does not need the field sums -- the vacuum
+        // field and the surface normal at the proposal, log(u) of the accept test -- and the normals of the NEXT jump
+        double fE_x = 0.0, fE_y = 0.0, fE_z = 0.0, nrm[3] = {0.0, 0.0, 1.0}, log_u = 0.0;
+        if (live && valid) {
+            rb2_tip_field_E(TP, qx, qy, qz, fE_x, fE_y, fE_z);
+            tip_surface_normal(T, qx, qy, nrm);
+            if (iter >= 1) {
+                double u, v;
+                rand2(T.seed, chain, iter, 2, 0, u, v);
+                log_u = log(u);
+            }
+        }
+        if (live && !searching && jump < Q.ndim) { ahead_iter = jump + 1; tip_normals(T.seed, ahead_iter, chain, ahead_g0, ahead_g1); }
+        small_barrier_wait(Q.bar, phase * (unsigned)Q.G);
+        // join: warp w adds the partial sums of CTAs w, w + WPB, ... of every tile (ascending), three components
+        // (the loads of four tiles are issued together: tile after tile, each join paid its own L2 round trip)
+        for (int t0 = 0; t0 < Q.T; t0 += 4) {
+            double st[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { st[u][0] = 0.0; st[u][1] = 0.0; st[u][2] = 0.0; }
+            for (int k = warp; k < Q.Gs; k += WPB) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (t0 + u < Q.T) {
+                        const double *src = part + ((size_t)((t0 + u) * Q.Gs + k) * 3) * 32 + lane;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) st[u][c] += __ldcg(src + c * 32);
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t0 + u < Q.T) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) strands[(((size_t)(t0 + u) * WPB + warp) * 3 + c) * 32 + lane] = st[u][c];
+                }
+        }
+        __syncthreads();
+        bool acc_ = false, rej_ = false, bad_ = false;
+        if (warp < Q.T) {
+            double f3[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double *sw = strands + (((size_t)warp * WPB) * 3 + c) * 32 + lane;
+                double sum = sw[0];
+#pragma unroll
+                for (int w = 1; w < WPB; ++w) sum += sw[(size_t)w * 96];
+                f3[c] = sum;
+            }
+            if (live) {
+                // E = E_vac(point) + 1/(4 pi eps0) * sum (k_tip_field_point), then the normal component (Field_normal)
+                const double ef = nrm[0] * (fE_x + rb2k::div_fac_c * f3[0]) + nrm[1] * (fE_y + rb2k::div_fac_c * f3[1]) +
+                                  nrm[2] * (fE_z + rb2k::div_fac_c * f3[2]);
+                if (iter < 0) {
+                    if (!ok) {
+                        if (ef < 0.0) { xi = nxi; phi = nphi; eta_f = ef; ok = 1; cx = qx; cy = qy; cz = qz; sup = tip_target_log(P, T, ef, nxi); }
+                        else bad_ = true;
+                    }
+                } else if (ok) {
+                    bool accept = false;
+                    if (valid && ef < 0.0) {
+                        const double sup_new = tip_target_log(P, T, ef, nxi);
+                        accept = (sup_new >= sup) || (log_u <= sup_new - sup);
+                        if (accept) { xi = nxi; phi = nphi; eta_f = ef; sup = sup_new; cx = qx; cy = qy; cz = qz; }
+                    }
+                    acc_ = accept; rej_ = !accept;
+                }
+            }
+            const int na = __popc(__ballot_sync(0xffffffffu, acc_)), nr = __popc(__ballot_sync(0xffffffffu, rej_));
+            const int nb = __popc(__ballot_sync(0xffffffffu, bad_));
+            if (lane == 0) { s_acc[warp] = na; s_rej[warp] = nr; s_bad[warp] = nb; }
+        }
+        __syncthreads();
+        {
+            int a = 0, r = 0, nb = 0;
+#pragma unroll
+            for (int w = 0; w < WPB; ++w) { a += s_acc[w]; r += s_rej[w]; nb += s_bad[w]; }
+            if (iter > T.ndim_first && a + r > 0) {  // :1370-1380
+                a_rate = (double)a / (double)(a + r);
+                mh_std = fmin(fmax(mh_std * exp(0.025 * (a_rate - 0.35)), 0.0005), 0.125);
+            }
+            if (searching) { bad = nb; ++round; } else ++jump;
+        }
+    }
+    if (blockIdx.x == 0) {
+        if (live) {
+            const int k = chain;
+            if (ok) {
+                Q.pos_out[3 * k] = cx; Q.pos_out[3 * k + 1] = cy; Q.pos_out[3 * k + 2] = cz;
+                Q.eta_f_out[k] = eta_f;
+                Q.df_out[k] = exp(T.esc_fac * v_y(P, eta_f, TIP_W) / fabs(eta_f));  // Escape_Prob_Tip, :1734-1760
+            } else {  // no favourable spot: defined outputs, no emission
+                double c3[3];
+                tip_xyz(T, 1.0, 0.0, c3);
+                Q.pos_out[3 * k] = c3[0]; Q.pos_out[3 * k + 1] = c3[1]; Q.pos_out[3 * k + 2] = c3[2];
+                Q.eta_f_out[k] = 1.0;
+                Q.df_out[k] = 0.0;
+            }
+        }
+        if (tid == 0) { Q.scal_out[0] = mh_std; Q.scal_out[1] = a_rate; }
+    }
+}
+
+// Returns RB2_ERR_ARG - 1000 ("does not apply") when the problem is too large for the persistent kernel.
+static int launch_mh_tip_small(Rb2Ctx &ctx, const MhParams &P, TipMh T, int M, int ndim, double *eta_f_out, double *df_out,
+                               double *pos_out, double *a_rate_io, double *mh_std_io)
+{
+    const rb2_config &gc = ctx.cfg;
+    const int n = ctx.n;
+    TipSmall Q{};
+    Q.T = (M + 31) / 32;
+    if (Q.T > 16) return RB2_ERR_ARG - 1000;
+    const int WPB = Q.T <= 4 ? 4 : 16;
+    const int max_ctas = (WPB == 4 ? 2 : 1) * ctx.sm_count;
+    Q.S = std::max(1, (n + TSUB - 1) / TSUB);
+    Q.Gs = std::max(1, std::min(Q.S, max_ctas / Q.T));
+    Q.G = Q.T * Q.Gs;
+    Q.R = std::max(1, (Q.S + Q.Gs - 1) / Q.Gs);
+    if (Q.R > 32) return RB2_ERR_ARG - 1000;
+    Q.n = n; Q.ndim = ndim; Q.max_init = 10000; Q.do_ic = gc.image_charge ? 1 : 0;
+    Q.mh_std0 = fmin(fmax(*mh_std_io, 0.0005), 0.125);  // the clamp of :1250-1254 at entry
+    Q.a_rate0 = *a_rate_io;
+    const size_t off_part = (size_t)5 * M + 2;
+    int rc = rb2_ensure_stage(ctx, off_part + (size_t)2 * Q.G * 96 + 2, 4);
+    if (rc) return rc;
+    double *d = ctx.d_stage_d;
+    Q.eta_f_out = d; Q.df_out = d + M; Q.pos_out = d + 2 * (size_t)M; Q.scal_out = d + 5 * (size_t)M;
+    Q.partial = d + off_part;
+    Q.bar = reinterpret_cast<unsigned *>(ctx.d_stage_i);
+    cudaStream_t st = ctx.stream;
+    RB2_CUDA(cudaMemsetAsync(ctx.d_stage_i, 0, 4 * sizeof(int), st));
+    void *kern = WPB == 4 ? (void *)k_mh_tip_small<4> : (void *)k_mh_tip_small<16>;
+    const size_t smem = (size_t)Q.R * TSUB * sizeof(double4) + (size_t)Q.T * WPB * 96 * sizeof(double);
+    if (smem > 48 * 1024) RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        int occ = 0;
+        RB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem));
+        if ((long long)occ * ctx.sm_count < Q.G) return RB2_ERR_ARG - 1000;
+    }
+    const StepParams SP = rb2_make_step_params(gc);
+    TipParams TP = SP.tip;
+    MhParams Pm = P;
+    const double4 *pq = ctx.a.pq;
+    void *args[] = {&Pm, &T, &TP, &Q, &pq};
+    RB2_CUDA(cudaLaunchCooperativeKernel(kern, dim3(Q.G), dim3(WPB * 32), args, smem, st));
+    RB2_LAUNCHED(1);
+    double scal1[2];
+    RB2_CUDA(cudaMemcpyAsync(eta_f_out, Q.eta_f_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(df_out, Q.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(pos_out, Q.pos_out, (size_t)3 * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(scal1, Q.scal_out, sizeof(scal1), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    *mh_std_io = scal1[0];
+    *a_rate_io = scal1[1];
+    return RB2_OK;
+}
+
 int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
                       double *a_rate_io, double *mh_std_io)
 {
@@ -957,6 +1250,10 @@ int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, dou
     T.max_xi = gc.max_xi; T.eta_1 = gc.eta_1; T.a_foci = gc.a_foci; T.shift_z = gc.shift_z;
     T.sup_fac = (gc.time_step / rb2k::q_0) * a_FN / TIP_W;
     { const double sw = sqrt(TIP_W); T.esc_fac = P.b_FN * (sw * sw * sw); }
+    if (ctx.mh_small && M <= ctx.mh_small_max) {  // few chains, few particles: everything in one persistent kernel
+        const int rc_small = launch_mh_tip_small(ctx, P, T, M, ndim, eta_f_out, df_out, pos_out, a_rate_io, mh_std_io);
+        if (rc_small != RB2_ERR_ARG - 1000) return rc_small;
+    }
     // scratch: 17 M doubles + 2 scalars, 2 M + 1 ints
     int rc = rb2_ensure_stage(ctx, (size_t)18 * M + 4, (size_t)2 * M + 4);
     if (rc) return rc;

@@ -20,6 +20,7 @@
 //     the tiles that overlap the CTA's own i-range.
 #include "rb2_internal.cuh"
 #include "rb2_planar_math.cuh"
+#include "rb2_tip_math.cuh"
 
 namespace {
 
@@ -70,38 +71,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-}
-
-// ---- hyperboloid tip math (IEEE sqrt / divide: N is small for this geometry) -----------------
-struct TipImage {
-    double dis_a, x_im, y_im, z_im;
-};
-// src/acc_tip_image_point.inc:14-18
-__device__ __forceinline__ TipImage tip_image_point(const TipParams &T, double x_a, double y_a, double z_a)
-{
-    TipImage im;
-    const double zr = z_a - T.z_0;
-    const double zz = zr * zr;
-    im.dis_a = sqrt(x_a * x_a + y_a * y_a + zz);
-    im.z_im = T.z_0 + (T.r_tip * T.r_tip) / (sqrt(1.0 + (x_a * x_a) / zz + (y_a * y_a) / zz) * im.dis_a);
-    im.x_im = (im.z_im - T.z_0) * x_a / zr;
-    im.y_im = (im.z_im - T.z_0) * y_a / zr;
-    return im;
-}
-// src/acc_tip_ic_force.inc:17-22 -- carries q_0/(4 pi eps0) itself, like Sphere_IC_field
-__device__ __forceinline__ void tip_ic_force(const TipParams &T, const TipImage &im, double x_a, double y_a, double z_a,
-                                             double x_b, double y_b, double z_b, double &ic_x, double &ic_y, double &ic_z)
-{
-    const double pre = 1.0 * rb2k::q_0 / (4.0 * RB2_PI * rb2k::epsilon_0);
-    const double sa = (x_b - x_a) * (x_b - x_a) + (y_b - y_a) * (y_b - y_a) + (z_b - z_a) * (z_b - z_a);
-    const double sb = (x_b - im.x_im) * (x_b - im.x_im) + (y_b - im.y_im) * (y_b - im.y_im) + (z_b - im.z_im) * (z_b - im.z_im);
-    const double tmp_dis_a = sa * sqrt(sa);  // (..)**(3/2)
-    const double tmp_dis_b = sb * sqrt(sb);
-    // two IEEE divides instead of the six of the source line by line (same value to rounding: 1e-16, the parity bar is 1e-11)
-    const double wa = 1.0 / tmp_dis_a, wb = T.r_tip / (im.dis_a * tmp_dis_b);
-    ic_x = pre * ((x_a - x_b) * wa - (im.x_im - x_b) * wb);
-    ic_y = pre * ((y_a - y_b) * wa - (im.y_im - y_b) * wb);
-    ic_z = pre * ((z_a - z_b) * wa - (im.z_im - z_b) * wb);
 }
 
 // Slow path of a (target, source tile) whose fast sweep flagged a laterally close pair (rb2_is_close): the whole

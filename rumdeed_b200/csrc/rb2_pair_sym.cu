@@ -23,6 +23,8 @@
 // Per unordered pair at N_ic_max = 1: 81 FP64-pipe instructions + 6 MUFU + 14 SHFL, i.e. about
 // 40 FP64 instructions per ordered pair interaction against 74 in the gather kernel.  Image roles
 // (F8-ii) need no test here: J > I implies i < j for every pair of the tile.
+#include <algorithm>
+
 #include "rb2_internal.cuh"
 #include "rb2_planar_math.cuh"
 
@@ -51,7 +53,8 @@ struct SymGeom {
     int nIb;                   // target superblocks (T * 128 particles each)
     int band_start, band_len;  // source tiles [band_start, band_start + band_len)
     int G, ngroups;            // source tiles per CTA group, groups in this band
-    int rank, world;           // CTA (I, grp) is owned by rank (I + grp) % world
+    int K, nIsets;             // target superblocks a CTA takes one after the other (a "set"), sets in all
+    int rank, world;           // CTA (set, grp) is owned by rank (set + grp) % world
 };
 
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
@@ -143,132 +146,156 @@ template <int NIC, int T>
 __global__ void __launch_bounds__(SB, T == 1 ? RB2_SYM_MINB : RB2_SYM_MINB2)
 k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
 {
-    const int I = blockIdx.x;
+    const int iset = blockIdx.x;
     const int grp = blockIdx.y;
-    if (((I + grp) % g.world) != g.rank) return;
+    if (((iset + grp) % g.world) != g.rank) return;
+    const int I0 = iset * g.K;
     const int J0 = g.band_start + grp * g.G;
     const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
-    const int Jbeg = max(J0, T * I);
-    if (Jbeg >= J1) return;
+    if (max(J0, T * I0) >= J1) return;
 
     // source tile, double buffered (one CTA barrier per tile), and the visitors' reaction sums: one private copy per
     // warp (warp w meets each 32-particle block of the tile exactly once, so it just stores), again double buffered
     // because the sums of tile J are read after the barrier while the sweep of tile J+1 has started
     __shared__ double xs[2][SB], ys[2][SB], zs[2][SB], qs[2][SB];
     __shared__ double jacc[2][4][3][SB];
+    // reaction sums of the group's source tiles, accumulated over the K target superblocks of this CTA (ascending I:
+    // a fixed order) and stored ONCE at the end: [G][3][128]; element (.., tid) is only ever touched by thread tid
+    extern __shared__ double accJ[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool direct = (g.K == 1);  // one superblock per CTA: the tile sums go straight to bufJ
+    if (!direct)
+        for (int k = tid; k < (J1 - J0) * 3 * SB; k += SB) accJ[k] = 0.0;
     // slots beyond the last particle: charge 0 and a position of their own, metres away from everything (at a shared
     // position -- e.g. the last particle's -- every pair among them would look "laterally close" and take the slow path)
     auto load = [&](int k) { return k < g.n ? pq[k] : make_double4(1.0 + (double)(k - g.n), 0.0, 1.0, 0.0); };
-    double xi[T], yi[T], zi[T], qi[T], ax[T], ay[T], az[T];
-#pragma unroll
-    for (int s = 0; s < T; ++s) {
-        const int i = (I * T + s) * SB + tid;
-        const double4 p = load(i);
-        xi[s] = p.x; yi[s] = p.y; zi[s] = p.z;
-        qi[s] = (i < g.n) ? p.w : 0.0;  // padding lanes: charge 0, any finite position
-        ax[s] = 0.0; ay[s] = 0.0; az[s] = 0.0;
-    }
     const int src_lane = (lane + 1) & 31;
 
-    double4 pj_next;
-    {
-        const int j = Jbeg * SB + tid;
-        const double4 pj = load(j);
-        xs[0][tid] = pj.x; ys[0][tid] = pj.y; zs[0][tid] = pj.z;
-        qs[0][tid] = (j < g.n) ? pj.w : 0.0;
-        const int jn = j + SB;
-        pj_next = load(jn);
-    }
-    __syncthreads();
-    int cur = 0;
-    for (int J = Jbeg; J < J1; ++J, cur ^= 1) {
-        const double *__restrict__ X = xs[cur], *__restrict__ Y = ys[cur], *__restrict__ Z = zs[cur], *__restrict__ Q = qs[cur];
-        const int rel = J - T * I;  // >= 0; sub-set s is symmetric iff s < rel, diagonal iff s == rel
-        if (rel < T) {
-            // gather form of tile J against itself (ordered pairs, per-element self mask and role sign)
+    for (int pass = 0; pass < g.K; ++pass) {
+        const int I = I0 + pass;
+        const int Jbeg = max(J0, T * I);
+        if (I >= g.nIb || Jbeg >= J1) break;  // the triangle: later superblocks start even further right
+        double xi[T], yi[T], zi[T], qi[T], ax[T], ay[T], az[T];
 #pragma unroll
-            for (int s = 0; s < T; ++s) {
-                if (s != rel) continue;
-                Acc4 a = {0.0, 0.0, 0.0, 0.0};
-                bool close = false;
-                for (int jj = 0; jj < SB; ++jj) {
-                    const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
-                    const double qe = (jj == tid) ? 0.0 : sj.w;
-                    const double qsg = (jj > tid) ? qe : -qe;
-                    bool c1 = false;  // the self pair (offset 0) is not a close pair: it is masked out by qe = 0
-                    planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, c1);
-                    close = close || (c1 && jj != tid);
-                }
-                if (close) a = sym_diag_exact<NIC>(X, Y, Z, Q, tid, xi[s], yi[s], zi[s], P);
-                ax[s] += a.x; ay[s] += a.y; az[s] += a.z + a.t;
-            }
+        for (int s = 0; s < T; ++s) {
+            const int i = (I * T + s) * SB + tid;
+            const double4 p = load(i);
+            xi[s] = p.x; yi[s] = p.y; zi[s] = p.z;
+            qi[s] = (i < g.n) ? p.w : 0.0;  // padding lanes: charge 0
+            ax[s] = 0.0; ay[s] = 0.0; az[s] = 0.0;
         }
-        if (rel >= 1) {
-            double qe[T];  // a sub-set that is not symmetric against this tile neither pushes nor collects
-#pragma unroll
-            for (int s = 0; s < T; ++s) qe[s] = (s < rel) ? qi[s] : 0.0;
-            for (int r = 0; r < 4; ++r) {
-                const int wb0 = ((warp + r) & 3) * 32;
-                const int home = wb0 + lane;
-                double bx, by, bz;          // reaction on the visitor, travels with it
-                double tx[T], ty[T], tz[T]; // force on my particles from this round
-                bool close = false;
-                sym_round<NIC, T, false>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
-                // a laterally close pair anywhere in this warp's 32 x 32T block: the round again with the reference's
-                // sqrt / divide (warp-uniform branch: the shuffles inside need every lane)
-#if RB2_EXACT_INLINE
-                if (__any_sync(0xffffffffu, close))
-                    sym_round<NIC, T, true>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
-#else
-                if (__any_sync(0xffffffffu, close)) {
-                    RoundIO<T> io;
-#pragma unroll
-                    for (int s = 0; s < T; ++s) { io.xi[s] = xi[s]; io.yi[s] = yi[s]; io.zi[s] = zi[s]; io.qe[s] = qe[s]; }
-                    io = sym_round_exact<NIC, T>(X, Y, Z, Q, wb0, lane, src_lane, io, P);
-#pragma unroll
-                    for (int s = 0; s < T; ++s) { tx[s] = io.tx[s]; ty[s] = io.ty[s]; tz[s] = io.tz[s]; }
-                    bx = io.bx; by = io.by; bz = io.bz;
-                }
-#endif
-                // 32 rotations by one lane: every visitor is back at its home lane
-#pragma unroll
-                for (int s = 0; s < T; ++s)
-                    if (s < rel) { ax[s] += tx[s]; ay[s] += ty[s]; az[s] += tz[s]; }
-                jacc[cur][warp][0][home] = bx; jacc[cur][warp][1][home] = by; jacc[cur][warp][2][home] = bz;
-            }
-        }
-        // stage the next tile into the other buffer (its last readers passed the previous barrier)
-        if (J + 1 < J1) {
-            const int jn = (J + 1) * SB + tid;
-            xs[cur ^ 1][tid] = pj_next.x; ys[cur ^ 1][tid] = pj_next.y; zs[cur ^ 1][tid] = pj_next.z;
-            qs[cur ^ 1][tid] = (jn < g.n) ? pj_next.w : 0.0;
-            const int jnn = jn + SB;
-            if (J + 2 < J1) pj_next = load(jnn);
+        double4 pj_next;
+        __syncthreads();  // the previous pass is done with the staging buffers
+        {
+            const int j = Jbeg * SB + tid;
+            const double4 pj = load(j);
+            xs[0][tid] = pj.x; ys[0][tid] = pj.y; zs[0][tid] = pj.z;
+            qs[0][tid] = (j < g.n) ? pj.w : 0.0;
+            const int jn = j + SB;
+            pj_next = load(jn);
         }
         __syncthreads();
-        if (rel >= 1) {
-            // block b of the tile was met by warp (b - r) & 3 in round r: add in round order
-            const int b = warp;
-            const size_t base = (((size_t)(J - g.band_start) * g.nIb + I) * 3) * SB + tid;
+        int cur = 0;
+        for (int J = Jbeg; J < J1; ++J, cur ^= 1) {
+            const double *__restrict__ X = xs[cur], *__restrict__ Y = ys[cur], *__restrict__ Z = zs[cur], *__restrict__ Q = qs[cur];
+            const int rel = J - T * I;  // >= 0; sub-set s is symmetric iff s < rel, diagonal iff s == rel
+            if (rel < T) {
+                // gather form of tile J against itself (ordered pairs, per-element self mask and role sign)
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                bufJ[base + c * SB] = ((jacc[cur][b][c][tid] + jacc[cur][(b + 3) & 3][c][tid]) + jacc[cur][(b + 2) & 3][c][tid]) +
-                                      jacc[cur][(b + 1) & 3][c][tid];
+                for (int s = 0; s < T; ++s) {
+                    if (s != rel) continue;
+                    Acc4 a = {0.0, 0.0, 0.0, 0.0};
+                    bool close = false;
+                    for (int jj = 0; jj < SB; ++jj) {
+                        const double4 sj = make_double4(X[jj], Y[jj], Z[jj], Q[jj]);
+                        const double qe = (jj == tid) ? 0.0 : sj.w;
+                        const double qsg = (jj > tid) ? qe : -qe;
+                        bool c1 = false;  // the self pair (offset 0) is not a close pair: it is masked out by qe = 0
+                        planar_term<NIC>(xi[s], yi[s], zi[s], sj, qe, qsg, P, a, c1);
+                        close = close || (c1 && jj != tid);
+                    }
+                    if (close) a = sym_diag_exact<NIC>(X, Y, Z, Q, tid, xi[s], yi[s], zi[s], P);
+                    ax[s] += a.x; ay[s] += a.y; az[s] += a.z + a.t;
+                }
+            }
+            if (rel >= 1) {
+                double qe[T];  // a sub-set that is not symmetric against this tile neither pushes nor collects
+#pragma unroll
+                for (int s = 0; s < T; ++s) qe[s] = (s < rel) ? qi[s] : 0.0;
+                for (int r = 0; r < 4; ++r) {
+                    const int wb0 = ((warp + r) & 3) * 32;
+                    const int home = wb0 + lane;
+                    double bx, by, bz;          // reaction on the visitor, travels with it
+                    double tx[T], ty[T], tz[T]; // force on my particles from this round
+                    bool close = false;
+                    sym_round<NIC, T, false>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
+                    // a laterally close pair anywhere in this warp's 32 x 32T block: the round again with the reference's
+                    // sqrt / divide (warp-uniform branch: the shuffles inside need every lane)
+#if RB2_EXACT_INLINE
+                    if (__any_sync(0xffffffffu, close))
+                        sym_round<NIC, T, true>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
+#else
+                    if (__any_sync(0xffffffffu, close)) {
+                        RoundIO<T> io;
+#pragma unroll
+                        for (int s = 0; s < T; ++s) { io.xi[s] = xi[s]; io.yi[s] = yi[s]; io.zi[s] = zi[s]; io.qe[s] = qe[s]; }
+                        io = sym_round_exact<NIC, T>(X, Y, Z, Q, wb0, lane, src_lane, io, P);
+#pragma unroll
+                        for (int s = 0; s < T; ++s) { tx[s] = io.tx[s]; ty[s] = io.ty[s]; tz[s] = io.tz[s]; }
+                        bx = io.bx; by = io.by; bz = io.bz;
+                    }
+#endif
+                    // 32 rotations by one lane: every visitor is back at its home lane
+#pragma unroll
+                    for (int s = 0; s < T; ++s)
+                        if (s < rel) { ax[s] += tx[s]; ay[s] += ty[s]; az[s] += tz[s]; }
+                    jacc[cur][warp][0][home] = bx; jacc[cur][warp][1][home] = by; jacc[cur][warp][2][home] = bz;
+                }
+            }
+            // stage the next tile into the other buffer (its last readers passed the previous barrier)
+            if (J + 1 < J1) {
+                const int jn = (J + 1) * SB + tid;
+                xs[cur ^ 1][tid] = pj_next.x; ys[cur ^ 1][tid] = pj_next.y; zs[cur ^ 1][tid] = pj_next.z;
+                qs[cur ^ 1][tid] = (jn < g.n) ? pj_next.w : 0.0;
+                const int jnn = jn + SB;
+                if (J + 2 < J1) pj_next = load(jnn);
+            }
+            __syncthreads();
+            if (rel >= 1) {
+                // block b of the tile was met by warp (b - r) & 3 in round r: add in round order, then onto the tile's
+                // running sum over this CTA's target superblocks
+                const int b = warp;
+                double *aj = accJ + (size_t)(J - J0) * 3 * SB + tid;
+                const size_t base = (((size_t)iset * g.band_len + (J - g.band_start)) * 3) * SB + tid;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double sum = ((jacc[cur][b][c][tid] + jacc[cur][(b + 3) & 3][c][tid]) + jacc[cur][(b + 2) & 3][c][tid]) +
+                                       jacc[cur][(b + 1) & 3][c][tid];
+                    if (direct) bufJ[base + c * SB] = sum;
+                    else aj[c * SB] += sum;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const size_t ib = (size_t)grp * 3 * g.n_pad + (size_t)(I * T + s) * SB + tid;
+            bufI[ib] = ax[s];
+            bufI[ib + g.n_pad] = ay[s];
+            bufI[ib + 2 * (size_t)g.n_pad] = az[s];
         }
     }
+    // the group's source sums over this CTA's superblocks, once: bufJ[set][tile of the band][3][128]
+    for (int J = max(J0, T * I0); J < J1 && !direct; ++J) {
+        const size_t base = (((size_t)iset * g.band_len + (J - g.band_start)) * 3) * SB + tid;
+        const double *aj = accJ + (size_t)(J - J0) * 3 * SB + tid;
 #pragma unroll
-    for (int s = 0; s < T; ++s) {
-        const size_t ib = (size_t)grp * 3 * g.n_pad + (size_t)(I * T + s) * SB + tid;
-        bufI[ib] = ax[s];
-        bufI[ib + g.n_pad] = ay[s];
-        bufI[ib + 2 * (size_t)g.n_pad] = az[s];
+        for (int c = 0; c < 3; ++c) bufJ[base + c * SB] = aj[c * SB];
     }
 }
 
-// raw[c][p] += (sum over this band's groups of the target sums) + (sum over the target superblocks that met
-// tile J(p) symmetrically of the source sums); only slots written by this rank are read.  One CTA per 128-particle
+// raw[c][p] += (sum over this band's groups of the target sums) + (sum over the sets of target superblocks that met
+// tile J(p) of the source sums); only slots written by this rank are read.  One CTA per 128-particle
 // tile, RQ threads per particle: thread (q, tid) adds every RQ-th term in ascending order, the RQ sums are joined
 // in ascending q -- a fixed order, and short dependent chains (at N = 1e4 a single thread per particle spent 55 us
 // on ~160 sequential loads next to a 300 us pair kernel).
@@ -280,30 +307,30 @@ k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restric
     __shared__ double part[RQ][3][SB];
     const int Jp = blockIdx.x;  // 128-particle tile of this particle
     const int It = Jp / T;      // its target superblock
+    const int Iset_t = It / g.K;
     const int tid = threadIdx.x & (SB - 1), q = threadIdx.x / SB;
     const int p = Jp * SB + tid;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    // as a target (superblock It)
+    // as a target (superblock It, taken by the CTAs of its set)
     for (int grp = q; grp < g.ngroups; grp += RQ) {
         const int J0 = g.band_start + grp * g.G;
         const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
         if (max(J0, T * It) >= J1) continue;
-        if (((It + grp) % g.world) != g.rank) continue;
+        if (((Iset_t + grp) % g.world) != g.rank) continue;
         const size_t ib = (size_t)grp * 3 * g.n_pad + p;
         s0 += bufI[ib];
         s1 += bufI[ib + g.n_pad];
         s2 += bufI[ib + 2 * (size_t)g.n_pad];
     }
-    // as a source (tile Jp), when Jp lies in this band: target superblocks I with T*I < Jp
+    // as a source (tile Jp), when Jp lies in this band: the sets whose first superblock starts left of Jp
     if (Jp >= g.band_start && Jp < g.band_start + g.band_len) {
         const int grp = (Jp - g.band_start) / g.G;
-        const size_t col = (size_t)(Jp - g.band_start) * g.nIb;
-        const int Iend = (Jp + T - 1) / T;
+        const int nset = min(g.nIsets, (Jp + T * g.K - 1) / (T * g.K));  // T * K * set < Jp: the set's first superblock lies left of the tile
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll 4
-        for (int I = q; I < Iend; I += RQ) {
-            if (((I + grp) % g.world) != g.rank) continue;
-            const size_t base = ((col + I) * 3) * SB + tid;
+        for (int st = q; st < nset; st += RQ) {
+            if (((st + grp) % g.world) != g.rank) continue;
+            const size_t base = (((size_t)st * g.band_len + (Jp - g.band_start)) * 3) * SB + tid;
             t0 += bufJ[base];
             t1 += bufJ[base + SB];
             t2 += bufJ[base + 2 * SB];
@@ -373,33 +400,57 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     g.n_pad = g.nIb * T * SB;
     g.rank = ctx.pair_rank;
     g.world = ctx.pair_world < 1 ? 1 : ctx.pair_world;
-    // band width from the scratch budget (3 KB per (source tile, target superblock) pair)
-    const size_t col_bytes = (size_t)g.nIb * 3 * SB * sizeof(double);
+    // Work units: a CTA takes a SET of K consecutive target superblocks one after the other against a GROUP of G source
+    // tiles whose reaction sums it keeps in shared memory (3 KB per tile) and stores once.  Per (superblock, tile) pair
+    // that is 3 KB T / G of target sums + 3 KB / K of source sums written (and read back by the reduce kernel) instead
+    // of 3 KB per pair with K = 1 (round 1: 96 GB per evaluation at N = 1e6).  K x G is sized for about sym_waves waves
+    // of CTAs per launch, times world^2: the CTAs of a band are dealt round-robin to the ranks, so each rank needs that
+    // many waves of its own (x world), and the deal (set + grp) % world only balances when there are many more units
+    // than ranks (x world again; tools/sym_rank_sweep.py).  The source tiles are processed in bands that fit the
+    // scratch budget (default 2 GiB).
+    const int Gmax = (T == 1) ? 12 : 24;   // shared memory: 32 KB static + 3 KB x G, 3 (T = 1) or 2 CTAs per SM
+    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world * g.world;
     size_t budget = ctx.sym_budget_bytes;
-    if ((size_t)g.nsb * col_bytes > ctx.sym_bufJ_bytes) {
+    auto plan = [&](int Wb_in, int &K, int &G) {
+        const double KG = (double)g.nIb * Wb_in / want_ctas;
+        G = (int)sqrt((double)T * KG);     // traffic per pair ~ T / G + 1 / K: G = T K at the optimum
+        if (G > Gmax) G = Gmax;
+        if (G > ctx.sym_gmax) G = ctx.sym_gmax;
+        if (G > Wb_in) G = Wb_in;
+        if (G < 1) G = 1;
+        K = (int)(KG / G);
+        if (K > ctx.sym_kmax) K = ctx.sym_kmax;
+        if (K < 1) K = 1;
+    };
+    auto band_bytes = [&](int Wb_in, int K, int G) {
+        const size_t nsets = (size_t)(g.nIb + K - 1) / K, ngr = (size_t)(Wb_in + G - 1) / G;
+        return nsets * Wb_in * 3 * SB * sizeof(double) + ngr * 3 * g.n_pad * sizeof(double);
+    };
+    int Wb = g.nsb, K = 1, G = 1;
+    plan(Wb, K, G);
+    if (band_bytes(Wb, K, G) > ctx.sym_bufJ_bytes + ctx.sym_bufI_bytes) {
         // the whole triangle does not fit what we hold: never ask for more than half of what is free (plus what we
         // already hold).  cudaMemGetInfo costs a fraction of a millisecond, so only look when it can matter.
         size_t fr = 0, tot = 0;
         if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
-            const size_t cap = (fr + ctx.sym_bufJ_bytes) / 2;
+            const size_t cap = (fr + ctx.sym_bufJ_bytes + ctx.sym_bufI_bytes) / 2;
             if (budget > cap) budget = cap;
         }
     }
-    size_t wb = budget / col_bytes;
-    if (wb < 1) wb = 1;
-    if (wb > (size_t)g.nsb) wb = (size_t)g.nsb;
-    const int Wb = (int)wb;
-    // group size: enough CTAs to fill the resident CTA slots for sym_waves waves per band launch, times world^2: the
-    // CTAs of a band are dealt round-robin to the ranks, so each rank needs that many waves of its own (x world), and
-    // the deal (I + grp) % world only balances when there are many more groups than ranks (x world again).
-    // tools/sym_rank_sweep.py at 8 ranks, N = 1e6: 93.6 % of the ideal split with x world, 99.4 % with x world^2;
-    // N = 1e5 at 4 ranks: 36 % vs 98 %.
-    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world * g.world;
-    int G = (int)((double)g.nIb * Wb / want_ctas);
-    if (G < 1) G = 1;
-    if (G > Wb) G = Wb;
+    for (int it = 0; it < 8 && band_bytes(Wb, K, G) > budget && Wb > 1; ++it) {
+        // shrink the band in proportion and re-plan (the set size depends on the band width)
+        int Wn = (int)((double)Wb * (double)budget / (double)band_bytes(Wb, K, G) * 0.97);
+        if (Wn >= Wb) Wn = Wb - 1;
+        if (Wn < 1) Wn = 1;
+        Wb = Wn;
+        plan(Wb, K, G);
+    }
+    if (G > 1) Wb = std::max(G, (Wb / G) * G);  // whole groups per band
+    if (Wb > g.nsb) Wb = g.nsb;
+    g.K = K;
+    g.nIsets = (g.nIb + K - 1) / K;
     const int ngroups_max = (Wb + G - 1) / G;
-    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, (size_t)Wb * col_bytes, budget);
+    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, (size_t)g.nIsets * Wb * 3 * SB * sizeof(double));
     if (rc) return rc;
     rc = ensure_bytes(&ctx.sym_bufI, &ctx.sym_bufI_bytes, (size_t)ngroups_max * 3 * g.n_pad * sizeof(double));
     if (rc) return rc;
@@ -424,11 +475,19 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         g.G = G;
         g.ngroups = (g.band_len + G - 1) / G;
         const int nI = (b0 + g.band_len - 1) / T + 1;  // target superblocks that start at or below the band's last tile
-        dim3 grid(nI, g.ngroups), block(SB);
-#define RB2_GO(N)                                                                                      \
-    do {                                                                                               \
-        if (T == 1) k_pair_sym<N, 1><<<grid, block, 0, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ); \
-        else k_pair_sym<N, 2><<<grid, block, 0, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);        \
+        dim3 grid((nI + K - 1) / K, g.ngroups), block(SB);
+        const size_t dyn = (size_t)G * 3 * SB * sizeof(double);
+#define RB2_GO(N)                                                                                        \
+    do {                                                                                                 \
+        if (T == 1) {                                                                                    \
+            static bool attr1 = false;                                                                   \
+            if (!attr1) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 3 * SB * 8)); attr1 = true; } \
+            k_pair_sym<N, 1><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);          \
+        } else {                                                                                         \
+            static bool attr2 = false;                                                                   \
+            if (!attr2) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 3 * SB * 8)); attr2 = true; } \
+            k_pair_sym<N, 2><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);          \
+        }                                                                                                \
     } while (0)
         if (!c.image_charge) RB2_GO(-1);
         else if (c.N_ic_max == 0) RB2_GO(0);
@@ -442,7 +501,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         launches += 2;
     }
     RB2_LAUNCHED(launches);
-    ctx.last_grid_x = g.nsb; ctx.last_grid_y = (g.nsb + Wb - 1) / Wb; ctx.last_block = SB; ctx.last_split = G;
+    ctx.last_grid_x = g.nsb; ctx.last_grid_y = (g.nsb + Wb - 1) / Wb; ctx.last_block = SB; ctx.last_split = G * 1000 + K;
     return RB2_OK;
 }
 

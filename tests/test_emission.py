@@ -365,6 +365,45 @@ def test_device_resident_tip_sampler(orc):
         assert df_d[k] == pytest.approx(orc.tip_escape_prob(p, eta_d[k], 4.7), rel=1e-10)
 
 
+@gpu
+@pytest.mark.parametrize("M,n_pre", [(100, 60), (214, 60), (214, 1500), (512, 700), (33, 0)])
+def test_tip_sampler_persistent_kernel(orc, M, n_pre):
+    """k_mh_tip_small: the tip chains of a time step as ONE persistent kernel (<= 512 chains): the same proposals,
+    targets and generator keys as the three-launches-per-jump path (option mh_small = 0), so for one seed almost every
+    chain ends in the same spot (the field sums differ in rounding only: a knife-edge accept decision may flip); same
+    shared-step adaptation; distributions equal to the oracle's serial chains."""
+    sim, p, st, em = _tip_pair(orc, 47, mh_batch=True)
+    with sim:
+        hp = rb.HotPath.attach()
+        if n_pre:
+            rng = np.random.default_rng(3)
+            pos = np.stack([rng.uniform(-40, 40, n_pre), rng.uniform(-40, 40, n_pre), rng.uniform(503, 900, n_pre)], axis=1) * NM
+            hp.Add_Particles(pos, np.zeros((n_pre, 3)), np.ones(n_pre, dtype=np.int32), 0)
+            if n_pre <= 100:
+                for r in pos:
+                    st.add(p, r, [0, 0, 0], 1, 0, 1)
+        l0 = hp.launch_count()
+        eta_s, df_s, pos_s, a_s, std_s = hp.mh_tip(M, seed=777)
+        l1 = hp.launch_count()
+        again = hp.mh_tip(M, seed=777)
+        hp.set_option("mh_small", 0)
+        eta_l, df_l, pos_l, a_l, std_l = hp.mh_tip(M, seed=777)
+        l2 = hp.launch_count()
+        hp.set_option("mh_small", 1)
+        if n_pre <= 100:
+            b = np.array([em.metro_algo_tip_v3(80)[1:5] for _ in range(300)])
+    assert l1 - l0 == 1 and l2 - l1 > 200          # one kernel against three launches per jump
+    for x, y in zip(again[:3], (eta_s, df_s, pos_s)):
+        assert np.array_equal(x, y)
+    same = np.all(pos_s == pos_l, axis=1) | (np.linalg.norm(pos_s - pos_l, axis=1) < 1e-15)
+    assert same.mean() > 0.9, same.mean()
+    assert std_s == pytest.approx(std_l, rel=0.15) and a_s == pytest.approx(a_l, abs=0.1)
+    assert np.all(eta_s < 0) and np.all((df_s > 0) & (df_s <= 1))
+    assert np.allclose(eta_s[same], eta_l[same], rtol=1e-9)
+    if n_pre <= 100 and M >= 100:
+        assert _ks(eta_s, b[:, 2]) > 1e-3 and _ks(df_s, b[:, 3]) > 1e-3
+
+
 # ---------------------------------------------------------------------------------------------------------
 # GPU: whole-system runs
 @gpu
