@@ -270,12 +270,16 @@ def run_ours(args):
     cfg = rb.planar_config(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic,
                            capacity=cap, device=local)
     hp = rb.HotPath(cfg)
+    ngpu = world
+    if args.single_process and world == 1 and args.gpus > 1:
+        hp.set_devices(list(range(args.gpus)))  # replicas + split pair work inside this one process
+        ngpu = args.gpus
     hp.upload(pos, q, m)
     # pair kernel: "sym" = each unordered pair once (default from 3500 particles on), "gather" = ordered pairs
     sym = (args.pair_mode == "sym") or (args.pair_mode == "auto" and n >= 3500)
     hp.set_option("pair_mode", 2 if sym else 1)
     p2p = sym and world > 1 and args.exchange == "p2p"
-    if sym:
+    if sym and ngpu == world:
         hp.set_pair_rank(rank, world)   # (target superblock, source group) work units dealt round-robin
         if p2p:
             # the one exchange step over NVLink peer memory, fused into the finalise kernel (rb2_p2p.cu): every rank
@@ -410,7 +414,7 @@ def run_ours(args):
     def contract_and_executed(n_, acc_ms_):
         """Fractions of the measured FP64 peak for one acceleration evaluation of n_ particles in acc_ms_ (slowest rank's
         share): the contract figure (99 algorithmic flops per ORDERED pair) and what the kernel executed."""
-        pairs_ = float(n_) * float(n_ - 1) / world
+        pairs_ = float(n_) * float(n_ - 1) / ngpu
         pk = peak_sust if acc_ms_ > 200.0 else peak_burst
         a = flops_per_pair(True, args.nic) * pairs_ / (acc_ms_ * 1e-3) / 1e12
         ex = EXECUTED[kern]
@@ -421,7 +425,7 @@ def run_ours(args):
 
     # ---- field batches through the C ABI with HOST buffers (M points on z = 0 against the N particles) ----
     field_batch = None
-    if world == 1 and not args.no_sweep:
+    if ngpu == 1 and not args.no_sweep:
         field_batch = []
         rngp = np.random.default_rng(np.random.PCG64(20261018))
         for M in (1, 32, 256, 4096, 65536):
@@ -492,9 +496,10 @@ def run_ours(args):
             except Exception:
                 traffic = None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, ngpu),
+            "processes": world,
             "md_steps_per_s": 1e3 / ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
             "ms_steps_rank0": [round(x, 4) for x in step_ms_list], "accel_ms_steps_rank0": [round(x, 4) for x in accel_ms],
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -524,7 +529,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clk,
             "acc_checksum": checksum, "sweep": sweep, "field_batch": field_batch,
         }
-        if world == 1 and not args.no_cpu:
+        if ngpu == 1 and not args.no_cpu:
             try:
                 orc, how = load_fast_oracle()
                 p = orc.params_planar(2000.0, 1000 * NM, (1000 * NM, 1000 * NM, 1000 * NM), 1.0e-16, True, args.nic)
@@ -553,6 +558,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the N = 1e4 / 1e5 sweep and the field-batch table")
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N and NO torchrun: one process drives the N GPUs (rb2_set_devices), the way the "
+                         "single-process Fortran host would")
     ap.add_argument("--no-flush", action="store_true", help="diagnostics only: no L2 flush between steps (not a valid bench line)")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostics only: no nvidia-smi sampling")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

@@ -202,6 +202,14 @@ int rb2_accel_finalize(void);
 int rb2_p2p_export(int n_max, void *handle_out);
 int rb2_p2p_attach(int world, int rank, const void *handles);
 int rb2_p2p_detach(void);
+/* ONE process driving several GPUs (the Fortran host is a single process, src/main.F90:5-29): call once after rb2_init,
+ * before any particle exists.  devices[0] must be the device of rb2_init.  A replica of the particle store is kept on
+ * every listed device (all state-changing calls go to all of them), the pair work of rb2_step / rb2_accel_only /
+ * rb2_accel_host is split over them and the partial sums are exchanged through NVLink peer memory inside the finalise
+ * kernel -- the scheme of rb2_p2p_attach without the handle exchange.  Everything that only reads the state (field
+ * batches, samplers, downloads, counters) is served by the first device.  Planar geometry; not combinable with
+ * rb2_p2p_attach or the collision step. */
+int rb2_set_devices(int n_devices, const int *devices);
 /* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
  * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "step_graph" (1 / 0: replay rb2_step as a CUDA graph while
  * consecutive steps queue identical work), "ramo_sections" / "ramo_emitters" (size

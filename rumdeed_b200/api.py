@@ -135,7 +135,7 @@ EXPORTS = (
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_get_ramo_sections", "rb2_accel_host",
     "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_tip",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
-    "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_nearest_electron",
+    "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_set_devices", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
     "rb2_do_collisions", "rb2_get_recombination_records", "rb2_get_ionization_records", "rb2_probe_quartic_roots",
     "rb2_fp64_peak", "rb2_launch_count", "rb2_get_stat", "rb2_last_accel_info",
@@ -163,6 +163,7 @@ def load_library(path: str | None = None):
     lib.rb2_get_counts.argtypes = [C.POINTER(Counts)]
     lib.rb2_add_particles.argtypes = [C.c_int, _PD, _PD, _PI, C.c_int, _PI, _PI, _PI]
     lib.rb2_capacity_left.argtypes = [_PI]
+    lib.rb2_set_devices.argtypes = [C.c_int, _PI]
     lib.rb2_get_stat.argtypes = [C.c_char_p, _PD]
     lib.rb2_mark_remove.argtypes = [C.c_int, _PI, _PI]
     lib.rb2_remove_marked.argtypes = [C.c_int, C.POINTER(Counts)]
@@ -490,6 +491,11 @@ class HotPath:
         self._check(self.lib.rb2_field_window_close())
 
     # -- multi-GPU / measurement ---------------------------------------------------------------------
+    def set_devices(self, devices):
+        """One process, several GPUs: replicas of the store on every listed device, the pair work split over them."""
+        d = np.ascontiguousarray(devices, dtype=np.int32)
+        self._check(self.lib.rb2_set_devices(d.size, _i(d)))
+
     def set_partition(self, i_begin, i_end):
         self._check(self.lib.rb2_set_partition(int(i_begin), int(i_end)))
 

@@ -8,8 +8,27 @@
 
 #include "rb2_internal.cuh"
 
-Rb2Ctx g_rb2;
-char   g_rb2_err[512] = "no error";
+Rb2Ctx  g_rb2_all[RB2_P2P_MAX];
+Rb2Ctx *g_rb2_cur = &g_rb2_all[0];
+int     g_rb2_ndev = 1;
+char    g_rb2_err[512] = "no error";
+
+// Run f on the context of every device of this process (rb2_set_devices), the first device last-selected again.
+template <class F>
+static int each_device(F f)
+{
+    if (g_rb2_ndev <= 1) return f();
+    int rc0 = RB2_OK;
+    for (int d = 0; d < g_rb2_ndev; ++d) {
+        g_rb2_cur = &g_rb2_all[d];
+        cudaSetDevice(g_rb2_cur->dev);
+        const int rc = f();
+        if (rc != RB2_OK && rc0 == RB2_OK) rc0 = rc;
+    }
+    g_rb2_cur = &g_rb2_all[0];
+    cudaSetDevice(g_rb2_cur->dev);
+    return rc0;
+}
 
 int rb2_fail(int code, const char *fmt, ...)
 {
@@ -327,8 +346,8 @@ static int init_impl(Rb2Ctx &c, const rb2_config *cfg)
 
 int rb2_init(const rb2_config *cfg)
 {
+    rb2_finalize();  // every device context of a previous set-up
     Rb2Ctx &c = g_rb2;
-    if (c.init) rb2_finalize();
     int rc = check_config(cfg);
     if (rc) return rc;
     if (cfg->capacity < 1) return rb2_fail(RB2_ERR_ARG, "capacity must be >= 1");
@@ -339,13 +358,84 @@ int rb2_init(const rb2_config *cfg)
 
 int rb2_finalize(void)
 {
-    Rb2Ctx &c = g_rb2;
-    if (!c.init) return RB2_OK;
-    release_all(c);
+    for (int d = g_rb2_ndev - 1; d >= 0; --d) {
+        Rb2Ctx &c = g_rb2_all[d];
+        if (!c.init) continue;
+        g_rb2_cur = &c;
+        cudaSetDevice(c.dev);
+        release_all(c);
+    }
+    g_rb2_cur = &g_rb2_all[0];
+    g_rb2_ndev = 1;
     return RB2_OK;
 }
 
-int rb2_update_config(const rb2_config *cfg)
+// One process, several GPUs.  devices[0] must be the device of rb2_init; a replica of the (still empty) particle store is
+// set up on each further device, peer access is enabled between all of them and every context gets the exchange block
+// of every other one (plain peer pointers -- no IPC), so that the pair work of rb2_step / rb2_accel_only /
+// rb2_accel_host is split over the devices exactly as it is over the ranks of the one-process-per-GPU set-up.
+int rb2_set_devices(int n_devices, const int *devices)
+{
+    RB2_REQUIRE_INIT();
+    if (n_devices < 1 || n_devices > RB2_P2P_MAX || !devices) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices: 1..%d devices", RB2_P2P_MAX);
+    if (g_rb2_ndev > 1) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices: already set (call rb2_init again first)");
+    Rb2Ctx &c0 = g_rb2_all[0];
+    if (devices[0] != c0.dev) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices: devices[0] must be the device of rb2_init (%d)", c0.dev);
+    if (c0.n != 0) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices must be called before particles are uploaded or added");
+    if (c0.p2p_world > 1) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices: this context is attached to other processes (rb2_p2p_attach)");
+    if (c0.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_set_devices: the pair work is split for the planar geometry only");
+    if (n_devices == 1) return RB2_OK;
+    int count = 0;
+    RB2_CUDA(cudaGetDeviceCount(&count));
+    for (int d = 0; d < n_devices; ++d) {
+        if (devices[d] < 0 || devices[d] >= count) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices: no device %d", devices[d]);
+        for (int e = 0; e < d; ++e)
+            if (devices[e] == devices[d]) return rb2_fail(RB2_ERR_ARG, "rb2_set_devices: device %d listed twice", devices[d]);
+    }
+    int rc = RB2_OK;
+    for (int d = 1; d < n_devices && rc == RB2_OK; ++d) {
+        rb2_config cfg = c0.cfg;
+        cfg.device = devices[d];
+        g_rb2_cur = &g_rb2_all[d];
+        rc = init_impl(g_rb2_all[d], &cfg);
+        if (rc == RB2_OK) {
+            Rb2Ctx &cd = g_rb2_all[d];
+            cd.pair_mode = c0.pair_mode; cd.sym_min_n = c0.sym_min_n; cd.sym_tpl = c0.sym_tpl; cd.sym_waves = c0.sym_waves;
+            cd.sym_budget_bytes = c0.sym_budget_bytes; cd.sym_kmax = c0.sym_kmax; cd.sym_gmax = c0.sym_gmax; cd.ev_min = c0.ev_min;
+            cd.ramo_n_sec = c0.ramo_n_sec; cd.ramo_n_emit = c0.ramo_n_emit;
+        }
+        g_rb2_ndev = d + 1;
+    }
+    for (int a = 0; a < n_devices && rc == RB2_OK; ++a)
+        for (int b = 0; b < n_devices && rc == RB2_OK; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            if (!can) { rc = rb2_fail(RB2_ERR_CUDA, "rb2_set_devices: device %d cannot access the memory of device %d", devices[a], devices[b]); break; }
+            cudaSetDevice(devices[a]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = rb2_fail(RB2_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[a], devices[b], cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    if (rc == RB2_OK) rc = rb2_p2p_link_local(g_rb2_all, n_devices);
+    g_rb2_cur = &g_rb2_all[0];
+    cudaSetDevice(c0.dev);
+    if (rc != RB2_OK) {  // back to one device
+        for (int d = g_rb2_ndev - 1; d >= 1; --d) {
+            g_rb2_cur = &g_rb2_all[d];
+            cudaSetDevice(g_rb2_all[d].dev);
+            release_all(g_rb2_all[d]);
+        }
+        g_rb2_cur = &g_rb2_all[0];
+        g_rb2_ndev = 1;
+        cudaSetDevice(c0.dev);
+        rb2_p2p_release(c0);
+        c0.pair_rank = 0; c0.pair_world = 1;
+    }
+    return rc;
+}
+
+static int update_config_one(const rb2_config *cfg)
 {
     RB2_REQUIRE_INIT();
     int rc = check_config(cfg);
@@ -356,8 +446,12 @@ int rb2_update_config(const rb2_config *cfg)
     g_rb2.cfg.device = dev;
     return RB2_OK;
 }
+int rb2_update_config(const rb2_config *cfg)
+{
+    return each_device([&]() -> int { return update_config_one(cfg); });
+}
 
-int rb2_upload_particles(int n, const double *pos, const double *prev_pos, const double *vel, const double *acc,
+static int upload_particles_one(int n, const double *pos, const double *prev_pos, const double *vel, const double *acc,
                          const double *acc_prev, const double *acc_prev2, const double *charge, const double *mass,
                          const int *species, const int *step, const int *emitter, const int *section, const int *life,
                          const int *id, int nrID)
@@ -416,6 +510,13 @@ int rb2_upload_particles(int n, const double *pos, const double *prev_pos, const
     c.host_events.clear();
     return RB2_OK;
 }
+int rb2_upload_particles(int n, const double *pos, const double *prev_pos, const double *vel, const double *acc,
+                         const double *acc_prev, const double *acc_prev2, const double *charge, const double *mass,
+                         const int *species, const int *step, const int *emitter, const int *section, const int *life,
+                         const int *id, int nrID)
+{
+    return each_device([&]() -> int { return upload_particles_one(n, pos, prev_pos, vel, acc, acc_prev, acc_prev2, charge, mass, species, step, emitter, section, life, id, nrID); });
+}
 
 int rb2_download_particles(double *pos, double *prev_pos, double *vel, double *acc, double *acc_prev, double *acc_prev2,
                            double *charge, double *mass, int *species, int *step, int *emitter, int *section, int *life,
@@ -460,7 +561,7 @@ int rb2_get_counts(rb2_counts *out)
     return RB2_OK;
 }
 
-int rb2_add_particles(int k, const double *pos, const double *vel, const int *species, int step, const int *emit,
+static int add_particles_one(int k, const double *pos, const double *vel, const int *species, int step, const int *emit,
                       const int *sec, const int *life)
 {
     RB2_REQUIRE_INIT();
@@ -505,6 +606,11 @@ int rb2_add_particles(int k, const double *pos, const double *vel, const int *sp
     c.counts.nrID += kk;
     return RB2_OK;
 }
+int rb2_add_particles(int k, const double *pos, const double *vel, const int *species, int step, const int *emit,
+                      const int *sec, const int *life)
+{
+    return each_device([&]() -> int { return add_particles_one(k, pos, vel, species, step, emit, sec, life); });
+}
 
 int rb2_capacity_left(int *out)
 {
@@ -514,7 +620,7 @@ int rb2_capacity_left(int *out)
     return RB2_OK;
 }
 
-int rb2_mark_remove(int k, const int *index, const int *reason)
+static int mark_remove_one(int k, const int *index, const int *reason)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
@@ -533,8 +639,12 @@ int rb2_mark_remove(int k, const int *index, const int *reason)
     if (rc) return rc;
     return fetch_counters(c);
 }
+int rb2_mark_remove(int k, const int *index, const int *reason)
+{
+    return each_device([&]() -> int { return mark_remove_one(k, index, reason); });
+}
 
-int rb2_remove_marked(int step, rb2_counts *out)
+static int remove_marked_one(int step, rb2_counts *out)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
@@ -564,6 +674,10 @@ int rb2_remove_marked(int step, rb2_counts *out)
     if (out) *out = c.counts;
     return RB2_OK;
 }
+int rb2_remove_marked(int step, rb2_counts *out)
+{
+    return each_device([&]() -> int { return remove_marked_one(step, out); });
+}
 
 int rb2_get_life_time(long long *out)
 {
@@ -575,7 +689,7 @@ int rb2_get_life_time(long long *out)
     return RB2_OK;
 }
 
-int rb2_update_position(int step)
+static int update_position_one(int step)
 {
     (void)step;
     RB2_REQUIRE_INIT();
@@ -585,21 +699,33 @@ int rb2_update_position(int step)
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     return finish_position(c, false);
 }
+int rb2_update_position(int step)
+{
+    return each_device([&]() -> int { return update_position_one(step); });
+}
 
 int rb2_accel_only(void)
 {
     RB2_REQUIRE_INIT();
-    Rb2Ctx &c = g_rb2;
-    int i0 = c.part_begin < 0 ? 0 : c.part_begin;
-    int i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
-    int rc = launch_accel_any(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
-    if (rc) return rc;
-    c.accel_timed = (c.n > 0 && i1 > i0);
-    RB2_CUDA(cudaStreamSynchronize(c.stream));
-    return rb2_p2p_check(c);
+    // queue on every device first, wait afterwards: the devices work side by side and exchange inside their kernels
+    int rc = each_device([&]() -> int {
+        Rb2Ctx &c = g_rb2;
+        int i0 = c.part_begin < 0 ? 0 : c.part_begin;
+        int i1 = (c.part_end < 0 || c.part_end > c.n) ? c.n : c.part_end;
+        int rc1 = launch_accel_any(c, c.a.pq, c.a.mass, c.n, i0, i1, c.a.acc);
+        if (rc1) return rc1;
+        c.accel_timed = (c.n > 0 && i1 > i0);
+        return RB2_OK;
+    });
+    const int rc2 = each_device([&]() -> int {
+        Rb2Ctx &c = g_rb2;
+        RB2_CUDA(cudaStreamSynchronize(c.stream));
+        return rb2_p2p_check(c);
+    });
+    return rc ? rc : rc2;
 }
 
-int rb2_update_velocity(rb2_step_result *out)
+static int update_velocity_one(rb2_step_result *out)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
@@ -615,6 +741,10 @@ int rb2_update_velocity(rb2_step_result *out)
         out->counts = c.counts;
     }
     return RB2_OK;
+}
+int rb2_update_velocity(rb2_step_result *out)
+{
+    return each_device([&]() -> int { return update_velocity_one(out); });
 }
 
 // Everything rb2_step queues on the stream, from the first event record to the last.
@@ -665,10 +795,22 @@ static unsigned long long step_key(const Rb2Ctx &c)
     return h ? h : 1;
 }
 
+static int step_finish(rb2_step_result *out);
+static int step_queue(void);
+
 int rb2_step(int step, rb2_step_result *out)
 {
     (void)step;
     RB2_REQUIRE_INIT();
+    // queue on every device first, wait afterwards (rb2_set_devices): the devices integrate their replicas side by side
+    // and exchange the partial pair sums inside the finalise kernel
+    const int rc = each_device([&]() -> int { return step_queue(); });
+    const int rc2 = each_device([&]() -> int { return step_finish(out); });
+    return rc ? rc : rc2;
+}
+
+static int step_queue(void)
+{
     Rb2Ctx &c = g_rb2;
     {   // the fused step integrates EVERY row: with an i-partition in effect only rows [i_begin, i_end) would get an
         // acceleration and the rest would be integrated with a = 0.  Partitioned runs use the three phases
@@ -725,6 +867,13 @@ int rb2_step(int step, rb2_step_result *out)
         if ((rc = queue_step(c))) return rc;
     }
     c.prev_step_key = key;
+    return RB2_OK;
+}
+
+static int step_finish(rb2_step_result *out)
+{
+    Rb2Ctx &c = g_rb2;
+    int rc = RB2_OK;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     if ((rc = rb2_p2p_check(c))) return rc;
     rc = finish_position(c, true);
@@ -770,30 +919,43 @@ int rb2_get_events(int max_events, rb2_event *out, int *n_out)
 int rb2_accel_host(int n, const double *pos, const double *charge, const double *mass, double *acc_out)
 {
     RB2_REQUIRE_INIT();
-    Rb2Ctx &c = g_rb2;
-    if (n < 0 || n > c.cap) return rb2_fail(RB2_ERR_CAPACITY, "n = %d exceeds capacity %d", n, c.cap);
+    if (n < 0 || n > g_rb2.cap) return rb2_fail(RB2_ERR_CAPACITY, "n = %d exceeds capacity %d", n, g_rb2.cap);
     if (n == 0) return RB2_OK;
     if (!pos || !charge || !mass || !acc_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
-    // scratch = the spare array set; the resident particle state is untouched
-    const size_t b3 = (size_t)n * 3 * sizeof(double), b1 = (size_t)n * sizeof(double);
-    cudaStream_t st = c.stream;
-    RB2_CUDA(cudaMemcpyAsync(c.b.prev_pos, pos, b3, cudaMemcpyHostToDevice, st));
-    RB2_CUDA(cudaMemcpyAsync(c.b.mass, charge, b1, cudaMemcpyHostToDevice, st));
-    RB2_CUDA(cudaMemcpyAsync(c.b.vel, mass, b1, cudaMemcpyHostToDevice, st));
-    int rc = rb2_launch_pack(c, c.b.prev_pos, c.b.mass, n, c.b.pq);
-    if (rc) return rc;
-    // honours the i-partition: this process evaluates and returns rows [i0, i1) only
-    int i0 = c.part_begin < 0 ? 0 : c.part_begin;
-    int i1 = (c.part_end < 0 || c.part_end > n) ? n : c.part_end;
-    if (i0 > i1) i0 = i1;
-    rc = launch_accel_any(c, c.b.pq, c.b.vel, n, i0, i1, c.b.acc);
-    if (rc) return rc;
-    c.accel_timed = (i1 > i0);
-    if (i1 > i0)
-        RB2_CUDA(cudaMemcpyAsync(acc_out + (size_t)3 * i0, c.b.acc + (size_t)3 * i0, (size_t)(i1 - i0) * 3 * sizeof(double),
-                                 cudaMemcpyDeviceToHost, st));
-    RB2_CUDA(cudaStreamSynchronize(st));
-    return rb2_p2p_check(c);
+    // every device gets the inputs and queues its share of the pair work; the first one returns the accelerations
+    const int rc = each_device([&]() -> int {
+        Rb2Ctx &c = g_rb2;
+        // scratch = the spare array set; the resident particle state is untouched
+        const size_t b3 = (size_t)n * 3 * sizeof(double), b1 = (size_t)n * sizeof(double);
+        cudaStream_t st = c.stream;
+        RB2_CUDA(cudaMemcpyAsync(c.b.prev_pos, pos, b3, cudaMemcpyHostToDevice, st));
+        RB2_CUDA(cudaMemcpyAsync(c.b.mass, charge, b1, cudaMemcpyHostToDevice, st));
+        RB2_CUDA(cudaMemcpyAsync(c.b.vel, mass, b1, cudaMemcpyHostToDevice, st));
+        int rc1 = rb2_launch_pack(c, c.b.prev_pos, c.b.mass, n, c.b.pq);
+        if (rc1) return rc1;
+        // honours the i-partition: this process evaluates and returns rows [i0, i1) only
+        int i0 = c.part_begin < 0 ? 0 : c.part_begin;
+        int i1 = (c.part_end < 0 || c.part_end > n) ? n : c.part_end;
+        if (i0 > i1) i0 = i1;
+        rc1 = launch_accel_any(c, c.b.pq, c.b.vel, n, i0, i1, c.b.acc);
+        if (rc1) return rc1;
+        c.accel_timed = (i1 > i0);
+        return RB2_OK;
+    });
+    // the copy-out only once every device has its work queued: into pageable memory it blocks the host until the
+    // finalise kernel is through, and that kernel waits for the other devices' partial sums
+    const int rc2 = each_device([&]() -> int {
+        Rb2Ctx &c = g_rb2;
+        int i0 = c.part_begin < 0 ? 0 : c.part_begin;
+        int i1 = (c.part_end < 0 || c.part_end > n) ? n : c.part_end;
+        if (i0 > i1) i0 = i1;
+        if (rc == RB2_OK && i1 > i0 && &c == &g_rb2_all[0])
+            RB2_CUDA(cudaMemcpyAsync(acc_out + (size_t)3 * i0, c.b.acc + (size_t)3 * i0, (size_t)(i1 - i0) * 3 * sizeof(double),
+                                     cudaMemcpyDeviceToHost, c.stream));
+        RB2_CUDA(cudaStreamSynchronize(c.stream));
+        return rb2_p2p_check(c);
+    });
+    return rc ? rc : rc2;
 }
 
 static int ensure_field_buffers(Rb2Ctx &c, int M)
@@ -815,6 +977,43 @@ static int ensure_field_buffers(Rb2Ctx &c, int M)
     return RB2_OK;
 }
 
+// Several devices in this process (rb2_set_devices), many points: every device holds the whole particle store, so the
+// POINTS are dealt out in contiguous slices -- no reduction (the result of a point agrees with the one-device result to
+// rounding: the chunking of the particle range depends on the number of points of a launch).
+// surface: E_z only (rb2_field_surface_z), else the three components.
+static int field_batch_sharded(int M, const double *pos_in, double *out, bool surface)
+{
+    const int nd = g_rb2_ndev;
+    const int ncomp = surface ? 1 : 3;
+    int d = 0;
+    int rc = each_device([&]() -> int {
+        Rb2Ctx &c = g_rb2;
+        const int m0 = (int)((long long)M * d / nd), m1 = (int)((long long)M * (d + 1) / nd);
+        ++d;
+        const int Md = m1 - m0;
+        if (Md < 1) return RB2_OK;
+        int rc1 = ensure_field_buffers(c, Md);
+        if (rc1) return rc1;
+        const size_t b3 = (size_t)3 * Md * sizeof(double);
+        memcpy(c.h_pts, pos_in + (size_t)3 * m0, b3);
+        RB2_CUDA(cudaMemcpyAsync(c.d_pts, c.h_pts, b3, cudaMemcpyHostToDevice, c.stream));
+        rc1 = surface ? rb2_launch_surface_field(c, c.d_pts, Md, c.d_fld) : rb2_launch_field(c, c.a.pq, c.n, nullptr, 0, c.d_pts, Md, c.d_fld);
+        if (rc1) return rc1;
+        RB2_CUDA(cudaMemcpyAsync(c.h_fld, c.d_fld, (size_t)ncomp * Md * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        return RB2_OK;
+    });
+    d = 0;
+    const int rc2 = each_device([&]() -> int {
+        Rb2Ctx &c = g_rb2;
+        const int m0 = (int)((long long)M * d / nd), m1 = (int)((long long)M * (d + 1) / nd);
+        ++d;
+        RB2_CUDA(cudaStreamSynchronize(c.stream));
+        if (rc == RB2_OK && m1 > m0) memcpy(out + (size_t)ncomp * m0, c.h_fld, (size_t)ncomp * (m1 - m0) * sizeof(double));
+        return RB2_OK;
+    });
+    return rc ? rc : rc2;
+}
+
 int rb2_field_batch_delta(int M, const double *pos_in, int n_new, const double *new_pos, const double *new_charge,
                           double *field_out)
 {
@@ -823,6 +1022,7 @@ int rb2_field_batch_delta(int M, const double *pos_in, int n_new, const double *
     if (M < 1) return RB2_OK;  // src/mod_verlet.F90:1658
     if (!pos_in || !field_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
     if (n_new < 0 || (n_new > 0 && (!new_pos || !new_charge))) return rb2_fail(RB2_ERR_ARG, "bad pending-particle arguments");
+    if (g_rb2_ndev > 1 && n_new == 0 && M >= 512 * g_rb2_ndev) return field_batch_sharded(M, pos_in, field_out, false);
     int rc = ensure_field_buffers(c, M);
     if (rc) return rc;
     cudaStream_t st = c.stream;
@@ -866,6 +1066,7 @@ int rb2_field_surface_z(int M, const double *pos_in, double *Ez_out)
     if (c.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_field_surface_z: planar geometry only");
     for (int k = 0; k < M; ++k)
         if (pos_in[3 * (size_t)k + 2] != 0.0) return rb2_fail(RB2_ERR_ARG, "rb2_field_surface_z: point %d is not on the cathode plane z = 0", k);
+    if (g_rb2_ndev > 1 && M >= 512 * g_rb2_ndev) return field_batch_sharded(M, pos_in, Ez_out, true);
     int rc = ensure_field_buffers(c, M);
     if (rc) return rc;
     cudaStream_t st = c.stream;
@@ -906,7 +1107,7 @@ int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, doub
 int rb2_field_window_open(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 int rb2_field_window_close(void) { RB2_REQUIRE_INIT(); return RB2_OK; }
 
-int rb2_set_option(const char *name, double value)
+static int set_option_one(const char *name, double value)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
@@ -965,11 +1166,16 @@ int rb2_set_option(const char *name, double value)
     }
     return RB2_OK;
 }
+int rb2_set_option(const char *name, double value)
+{
+    return each_device([&]() -> int { return set_option_one(name, value); });
+}
 
 int rb2_set_pair_rank(int rank, int world)
 {
     RB2_REQUIRE_INIT();
     if (world < 1 || rank < 0 || rank >= world) return rb2_fail(RB2_ERR_ARG, "bad rank %d of %d", rank, world);
+    if (g_rb2_ndev > 1) return rb2_fail(RB2_ERR_ARG, "rb2_set_pair_rank: the devices of this process already share the pair work (rb2_set_devices)");
     g_rb2.pair_rank = rank;
     g_rb2.pair_world = world;
     return RB2_OK;
@@ -980,6 +1186,7 @@ int rb2_accel_partial(void)
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
     if (c.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_accel_partial: planar geometry only");
+    if (g_rb2_ndev > 1) return rb2_fail(RB2_ERR_ARG, "rb2_accel_partial / rb2_accel_finalize are the multi-process plumbing: not with rb2_set_devices");
     int rc = rb2_launch_accel_sym_partial(c, c.a.pq, c.n);
     if (rc) return rc;
     c.last_pair_kernel = 2;
@@ -999,13 +1206,17 @@ int rb2_accel_finalize(void)
     return rb2_p2p_check(c);
 }
 
-int rb2_set_partition(int i_begin, int i_end)
+static int set_partition_one(int i_begin, int i_end)
 {
     RB2_REQUIRE_INIT();
     if (i_begin < 0 || (i_end >= 0 && i_end < i_begin)) return rb2_fail(RB2_ERR_ARG, "bad partition [%d, %d)", i_begin, i_end);
     g_rb2.part_begin = i_begin;
     g_rb2.part_end = i_end;
     return RB2_OK;
+}
+int rb2_set_partition(int i_begin, int i_end)
+{
+    return each_device([&]() -> int { return set_partition_one(i_begin, i_end); });
 }
 
 int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes)
@@ -1029,11 +1240,15 @@ int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes)
     return RB2_OK;
 }
 
-int rb2_synchronize(void)
+static int synchronize_one(void)
 {
     RB2_REQUIRE_INIT();
     RB2_CUDA(cudaStreamSynchronize(g_rb2.stream));
     return RB2_OK;
+}
+int rb2_synchronize(void)
+{
+    return each_device([&]() -> int { return synchronize_one(); });
 }
 
 int rb2_stream(void **stream_out)

@@ -990,6 +990,7 @@ int rb2_collisions_init(const rb2_collision_config *cfg)
 {
     RB2_REQUIRE_INIT();
     if (!cfg) return rb2_fail(RB2_ERR_ARG, "config is NULL");
+    if (g_rb2_ndev > 1) return rb2_fail(RB2_ERR_ARG, "the collision step keeps its state for one device: not available with rb2_set_devices");
     if (cfg->collision_mode != 1 && cfg->collision_mode != 2)
         return rb2_fail(RB2_ERR_ARG, "collision_mode %d: only 1 (continuous ionisation) and 2 (+ discrete recombination) run on "
                                      "the device", cfg->collision_mode);

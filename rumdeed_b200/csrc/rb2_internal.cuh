@@ -122,6 +122,8 @@ struct Rb2Ctx {
     void  *p2p_peer[RB2_P2P_MAX] = {};    // every rank's block as mapped here ([rank] == p2p_local)
     int    p2p_world = 0, p2p_npad_max = 0;
     unsigned long long p2p_epoch = 0;     // evaluations since attach; parity selects the partial-sum slot
+    bool   p2p_ipc = false;               // peers mapped through CUDA IPC (one process per GPU) -- else plain peer access
+    unsigned sym_attr_mask = 0;           // k_pair_sym instantiations whose shared-memory limit has been raised on this device
     volatile int *p2p_err = nullptr;      // mapped host word the finalise kernel reports a failed exchange in
     int   *p2p_err_dev = nullptr;         // ... its device address
     int    last_pair_kernel = 0;          // 1 gather, 2 symmetric
@@ -154,7 +156,15 @@ struct Rb2Ctx {
     long long launches = 0;
 };
 
-extern Rb2Ctx g_rb2;
+// One context per device.  The classic set-up has one (one GPU per process); rb2_set_devices adds a replica of the whole
+// particle state on each further device of THIS process: every state-changing call is made on all of them, the pair
+// work of the pair-symmetric kernel is split over them and exchanged through peer memory (rb2_p2p.cu), everything that
+// only reads the state (field batches, samplers, downloads) uses the first one.  g_rb2 is the context the current call
+// works on.
+extern Rb2Ctx  g_rb2_all[RB2_P2P_MAX];
+extern Rb2Ctx *g_rb2_cur;
+extern int     g_rb2_ndev;
+#define g_rb2 (*g_rb2_cur)
 extern char   g_rb2_err[512];
 
 int rb2_fail(int code, const char *fmt, ...);
@@ -198,6 +208,7 @@ int rb2_launch_nearest(Rb2Ctx &ctx, double *d_dist, int *d_id);
 double *rb2_p2p_begin_evaluation(Rb2Ctx &ctx, int n_pad);
 int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, double *acc_out);
 int rb2_p2p_release(Rb2Ctx &ctx);
+int rb2_p2p_link_local(Rb2Ctx *all, int n);  // rb2_set_devices: exchange blocks + peer pointers inside one process
 int rb2_p2p_check(Rb2Ctx &ctx);  // after a stream synchronisation: RB2_ERR_CUDA when the last exchange failed
 // pair-symmetric kernel (rb2_pair_sym.cu)
 int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n);

@@ -171,10 +171,40 @@ int rb2_launch_accel_sym_exchange_finalize(Rb2Ctx &ctx, const double4 *pq, const
     return RB2_OK;
 }
 
+// One process, several devices (rb2_set_devices): every context gets an exchange block and the plain device pointers of
+// all the others (peer access is on); from there the protocol is the one of the attached processes.
+int rb2_p2p_link_local(Rb2Ctx *all, int n)
+{
+    const int npad_max = ((all[0].cap + 255) / 256) * 256;
+    const size_t bytes = P2P_FLAG_BYTES + 2 * 3 * (size_t)npad_max * sizeof(double);
+    for (int d = 0; d < n; ++d) {
+        Rb2Ctx &c = all[d];
+        RB2_CUDA(cudaSetDevice(c.dev));
+        RB2_CUDA(cudaMalloc(&c.p2p_local, bytes));
+        RB2_CUDA(cudaMemset(c.p2p_local, 0, bytes));
+        const P2PHeader hdr = {P2P_MAGIC, (unsigned long long)npad_max};
+        RB2_CUDA(cudaMemcpy(static_cast<char *>(c.p2p_local) + P2P_HEADER_OFFSET, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+        c.p2p_npad_max = npad_max;
+        RB2_CUDA(cudaHostAlloc((void **)&c.p2p_err, sizeof(int), cudaHostAllocMapped));
+        *c.p2p_err = 0;
+        RB2_CUDA(cudaHostGetDevicePointer((void **)&c.p2p_err_dev, (void *)c.p2p_err, 0));
+    }
+    for (int d = 0; d < n; ++d) {
+        Rb2Ctx &c = all[d];
+        for (int r = 0; r < n; ++r) c.p2p_peer[r] = all[r].p2p_local;
+        c.p2p_world = n;
+        c.p2p_ipc = false;
+        c.pair_rank = d;
+        c.pair_world = n;
+        c.p2p_epoch = 0;
+    }
+    return RB2_OK;
+}
+
 int rb2_p2p_release(Rb2Ctx &c)
 {
     for (int r = 0; r < c.p2p_world; ++r)
-        if (c.p2p_peer[r] && c.p2p_peer[r] != c.p2p_local) cudaIpcCloseMemHandle(c.p2p_peer[r]);
+        if (c.p2p_ipc && c.p2p_peer[r] && c.p2p_peer[r] != c.p2p_local) cudaIpcCloseMemHandle(c.p2p_peer[r]);
     for (int r = 0; r < RB2_P2P_MAX; ++r) c.p2p_peer[r] = nullptr;
     c.p2p_world = 0;
     if (c.p2p_local) cudaFree(c.p2p_local);
@@ -193,6 +223,7 @@ int rb2_p2p_export(int n_max, void *handle_out)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
+    if (g_rb2_ndev > 1) return rb2_fail(RB2_ERR_ARG, "rb2_p2p_export: this process already drives several devices (rb2_set_devices)");
     if (n_max < 1 || !handle_out) return rb2_fail(RB2_ERR_ARG, "rb2_p2p_export: n_max >= 1 and a handle buffer are required");
     static_assert(sizeof(cudaIpcMemHandle_t) == RB2_P2P_HANDLE_BYTES, "handle size");
     RB2_CUDA(cudaStreamSynchronize(c.stream));
@@ -217,6 +248,7 @@ int rb2_p2p_attach(int world, int rank, const void *handles)
 {
     RB2_REQUIRE_INIT();
     Rb2Ctx &c = g_rb2;
+    if (g_rb2_ndev > 1) return rb2_fail(RB2_ERR_ARG, "rb2_p2p_attach: this process already drives several devices (rb2_set_devices)");
     if (!c.p2p_local) return rb2_fail(RB2_ERR_ARG, "rb2_p2p_attach before rb2_p2p_export");
     if (world < 1 || world > RB2_P2P_MAX || rank < 0 || rank >= world || !handles)
         return rb2_fail(RB2_ERR_ARG, "rb2_p2p_attach: bad rank %d of %d (at most %d)", rank, world, RB2_P2P_MAX);
@@ -239,6 +271,7 @@ int rb2_p2p_attach(int world, int rank, const void *handles)
         }
     }
     c.p2p_world = world;
+    c.p2p_ipc = true;
     c.pair_rank = rank;
     c.pair_world = world;
     c.p2p_epoch = 0;

@@ -479,13 +479,12 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         const size_t dyn = (size_t)G * 3 * SB * sizeof(double);
 #define RB2_GO(N)                                                                                        \
     do {                                                                                                 \
+        const unsigned bit = 1u << (((N) + 1) * 2 + (T - 1));                                            \
         if (T == 1) {                                                                                    \
-            static bool attr1 = false;                                                                   \
-            if (!attr1) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 3 * SB * 8)); attr1 = true; } \
+            if (!(ctx.sym_attr_mask & bit)) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 3 * SB * 8)); ctx.sym_attr_mask |= bit; } \
             k_pair_sym<N, 1><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);          \
         } else {                                                                                         \
-            static bool attr2 = false;                                                                   \
-            if (!attr2) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 3 * SB * 8)); attr2 = true; } \
+            if (!(ctx.sym_attr_mask & bit)) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 3 * SB * 8)); ctx.sym_attr_mask |= bit; } \
             k_pair_sym<N, 2><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);          \
         }                                                                                                \
     } while (0)
