@@ -269,7 +269,7 @@ static void release_all(Rb2Ctx &c)
     cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
     cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec);
     if (c.h_ramo_sec) cudaFreeHost(c.h_ramo_sec);
-    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw);
+    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw); cudaFree(c.sym_owner);
     cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
     if (c.h_counters) cudaFreeHost(c.h_counters);
     if (c.h_red) cudaFreeHost(c.h_red);
@@ -337,6 +337,7 @@ static int init_impl(Rb2Ctx &c, const rb2_config *cfg)
     if ((rc = rb2_launch_fill_mask(c, c.cap))) return rc;
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     if (const char *e = getenv("RB2_NO_GRAPH")) c.use_graph = atoi(e) != 0 ? 0 : 1;       // same as rb2_set_option("step_graph", 0)
+    if (const char *e = getenv("RB2_SYM_WAVES")) { const double v = atof(e); if (v >= 1.0) c.sym_waves = v; }                   // measurement scripts
     if (const char *e = getenv("RB2_PAIR_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c.pair_mode = v; }
     if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;
     if (const char *e = getenv("RB2_MH_SMALL_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c.mh_small_max = v; }

@@ -112,11 +112,13 @@ struct Rb2Ctx {
     size_t sym_budget_bytes = (size_t)2048 << 20;  // scratch for the (set, source tile) / (group, target) partial sums
     int    sym_tpl = 0;                   // targets per lane of the pair-symmetric kernel: 0 auto, 1, 2
     int    sym_kmax = 12, sym_gmax = 24;  // caps of the work-unit shape (options "sym_kmax", "sym_gmax"; tools/sym_unit_sweep.py)
-    double sym_waves = 16.0;              // CTA groups are sized for about this many waves per band launch
+    double sym_waves = 64.0;              // work units are sized for about this many waves per band launch and rank (tools/run_r2_2gpu_waves.sh)
     double *sym_bufI = nullptr, *sym_bufJ = nullptr, *sym_raw = nullptr;
     size_t sym_bufI_bytes = 0, sym_bufJ_bytes = 0, sym_raw_bytes = 0;
     int    sym_n_pad = 0;
     double *sym_raw_cur = nullptr;        // partial sums of the current evaluation (sym_raw, or a slot of the exchange block)
+    unsigned char *sym_owner = nullptr; size_t sym_owner_cap = 0;  // cost-balanced deal of the work units to the ranks
+    unsigned long long sym_owner_key[6] = {0, 0, 0, 0, 0, 0};      // ... valid for (n, T, K, G, band width, world)
     // peer-memory exchange (rb2_p2p.cu)
     void  *p2p_local = nullptr;           // this rank's exchange block (exported over CUDA IPC)
     void  *p2p_peer[RB2_P2P_MAX] = {};    // every rank's block as mapped here ([rank] == p2p_local)

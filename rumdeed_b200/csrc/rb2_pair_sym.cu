@@ -23,7 +23,11 @@
 // Per unordered pair at N_ic_max = 1: 81 FP64-pipe instructions + 6 MUFU + 14 SHFL, i.e. about
 // 40 FP64 instructions per ordered pair interaction against 74 in the gather kernel.  Image roles
 // (F8-ii) need no test here: J > I implies i < j for every pair of the tile.
+#include <string.h>
+
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "rb2_internal.cuh"
 #include "rb2_planar_math.cuh"
@@ -54,7 +58,8 @@ struct SymGeom {
     int band_start, band_len;  // source tiles [band_start, band_start + band_len)
     int G, ngroups;            // source tiles per CTA group, groups in this band
     int K, nIsets;             // target superblocks a CTA takes one after the other (a "set"), sets in all
-    int rank, world;           // CTA (set, grp) is owned by rank (set + grp) % world
+    int rank, world;           // CTA (set, grp) is owned by rank owner[set * ngroups + grp] (world > 1)
+    const unsigned char *owner;  // this band's slice of the cost-balanced deal (null: one rank)
 };
 
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
@@ -148,7 +153,7 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
 {
     const int iset = blockIdx.x;
     const int grp = blockIdx.y;
-    if (((iset + grp) % g.world) != g.rank) return;
+    if (g.owner && g.owner[iset * g.ngroups + grp] != g.rank) return;
     const int I0 = iset * g.K;
     const int J0 = g.band_start + grp * g.G;
     const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
@@ -316,7 +321,7 @@ k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restric
         const int J0 = g.band_start + grp * g.G;
         const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
         if (max(J0, T * It) >= J1) continue;
-        if (((Iset_t + grp) % g.world) != g.rank) continue;
+        if (g.owner && g.owner[Iset_t * g.ngroups + grp] != g.rank) continue;
         const size_t ib = (size_t)grp * 3 * g.n_pad + p;
         s0 += bufI[ib];
         s1 += bufI[ib + g.n_pad];
@@ -329,7 +334,7 @@ k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restric
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll 4
         for (int st = q; st < nset; st += RQ) {
-            if (((st + grp) % g.world) != g.rank) continue;
+            if (g.owner && g.owner[st * g.ngroups + grp] != g.rank) continue;
             const size_t base = (((size_t)st * g.band_len + (Jp - g.band_start)) * 3) * SB + tid;
             t0 += bufJ[base];
             t1 += bufJ[base + SB];
@@ -404,31 +409,31 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     // tiles whose reaction sums it keeps in shared memory (3 KB per tile) and stores once.  Per (superblock, tile) pair
     // that is 3 KB T / G of target sums + 3 KB / K of source sums written (and read back by the reduce kernel) instead
     // of 3 KB per pair with K = 1 (round 1: 96 GB per evaluation at N = 1e6).  K x G is sized for about sym_waves waves
-    // of CTAs per launch, times world^2: the CTAs of a band are dealt round-robin to the ranks, so each rank needs that
-    // many waves of its own (x world), and the deal (set + grp) % world only balances when there are many more units
-    // than ranks (x world again; tools/sym_rank_sweep.py).  The source tiles are processed in bands that fit the
-    // scratch budget (default 2 GiB).
+    // of CTAs per launch and rank.  Over several ranks the units of a band are dealt out by COST (tile pairs in the
+    // unit: the triangle clips the ones near the diagonal), largest first to the least loaded rank -- every rank computes
+    // the same table, cached until the geometry changes.  (Round 1 dealt them round-robin, (I + grp) % world, and needed
+    // world^2 times more, i.e. smaller, units to balance: at N = 1e5 on 8 GPUs single-tile CTAs whose fixed cost was 10 %.)
+    // The source tiles are processed in bands that fit the scratch budget (default 2 GiB).
     const int Gmax = (T == 1) ? 12 : 24;   // shared memory: 32 KB static + 3 KB x G, 3 (T = 1) or 2 CTAs per SM
-    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world * g.world;
-    size_t budget = ctx.sym_budget_bytes;
-    auto plan = [&](int Wb_in, int &K, int &G) {
-        const double KG = (double)g.nIb * Wb_in / want_ctas;
-        G = (int)sqrt((double)T * KG);     // traffic per pair ~ T / G + 1 / K: G = T K at the optimum
-        if (G > Gmax) G = Gmax;
-        if (G > ctx.sym_gmax) G = ctx.sym_gmax;
-        if (G > Wb_in) G = Wb_in;
-        if (G < 1) G = 1;
-        K = (int)(KG / G);
-        if (K > ctx.sym_kmax) K = ctx.sym_kmax;
-        if (K < 1) K = 1;
-    };
-    auto band_bytes = [&](int Wb_in, int K, int G) {
-        const size_t nsets = (size_t)(g.nIb + K - 1) / K, ngr = (size_t)(Wb_in + G - 1) / G;
-        return nsets * Wb_in * 3 * SB * sizeof(double) + ngr * 3 * g.n_pad * sizeof(double);
-    };
-    int Wb = g.nsb, K = 1, G = 1;
-    plan(Wb, K, G);
-    if (band_bytes(Wb, K, G) > ctx.sym_bufJ_bytes + ctx.sym_bufI_bytes) {
+    // unit size from the whole triangle: about sym_waves waves of units per rank and evaluation (not per band: tying the
+    // unit to the band width shrank the units whenever the budget shrank the bands, which costs more scratch per tile,
+    // which shrinks the bands ...)
+    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world;
+    const double KG = 0.5 * (double)g.nIb * (double)g.nsb / want_ctas;
+    int G = (int)sqrt((double)T * KG);     // traffic per pair ~ T / G + 1 / K: G = T K at the optimum
+    if (G > Gmax) G = Gmax;
+    if (G > ctx.sym_gmax) G = ctx.sym_gmax;
+    if (G > g.nsb) G = g.nsb;
+    if (G < 1) G = 1;
+    int K = (int)(KG / G);
+    if (K > ctx.sym_kmax) K = ctx.sym_kmax;
+    if (K < 1) K = 1;
+    // band width from the scratch budget.  The layout is not compacted by owner: over `world` ranks every rank fills
+    // 1 / world of the slots it allocates, so the budget (2 GiB of partial sums a rank actually writes) scales with it.
+    size_t budget = ctx.sym_budget_bytes * (size_t)g.world;
+    const size_t nsets = (size_t)(g.nIb + K - 1) / K;
+    const double tile_bytes = (double)nsets * 3 * SB * sizeof(double) + 3.0 * g.n_pad * sizeof(double) / G;
+    if (tile_bytes * g.nsb > (double)(ctx.sym_bufJ_bytes + ctx.sym_bufI_bytes)) {
         // the whole triangle does not fit what we hold: never ask for more than half of what is free (plus what we
         // already hold).  cudaMemGetInfo costs a fraction of a millisecond, so only look when it can matter.
         size_t fr = 0, tot = 0;
@@ -437,22 +442,20 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
             if (budget > cap) budget = cap;
         }
     }
-    for (int it = 0; it < 8 && band_bytes(Wb, K, G) > budget && Wb > 1; ++it) {
-        // shrink the band in proportion and re-plan (the set size depends on the band width)
-        int Wn = (int)((double)Wb * (double)budget / (double)band_bytes(Wb, K, G) * 0.97);
-        if (Wn >= Wb) Wn = Wb - 1;
-        if (Wn < 1) Wn = 1;
-        Wb = Wn;
-        plan(Wb, K, G);
+    int Wb = g.nsb;
+    if (tile_bytes * g.nsb > (double)budget) {
+        Wb = (int)((double)budget / tile_bytes);
+        Wb = std::max(G, (Wb / G) * G);  // whole groups per band
+        if (Wb > g.nsb) Wb = g.nsb;
     }
-    if (G > 1) Wb = std::max(G, (Wb / G) * G);  // whole groups per band
-    if (Wb > g.nsb) Wb = g.nsb;
     g.K = K;
     g.nIsets = (g.nIb + K - 1) / K;
     const int ngroups_max = (Wb + G - 1) / G;
-    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, (size_t)g.nIsets * Wb * 3 * SB * sizeof(double));
+    // banded: the sizes sit at the budget already -- allocate exactly (no head room for a growing particle count)
+    const size_t wantJ = (size_t)g.nIsets * Wb * 3 * SB * sizeof(double), wantI = (size_t)ngroups_max * 3 * g.n_pad * sizeof(double);
+    int rc = ensure_bytes(&ctx.sym_bufJ, &ctx.sym_bufJ_bytes, wantJ, Wb < g.nsb ? wantJ : 0);
     if (rc) return rc;
-    rc = ensure_bytes(&ctx.sym_bufI, &ctx.sym_bufI_bytes, (size_t)ngroups_max * 3 * g.n_pad * sizeof(double));
+    rc = ensure_bytes(&ctx.sym_bufI, &ctx.sym_bufI_bytes, wantI, Wb < g.nsb ? wantI : 0);
     if (rc) return rc;
     if (ctx.p2p_world > 1) {
         // peers read the partial sums in place: they live in the exported exchange block (rb2_p2p.cu)
@@ -466,6 +469,58 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     ctx.sym_n_pad = g.n_pad;
     cudaStream_t st = ctx.stream;
     const StepParams SP = rb2_make_step_params(c);
+    // the deal of the work units to the ranks, all bands in one table
+    std::vector<size_t> owner_off;
+    if (g.world > 1) {
+        const unsigned long long key[6] = {(unsigned long long)n, (unsigned long long)T, (unsigned long long)K, (unsigned long long)G,
+                                           (unsigned long long)Wb, (unsigned long long)g.world};
+        size_t total = 0;
+        for (int b0 = 0; b0 < g.nsb; b0 += Wb) {
+            const int blen = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
+            const int nI = (b0 + blen - 1) / T + 1;
+            owner_off.push_back(total);
+            total += (size_t)((nI + K - 1) / K) * ((blen + G - 1) / G);
+        }
+        if (memcmp(key, ctx.sym_owner_key, sizeof(key)) != 0 || !ctx.sym_owner) {
+            std::vector<unsigned char> tab(total, 0);
+            std::vector<std::pair<long long, int>> units;  // (-cost, index): ascending sort = largest first, index order on ties
+            size_t bi = 0;
+            for (int b0 = 0; b0 < g.nsb; b0 += Wb, ++bi) {
+                const int blen = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
+                const int nI = (b0 + blen - 1) / T + 1, nsets = (nI + K - 1) / K, ngr = (blen + G - 1) / G;
+                units.clear();
+                for (int is = 0; is < nsets; ++is)
+                    for (int gr = 0; gr < ngr; ++gr) {
+                        const int J0 = b0 + gr * G, J1 = std::min(J0 + G, std::min(b0 + blen, g.nsb));
+                        long long cost = 0;
+                        for (int I = is * K; I < std::min(is * K + K, g.nIb); ++I) {
+                            const int Jb = std::max(J0, T * I);
+                            if (Jb >= J1) break;
+                            cost += (long long)T * (J1 - Jb);          // T sub-sets x tiles ...
+                            for (int J = Jb; J < std::min(J1, T * I + T); ++J) cost -= (T - 1 - (J - T * I));  // ... less what the diagonal clips
+                        }
+                        if (cost > 0) units.emplace_back(-cost, is * ngr + gr);
+                    }
+                std::sort(units.begin(), units.end());
+                std::vector<long long> load((size_t)g.world, 0);
+                for (const auto &u : units) {
+                    int best = 0;
+                    for (int r = 1; r < g.world; ++r) if (load[(size_t)r] < load[(size_t)best]) best = r;
+                    load[(size_t)best] += -u.first;
+                    tab[owner_off[bi] + (size_t)u.second] = (unsigned char)best;
+                }
+            }
+            if (total > ctx.sym_owner_cap) {
+                if (ctx.sym_owner) RB2_CUDA(cudaFree(ctx.sym_owner));
+                ctx.sym_owner = nullptr; ctx.sym_owner_cap = 0;
+                RB2_CUDA(cudaMalloc(&ctx.sym_owner, total + total / 2 + 256));
+                ctx.sym_owner_cap = total + total / 2 + 256;
+            }
+            RB2_CUDA(cudaMemcpyAsync(ctx.sym_owner, tab.data(), total, cudaMemcpyHostToDevice, st));
+            RB2_CUDA(cudaStreamSynchronize(st));  // tab goes out of scope
+            memcpy(ctx.sym_owner_key, key, sizeof(key));
+        }
+    }
     RB2_CUDA(rb2_event_record(ctx, ctx.ev_a0));
     RB2_CUDA(cudaMemsetAsync(ctx.sym_raw_cur, 0, (size_t)3 * g.n_pad * sizeof(double), st));
     int launches = 0;
@@ -474,6 +529,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         g.band_len = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
         g.G = G;
         g.ngroups = (g.band_len + G - 1) / G;
+        g.owner = (g.world > 1) ? ctx.sym_owner + owner_off[(size_t)(b0 / Wb)] : nullptr;
         const int nI = (b0 + g.band_len - 1) / T + 1;  // target superblocks that start at or below the band's last tile
         dim3 grid((nI + K - 1) / K, g.ngroups), block(SB);
         const size_t dyn = (size_t)G * 3 * SB * sizeof(double);

@@ -15,3 +15,11 @@ for f in ('r2_2gpu_single_process_1e6','r2_2gpu_torchrun_1e6'):
     except Exception as e: print(f, 'failed', e)
 PY
 tail -5 gpurun_out/r2_2gpu.err
+python -m pytest tests/test_gpu_parity.py -m gpu -q -k "split_over_two_ranks or symmetric_kernel" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --particles 100000 --steps 10 --no-cpu --no-sweep > gpurun_out/r2_2gpu_torchrun_1e5.json 2>> gpurun_out/r2_2gpu.err
+python bench.py --gpus 1 --particles 100000 --steps 10 --no-cpu --no-sweep > gpurun_out/r2_1gpu_1e5.json 2>> gpurun_out/r2_2gpu.err
+python - <<'PY'
+import json
+a=json.loads(open('gpurun_out/r2_1gpu_1e5.json').read().strip().splitlines()[-1]); b=json.loads(open('gpurun_out/r2_2gpu_torchrun_1e5.json').read().strip().splitlines()[-1])
+print('1e5: 1 GPU', a['ms_per_step'], ' 2 GPUs', b['ms_per_step'], ' efficiency', a['ms_per_step']/b['ms_per_step']/2, 'kernel', a['roofline']['kernel_ms'], b['roofline']['kernel_ms'])
+PY
