@@ -262,6 +262,17 @@ typedef struct rb2_mh_config {
 int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed,
                   double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 
+/* The reference's DEFAULT sampler, mh_batch = .false.: the chains of a time step one after the other, chain s on the field
+ * of the store plus the electrons emitted by chains 0 .. s-1 in this call, the shared step adapted once per chain
+ * (Metropolis_Hastings_rectangle_J inside the insert loop of Do_Field_Emission_Planar_rectangle,
+ * src/mod_field_emission_v2.F90:1122-1265, :322-380; kind 2: src/mod_field_thermo_emission.F90:198-364).  Strictly
+ * sequential by construction; the whole loop runs in ONE kernel (one CTA, ~3 us per field evaluation instead of one
+ * ~40 us host round trip each).  emit_out[k] = 1: candidate k passed the emission test ln u <= D_f (kind 2: found a
+ * start) and was counted in the field of the later chains -- the caller inserts exactly those, in order, at z = 1 nm
+ * (rb2_add_particles).  At most 1024 emitted electrons per call. */
+int rb2_mh_planar_serial(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed,
+                         double *df_out, double *F_out, double *pos_out, int *emit_out, double *a_rate_io, double *mh_std_io);
+
 /* Lock-step chains on the hyperboloid tip: Metro_algo_tip_v3 (src/mod_emission_tip.f90:1241-1390) for the M candidates
  * of a time step together -- (xi, phi) proposals with reflection in xi and wrap in phi, target ln S + 1/2 ln(xi^2 - eta_1^2)
  * on the NORMAL field component, shared adaptive step (one update per jump after the warm-up quarter).  Every jump is

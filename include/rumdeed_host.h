@@ -21,7 +21,8 @@ typedef struct rh_setup {
     double emitters_pos[3], emitters_dim[3]; /* m; for the tip: d_tip, R_base, h_tip */
     int    emitters_type, emitters_delay;
     double T_temp;
-    int    mh_batch;           /* 0 serial chains, 1 lock-step chains (host loop), 2 lock-step chains resident on the GPU */
+    int    mh_batch;           /* 0 serial chains (the reference's default; one device kernel per step), -1 serial chains as a host
+                                  loop of single-point field calls, 1 lock-step chains (host loop), 2 lock-step chains on the GPU */
     int    planes_N;
     double planes_z[10];       /* m */
     double cuba_epsabs, cuba_epsrel;

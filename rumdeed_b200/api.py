@@ -133,7 +133,7 @@ EXPORTS = (
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
     "rb2_add_particles", "rb2_capacity_left", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_get_ramo_sections", "rb2_accel_host",
-    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_tip",
+    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_set_devices", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
@@ -178,6 +178,7 @@ def load_library(path: str | None = None):
     lib.rb2_field_batch_delta.argtypes = [C.c_int, _PD, C.c_int, _PD, _PD, _PD]
     lib.rb2_field_surface_z.argtypes = [C.c_int, _PD, _PD]
     lib.rb2_mh_planar.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
+    lib.rb2_mh_planar_serial.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PI, _PD, _PD]
     lib.rb2_mh_tip.argtypes = [C.c_int, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
     lib.rb2_set_partition.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_pair_rank.argtypes = [C.c_int, C.c_int]
@@ -475,6 +476,29 @@ class HotPath:
         ar, sd = C.c_double(a_rate), C.c_double(MH_std)
         self._check(self.lib.rb2_mh_planar(C.byref(c), _d(w), M, seed, _d(df), _d(F), _d(pos), C.byref(ar), C.byref(sd)))
         return df, F, pos, ar.value, sd.value
+
+    def mh_planar_serial(self, M, emit_pos, emit_dim, w_theta, seed, kind=1, image_charge=True, T_temp=293.15,
+                         a_rate=1.0, MH_std=0.0125, ndim=None, ndim_first=None):
+        """The reference's default serial chains (mh_batch = .false.) of one time step in one kernel: chain s sees the
+        electrons emitted by chains < s.  Returns (df, F, pos, emitted, a_rate, MH_std)."""
+        w = np.ascontiguousarray(w_theta, dtype=np.float64)
+        if w.ndim != 2:
+            w = w.reshape(1, -1)
+        c = MhConfig()
+        c.kind = kind
+        c.ndim = (25 if kind == 2 else 200) if ndim is None else ndim
+        c.ndim_first = (0 if kind == 2 else int(round(c.ndim * 0.25))) if ndim_first is None else ndim_first
+        c.image_charge = int(bool(image_charge))
+        c.y_num, c.x_num = w.shape
+        c.emit_pos[:] = list(emit_pos)[:2]
+        c.emit_dim[:] = list(emit_dim)[:2]
+        c.T_temp = T_temp
+        c.init_std, c.target_rate, c.std_gain = 0.10, 0.35, 0.025
+        c.std_min, c.std_max = (0.005 if kind == 2 else 0.00005), 0.1250
+        df, F, pos, em = np.zeros(M), np.zeros(M), np.zeros((M, 3)), np.zeros(M, dtype=np.int32)
+        ar, sd = C.c_double(a_rate), C.c_double(MH_std)
+        self._check(self.lib.rb2_mh_planar_serial(C.byref(c), _d(w), M, seed, _d(df), _d(F), _d(pos), _i(em), C.byref(ar), C.byref(sd)))
+        return df, F, pos, em, ar.value, sd.value
 
     def mh_tip(self, M, seed, ndim=80, a_rate=0.5, MH_std=1.0):
         """Device-resident lock-step tip chains (Metro_algo_tip_v3, src/mod_emission_tip.f90:1241-1390).

@@ -1095,6 +1095,19 @@ int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsign
     return rb2_launch_mh_planar(c, cfg, w_theta, M, seed, df_out, F_out, pos_out, a_rate_io, mh_std_io);
 }
 
+int rb2_mh_planar_serial(const rb2_mh_config *cfg, const double *w_theta, int M, unsigned long long seed, double *df_out,
+                         double *F_out, double *pos_out, int *emit_out, double *a_rate_io, double *mh_std_io)
+{
+    RB2_REQUIRE_INIT();
+    Rb2Ctx &c = g_rb2;
+    if (M < 1) return RB2_OK;
+    if (!cfg || !w_theta || !df_out || !F_out || !pos_out || !emit_out || !a_rate_io || !mh_std_io) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    if (c.cfg.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_mh_planar_serial: planar geometry only");
+    if (cfg->kind != 1 && cfg->kind != 2) return rb2_fail(RB2_ERR_ARG, "rb2_mh_planar_serial: kind must be 1 or 2");
+    if (cfg->ndim < 0 || cfg->emit_dim[0] <= 0.0 || cfg->emit_dim[1] <= 0.0) return rb2_fail(RB2_ERR_ARG, "rb2_mh_planar_serial: bad chain setup");
+    return rb2_launch_mh_planar_serial(c, cfg, w_theta, M, seed, df_out, F_out, pos_out, emit_out, a_rate_io, mh_std_io);
+}
+
 int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out, double *a_rate_io,
                double *mh_std_io)
 {

@@ -199,6 +199,8 @@ int rb2_launch_field(Rb2Ctx &ctx, const double4 *pq, int n, const double4 *extra
 int rb2_launch_mh_planar(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
                          double *df_out, double *F_out, double *pos_out, double *a_rate_io, double *mh_std_io);
 int rb2_launch_surface_field(Rb2Ctx &ctx, const double *d_pts, int M, double *d_Ez);
+int rb2_launch_mh_planar_serial(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
+                                double *df_out, double *F_out, double *pos_out, int *emit_out, double *a_rate_io, double *mh_std_io);
 int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
                       double *a_rate_io, double *mh_std_io);
 // collisions (rb2_collisions.cu)

@@ -739,6 +739,156 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
     }
 }
 
+// ---- the reference's DEFAULT sampler: serial chains (mh_batch = .false.) ---------------------------------------------
+// Metropolis_Hastings_rectangle_J (src/mod_field_emission_v2.F90:1122-1265) is called once per emission candidate from
+// the insert loop of Do_Field_Emission_Planar_rectangle (:322-380): chain s runs on the field of the store PLUS the
+// electrons that the chains before it emitted in this same time step, and the shared step MH_std is adapted once per
+// chain from that chain's own acceptance rate.  Both couplings are strict -- chain s needs the complete outcome of
+// chain s - 1 -- so the N_round x (1 + 200) field evaluations of a time step are sequential by construction.  The host
+// loop paid one M = 1 round trip (~40 us) per evaluation; here ONE CTA of 1024 threads runs the whole step: per jump the
+// threads sum the particle records (resident in shared memory as far as they fit, the rest from L2) and the pending
+// electrons of this step for the single proposal, a fixed-shape tree joins them, and warp 0 does the accept step, the
+// chain bookkeeping, the emission test (ln u <= D_f, :339-379) and the next proposal: two CTA barriers per jump, no
+// global memory traffic, ~3 us per evaluation.  kind 2: the chains of src/mod_field_thermo_emission.F90:198-364 (25
+// jumps, every chain that found a start emits).  Generator keys (seed, chain, iteration) as in the lock-step kernels.
+struct MhSerial {
+    int M, n, resident;           // chains, particle records, how many of them live in shared memory
+    double mh_std0, a_rate0;
+    const SurfRec *recs;          // [n]
+    double *df_out, *F_out, *pos_out, *scal_out;
+    int *emit_out;                // [M] 1: the candidate was emitted
+};
+constexpr int SER_T = 1024, SER_PMAX = 1024;  // threads; most electrons one time step can emit through this path
+
+template <int NIC>
+__global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, MhSerial Q)
+{
+    extern __shared__ __align__(16) unsigned char ser_smem[];
+    SurfRec *res = reinterpret_cast<SurfRec *>(ser_smem);            // [resident]
+    SurfRec *pend = res + Q.resident;                                // [SER_PMAX] electrons emitted in this step
+    __shared__ double red[SER_T / 32];
+    __shared__ double sp_x, sp_y;
+    __shared__ int s_npend, s_done;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < Q.resident; i += SER_T) res[i] = Q.recs[i];
+    if (tid == 0) { s_npend = 0; s_done = 0; }
+    const rb2_mh_config &c = P.c;
+    // chain state, kept by every lane of warp 0 (identical)
+    int s = 0, round = 0, jump = 0, ok = 0, jump_a = 0, jump_r = 0, npend = 0;
+    double cx = 0.0, cy = 0.0, sup = 0.0, Fc = 1.0, mh_std = Q.mh_std0, a_rate = Q.a_rate0;
+    double qx = 0.0, qy = 0.0, w_q = 0.0, log_u = 0.0;
+    int iter = 0;
+    for (;;) {
+        if (warp == 0) {
+            // the proposal of the current (chain, iteration)
+            if (s >= Q.M) { if (lane == 0) s_done = 1; }
+            else {
+                qx = cx; qy = cy;
+                if (!ok) {  // search for a favourable start, :1150-1180 (uniform over the emitter)
+                    iter = -(round + 1);
+                    double u, v;
+                    rand2(L.seed, s, iter, 0, 0, u, v);
+                    qx = u * c.emit_dim[0] + c.emit_pos[0];
+                    qy = v * c.emit_dim[1] + c.emit_pos[1];
+                } else {
+                    iter = jump;
+                    double g0, g1;
+                    draw_jump_normals(L, iter, s, g0, g1);
+                    propose_apply(P, iter, mh_std, g0, g1, qx, qy);
+                    double u, v;
+                    rand2(L.seed, s, iter, 2, 0, u, v);
+                    log_u = log(u);
+                }
+                w_q = w_theta_xy(P, qx, qy);
+                if (lane == 0) { sp_x = qx; sp_y = qy; }
+            }
+        }
+        __syncthreads();
+        if (s_done) break;
+        const double px = sp_x, py = sp_y;
+        const int n_tot = Q.n + s_npend;
+        double acc = 0.0;
+        bool close = false;
+        for (int i = tid; i < n_tot; i += SER_T) {
+            const SurfRec &r = (i < Q.resident) ? res[i] : (i < Q.n ? Q.recs[i] : pend[i - Q.n]);
+            acc = surf_term<NIC, false>(r, px, py, acc, L, close);
+        }
+        if (close) {  // a laterally close record: this thread's records again with the reference's sqrt / divide
+            acc = 0.0;
+            for (int i = tid; i < n_tot; i += SER_T) {
+                const SurfRec &r = (i < Q.resident) ? res[i] : (i < Q.n ? Q.recs[i] : pend[i - Q.n]);
+                acc = surf_term<NIC, true>(r, px, py, acc, L, close);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double sum = red[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const double Fz = L.E_vac - L.fac * sum;
+            bool chain_done = false;
+            if (!ok) {
+                if (Fz < 0.0) { cx = qx; cy = qy; Fc = Fz; sup = target_log_w(P, Fz, w_q); ok = 1; jump = 1; jump_a = 0; jump_r = 0; }
+                else if (++round >= L.max_init) chain_done = true;  // "Failed to find spot for emission", :1160-1170
+                if (ok && c.ndim < 1) chain_done = true;
+            } else {
+                const bool counted = jump > c.ndim_first;
+                const bool unfav = (c.kind == 2) ? (Fz > 0.0) : (Fz >= 0.0);
+                bool accept = false;
+                if (!unfav) {
+                    const double sup_new = target_log_w(P, Fz, w_q);
+                    accept = (sup_new >= sup) || (log_u <= sup_new - sup);
+                    if (accept) { cx = qx; cy = qy; sup = sup_new; Fc = Fz; }
+                }
+                if (counted) { if (accept) ++jump_a; else ++jump_r; }
+                if (++jump > c.ndim) chain_done = true;
+            }
+            if (chain_done) {
+                int emitted = 0;
+                double D_f = HUGE_NEG, F_out = 1.0, ox = c.emit_pos[0], oy = c.emit_pos[1];
+                if (ok) {
+                    if (jump_a + jump_r > 0) {  // the per-chain step adaptation, :1250-1256 / MH_std_update :603-612
+                        a_rate = (double)jump_a / (double)(jump_a + jump_r);
+                        mh_std = fmin(fmax(mh_std * exp(c.std_gain * (a_rate - c.target_rate)), c.std_min), c.std_max);
+                    }
+                    const double w = w_theta_xy(P, cx, cy), sw = sqrt(w);
+                    F_out = Fc; ox = cx; oy = cy;
+                    if (c.kind == 2) { D_f = 0.0; emitted = 1; }
+                    else {
+                        D_f = P.b_FN * (sw * sw * sw) * v_y(P, Fc, w) / (-1.0 * Fc);  // Escape_Prob_log
+                        double u, v;
+                        rand2(L.seed, s, c.ndim + 1, 3, 0, u, v);
+                        emitted = (Fc < 0.0 && log(u) <= D_f) ? 1 : 0;                // :339-379
+                    }
+                    if (emitted && npend >= SER_PMAX) emitted = 0;  // (never in practice: ~N_round / 10 emit)
+                    if (emitted) {  // Add_Particle at z = 1 nm: the chains that follow see it
+                        if (lane == 0) {
+                            const double z = 1.0 * rb2k::length_scale, q = -1.0 * rb2k::q_0;
+                            SurfRec r;
+                            r.x = cx; r.y = cy; r.h0 = z; r.g0 = q * z;
+                            if (L.nic >= 2) { r.h1 = 0.0; r.g1 = q; r.h2 = 0.0; r.g2 = 0.0; }
+                            else { r.h1 = z - L.two_d; r.g1 = q * r.h1; r.h2 = z + L.two_d; r.g2 = q * r.h2; }
+                            pend[npend] = r;
+                        }
+                        ++npend;
+                    }
+                }
+                if (lane == 0) {
+                    Q.df_out[s] = D_f; Q.F_out[s] = F_out; Q.emit_out[s] = emitted;
+                    Q.pos_out[3 * s] = ox; Q.pos_out[3 * s + 1] = oy; Q.pos_out[3 * s + 2] = 0.0;
+                    s_npend = npend;
+                }
+                ++s; ok = 0; round = 0; jump = 0; Fc = 1.0;
+            }
+        }
+        // (warp 0 publishes the next proposal behind the barrier at the top of the loop)
+    }
+    if (tid == 0) { Q.scal_out[0] = mh_std; Q.scal_out[1] = a_rate; }
+}
+
 // work units: (tiles of 32 points) x (particle chunks, whole 128-record sub-tiles)
 MhPlan make_plan(const Rb2Ctx &ctx, int M, int G_max)
 {
@@ -1374,6 +1524,68 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     RB2_CUDA(cudaMemcpyAsync(F_out, S.F_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
     RB2_CUDA(cudaMemcpyAsync(pos_out, S.pos_out, (size_t)3 * M * sizeof(double), cudaMemcpyDeviceToHost, st));
     RB2_CUDA(cudaMemcpyAsync(scal1, S.scal_out, sizeof(scal1), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    *mh_std_io = scal1[0];
+    *a_rate_io = scal1[1];
+    return RB2_OK;
+}
+
+int rb2_launch_mh_planar_serial(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
+                                double *df_out, double *F_out, double *pos_out, int *emit_out, double *a_rate_io, double *mh_std_io)
+{
+    if (M < 1) return RB2_OK;
+    const int nw = cfg->y_num * cfg->x_num;
+    if (nw < 1 || nw > 96 * 96) return rb2_fail(RB2_ERR_ARG, "work function table must have 1..9216 cells");
+    const rb2_config &gc = ctx.cfg;
+    const int n = ctx.n;
+    const int NIC = !gc.image_charge ? -1 : (gc.N_ic_max >= 2 ? 2 : gc.N_ic_max);
+    MhPlan L{};
+    L.M = M; L.n = n; L.max_init = 10000; L.seed = seed;
+    L.two_d = 2.0 * gc.d;
+    L.E_vac = rb2_make_step_params(gc).pl.E_z;
+    L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
+    L.nic = gc.N_ic_max;
+    MhSerial Q{};
+    Q.M = M; Q.n = n;
+    Q.mh_std0 = *mh_std_io; Q.a_rate0 = *a_rate_io;
+    // scratch (doubles): 5M outputs + 2 scalars + table + 8n records; (ints): M flags
+    const size_t off_recs = ((size_t)5 * M + 2 + nw + 1) & ~(size_t)1;
+    int rc = rb2_ensure_stage(ctx, off_recs + (size_t)8 * n + 2, (size_t)M + 4);
+    if (rc) return rc;
+    cudaStream_t st = ctx.stream;
+    double *d = ctx.d_stage_d;
+    Q.df_out = d; Q.F_out = d + M; Q.pos_out = d + 2 * (size_t)M; Q.scal_out = d + 5 * (size_t)M;
+    double *d_w = Q.scal_out + 2;
+    SurfRec *d_recs = reinterpret_cast<SurfRec *>(d + off_recs);
+    Q.recs = d_recs;
+    Q.emit_out = ctx.d_stage_i;
+    MhParams P;
+    P.c = *cfg;
+    P.w_theta = d_w;
+    const double pi = RB2_PI, h_bar = 6.62607015e-34 / (2.0 * pi);
+    P.b_FN = -4.0 / (3.0 * h_bar) * sqrt(2.0 * rb2k::m_0 * rb2k::q_0);
+    P.l_const = rb2k::q_0 / (4.0 * pi * rb2k::epsilon_0);
+    RB2_CUDA(cudaMemcpyAsync(d_w, w_theta_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice, st));
+    int launches = 1;
+    if (n > 0) {
+        k_surf_pack<<<(n + 255) / 256, 256, 0, st>>>(ctx.a.pq, n, L.two_d, gc.image_charge ? gc.N_ic_max : 0, d_recs);
+        launches++;
+    }
+    void *kern = NIC < 0 ? (void *)k_mh_serial<-1> : NIC == 0 ? (void *)k_mh_serial<0> : NIC == 1 ? (void *)k_mh_serial<1> : (void *)k_mh_serial<2>;
+    const size_t smem_max = 200 * 1024;
+    const size_t pend_bytes = (size_t)SER_PMAX * sizeof(SurfRec);
+    Q.resident = (int)std::min<size_t>((size_t)n, (smem_max - pend_bytes) / sizeof(SurfRec));
+    const size_t smem = (size_t)Q.resident * sizeof(SurfRec) + pend_bytes;
+    RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    void *args[] = {&P, &L, &Q};
+    RB2_CUDA(cudaLaunchKernel(kern, dim3(1), dim3(SER_T), args, smem, st));
+    RB2_LAUNCHED(launches);
+    double scal1[2];
+    RB2_CUDA(cudaMemcpyAsync(df_out, Q.df_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(F_out, Q.F_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(pos_out, Q.pos_out, (size_t)3 * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(emit_out, Q.emit_out, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaMemcpyAsync(scal1, Q.scal_out, sizeof(scal1), cudaMemcpyDeviceToHost, st));
     RB2_CUDA(cudaStreamSynchronize(st));
     *mh_std_io = scal1[0];
     *a_rate_io = scal1[1];

@@ -47,8 +47,9 @@ void *rh_create(const rh_setup *u)
     g.emitters_type = u->emitters_type;
     g.emitters_delay = u->emitters_delay;
     g.T_temp = u->T_temp;
-    g.mh_batch = u->mh_batch != 0;
+    g.mh_batch = u->mh_batch > 0;
     g.mh_device = u->mh_batch >= 2;
+    g.mh_host = u->mh_batch < 0;
     g.planes_N = u->planes_N;
     for (int k = 0; k < 10; ++k) g.planes_z[k] = u->planes_z[k];
     if (u->cuba_epsabs > 0) g.cuba_epsabs = u->cuba_epsabs;

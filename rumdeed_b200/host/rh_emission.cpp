@@ -330,12 +330,34 @@ int Metropolis_Hastings_rectangle_J(Sim &s, int emit, double *df_out, double *F_
     return 0;
 }
 
+static void fill_mh_config(const Sim &s, int kind, rb2_mh_config &c);
+
+// The DEFAULT sampler (mh_batch = .false.): the serial chains of a time step, each seeing the electrons emitted by the
+// ones before it, as ONE device kernel (rb2_mh_planar_serial) instead of one host/device round trip per jump.
+// emit_out[k] = 1: candidate k was emitted (and already counted in the field of the later chains).
+static int MH_planar_serial_device(Sim &s, int kind, int M, double *df_out, double *F_out, double *pos_out, int *emit_out)
+{
+    rb2_mh_config c{};
+    fill_mh_config(s, kind, c);
+    if (s.check(rb2_mh_planar_serial(&c, s.work.w_theta_arr.data(), M, s.rng.next(), df_out, F_out, pos_out, emit_out, &s.a_rate, &s.MH_std),
+                "rb2_mh_planar_serial")) return -2;
+    return 0;
+}
+
 // mh_device: the same lock-step chains with every jump iteration enqueued on the GPU (rb2_mh_planar);
 // kind 1 = field emission (:1284-1458), kind 2 = thermal-field chains (src/mod_field_thermo_emission.F90:198-364)
 static int MH_planar_device(Sim &s, int kind, int M, double *df_out, double *F_out, double *pos_out)
 {
-    const Globals &g = s.g;
     rb2_mh_config c{};
+    fill_mh_config(s, kind, c);
+    if (s.check(rb2_mh_planar(&c, s.work.w_theta_arr.data(), M, s.rng.next(), df_out, F_out, pos_out, &s.a_rate, &s.MH_std), "rb2_mh_planar"))
+        return -2;
+    return 0;
+}
+
+static void fill_mh_config(const Sim &s, int kind, rb2_mh_config &c)
+{
+    const Globals &g = s.g;
     c.kind = kind;
     c.ndim = (kind == 2) ? 25 : 25 * 8;
     c.ndim_first = (kind == 2) ? 0 : (int)lround(c.ndim * 0.25);
@@ -345,9 +367,6 @@ static int MH_planar_device(Sim &s, int kind, int M, double *df_out, double *F_o
     c.T_temp = g.T_temp;
     c.init_std = 0.10; c.target_rate = 0.35; c.std_gain = 0.025;
     c.std_min = (kind == 2) ? 0.005 : 0.00005; c.std_max = 0.1250;
-    if (s.check(rb2_mh_planar(&c, s.work.w_theta_arr.data(), M, s.rng.next(), df_out, F_out, pos_out, &s.a_rate, &s.MH_std), "rb2_mh_planar"))
-        return -2;
-    return 0;
 }
 
 // Lock-step batch, :1284-1458: one device batch per jump iteration
@@ -447,9 +466,16 @@ static int Do_Field_Emission_Planar_rectangle(Sim &s, int step, int emit)
     if (s.ud_integrand)
         fprintf(s.ud_integrand, "%3d  %8d  %8d  %4d  %12.4E  %12.4E  %12.4E\n", emit, 1, q.neval, q.fail, q.integral, q.error, 0.0);
     std::vector<double> mh_df, mh_F, mh_pos;
-    if (g.mh_batch && N_round > 0) {
+    std::vector<int> mh_emit;
+    // mh_batch = .false. (the reference's default): the serial chains run on the device in one kernel unless MH_HOST asks
+    // for the host loop (one M = 1 field call per jump)
+    const bool serial_dev = !g.mh_batch && !g.mh_host && N_round > 0;
+    if ((g.mh_batch || serial_dev) && N_round > 0) {
         mh_df.resize(N_round); mh_F.resize(N_round); mh_pos.resize((size_t)3 * N_round);
-        if (Metropolis_Hastings_rectangle_J_batch(s, N_round, emit, mh_df.data(), mh_F.data(), mh_pos.data()) == -2) return -1;
+        if (serial_dev) {
+            mh_emit.resize(N_round);
+            if (MH_planar_serial_device(s, 1, N_round, mh_df.data(), mh_F.data(), mh_pos.data(), mh_emit.data()) == -2) return -1;
+        } else if (Metropolis_Hastings_rectangle_J_batch(s, N_round, emit, mh_df.data(), mh_F.data(), mh_pos.data()) == -2) return -1;
     }
     const auto t2 = clk::now();
     s.t_em_mh += secs(t1, t2);
@@ -461,17 +487,18 @@ static int Do_Field_Emission_Planar_rectangle(Sim &s, int step, int emit)
     std::vector<int> add_sec;
     for (int k = 0; k < N_round; ++k) {
         double D_f, F, par_pos[3];
-        if (g.mh_batch) { D_f = mh_df[k]; F = mh_F[k]; memcpy(par_pos, &mh_pos[(size_t)3 * k], sizeof(par_pos)); }
+        if (g.mh_batch || serial_dev) { D_f = mh_df[k]; F = mh_F[k]; memcpy(par_pos, &mh_pos[(size_t)3 * k], sizeof(par_pos)); }
         else if (Metropolis_Hastings_rectangle_J(s, emit, &D_f, &F, par_pos) == -2) return -1;
         if (F >= 0.0) D_f = HUGE_NEG;
         df_avg += exp(D_f);
-        const double rnd = s.rng.uniform();
-        if (log(rnd) <= D_f) {
+        // the device's serial loop has made the emission test itself (the later chains had to see the result)
+        const bool emitted = serial_dev ? (mh_emit[k] != 0) : (log(s.rng.uniform()) <= D_f);
+        if (emitted) {
             par_pos[2] = 1.0 * length_scale;
             const double par_vel[3] = {0.0, 0.0, 0.0};
             int sec = 1;
             (void)s.work.w_theta_xy(g, par_pos, &sec);
-            if (g.mh_batch) { add_pos.insert(add_pos.end(), par_pos, par_pos + 3); add_sec.push_back(sec); }
+            if (g.mh_batch || serial_dev) { add_pos.insert(add_pos.end(), par_pos, par_pos + 3); add_sec.push_back(sec); }
             else if (s.Add_Particle(par_pos, par_vel, species_elec, step, emit, -1, sec)) return -1;
             nrElecEmit++;
         }
@@ -613,13 +640,20 @@ static int Do_Field_Thermo_Emission(Sim &s, int step)
     int nrElecEmit = 0;
     std::vector<double> b_pos;
     std::vector<int> b_ok;
+    const bool serial_dev = !g.mh_device && !g.mh_host && N_round > 0;  // the default serial chains, one device kernel
     if (g.mh_device && N_round > 0) {
         b_pos.resize((size_t)3 * N_round); b_ok.resize(N_round);
         if (Metropolis_Hastings_rectangle_J_thermo_batch(s, N_round, b_pos.data(), b_ok.data())) return -1;
+    } else if (serial_dev) {
+        std::vector<double> df(N_round), F(N_round);
+        b_pos.resize((size_t)3 * N_round); b_ok.resize(N_round);
+        if (MH_planar_serial_device(s, 2, N_round, df.data(), F.data(), b_pos.data(), b_ok.data())) return -1;
     }
+    std::vector<double> add_pos, add_vel;
+    std::vector<int> add_sec;
     for (int i = 0; i < N_round; ++i) {
         double par_pos[3], par_vel[3];
-        if (g.mh_device) {
+        if (g.mh_device || serial_dev) {
             if (!b_ok[i]) continue;
             memcpy(par_pos, &b_pos[(size_t)3 * i], sizeof(par_pos));
         } else {
@@ -631,9 +665,12 @@ static int Do_Field_Thermo_Emission(Sim &s, int step)
         Get_MB_Velocity(s, par_vel);
         int sec = 1;
         (void)s.work.w_theta_xy(g, par_pos, &sec);
-        if (s.Add_Particle(par_pos, par_vel, species_elec, step, 1, -1, sec)) return -1;
+        if (serial_dev) {  // the device loop has already counted these electrons in the later chains' fields: one insert call
+            add_pos.insert(add_pos.end(), par_pos, par_pos + 3); add_vel.insert(add_vel.end(), par_vel, par_vel + 3); add_sec.push_back(sec);
+        } else if (s.Add_Particle(par_pos, par_vel, species_elec, step, 1, -1, sec)) return -1;
         nrElecEmit++;
     }
+    if (!add_sec.empty() && s.Add_Particles((int)add_sec.size(), add_pos.data(), add_vel.data(), species_elec, step, 1, -1, add_sec.data())) return -1;
     s.slog.nrElecEmit = nrElecEmit;
     if (s.ud_field)
         fprintf(s.ud_field, "%8d  %16.8E  %16.8E  %16.8E  %16.8E  %16.8E  %16.8E  %16.8E\n", step, q.F_avg[0], q.F_avg[1], q.F_avg[2],

@@ -70,6 +70,7 @@ struct Globals {
     double planes_z[RB2_PLANES_MAX] = {5.0, 10.0, 25.0, 50.0, 75.0, 100.0, 125.0, 250.0, 500.0, 750.0};
     bool mh_batch = false;
     bool mh_device = false;  // lock-step chains run by rb2_mh_planar (implies mh_batch)
+    bool mh_host = false;    // mh_batch = .false.: the serial chains as a HOST loop of M = 1 field calls (default: one device kernel)
     bool write_ramo_sec = false;                             // src/mod_global.F90:352: ramo_current.bin per section
     bool write_position_file = false;                        // src/mod_global.F90:353
     bool sample_elec_file = false; int sample_elec_rate = 500;  // src/mod_global.F90:360-361

@@ -150,6 +150,7 @@ int Read_Input_Variables(const std::string &path, Globals &g, std::string &err)
     logical("MH_BATCH", g.mh_batch);
     logical("MH_DEVICE", g.mh_device);  // extension: lock-step chains resident on the GPU (rb2_mh_planar)
     if (g.mh_device) g.mh_batch = true;
+    logical("MH_HOST", g.mh_host);      // extension: run the default serial chains as a host loop (one field call per jump)
     logical("WRITE_RAMO_SEC", g.write_ramo_sec);
     logical("WRITE_POSITION_FILE", g.write_position_file);
     logical("SAMPLE_ELEC_FILE", g.sample_elec_file);

@@ -365,6 +365,120 @@ def test_device_resident_tip_sampler(orc):
         assert df_d[k] == pytest.approx(orc.tip_escape_prob(p, eta_d[k], 4.7), rel=1e-10)
 
 
+M32 = 0xFFFFFFFF
+
+
+def _philox(ctr, key):
+    """Philox4x32-10, the generator of the device samplers (rb2_mh.cu)."""
+    ctr, key = list(ctr), list(key)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * ctr[0], 0xCD9E8D57 * ctr[2]
+        ctr = [((p1 >> 32) ^ ctr[1] ^ key[0]) & M32, p1 & M32, ((p0 >> 32) ^ ctr[3] ^ key[1]) & M32, p0 & M32]
+        key = [(key[0] + 0x9E3779B9) & M32, (key[1] + 0xBB67AE85) & M32]
+    return ctr
+
+
+def _rand2(seed, chain, it, purpose, attempt):
+    key = [(seed & M32) ^ ((chain * 0x9E3779B1) & M32), ((seed >> 32) + chain) & M32]
+    r = _philox([it & M32, purpose, attempt, chain], key)
+    u53 = lambda hi, lo: ((hi >> 5) * 67108864.0 + (lo >> 6)) * (1.0 / 9007199254740992.0)
+    return u53(r[0], r[1]), u53(r[2], r[3])
+
+
+@gpu
+@pytest.mark.parametrize("n_pre,w", [(0, ((2.0,),)), (300, ((2.0, 2.3), (2.3, 2.0)))])
+def test_serial_sampler_kernel_follows_the_serial_algorithm(orc, n_pre, w):
+    """rb2_mh_planar_serial (the reference's default mh_batch = .false. semantics in one kernel) against a line-by-line
+    host replay of Metropolis_Hastings_rectangle_J inside the insert loop (mod_field_emission_v2.F90:1122-1265,
+    :322-380) that uses the SAME counter-based random numbers and one rb2_field_surface_z call per jump, with every
+    emitted electron inserted into the store before the next chain starts: same emission decisions, same positions
+    (to rounding: libm vs CUDA log / sqrt), same step adaptation.  Chain s therefore sees the electrons of chains < s."""
+    emit, d, V = 60 * NM, 500 * NM, 3000.0
+    sim, p, st, em = _planar_pair(orc, 3, w=w, V=V, d=d, emit=emit, dt=1e-16)
+    epos, edim = (-0.5 * emit, -0.5 * emit), (emit, emit)
+    M, ndim, nfirst, seed = 16, 40, 10, 987654321
+    warr = np.atleast_2d(np.asarray(w, dtype=float))
+    h_bar = 6.62607015e-34 / (2.0 * math.pi)
+    b_FN = -4.0 / (3.0 * h_bar) * math.sqrt(2.0 * rb.api.M_0 * rb.api.Q_0)
+    eps0 = 1.0 / (1.25663706212e-6 * 299792458.0 ** 2)
+    l_const = rb.api.Q_0 / (4.0 * math.pi * eps0)
+
+    def w_at(x, y):
+        return sim.w_theta_xy(np.array([x, y, 0.0]))[0]
+
+    def fn_l(F, wv):
+        return min(1.0, l_const * (-F) / (wv * wv))
+
+    def target(F, wv):
+        l = fn_l(F, wv)
+        return 2.0 * math.log(-F) - 2.0 * math.log(1.0 + l * (1.0 / 9.0 - math.log(l) / 18.0)) - math.log(wv)
+
+    with sim:
+        hp = rb.HotPath.attach()
+        if n_pre:
+            _preload(sim, st, p, n_pre, 8, emit=emit, d=d)
+        df_d, F_d, pos_d, em_d, ar_d, sd_d = hp.mh_planar_serial(M, epos, edim, warr, seed, ndim=ndim, ndim_first=nfirst)
+        again = hp.mh_planar_serial(M, epos, edim, warr, seed, ndim=ndim, ndim_first=nfirst)
+        # host replay
+        field = lambda x, y: float(hp.field_surface_z(np.array([[x, y, 0.0]]))[0])
+        mh_std, a_rate = 0.0125, 1.0
+        out = []
+        for s in range(M):
+            ok, rnd = False, 0
+            while not ok and rnd < 10000:
+                u, v = _rand2(seed, s, -(rnd + 1), 0, 0)
+                cx, cy = u * edim[0] + epos[0], v * edim[1] + epos[1]
+                Fc = field(cx, cy)
+                ok = Fc < 0.0
+                rnd += 1
+            assert ok
+            sup = target(Fc, w_at(cx, cy))
+            ja = jr = 0
+            for it in range(1, ndim + 1):
+                for attempt in range(64):
+                    u, v = _rand2(seed, s, it, 1, attempt)
+                    a, b = 2.0 * u - 1.0, 2.0 * v - 1.0
+                    ww = a * a + b * b
+                    if 0.0 < ww < 1.0:
+                        f = math.sqrt((-2.0 * math.log(ww)) / ww)
+                        g0, g1 = a * f, b * f
+                        break
+                frac = mh_std if it > nfirst else 0.10
+                qx, qy = cx + g0 * (edim[0] * frac), cy + g1 * (edim[1] * frac)
+                x_min, x_max, y_min, y_max = epos[0], epos[0] + edim[0], epos[1], epos[1] + edim[1]
+                if qx > x_max: qx = x_max - (qx - x_max)
+                elif qx < x_min: qx = (x_min - qx) + x_min
+                if qy > y_max: qy = y_max - (qy - y_max)
+                elif qy < y_min: qy = (y_min - qy) + y_min
+                Fz = field(qx, qy)
+                acc = False
+                if Fz < 0.0:
+                    sup_new = target(Fz, w_at(qx, qy))
+                    acc = sup_new >= sup or math.log(_rand2(seed, s, it, 2, 0)[0]) <= sup_new - sup
+                    if acc:
+                        cx, cy, sup, Fc = qx, qy, sup_new, Fz
+                if it > nfirst:
+                    ja, jr = ja + acc, jr + (not acc)
+            if ja + jr > 0:
+                a_rate = ja / (ja + jr)
+                mh_std = min(max(mh_std * math.exp(0.025 * (a_rate - 0.35)), 0.00005), 0.125)
+            wv = w_at(cx, cy)
+            l = fn_l(Fc, wv)
+            D_f = b_FN * math.sqrt(wv) ** 3 * (1.0 - l + l * math.log(l) / 6.0) / (-Fc)
+            emitted = math.log(_rand2(seed, s, ndim + 1, 3, 0)[0]) <= D_f
+            out.append((cx, cy, Fc, D_f, emitted))
+            if emitted:  # Add_Particle at z = 1 nm: the next chains see it
+                hp.Add_Particle([cx, cy, 1.0 * NM], [0.0, 0.0, 0.0], 1, 1, 1)
+    for x, y in zip(again[:4], (df_d, F_d, pos_d, em_d)):
+        assert np.array_equal(x, y)
+    ref = np.array([(o[0], o[1], o[2], o[3]) for o in out])
+    assert [bool(e) for e in em_d] == [o[4] for o in out]
+    assert 1 <= int(em_d.sum()) < M                      # some chains did run against same-step electrons
+    assert np.allclose(pos_d[:, 0], ref[:, 0], rtol=0, atol=1e-9 * emit) and np.allclose(pos_d[:, 1], ref[:, 1], rtol=0, atol=1e-9 * emit)
+    assert np.allclose(F_d, ref[:, 2], rtol=1e-9) and np.allclose(df_d, ref[:, 3], rtol=1e-9)
+    assert sd_d == pytest.approx(mh_std, rel=1e-12) and ar_d == pytest.approx(a_rate, rel=1e-12)
+
+
 @gpu
 @pytest.mark.parametrize("M,n_pre", [(100, 60), (214, 60), (214, 1500), (512, 700), (33, 0)])
 def test_tip_sampler_persistent_kernel(orc, M, n_pre):
@@ -407,7 +521,7 @@ def test_tip_sampler_persistent_kernel(orc, M, n_pre):
 # ---------------------------------------------------------------------------------------------------------
 # GPU: whole-system runs
 @gpu
-@pytest.mark.parametrize("mh_batch", [False, True, 2])
+@pytest.mark.parametrize("mh_batch", [-1, False, True, 2])
 def test_planar_system_reference_test(orc, mh_batch):
     """mod_tests.F90:2013-2125 (Test_Planar_System): 250 steps, 1 kV over 500 nm, 100 x 100 nm emitter,
     2.0 eV, N_ic_max = 0.  Same assertions as the reference, plus agreement with an oracle run."""
@@ -438,7 +552,7 @@ def test_planar_system_reference_test(orc, mh_batch):
     Qo = 0.0
     for i in range(1, n_steps + 1):
         N_sup, _ = em.supply_grid(SUPPLY_FE, 16)
-        em.do_field_emission_planar(i, N_sup, bool(mh_batch))
+        em.do_field_emission_planar(i, N_sup, mh_batch in (True, 2))
         st.step(p)
         if i > n_steps // 2:
             Qo += st.s.ramo_current[1] * dt
@@ -487,7 +601,7 @@ def test_tip_system_reference_test(orc, mh_batch):
 
 
 @gpu
-@pytest.mark.parametrize("mh_batch", [False, 2])
+@pytest.mark.parametrize("mh_batch", [-1, False, 2])
 def test_thermo_field_system(orc, mh_batch):
     w = ((2.0, 2.5), (2.5, 2.0))
     sim, p, st, em = _planar_pair(orc, 99, w=w, mode=9, T=1000.0, V=2000.0, d=1000 * NM, dt=1e-16, mh_batch=mh_batch)

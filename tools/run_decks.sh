@@ -33,6 +33,8 @@ if [ "$WHICH" = all ] || [ "$WHICH" = device ]; then run "Planar-FE 4.7eV MH_DEV
 if [ "$WHICH" = all ] || [ "$WHICH" = tip ]; then run "Tip-FE MH_BATCH"          tip_fe $ST "MH_BATCH = .True.,"; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = tip ]; then run "Tip-FE MH_DEVICE"         tip_fe $ST "MH_DEVICE = .True.,"; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = ion ]; then run "Ion (collisions) MH_DEVICE" ion $SP "MH_DEVICE = .True.,"; fi
+if [ "$WHICH" = all ] || [ "$WHICH" = serial ]; then run "Planar-FE 4.7eV as shipped (serial chains, device)" planar_fe_4p7 300 ""; fi
+if [ "$WHICH" = all ] || [ "$WHICH" = serial ]; then run "Planar-FE 4.7eV MH_HOST (serial chains, host loop)" planar_fe_4p7 40 "MH_HOST = .True.,"; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = photo ]; then run "Photo (500 nm, 300 steps)"  photo 300 ""; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = tfe ]; then run "Checkerboard-TFE"          checkerboard_tfe $SP ""; fi
 if [ "$WHICH" = all ] || [ "$WHICH" = tfe ]; then run "Checkerboard-TFE MH_DEVICE" checkerboard_tfe $SP "MH_DEVICE = .True.,"; fi
