@@ -241,6 +241,39 @@ module mod_b200_bridge
     integer(c_int) function rb2_p2p_detach() bind(C, name='rb2_p2p_detach')
       import :: c_int
     end function
+    ! ONE process, several GPUs (this program is a single process): after B200_Init, before the first particle
+    integer(c_int) function rb2_set_devices(n_devices, devices) bind(C, name='rb2_set_devices')
+      import :: c_int
+      integer(c_int), value :: n_devices
+      integer(c_int), intent(in) :: devices(*)           ! devices(1) = the device of rb2_init
+    end function
+    integer(c_int) function rb2_set_option(name, value) bind(C, name='rb2_set_option')
+      import :: c_int, c_char, c_double
+      character(kind=c_char), intent(in) :: name(*)      ! null terminated
+      real(c_double), value :: value
+    end function
+    ! ramo_current_emit(1:n_sec, 1:n_emit) of the last velocity update (mod_verlet.F90:489-492)
+    integer(c_int) function rb2_get_ramo_sections(n_sec, n_emit, ramo_out) bind(C, name='rb2_get_ramo_sections')
+      import :: c_int, c_double
+      integer(c_int), value :: n_sec, n_emit
+      real(c_double), intent(out) :: ramo_out(n_sec, *)
+    end function
+    integer(c_int) function rb2_capacity_left(room) bind(C, name='rb2_capacity_left')
+      import :: c_int
+      integer(c_int), intent(out) :: room
+    end function
+    ! the default sampler (mh_batch = .false.): the serial chains of a time step in one kernel
+    integer(c_int) function rb2_mh_planar_serial(cfg, w_theta, M, seed, df_out, F_out, pos_out, emit_out, a_rate_io, mh_std_io) &
+        bind(C, name='rb2_mh_planar_serial')
+      import :: c_int, c_double, c_long_long, rb2_mh_config
+      type(rb2_mh_config), intent(in) :: cfg
+      real(c_double), intent(in) :: w_theta(*)
+      integer(c_int), value :: M
+      integer(c_long_long), value :: seed
+      real(c_double), intent(out) :: df_out(*), F_out(*), pos_out(3, *)
+      integer(c_int), intent(out) :: emit_out(*)         ! 1: candidate emitted (insert it with B200_Add_Particle, in order)
+      real(c_double), intent(inout) :: a_rate_io, mh_std_io
+    end function
     function rb2_last_error_string() bind(C, name='rb2_last_error_string') result(p)
       import :: c_ptr
       type(c_ptr) :: p
@@ -288,7 +321,15 @@ contains
     type(rb2_config)    :: cfg
     call Fill_Config(cfg, geom)
     call Check(rb2_init(cfg), 'rb2_init')
+    ! ramo_current_emit(sec, emit) is only accumulated on request (write_ramo_sec, mod_global.F90:352)
+    if (write_ramo_sec) call Check(rb2_set_option('ramo_sections'//c_null_char, real(MAX_SECTIONS, c_double)), 'rb2_set_option')
   end subroutine B200_Init
+
+  ! Optional: let this (single) process drive several GPUs.  devices(1) must be the current device.
+  subroutine B200_Set_Devices(devices)
+    integer, intent(in) :: devices(:)
+    call Check(rb2_set_devices(int(size(devices), c_int), int(devices, c_int)), 'rb2_set_devices')
+  end subroutine B200_Set_Devices
 
   subroutine B200_Finalize()
     call Check(rb2_finalize(), 'rb2_finalize')
@@ -374,6 +415,9 @@ contains
     nrIon_remove_top = r%counts%nrIon_remove_top;    nrIon_remove_bot = r%counts%nrIon_remove_bot
     nrPart_remove_ion = r%counts%nrPart_remove_ion;  nrElec_remove_ion = r%counts%nrElec_remove_ion
     nrAtom_remove_ion = r%counts%nrAtom_remove_ion
+    if (write_ramo_sec) then ! mod_verlet.F90:489-492; written by Write_Ramo_Current, mod_pair.F90:822-826
+      call Check(rb2_get_ramo_sections(int(MAX_SECTIONS, c_int), int(MAX_EMITTERS, c_int), ramo_current_emit), 'rb2_get_ramo_sections')
+    end if
     if (r%n_events > 0) then
       if (.not. allocated(ev_buf)) allocate(ev_buf(max(1024, int(r%n_events))))
       if (size(ev_buf) < r%n_events) then

@@ -806,8 +806,14 @@ int rb2_step(int step, rb2_step_result *out)
     // queue on every device first, wait afterwards (rb2_set_devices): the devices integrate their replicas side by side
     // and exchange the partial pair sums inside the finalise kernel
     const int rc = each_device([&]() -> int { return step_queue(); });
-    const int rc2 = each_device([&]() -> int { return step_finish(out); });
-    return rc ? rc : rc2;
+    if (rc) {  // nothing to read back; let whatever was queued drain
+        char msg[sizeof(g_rb2_err)];
+        memcpy(msg, g_rb2_err, sizeof(msg));
+        each_device([&]() -> int { cudaStreamSynchronize(g_rb2.stream); return RB2_OK; });
+        memcpy(g_rb2_err, msg, sizeof(msg));
+        return rc;
+    }
+    return each_device([&]() -> int { return step_finish(out); });
 }
 
 static int step_queue(void)

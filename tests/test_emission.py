@@ -386,7 +386,7 @@ def _rand2(seed, chain, it, purpose, attempt):
 
 
 @gpu
-@pytest.mark.parametrize("n_pre,w", [(0, ((2.0,),)), (300, ((2.0, 2.3), (2.3, 2.0)))])
+@pytest.mark.parametrize("n_pre,w", [(0, ((2.0,),)), (300, ((2.0, 3.2), (3.2, 2.0)))])
 def test_serial_sampler_kernel_follows_the_serial_algorithm(orc, n_pre, w):
     """rb2_mh_planar_serial (the reference's default mh_batch = .false. semantics in one kernel) against a line-by-line
     host replay of Metropolis_Hastings_rectangle_J inside the insert loop (mod_field_emission_v2.F90:1122-1265,
@@ -473,7 +473,7 @@ def test_serial_sampler_kernel_follows_the_serial_algorithm(orc, n_pre, w):
         assert np.array_equal(x, y)
     ref = np.array([(o[0], o[1], o[2], o[3]) for o in out])
     assert [bool(e) for e in em_d] == [o[4] for o in out]
-    assert 1 <= int(em_d.sum()) < M                      # some chains did run against same-step electrons
+    assert int(em_d.sum()) >= 1                          # the chains behind an emitted one ran against a same-step electron
     assert np.allclose(pos_d[:, 0], ref[:, 0], rtol=0, atol=1e-9 * emit) and np.allclose(pos_d[:, 1], ref[:, 1], rtol=0, atol=1e-9 * emit)
     assert np.allclose(F_d, ref[:, 2], rtol=1e-9) and np.allclose(df_d, ref[:, 3], rtol=1e-9)
     assert sd_d == pytest.approx(mh_std, rel=1e-12) and ar_d == pytest.approx(a_rate, rel=1e-12)
