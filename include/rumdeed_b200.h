@@ -266,7 +266,7 @@ int rb2_mh_planar(const rb2_mh_config *cfg, const double *w_theta, int M, unsign
  * of the store plus the electrons emitted by chains 0 .. s-1 in this call, the shared step adapted once per chain
  * (Metropolis_Hastings_rectangle_J inside the insert loop of Do_Field_Emission_Planar_rectangle,
  * src/mod_field_emission_v2.F90:1122-1265, :322-380; kind 2: src/mod_field_thermo_emission.F90:198-364).  Strictly
- * sequential by construction; the whole loop runs in ONE kernel (one CTA, ~3 us per field evaluation instead of one
+ * sequential by construction; the whole loop runs in ONE kernel (one CTA, ~2.5 us per field evaluation instead of one
  * ~40 us host round trip each).  emit_out[k] = 1: candidate k passed the emission test ln u <= D_f (kind 2: found a
  * start) and was counted in the field of the later chains -- the caller inserts exactly those, in order, at z = 1 nm
  * (rb2_add_particles).  At most 1024 emitted electrons per call. */

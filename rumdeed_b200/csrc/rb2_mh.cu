@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
 // threads sum the particle records (resident in shared memory as far as they fit, the rest from L2) and the pending
 // electrons of this step for the single proposal, a fixed-shape tree joins them, and warp 0 does the accept step, the
 // chain bookkeeping, the emission test (ln u <= D_f, :339-379) and the next proposal: two CTA barriers per jump, no
-// global memory traffic, ~3 us per evaluation.  kind 2: the chains of src/mod_field_thermo_emission.F90:198-364 (25
+// global memory traffic, ~2.5 us per evaluation.  kind 2: the chains of src/mod_field_thermo_emission.F90:198-364 (25
 // jumps, every chain that found a start emits).  Generator keys (seed, chain, iteration) as in the lock-step kernels.
 struct MhSerial {
     int M, n, resident;           // chains, particle records, how many of them live in shared memory
@@ -769,6 +769,10 @@ __global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, Mh
     __shared__ double red[SER_T / 32];
     __shared__ double sp_x, sp_y;
     __shared__ int s_npend, s_done;
+    // look-ahead of warp 1 (while warp 0 does the accept step): the random numbers of the three iterations that can
+    // follow the current one -- the next jump of this chain, the next search round, the first search round of the next chain
+    __shared__ double la_g0, la_g1, la_lu, la_nu, la_nv, la_ru, la_rv;
+    __shared__ int st_s, st_ok, st_jump, st_round;   // state of the evaluation in flight, published by warp 0
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < Q.resident; i += SER_T) res[i] = Q.recs[i];
     if (tid == 0) { s_npend = 0; s_done = 0; }
@@ -778,6 +782,8 @@ __global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, Mh
     double cx = 0.0, cy = 0.0, sup = 0.0, Fc = 1.0, mh_std = Q.mh_std0, a_rate = Q.a_rate0;
     double qx = 0.0, qy = 0.0, w_q = 0.0, log_u = 0.0;
     int iter = 0;
+    bool have_la = false;      // warp 0: the look-ahead of the previous iteration is valid
+    int prev_s = -1;           // warp 0: chain of the previous evaluation
     for (;;) {
         if (warp == 0) {
             // the proposal of the current (chain, iteration)
@@ -787,20 +793,26 @@ __global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, Mh
                 if (!ok) {  // search for a favourable start, :1150-1180 (uniform over the emitter)
                     iter = -(round + 1);
                     double u, v;
-                    rand2(L.seed, s, iter, 0, 0, u, v);
+                    if (have_la && s != prev_s && round == 0) { u = la_nu; v = la_nv; }
+                    else if (have_la && s == prev_s && round >= 1) { u = la_ru; v = la_rv; }
+                    else rand2(L.seed, s, iter, 0, 0, u, v);
                     qx = u * c.emit_dim[0] + c.emit_pos[0];
                     qy = v * c.emit_dim[1] + c.emit_pos[1];
                 } else {
                     iter = jump;
                     double g0, g1;
-                    draw_jump_normals(L, iter, s, g0, g1);
+                    if (have_la && s == prev_s) { g0 = la_g0; g1 = la_g1; log_u = la_lu; }
+                    else {
+                        draw_jump_normals(L, iter, s, g0, g1);
+                        double u, v;
+                        rand2(L.seed, s, iter, 2, 0, u, v);
+                        log_u = log(u);
+                    }
                     propose_apply(P, iter, mh_std, g0, g1, qx, qy);
-                    double u, v;
-                    rand2(L.seed, s, iter, 2, 0, u, v);
-                    log_u = log(u);
                 }
                 w_q = w_theta_xy(P, qx, qy);
-                if (lane == 0) { sp_x = qx; sp_y = qy; }
+                if (lane == 0) { sp_x = qx; sp_y = qy; st_s = s; st_ok = ok; st_jump = jump; st_round = round; }
+                prev_s = s;
             }
         }
         __syncthreads();
@@ -824,6 +836,17 @@ __global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, Mh
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) red[warp] = acc;
         __syncthreads();
+        if (warp == 1) {
+            // the randoms of whatever iteration follows (a function of seed, chain, iteration only), one item per lane
+            const int cs = st_s, cok = st_ok;
+            const int jn = cok ? st_jump + 1 : 1;
+            if (lane == 0 && jn <= c.ndim) { double g0, g1; draw_jump_normals(L, jn, cs, g0, g1); la_g0 = g0; la_g1 = g1; }
+            else if (lane == 1 && jn <= c.ndim) { double u, v; rand2(L.seed, cs, jn, 2, 0, u, v); la_lu = log(u); }
+            else if (lane == 2 && cs + 1 < Q.M) { double u, v; rand2(L.seed, cs + 1, -1, 0, 0, u, v); la_nu = u; la_nv = v; }
+            else if (lane == 3 && !cok) { double u, v; rand2(L.seed, cs, -(st_round + 2), 0, 0, u, v); la_ru = u; la_rv = v; }
+            __syncwarp();
+            asm volatile("bar.sync 1, 64;" ::: "memory");  // with warp 0, behind its accept step
+        }
         if (warp == 0) {
             double sum = red[lane];
 #pragma unroll
@@ -883,6 +906,8 @@ __global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, Mh
                 }
                 ++s; ok = 0; round = 0; jump = 0; Fc = 1.0;
             }
+            asm volatile("bar.sync 1, 64;" ::: "memory");  // warp 1's look-ahead is in shared memory
+            have_la = true;
         }
         // (warp 0 publishes the next proposal behind the barrier at the top of the loop)
     }

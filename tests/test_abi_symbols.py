@@ -80,3 +80,20 @@ def test_fails_loudly_without_gpu():
     # uninitialised calls report RB2_ERR_NOT_INIT instead of computing anything
     assert lib.rb2_accel_only() == -1
     assert lib.rb2_field_batch(1, None, None) == -1
+
+
+def test_bench_reference_arm_runs_on_the_cpu():
+    """`bench.py --impl reference` (the CPU restatement of the reference's pair loop on the host cores) needs no GPU and
+    none of the product: one JSON line with the contract's keys, the thread count stated, the same row sample rule."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--particles", "3000", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env={**os.environ, "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "pair_interactions_per_s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "100%" in cb["sample"].replace(" ", "")  # every row at this size
+    # the thread count is set explicitly: OMP_NUM_THREADS=1 (what torchrun exports) does not pin the arm to one core
+    assert cb["cores"] == len(os.sched_getaffinity(0))
