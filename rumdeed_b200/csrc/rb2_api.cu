@@ -53,6 +53,7 @@ StepParams rb2_make_step_params(const rb2_config &c)
     P.pl.E_z = c.E_z;
     P.pl.nic = c.N_ic_max;
     P.pl.do_ic = c.image_charge;
+    P.pl.far_ok = (c.d >= 1.0e-6) ? 1 : 0;
     P.tip.a_foci = c.a_foci;
     P.tip.shift_z = c.shift_z;
     P.tip.pre_fac_E_tip = c.pre_fac_E_tip;
@@ -338,6 +339,7 @@ static int init_impl(Rb2Ctx &c, const rb2_config *cfg)
     RB2_CUDA(cudaStreamSynchronize(c.stream));
     if (const char *e = getenv("RB2_NO_GRAPH")) c.use_graph = atoi(e) != 0 ? 0 : 1;       // same as rb2_set_option("step_graph", 0)
     if (const char *e = getenv("RB2_SYM_WAVES")) { const double v = atof(e); if (v >= 1.0) c.sym_waves = v; }                   // measurement scripts
+    if (const char *e = getenv("RB2_SYM_FAR")) c.sym_far = atoi(e) != 0;
     if (const char *e = getenv("RB2_PAIR_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c.pair_mode = v; }
     if (const char *e = getenv("RB2_MH_SMALL")) c.mh_small = atoi(e) != 0;
     if (const char *e = getenv("RB2_MH_SMALL_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c.mh_small_max = v; }
@@ -780,7 +782,7 @@ static unsigned long long step_key(const Rb2Ctx &c)
     k.n = c.n; k.cap = c.cap; k.pair_mode = c.pair_mode; k.sym_min_n = c.sym_min_n; k.pair_rank = c.pair_rank; k.pair_world = c.pair_world;
     k.sym_tpl = c.sym_tpl; k.ramo_n_sec = c.ramo_n_sec; k.ramo_n_emit = c.ramo_n_emit; k.ramo_blocks = c.ramo_blocks; k.ev_cap = c.ev_cap;
     k.redpart_blocks = c.redpart_blocks; k.part_begin = c.part_begin; k.part_end = c.part_end; k.sm_count = c.sm_count;
-    k.pad = c.sym_kmax * 64 + c.sym_gmax;
+    k.pad = (c.sym_kmax * 64 + c.sym_gmax) * 2 + c.sym_far;
     k.sym_waves = c.sym_waves; k.sym_budget = c.sym_budget_bytes; k.partial_bytes = c.partial_bytes;
     k.bufI_bytes = c.sym_bufI_bytes; k.bufJ_bytes = c.sym_bufJ_bytes; k.raw_bytes = c.sym_raw_bytes;
     const void *ptrs[] = {c.a.pq, c.a.prev_pos, c.a.vel, c.a.acc, c.a.acc_prev, c.a.acc_prev2, c.a.mass, c.a.species, c.a.step, c.a.emitter,
@@ -1169,6 +1171,8 @@ static int set_option_one(const char *name, double value)
         c.mh_small_max = (int)value;
     } else if (!strcmp(name, "mh_small")) {
         c.mh_small = (value != 0.0) ? 1 : 0;
+    } else if (!strcmp(name, "sym_far")) {
+        c.sym_far = (value != 0.0) ? 1 : 0;
     } else if (!strcmp(name, "sym_kmax")) {
         if (value < 1 || value > 4096) return rb2_fail(RB2_ERR_ARG, "sym_kmax must be 1..4096");
         c.sym_kmax = (int)value;

@@ -43,6 +43,7 @@ struct PlanarParams {
     double E_z;
     int    nic;    // N_ic_max
     int    do_ic;
+    int    far_ok; // d >= 1 um: the far image partners may skip the softening term (rb2_inv_r3_far)
 };
 struct TipParams {
     double a_foci, shift_z, pre_fac_E_tip, eta_1;
@@ -111,6 +112,7 @@ struct Rb2Ctx {
     int    pair_rank = 0, pair_world = 1; // ownership of (target, group) CTAs across processes
     size_t sym_budget_bytes = (size_t)2048 << 20;  // scratch for the (set, source tile) / (group, target) partial sums
     int    sym_tpl = 0;                   // targets per lane of the pair-symmetric kernel: 0 auto, 1, 2
+    int    sym_far = 1;                   // option "sym_far": allow the cheaper far-partner inverse cube when d >= 1 um
     int    sym_kmax = 12, sym_gmax = 24;  // caps of the work-unit shape (options "sym_kmax", "sym_gmax"; tools/sym_unit_sweep.py)
     double sym_waves = 64.0;              // work units are sized for about this many waves per band launch and rank (tools/run_r2_2gpu_waves.sh)
     double *sym_bufI = nullptr, *sym_bufJ = nullptr, *sym_raw = nullptr;
@@ -264,6 +266,18 @@ __device__ __forceinline__ double rb2_inv_r3_soft(double s)
     const double e = fma(-s, t, 1.0);
     const double c0 = fma(-3.0 * rb2k::soft, y0, 1.0);
     const double p = fma(e, fma(1.875, e, 1.5), c0);
+    return (y0 * t) * p;
+}
+
+// The same without the softening term: for partners that are at least a gap width d away (the n = +-1 images other than
+// the one behind the anode) 3 eps / r <= 3e-18 / d, i.e. <= 3e-12 for d >= 1 um -- below the 1e-11 bar even if such
+// partners carried the whole force; one FP64 instruction less each.  Only used when PlanarParams.far_ok says so.
+__device__ __forceinline__ double rb2_inv_r3_far(double s)
+{
+    const double y0 = rb2_rsqrt_seed(s);
+    const double t = y0 * y0;
+    const double e = fma(-s, t, 1.0);
+    const double p = fma(e, fma(1.875, e, 1.5), 1.0);
     return (y0 * t) * p;
 }
 

@@ -179,10 +179,19 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                     if (close) a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, j0, i, P);
                     az += a.t;
                 } else {
+                    if (NIC == 1 && !FIELD && P.far_ok) {
+                        // particles between the plates, d >= 1 um: the three far image partners without the softening term
 #pragma unroll UNROLL
-                    for (int jj = 0; jj < cnt; ++jj) {
-                        const double4 pj = tile[jj];
-                        planar_term<NIC>(xi, yi, zi, pj, pj.w, pj.w, P, a, close);
+                        for (int jj = 0; jj < cnt; ++jj) {
+                            const double4 pj = tile[jj];
+                            planar_term<NIC, true>(xi, yi, zi, pj, pj.w, pj.w, P, a, close);
+                        }
+                    } else {
+#pragma unroll UNROLL
+                        for (int jj = 0; jj < cnt; ++jj) {
+                            const double4 pj = tile[jj];
+                            planar_term<NIC>(xi, yi, zi, pj, pj.w, pj.w, P, a, close);
+                        }
                     }
                     if (close) {
                         // sources all above (or field points: no roles) / all below this CTA's rows; the slow path
@@ -365,7 +374,8 @@ int launch_pair(Rb2Ctx &ctx, const double4 *src, int n_src, const double4 *tgt_p
                 int i_end, const Split &sp, int slot0, double *partial)
 {
     const rb2_config &c = ctx.cfg;
-    const StepParams P = rb2_make_step_params(c);
+    StepParams P = rb2_make_step_params(c);
+    P.pl.far_ok = P.pl.far_ok && ctx.sym_far;  // option "sym_far" (on by default) governs both pair kernels
     dim3 grid(sp.nblk, sp.nsplit), block(BLOCK);
     cudaStream_t st = ctx.stream;
 #define RB2_GO(G, N) k_pair<G, N, FIELD><<<grid, block, 0, st>>>(src, n_src, tgt_pq, tgt_pts, i_begin, i_end, sp.j_chunk, slot0, P.pl, P.tip, partial)

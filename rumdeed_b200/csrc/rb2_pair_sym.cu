@@ -65,7 +65,7 @@ struct SymGeom {
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
 
 // One round of a symmetric tile: this warp's 32 T targets against the 32 visitors of block wb0 (see k_pair_sym).
-template <int NIC, int T, bool EXACT>
+template <int NIC, int T, bool EXACT, bool FAR = false>
 __device__ __forceinline__ void sym_round(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
                                           const double *__restrict__ Q, int wb0, int lane, int src_lane, const double (&xi)[T],
                                           const double (&yi)[T], const double (&zi)[T], const double (&qe)[T], const PlanarParams &P,
@@ -87,6 +87,20 @@ __device__ __forceinline__ void sym_round(const double *__restrict__ X, const do
 #endif
 #pragma unroll
         for (int s = 0; s < T; ++s) {
+            if (NIC == 1 && !EXACT) {
+                // the hot path: N_ic_max = 1, i < j: one FMA chain for the image z-sum, far partners without softening
+                const PairS w = FAR ? planar_weights_sym1<true>(xi[s], yi[s], zi[s], vx, vy, vz, P, close)
+                                    : planar_weights_sym1<false>(xi[s], yi[s], zi[s], vx, vy, vz, P, close);
+                const double ti = vq * w.U, tj = qe[s] * w.U;
+                tx[s] = fma(w.dx, ti, tx[s]);
+                ty[s] = fma(w.dy, ti, ty[s]);
+                bx = fma(-w.dx, tj, bx);
+                by = fma(-w.dy, tj, by);
+                const double czz = w.dz * w.wc;
+                tz[s] = fma(vq, w.icz + czz, tz[s]);
+                bz = fma(qe[s], w.icz - czz, bz);
+                continue;
+            }
             const PairW w = EXACT ? planar_weights_exact<NIC>(xi[s], yi[s], zi[s], vx, vy, vz, P, false)
                                   : planar_weights<NIC>(xi[s], yi[s], zi[s], vx, vy, vz, P, close);
             // i < j here: evaluation at (z_i, z_j); reaction mirrored in x, y (src/mod_verlet.F90:862-871)
@@ -147,7 +161,7 @@ __device__ __noinline__ RoundIO<T> sym_round_exact(const double *X, const double
 // symmetrically when its tile index is < J (then i < j for every pair), in the gather form when it IS tile J, and
 // not at all when its tile index is > J (those pairs belong to the sweep of the other sub-set).  T = 2 halves the
 // shared-memory reads, the shuffles and the partial-sum traffic per pair and doubles the independent work per warp.
-template <int NIC, int T>
+template <int NIC, int T, bool FAR = false>
 __global__ void __launch_bounds__(SB, T == 1 ? RB2_SYM_MINB : RB2_SYM_MINB2)
 k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
 {
@@ -234,7 +248,7 @@ k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__
                     double bx, by, bz;          // reaction on the visitor, travels with it
                     double tx[T], ty[T], tz[T]; // force on my particles from this round
                     bool close = false;
-                    sym_round<NIC, T, false>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
+                    sym_round<NIC, T, false, FAR>(X, Y, Z, Q, wb0, lane, src_lane, xi, yi, zi, qe, P, tx, ty, tz, bx, by, bz, close);
                     // a laterally close pair anywhere in this warp's 32 x 32T block: the round again with the reference's
                     // sqrt / divide (warp-uniform branch: the shuffles inside need every lane)
 #if RB2_EXACT_INLINE
@@ -533,21 +547,21 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         const int nI = (b0 + g.band_len - 1) / T + 1;  // target superblocks that start at or below the band's last tile
         dim3 grid((nI + K - 1) / K, g.ngroups), block(SB);
         const size_t dyn = (size_t)G * 3 * SB * sizeof(double);
-#define RB2_GO(N)                                                                                        \
+#define RB2_GO(N, F)                                                                                     \
     do {                                                                                                 \
-        const unsigned bit = 1u << (((N) + 1) * 2 + (T - 1));                                            \
+        const unsigned bit = 1u << ((((N) + 1) * 2 + (T - 1)) * 2 + ((F) ? 1 : 0));                      \
         if (T == 1) {                                                                                    \
-            if (!(ctx.sym_attr_mask & bit)) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 3 * SB * 8)); ctx.sym_attr_mask |= bit; } \
-            k_pair_sym<N, 1><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);          \
+            if (!(ctx.sym_attr_mask & bit)) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 1, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 3 * SB * 8)); ctx.sym_attr_mask |= bit; } \
+            k_pair_sym<N, 1, F><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);       \
         } else {                                                                                         \
-            if (!(ctx.sym_attr_mask & bit)) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 3 * SB * 8)); ctx.sym_attr_mask |= bit; } \
-            k_pair_sym<N, 2><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);          \
+            if (!(ctx.sym_attr_mask & bit)) { RB2_CUDA(cudaFuncSetAttribute(k_pair_sym<N, 2, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 3 * SB * 8)); ctx.sym_attr_mask |= bit; } \
+            k_pair_sym<N, 2, F><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);       \
         }                                                                                                \
     } while (0)
-        if (!c.image_charge) RB2_GO(-1);
-        else if (c.N_ic_max == 0) RB2_GO(0);
-        else if (c.N_ic_max == 1) RB2_GO(1);
-        else RB2_GO(2);
+        if (!c.image_charge) RB2_GO(-1, false);
+        else if (c.N_ic_max == 0) RB2_GO(0, false);
+        else if (c.N_ic_max == 1) { if (SP.pl.far_ok && ctx.sym_far) RB2_GO(1, true); else RB2_GO(1, false); }
+        else RB2_GO(2, false);
 #undef RB2_GO
         RB2_CUDA(cudaGetLastError());
         if (T == 1) k_sym_reduce<1><<<g.nsb, SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);

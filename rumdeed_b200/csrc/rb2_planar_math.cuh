@@ -28,7 +28,35 @@ struct PairW {
 
 // NIC: -1 image charge off, 0, 1, >= 2 (runtime N_ic_max loop).  `close` collects "lateral offset below 1e-11 m" over
 // the calls (rb2_is_close).
-template <int NIC>
+// The symmetric rounds (i < j throughout, no role sign) only need the image z-sum as a whole: icz = Zsame - Zopp in one
+// FMA chain; FAR: the three partners that are at least d away skip the softening term (PlanarParams.far_ok).  N_ic_max = 1.
+struct PairS {
+    double dx, dy, dz, U, wc, icz;
+};
+template <bool FAR>
+__device__ __forceinline__ PairS planar_weights_sym1(double xi, double yi, double zi, double xj, double yj, double zj,
+                                                     const PlanarParams &P, bool &close)
+{
+    PairS w;
+    w.dx = xi - xj;
+    w.dy = yi - yj;
+    w.dz = zi - zj;
+    const double dxy2 = fma(w.dy, w.dy, fma(w.dx, w.dx, RB2_S_FLOOR));
+    close = close || rb2_is_close(dxy2);
+    w.wc = rb2_inv_r3_soft(fma(w.dz, w.dz, dxy2));
+    const double S = zi + zj;
+    const double a1 = S - P.two_d, a2 = S + P.two_d, b1 = w.dz - P.two_d, b2 = w.dz + P.two_d;
+    const double w0 = rb2_inv_r3_soft(fma(S, S, dxy2));
+    const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
+    const double w2 = FAR ? rb2_inv_r3_far(fma(a2, a2, dxy2)) : rb2_inv_r3_soft(fma(a2, a2, dxy2));
+    const double w3 = FAR ? rb2_inv_r3_far(fma(b1, b1, dxy2)) : rb2_inv_r3_soft(fma(b1, b1, dxy2));
+    const double w4 = FAR ? rb2_inv_r3_far(fma(b2, b2, dxy2)) : rb2_inv_r3_soft(fma(b2, b2, dxy2));
+    w.U = w.wc + ((w3 + w4) - ((w0 + w1) + w2));
+    w.icz = fma(b2, w4, fma(b1, w3, fma(-a2, w2, fma(-a1, w1, -(S * w0)))));
+    return w;
+}
+
+template <int NIC, bool FAR = false>
 __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi, double xj, double yj, double zj,
                                                 const PlanarParams &P, bool &close)
 {
@@ -53,9 +81,9 @@ __device__ __forceinline__ PairW planar_weights(double xi, double yi, double zi,
     if (NIC == 1) {
         const double a1 = S - P.two_d, a2 = S + P.two_d, b1 = w.dz - P.two_d, b2 = w.dz + P.two_d;
         const double w1 = rb2_inv_r3_soft(fma(a1, a1, dxy2));
-        const double w2 = rb2_inv_r3_soft(fma(a2, a2, dxy2));
-        const double w3 = rb2_inv_r3_soft(fma(b1, b1, dxy2));
-        const double w4 = rb2_inv_r3_soft(fma(b2, b2, dxy2));
+        const double w2 = FAR ? rb2_inv_r3_far(fma(a2, a2, dxy2)) : rb2_inv_r3_soft(fma(a2, a2, dxy2));
+        const double w3 = FAR ? rb2_inv_r3_far(fma(b1, b1, dxy2)) : rb2_inv_r3_soft(fma(b1, b1, dxy2));
+        const double w4 = FAR ? rb2_inv_r3_far(fma(b2, b2, dxy2)) : rb2_inv_r3_soft(fma(b2, b2, dxy2));
         W = (w3 + w4) - ((w0 + w1) + w2);
         w.Zopp = fma(a2, w2, fma(a1, w1, w.Zopp));
         w.Zsame = fma(b2, w4, b1 * w3);
@@ -138,11 +166,11 @@ __device__ __forceinline__ void planar_apply(const PairW &w, double qj, double q
     a.z = fma(qj, fma(w.dz, w.wc, -w.Zopp), a.z);
     a.t = fma(qs, w.Zsame, a.t);
 }
-template <int NIC>
+template <int NIC, bool FAR = false>
 __device__ __forceinline__ void planar_term(double xi, double yi, double zi, const double4 pj, double qj, double qs,
                                             const PlanarParams &P, Acc4 &a, bool &close)
 {
-    planar_apply<NIC>(planar_weights<NIC>(xi, yi, zi, pj.x, pj.y, pj.z, P, close), qj, qs, a);
+    planar_apply<NIC>(planar_weights<NIC, FAR>(xi, yi, zi, pj.x, pj.y, pj.z, P, close), qj, qs, a);
 }
 // slow path of a laterally close pair; swapped: the source has the lower index (qs then carries the minus sign)
 template <int NIC>
