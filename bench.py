@@ -36,8 +36,8 @@ FLOPS_PER_PAIR = {(-1): 21, 0: 39, 1: 99, 2: 159}  # 21 + ic*(18 +
 # What the kernels EXECUTE at N_ic_max = 1 (ncu opcode counts, profiles/ncu_opmix_r02_n1e5.txt): FP64-pipe instructions and
 # flops (DFMA = 2, DMUL / DADD = 1) per pair evaluation.  The pair-symmetric kernel evaluates an UNORDERED pair
 # once (both ordered interactions), the gather kernel an ordered pair.
-EXECUTED = {"sym": {"fp64_instr": 79.94, "flops": 123.3, "per": "unordered pair"},
-            "gather": {"fp64_instr": 74.22, "flops": 114.3, "per": "ordered pair"}}
+EXECUTED = {"sym": {"fp64_instr": 75.57, "flops": 116.8, "per": "unordered pair"},
+            "gather": {"fp64_instr": 71.04, "flops": 108.0, "per": "ordered pair"}}
 SURFACE_FLOPS_PER_POINT_PARTICLE = 54  # k_surface_field at N_ic_max = 1: 31 FP64 instructions, 23 of them FMAs (+ 1 compare)
 METRIC = "pair_interactions_per_s"
 UNIT = "pair-interactions/s"

@@ -210,7 +210,9 @@ int rb2_p2p_detach(void);
  * batches, samplers, downloads, counters) is served by the first device.  Planar geometry; not combinable with
  * rb2_p2p_attach or the collision step. */
 int rb2_set_devices(int n_devices, const int *devices);
-/* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves",
+/* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves", "sym_kmax", "sym_gmax",
+ * "sym_far" (1 / 0: with d >= 1 um the acceleration kernels evaluate the three image partners that are at least d away
+ * without the softening term, a change of <= 3e-12 of those terms; 1 by default),
  * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "step_graph" (1 / 0: replay rb2_step as a CUDA graph while
  * consecutive steps queue identical work), "ramo_sections" / "ramo_emitters" (size
  * of the per-section Ramo table, 0 sections = off), "event_buffer" (initial number of
