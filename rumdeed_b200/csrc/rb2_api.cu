@@ -270,7 +270,7 @@ static void release_all(Rb2Ctx &c)
     cudaFree(c.d_counters); cudaFree(c.d_red); cudaFree(c.d_redpart); cudaFree(c.d_total); cudaFree(c.partial);
     cudaFree(c.d_ramo_part); cudaFree(c.d_ramo_sec);
     if (c.h_ramo_sec) cudaFreeHost(c.h_ramo_sec);
-    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw); cudaFree(c.sym_owner);
+    cudaFree(c.sym_bufI); cudaFree(c.sym_bufJ); cudaFree(c.sym_raw); cudaFree(c.sym_owner); cudaFree(c.sym_units);
     cudaFree(c.d_events); cudaFree(c.d_pts); cudaFree(c.d_fld); cudaFree(c.d_extra); cudaFree(c.d_stage_d); cudaFree(c.d_stage_i);
     if (c.h_counters) cudaFreeHost(c.h_counters);
     if (c.h_red) cudaFreeHost(c.h_red);
@@ -775,7 +775,7 @@ static unsigned long long step_key(const Rb2Ctx &c)
             part_begin, part_end, sm_count, pad;
         double sym_waves;
         size_t sym_budget, partial_bytes, bufI_bytes, bufJ_bytes, raw_bytes;
-        const void *p[32];
+        const void *p[34];
         rb2_config cfg;
     } k;
     memset(&k, 0, sizeof(k));
@@ -788,9 +788,9 @@ static unsigned long long step_key(const Rb2Ctx &c)
     const void *ptrs[] = {c.a.pq, c.a.prev_pos, c.a.vel, c.a.acc, c.a.acc_prev, c.a.acc_prev2, c.a.mass, c.a.species, c.a.step, c.a.emitter,
                           c.a.section, c.a.life, c.a.id, c.b.vel, c.mask, c.evcnt, c.evbits, c.prefix, c.blocksum, c.d_counters, c.d_red,
                           c.d_redpart, c.d_total, c.d_events, c.partial, c.sym_bufI, c.sym_bufJ, c.sym_raw, c.d_ramo_part, c.d_ramo_sec,
-                          c.h_ramo_sec, c.h_red};
-    static_assert(sizeof(ptrs) / sizeof(ptrs[0]) == 32, "pointer table");
-    for (int i = 0; i < 32; ++i) k.p[i] = ptrs[i];
+                          c.h_ramo_sec, c.h_red, c.sym_units, c.sym_owner};
+    static_assert(sizeof(ptrs) / sizeof(ptrs[0]) == 34, "pointer table");
+    for (int i = 0; i < 34; ++i) k.p[i] = ptrs[i];
     k.cfg = c.cfg;
     unsigned long long h = 1469598103934665603ull;
     const unsigned char *b = reinterpret_cast<const unsigned char *>(&k);

@@ -120,7 +120,9 @@ struct Rb2Ctx {
     int    sym_n_pad = 0;
     double *sym_raw_cur = nullptr;        // partial sums of the current evaluation (sym_raw, or a slot of the exchange block)
     unsigned char *sym_owner = nullptr; size_t sym_owner_cap = 0;  // cost-balanced deal of the work units to the ranks
-    unsigned long long sym_owner_key[6] = {0, 0, 0, 0, 0, 0};      // ... valid for (n, T, K, G, band width, world)
+    unsigned long long sym_owner_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ... valid for (tiles, superblocks, T, K, G, band width, world, rank)
+    int2 *sym_units = nullptr; size_t sym_units_cap = 0;           // this rank's units (set, group), all bands, in dealing order
+    std::vector<size_t> sym_unit_off; std::vector<int> sym_unit_cnt;  // ... per band
     // peer-memory exchange (rb2_p2p.cu)
     void  *p2p_local = nullptr;           // this rank's exchange block (exported over CUDA IPC)
     void  *p2p_peer[RB2_P2P_MAX] = {};    // every rank's block as mapped here ([rank] == p2p_local)

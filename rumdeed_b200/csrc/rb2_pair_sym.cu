@@ -60,6 +60,7 @@ struct SymGeom {
     int K, nIsets;             // target superblocks a CTA takes one after the other (a "set"), sets in all
     int rank, world;           // CTA (set, grp) is owned by rank owner[set * ngroups + grp] (world > 1)
     const unsigned char *owner;  // this band's slice of the cost-balanced deal (null: one rank)
+    const int2 *units;           // (set, grp) of this rank's units in this band, in the order they were dealt
 };
 
 __device__ __forceinline__ double rot1(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
@@ -165,9 +166,9 @@ template <int NIC, int T, bool FAR = false>
 __global__ void __launch_bounds__(SB, T == 1 ? RB2_SYM_MINB : RB2_SYM_MINB2)
 k_pair_sym(const double4 *__restrict__ pq, SymGeom g, PlanarParams P, double *__restrict__ bufI, double *__restrict__ bufJ)
 {
-    const int iset = blockIdx.x;
-    const int grp = blockIdx.y;
-    if (g.owner && g.owner[iset * g.ngroups + grp] != g.rank) return;
+    const int2 unit = g.units[blockIdx.x];  // this rank's units of the band, largest first
+    const int iset = unit.x;
+    const int grp = unit.y;
     const int I0 = iset * g.K;
     const int J0 = g.band_start + grp * g.G;
     const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
@@ -323,49 +324,43 @@ template <int T>
 __global__ void __launch_bounds__(SB * RQ)
 k_sym_reduce(SymGeom g, const double *__restrict__ bufI, const double *__restrict__ bufJ, double *__restrict__ raw)
 {
-    __shared__ double part[RQ][3][SB];
+    __shared__ double part[RQ][SB];
     const int Jp = blockIdx.x;  // 128-particle tile of this particle
+    const int c = blockIdx.y;   // component (x, y, z): one CTA each, so that small systems still fill the SMs
     const int It = Jp / T;      // its target superblock
     const int Iset_t = It / g.K;
     const int tid = threadIdx.x & (SB - 1), q = threadIdx.x / SB;
     const int p = Jp * SB + tid;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    double s0 = 0.0;
     // as a target (superblock It, taken by the CTAs of its set)
     for (int grp = q; grp < g.ngroups; grp += RQ) {
         const int J0 = g.band_start + grp * g.G;
         const int J1 = min(J0 + g.G, min(g.band_start + g.band_len, g.nsb));
         if (max(J0, T * It) >= J1) continue;
         if (g.owner && g.owner[Iset_t * g.ngroups + grp] != g.rank) continue;
-        const size_t ib = (size_t)grp * 3 * g.n_pad + p;
-        s0 += bufI[ib];
-        s1 += bufI[ib + g.n_pad];
-        s2 += bufI[ib + 2 * (size_t)g.n_pad];
+        s0 += bufI[((size_t)grp * 3 + c) * g.n_pad + p];
     }
     // as a source (tile Jp), when Jp lies in this band: the sets whose first superblock starts left of Jp
     if (Jp >= g.band_start && Jp < g.band_start + g.band_len) {
         const int grp = (Jp - g.band_start) / g.G;
         const int nset = min(g.nIsets, (Jp + T * g.K - 1) / (T * g.K));  // T * K * set < Jp: the set's first superblock lies left of the tile
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        double t0 = 0.0;
 #pragma unroll 4
         for (int st = q; st < nset; st += RQ) {
             if (g.owner && g.owner[st * g.ngroups + grp] != g.rank) continue;
-            const size_t base = (((size_t)st * g.band_len + (Jp - g.band_start)) * 3) * SB + tid;
-            t0 += bufJ[base];
-            t1 += bufJ[base + SB];
-            t2 += bufJ[base + 2 * SB];
+            t0 += bufJ[(((size_t)st * g.band_len + (Jp - g.band_start)) * 3 + c) * SB + tid];
         }
-        s0 += t0; s1 += t1; s2 += t2;
+        s0 += t0;
     }
-    part[q][0][tid] = s0; part[q][1][tid] = s1; part[q][2][tid] = s2;
+    part[q][tid] = s0;
     __syncthreads();
     if (q == 0) {
 #pragma unroll
-        for (int k = 1; k < RQ; ++k) { s0 += part[k][0][tid]; s1 += part[k][1][tid]; s2 += part[k][2][tid]; }
-        raw[p] += s0;
-        raw[(size_t)g.n_pad + p] += s1;
-        raw[2 * (size_t)g.n_pad + p] += s2;
+        for (int k = 1; k < RQ; ++k) s0 += part[k][tid];
+        raw[(size_t)c * g.n_pad + p] += s0;
     }
 }
+
 
 // a_i = ( q_i/(4 pi eps0) * raw_i + q_i * E_z zhat ) / m_i   (src/mod_verlet.F90:1333-1338)
 __global__ void k_sym_finalize(int n, int n_pad, const double *__restrict__ raw, const double4 *__restrict__ pq,
@@ -432,8 +427,12 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     // unit size from the whole triangle: about sym_waves waves of units per rank and evaluation (not per band: tying the
     // unit to the band width shrank the units whenever the budget shrank the bands, which costs more scratch per tile,
     // which shrinks the bands ...)
-    const double want_ctas = (double)ctx.sm_count * (4 / T) * ctx.sym_waves * g.world;
-    const double KG = 0.5 * (double)g.nIb * (double)g.nsb / want_ctas;
+    const double tri = 0.5 * (double)g.nIb * (double)g.nsb, slots = (double)ctx.sm_count * (4 / T) * g.world;
+    double KG = tri / (slots * ctx.sym_waves);
+    // single-tile units pay ~5 % for their fixed cost (prologue, 6 KB of sums stored per 128T x 128 pairs): when the work
+    // per rank is small, prefer K G = 4 over the full number of waves, down to 16 waves (8 ranks at N = 1e5: the slowest
+    // rank's kernel at 95 % of 1/8 of the undivided one instead of 90 %, profiles/rank_emulation_r02.log)
+    if (KG < 4.0 && ctx.sym_waves > 16.0) KG = std::min(4.0, tri / (slots * 16.0));
     int G = (int)sqrt((double)T * KG);     // traffic per pair ~ T / G + 1 / K: G = T K at the optimum
     if (G > Gmax) G = Gmax;
     if (G > ctx.sym_gmax) G = ctx.sym_gmax;
@@ -483,11 +482,14 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     ctx.sym_n_pad = g.n_pad;
     cudaStream_t st = ctx.stream;
     const StepParams SP = rb2_make_step_params(c);
-    // the deal of the work units to the ranks, all bands in one table
+    // the work units of every band: dealt to the ranks by cost (one table for the reduce kernel, which must know whose
+    // slots were written), and THIS rank's units as a list in the order they were dealt (largest first) -- the launch
+    // grid is that list, so no CTA starts just to find that its unit is empty or somebody else's (a full 2-D grid at
+    // N = 1e5 on 8 ranks launched 305 000 CTAs for 19 000 units), and the clipped units near the diagonal run last
     std::vector<size_t> owner_off;
-    if (g.world > 1) {
-        const unsigned long long key[6] = {(unsigned long long)n, (unsigned long long)T, (unsigned long long)K, (unsigned long long)G,
-                                           (unsigned long long)Wb, (unsigned long long)g.world};
+    {
+        const unsigned long long key[8] = {(unsigned long long)g.nsb, (unsigned long long)g.nIb, (unsigned long long)T, (unsigned long long)K,
+                                           (unsigned long long)G, (unsigned long long)Wb, (unsigned long long)g.world, (unsigned long long)g.rank};
         size_t total = 0;
         for (int b0 = 0; b0 < g.nsb; b0 += Wb) {
             const int blen = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
@@ -495,8 +497,12 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
             owner_off.push_back(total);
             total += (size_t)((nI + K - 1) / K) * ((blen + G - 1) / G);
         }
-        if (memcmp(key, ctx.sym_owner_key, sizeof(key)) != 0 || !ctx.sym_owner) {
-            std::vector<unsigned char> tab(total, 0);
+        if (memcmp(key, ctx.sym_owner_key, sizeof(key)) != 0 || !ctx.sym_units) {
+            if (ctx.capturing) return rb2_fail(RB2_ERR_CUDA, "pair-symmetric work units changed inside a graph capture");
+            std::vector<unsigned char> tab(g.world > 1 ? total : 0, 0);
+            std::vector<int2> mine;
+            ctx.sym_unit_off.clear(); ctx.sym_unit_cnt.clear();
+            static const bool order_gr_major = getenv("RB2_UNIT_ORDER") ? atoi(getenv("RB2_UNIT_ORDER")) != 0 : true;
             std::vector<std::pair<long long, int>> units;  // (-cost, index): ascending sort = largest first, index order on ties
             size_t bi = 0;
             for (int b0 = 0; b0 < g.nsb; b0 += Wb, ++bi) {
@@ -513,25 +519,37 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
                             cost += (long long)T * (J1 - Jb);          // T sub-sets x tiles ...
                             for (int J = Jb; J < std::min(J1, T * I + T); ++J) cost -= (T - 1 - (J - T * I));  // ... less what the diagonal clips
                         }
-                        if (cost > 0) units.emplace_back(-cost, is * ngr + gr);
+                        if (cost > 0) units.emplace_back(-cost, order_gr_major ? gr * nsets + is : is * ngr + gr);
                     }
                 std::sort(units.begin(), units.end());
                 std::vector<long long> load((size_t)g.world, 0);
+                ctx.sym_unit_off.push_back(mine.size());
                 for (const auto &u : units) {
                     int best = 0;
                     for (int r = 1; r < g.world; ++r) if (load[(size_t)r] < load[(size_t)best]) best = r;
                     load[(size_t)best] += -u.first;
-                    tab[owner_off[bi] + (size_t)u.second] = (unsigned char)best;
+                    const int is = order_gr_major ? u.second % nsets : u.second / ngr, gr = order_gr_major ? u.second / nsets : u.second % ngr;
+                    if (g.world > 1) tab[owner_off[bi] + (size_t)is * ngr + gr] = (unsigned char)best;
+                    if (best == g.rank) mine.push_back(make_int2(is, gr));
                 }
+                ctx.sym_unit_cnt.push_back((int)(mine.size() - ctx.sym_unit_off.back()));
             }
-            if (total > ctx.sym_owner_cap) {
+            if (g.world > 1 && total > ctx.sym_owner_cap) {
                 if (ctx.sym_owner) RB2_CUDA(cudaFree(ctx.sym_owner));
                 ctx.sym_owner = nullptr; ctx.sym_owner_cap = 0;
                 RB2_CUDA(cudaMalloc(&ctx.sym_owner, total + total / 2 + 256));
                 ctx.sym_owner_cap = total + total / 2 + 256;
             }
-            RB2_CUDA(cudaMemcpyAsync(ctx.sym_owner, tab.data(), total, cudaMemcpyHostToDevice, st));
-            RB2_CUDA(cudaStreamSynchronize(st));  // tab goes out of scope
+            if (mine.size() + 1 > ctx.sym_units_cap) {
+                if (ctx.sym_units) RB2_CUDA(cudaFree(ctx.sym_units));
+                ctx.sym_units = nullptr; ctx.sym_units_cap = 0;
+                const size_t cap = mine.size() + mine.size() / 2 + 256;
+                RB2_CUDA(cudaMalloc(&ctx.sym_units, cap * sizeof(int2)));
+                ctx.sym_units_cap = cap;
+            }
+            if (g.world > 1) RB2_CUDA(cudaMemcpyAsync(ctx.sym_owner, tab.data(), total, cudaMemcpyHostToDevice, st));
+            if (!mine.empty()) RB2_CUDA(cudaMemcpyAsync(ctx.sym_units, mine.data(), mine.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+            RB2_CUDA(cudaStreamSynchronize(st));  // the host vectors go out of scope
             memcpy(ctx.sym_owner_key, key, sizeof(key));
         }
     }
@@ -544,8 +562,9 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         g.G = G;
         g.ngroups = (g.band_len + G - 1) / G;
         g.owner = (g.world > 1) ? ctx.sym_owner + owner_off[(size_t)(b0 / Wb)] : nullptr;
-        const int nI = (b0 + g.band_len - 1) / T + 1;  // target superblocks that start at or below the band's last tile
-        dim3 grid((nI + K - 1) / K, g.ngroups), block(SB);
+        const size_t bi = (size_t)(b0 / Wb);
+        g.units = ctx.sym_units + ctx.sym_unit_off[bi];
+        dim3 grid((unsigned)ctx.sym_unit_cnt[bi]), block(SB);
         const size_t dyn = (size_t)G * 3 * SB * sizeof(double);
 #define RB2_GO(N, F)                                                                                     \
     do {                                                                                                 \
@@ -558,14 +577,15 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
             k_pair_sym<N, 2, F><<<grid, block, dyn, st>>>(pq, g, SP.pl, ctx.sym_bufI, ctx.sym_bufJ);       \
         }                                                                                                \
     } while (0)
-        if (!c.image_charge) RB2_GO(-1, false);
+        if (grid.x == 0) { /* nothing of this band is ours */ }
+        else if (!c.image_charge) RB2_GO(-1, false);
         else if (c.N_ic_max == 0) RB2_GO(0, false);
         else if (c.N_ic_max == 1) { if (SP.pl.far_ok && ctx.sym_far) RB2_GO(1, true); else RB2_GO(1, false); }
         else RB2_GO(2, false);
 #undef RB2_GO
         RB2_CUDA(cudaGetLastError());
-        if (T == 1) k_sym_reduce<1><<<g.nsb, SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
-        else k_sym_reduce<2><<<g.nIb * 2, SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
+        if (T == 1) k_sym_reduce<1><<<dim3(g.nsb, 3), SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
+        else k_sym_reduce<2><<<dim3(g.nIb * 2, 3), SB * RQ, 0, st>>>(g, ctx.sym_bufI, ctx.sym_bufJ, ctx.sym_raw_cur);
         RB2_CUDA(cudaGetLastError());
         launches += 2;
     }
