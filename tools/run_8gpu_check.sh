@@ -3,7 +3,7 @@
 G=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29521"
 for n in 1000000 100000; do
-  timeout 400 $TR bench.py --gpus $G --particles $n --steps 5 --warmup 3 2>gpurun_out/b${G}_${n}.err | tail -1 > gpurun_out/b${G}_${n}.json
+  timeout 400 $TR bench.py --gpus $G --particles $n --steps 5 --warmup 3 --no-cpu --no-sweep 2>gpurun_out/b${G}_${n}.err | tail -1 > gpurun_out/b${G}_${n}.json
   python - <<PY
 import json
 try:
