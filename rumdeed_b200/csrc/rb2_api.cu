@@ -1306,6 +1306,8 @@ int rb2_get_stat(const char *name, double *out)
     if (!strcmp(name, "graph_replays")) *out = (double)g_rb2.graph_replays;
     else if (!strcmp(name, "graph_launches")) *out = (double)g_rb2.graph_launches;
     else if (!strcmp(name, "launches")) *out = (double)g_rb2.launches;
+    else if (!strcmp(name, "sym_plans")) *out = (double)g_rb2.sym_plans;
+    else if (!strcmp(name, "sym_plan_ms")) *out = g_rb2.sym_plan_ms;
     else return rb2_fail(RB2_ERR_ARG, "unknown counter '%s'", name);
     return RB2_OK;
 }

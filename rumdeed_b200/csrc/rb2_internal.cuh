@@ -123,6 +123,7 @@ struct Rb2Ctx {
     unsigned long long sym_owner_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ... valid for (tiles, superblocks, T, K, G, band width, world, rank)
     int2 *sym_units = nullptr; size_t sym_units_cap = 0;           // this rank's units (set, group), all bands, in dealing order
     std::vector<size_t> sym_unit_off; std::vector<int> sym_unit_cnt;  // ... per band
+    long long sym_plans = 0; double sym_plan_ms = 0.0;               // how often the unit list was rebuilt, host time spent on it
     // peer-memory exchange (rb2_p2p.cu)
     void  *p2p_local = nullptr;           // this rank's exchange block (exported over CUDA IPC)
     void  *p2p_peer[RB2_P2P_MAX] = {};    // every rank's block as mapped here ([rank] == p2p_local)

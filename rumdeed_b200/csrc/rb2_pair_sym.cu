@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "rb2_internal.cuh"
+#include <chrono>
 #include "rb2_planar_math.cuh"
 
 namespace {
@@ -499,6 +500,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         }
         if (memcmp(key, ctx.sym_owner_key, sizeof(key)) != 0 || !ctx.sym_units) {
             if (ctx.capturing) return rb2_fail(RB2_ERR_CUDA, "pair-symmetric work units changed inside a graph capture");
+            const auto t_plan0 = std::chrono::steady_clock::now();
             std::vector<unsigned char> tab(g.world > 1 ? total : 0, 0);
             std::vector<int2> mine;
             ctx.sym_unit_off.clear(); ctx.sym_unit_cnt.clear();
@@ -551,6 +553,8 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
             if (!mine.empty()) RB2_CUDA(cudaMemcpyAsync(ctx.sym_units, mine.data(), mine.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
             RB2_CUDA(cudaStreamSynchronize(st));  // the host vectors go out of scope
             memcpy(ctx.sym_owner_key, key, sizeof(key));
+            ctx.sym_plans += 1;
+            ctx.sym_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
         }
     }
     RB2_CUDA(rb2_event_record(ctx, ctx.ev_a0));

@@ -238,6 +238,12 @@ int main(int argc, char **argv)
     if (st.nrIonizations_total || st.nrRecombinations_total || st.t_collisions > 0.0)
         printf("RUMDEED: collisions: %lld ionisations, %lld recombinations, %d ions in the gap; wall clock %.3f s, device %.3f s\n",
                st.nrIonizations_total, st.nrRecombinations_total, st.nrIon, st.t_collisions, st.t_dev_collisions);
+    {
+        double plans = 0.0, plan_ms = 0.0, replays = 0.0;
+        if (!rb2_get_stat("sym_plans", &plans) && !rb2_get_stat("sym_plan_ms", &plan_ms) && !rb2_get_stat("graph_replays", &replays))
+            printf("RUMDEED: pair-symmetric work-unit lists built %.0f times (%.3f s on the host), %.0f step-graph replays\n", plans,
+                   plan_ms * 1e-3, replays);
+    }
     rh_destroy(sim);
     printf("RUMDEED: Program finished\n");
     return 0;

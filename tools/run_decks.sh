@@ -2,12 +2,12 @@
 # Times rumdeed_b200_run on the example decks of tools/decks/ (copied to a scratch dir; outputs stay there).
 # usage: tools/run_decks.sh [steps for the planar decks] [steps for the tip deck]
 SP=${1:-2000}; ST=${2:-5000}
-EXE=$(dirname "$0")/../rumdeed_b200/rumdeed_b200_run
+EXE=${RB2_RUN_EXE:-$(dirname "$0")/../rumdeed_b200/rumdeed_b200_run}
 run() { # name deck steps extra-namelist-line
   d=$(mktemp -d); cp $(dirname "$0")/decks/$2/* $d/
   if [ -n "$4" ]; then sed -i "s|^/|  $4\n/|" $d/input; fi
   s=$(date +%s.%N)
-  timeout ${DECK_TIMEOUT:-300} $EXE $d 20261017 $3 1000000 > $d/log 2>&1; rc=$?
+  timeout ${DECK_TIMEOUT:-300} $DECK_PREFIX $EXE $d 20261017 $3 1000000 > $d/log 2>&1; rc=$?
   e=$(date +%s.%N)
   python - "$1" "$d" "$3" "$s" "$e" "$rc" <<'PY'
 import sys, numpy as np
@@ -22,7 +22,7 @@ phase = [l for l in log if "wall clock per phase" in l]
 print(f"{name:28s} rc={rc} steps={steps} wall={e-s:7.2f}s  steps/s={steps/(e-s):8.1f}  I(last quarter)={I:.4e} A  nrElec(end)={nel}")
 print("   ", phase[0] if phase else log[-2:])
 for l in log:
-    if "collisions:" in l or "emission split" in l: print("   ", l)
+    if "collisions:" in l or "emission split" in l or "work-unit lists" in l: print("   ", l)
 PY
   rm -rf $d
 }
