@@ -504,7 +504,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
             std::vector<unsigned char> tab(g.world > 1 ? total : 0, 0);
             std::vector<int2> mine;
             ctx.sym_unit_off.clear(); ctx.sym_unit_cnt.clear();
-            static const bool order_gr_major = getenv("RB2_UNIT_ORDER") ? atoi(getenv("RB2_UNIT_ORDER")) != 0 : true;
+            constexpr bool order_gr_major = true;  // ties in group-major order: neighbouring CTAs share their source tiles (0.4 % at 8 ranks)
             std::vector<std::pair<long long, int>> units;  // (-cost, index): ascending sort = largest first, index order on ties
             size_t bi = 0;
             for (int b0 = 0; b0 < g.nsb; b0 += Wb, ++bi) {

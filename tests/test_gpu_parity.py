@@ -211,6 +211,40 @@ def test_coincident_and_marked_particles(orc):
 
 
 @pytest.mark.parametrize("mode,tpl", [(1, 0), (2, 1), (2, 2)])
+@pytest.mark.parametrize("d_nm", [1000.0, 2500.0, 500.0])
+def test_far_partner_shortcut_stays_inside_the_bar(orc, d_nm, mode, tpl):
+    """Option sym_far (default on): with a gap d >= 1 um the three image partners that are at least d away are evaluated
+    without the softening term -- a change of at most 3e-18 / d of those terms.  With and without it the result is
+    within 1e-11 of the long-double oracle and the two differ by less than 4e-12; below 1 um the option changes nothing
+    (bit for bit).  Particles right at both electrodes included (the near partners keep the full form)."""
+    d = d_nm * NM
+    n = 3000
+    box = (1000 * NM, 1000 * NM, d)
+    cfg = rb.planar_config(2000.0, d, box, 1.0e-16, True, 1, capacity=n)
+    p = orc.params_planar(2000.0, d, box, 1.0e-16, True, 1)
+    pos, q, m, sp = cloud(n, 5150, box=(1000.0, 1000.0, d_nm), ions=True, zmin=0.0)
+    pos[:40, 2] = np.linspace(0.0, 2.0, 40) * NM            # grazing the cathode
+    pos[40:80, 2] = d - np.linspace(0.0, 2.0, 40) * NM      # ... and the anode
+    res = {}
+    with rb.HotPath(cfg) as hp:
+        hp.set_option("pair_mode", mode)
+        if tpl:
+            hp.set_option("sym_tpl", tpl)
+        hp.upload(pos, q, m, species=sp)
+        for far in (1, 0):
+            hp.set_option("sym_far", far)
+            hp.Calculate_Acceleration_Particles()
+            res[far] = hp.download(("acc",))["acc"]
+    truth = orc.accel_gather_ld(p, pos, q, m)
+    assert relerr(res[0], truth) < TOL and relerr(res[1], truth) < TOL
+    if d_nm >= 1000.0:
+        assert relerr(res[1], res[0]) < 4e-12
+        assert not np.array_equal(res[1], res[0])  # the shortcut is actually taken
+    else:
+        assert np.array_equal(res[1], res[0])
+
+
+@pytest.mark.parametrize("mode,tpl", [(1, 0), (2, 1), (2, 2)])
 @pytest.mark.parametrize("n", [300, 4000])
 def test_close_pairs_use_reference_arithmetic(orc, n, mode, tpl):
     """The fast inverse cube is first order in the 1e-18 m softening: good to 6 (eps/r)^2, i.e. not to 1e-11 below

@@ -15,7 +15,7 @@ for n in sizes:
         hp.upload(pos, np.full(n, -Q_0), np.full(n, M_0))
         hp.set_option("pair_mode", 2)
         for tpl in (1, 2):
-            for waves in (4, 8, 16, 32):
+            for waves in (16, 64):
                 hp.set_option("sym_tpl", tpl)
                 hp.set_option("sym_waves", waves)
                 ts = []
