@@ -405,9 +405,10 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     if (n < 1) return RB2_OK;
     const rb2_config &c = ctx.cfg;
     if (c.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "the pair-symmetric kernel implements the planar geometry only");
-    // targets per lane: two from 16384 particles on (tools/sym_crossover.py: 800 vs 812 us there, 2.90 vs 3.08 ms at
-    // 32768, 5.5 % at 1e6), one below (half as many, twice as long CTAs do not fill the machine at small N)
-    const int T = ctx.sym_tpl == 1 ? 1 : (ctx.sym_tpl == 2 ? 2 : (n >= 16384 ? 2 : 1));
+    // targets per lane: two from 25000 particles on (tools/sym_tpl_sweep.py, profiles/sym_tpl_sweep_r02.log: 1.521 vs
+    // 1.528 ms at 24000, 2.046 vs 2.022 at 28000, 0.690 vs 0.723 at 16000; 5.5 % for T = 2 at 1e6), one below (half as
+    // many, twice as long CTAs do not fill the machine at small N)
+    const int T = ctx.sym_tpl == 1 ? 1 : (ctx.sym_tpl == 2 ? 2 : (n >= 25000 ? 2 : 1));
     SymGeom g{};
     g.n = n;
     g.nsb = (n + SB - 1) / SB;
