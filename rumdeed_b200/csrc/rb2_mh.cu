@@ -175,6 +175,7 @@ struct MhPlan {
     unsigned long long seed;
     double two_d, E_vac, fac, mh_std0, a_rate0;
     int nic;
+    int far;  // d >= 1 um and option sym_far: the n = 1 partners of a cathode-plane point skip the softening term
 };
 
 // Grid-wide barrier on an arrival counter in global memory (zeroed by the host): release add by one thread per CTA,
@@ -208,7 +209,7 @@ __device__ __forceinline__ void small_barrier(unsigned *bar, unsigned target)
 
 // one particle against one surface point: sum of g_n / (rho^2 + h_n^2)^(3/2).  EXACT: reference sqrt / divide (slow
 // path of laterally close pairs, see rb2_is_close); otherwise `close` collects the flag.
-template <int NIC, bool EXACT>
+template <int NIC, bool EXACT, bool FAR = false>
 __device__ __forceinline__ double surf_term(const SurfRec &r, double px, double py, double acc, const MhPlan &L, bool &close)
 {
     const double dx = px - r.x, dy = py - r.y;
@@ -216,8 +217,10 @@ __device__ __forceinline__ double surf_term(const SurfRec &r, double px, double 
     if (!EXACT) close = close || rb2_is_close(d2);
     acc = fma(r.g0, rb2_inv_r3_sel<EXACT>(fma(r.h0, r.h0, d2)), acc);
     if (NIC == 1) {
-        acc = fma(r.g1, rb2_inv_r3_sel<EXACT>(fma(r.h1, r.h1, d2)), acc);
-        acc = fma(r.g2, rb2_inv_r3_sel<EXACT>(fma(r.h2, r.h2, d2)), acc);
+        // FAR (MhPlan.far: d >= 1 um): both n = 1 partners are at least d from the cathode plane -- no softening term,
+        // like the pair kernels' far partners (rb2_inv_r3_far)
+        acc = fma(r.g1, (FAR && !EXACT) ? rb2_inv_r3_far(fma(r.h1, r.h1, d2)) : rb2_inv_r3_sel<EXACT>(fma(r.h1, r.h1, d2)), acc);
+        acc = fma(r.g2, (FAR && !EXACT) ? rb2_inv_r3_far(fma(r.h2, r.h2, d2)) : rb2_inv_r3_sel<EXACT>(fma(r.h2, r.h2, d2)), acc);
     } else if (NIC >= 2) {
         for (int n = 1; n <= L.nic; ++n) {
             const double h = L.two_d * (double)n, hm = r.h0 - h, hp = r.h0 + h;
@@ -233,8 +236,13 @@ __device__ __forceinline__ double surf_block(const SurfRec *rr, double px, doubl
 {
     double part = 0.0;
     bool close = false;
+    if (NIC == 1 && L.far) {
 #pragma unroll 4
-    for (int k = 0; k < CNT; ++k) part = surf_term<NIC, false>(rr[k], px, py, part, L, close);
+        for (int k = 0; k < CNT; ++k) part = surf_term<NIC, false, true>(rr[k], px, py, part, L, close);
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < CNT; ++k) part = surf_term<NIC, false>(rr[k], px, py, part, L, close);
+    }
     if (close) {
         part = 0.0;
         for (int k = 0; k < CNT; ++k) part = surf_term<NIC, true>(rr[k], px, py, part, L, close);
@@ -821,9 +829,16 @@ __global__ void __launch_bounds__(SER_T, 1) k_mh_serial(MhParams P, MhPlan L, Mh
         const int n_tot = Q.n + s_npend;
         double acc = 0.0;
         bool close = false;
-        for (int i = tid; i < n_tot; i += SER_T) {
-            const SurfRec &r = (i < Q.resident) ? res[i] : (i < Q.n ? Q.recs[i] : pend[i - Q.n]);
-            acc = surf_term<NIC, false>(r, px, py, acc, L, close);
+        if (NIC == 1 && L.far) {
+            for (int i = tid; i < n_tot; i += SER_T) {
+                const SurfRec &r = (i < Q.resident) ? res[i] : (i < Q.n ? Q.recs[i] : pend[i - Q.n]);
+                acc = surf_term<NIC, false, true>(r, px, py, acc, L, close);
+            }
+        } else {
+            for (int i = tid; i < n_tot; i += SER_T) {
+                const SurfRec &r = (i < Q.resident) ? res[i] : (i < Q.n ? Q.recs[i] : pend[i - Q.n]);
+                acc = surf_term<NIC, false>(r, px, py, acc, L, close);
+            }
         }
         if (close) {  // a laterally close record: this thread's records again with the reference's sqrt / divide
             acc = 0.0;
@@ -937,6 +952,7 @@ MhPlan make_plan(const Rb2Ctx &ctx, int M, int G_max)
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
     L.nic = gc.N_ic_max;
+    L.far = (rb2_make_step_params(gc).pl.far_ok && ctx.sym_far) ? 1 : 0;
     return L;
 }
 
@@ -1500,6 +1516,7 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
     L.nic = gc.N_ic_max;
+    L.far = (rb2_make_step_params(gc).pl.far_ok && ctx.sym_far) ? 1 : 0;
     L.mh_std0 = *mh_std_io; L.a_rate0 = *a_rate_io;
     // scratch (doubles): 5M outputs + 2 scalars + table + 2 x G x 32 partials + 8n records; (ints): the arrival counter
     size_t off_part = (size_t)5 * M + 2 + nw;
@@ -1570,6 +1587,7 @@ int rb2_launch_mh_planar_serial(Rb2Ctx &ctx, const rb2_mh_config *cfg, const dou
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
     L.nic = gc.N_ic_max;
+    L.far = (rb2_make_step_params(gc).pl.far_ok && ctx.sym_far) ? 1 : 0;
     MhSerial Q{};
     Q.M = M; Q.n = n;
     Q.mh_std0 = *mh_std_io; Q.a_rate0 = *a_rate_io;

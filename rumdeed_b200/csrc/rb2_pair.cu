@@ -124,7 +124,9 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
         xi = pi.x; yi = pi.y; zi = pi.z;
     }
 
-    if (!active) { xi = 1.0 + (double)tid; yi = 0.0; zi = 1.0; }  // idle lanes: metres away from every source (never "laterally close")
+    // idle lanes: metres away from every source (never "laterally close"); planar: at a height inside the gap, so that
+    // they take the same branch as a field point between the plates (no divergence in a partly filled warp)
+    if (!active) { xi = 1.0 + (double)tid; yi = 0.0; zi = (GEOM == 1) ? 0.25 * P.two_d : 1.0; }
 
     const int j_begin = blockIdx.y * j_chunk;
     const int j_end = min(n_src, j_begin + j_chunk);
@@ -179,8 +181,9 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                     if (close) a = planar_tile_exact<NIC>(xi, yi, zi, tile, cnt, j0, i, P);
                     az += a.t;
                 } else {
-                    if (NIC == 1 && !FIELD && P.far_ok) {
-                        // particles between the plates, d >= 1 um: the three far image partners without the softening term
+                    // particles between the plates, d >= 1 um: the three far image partners without the softening term;
+                    // field points qualify one by one (a point's value must not depend on its neighbours in the batch)
+                    if (NIC == 1 && P.far_ok && (!FIELD || (zi >= 0.0 && zi <= 0.5 * P.two_d))) {
 #pragma unroll UNROLL
                         for (int jj = 0; jj < cnt; ++jj) {
                             const double4 pj = tile[jj];
