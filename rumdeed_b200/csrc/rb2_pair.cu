@@ -343,11 +343,15 @@ Split choose_split(int n_tgt, int n_src, int sm_count)
     s.nblk = (n_tgt + BLOCK - 1) / BLOCK;
     const int want_units = sm_count * RB2_MINB * 8;
     int ns = (want_units + s.nblk - 1) / s.nblk;
-    const int max_ns = (n_src + TJ - 1) / TJ;
+    // chunks are whole tiles -- unless that leaves less than one wave of CTAs (a thousand particles: 8 x 8 CTAs, each
+    // thread a serial chain over 128 sources; the tip deck spent 120 us per step there): then quarter tiles
+    int gran = TJ;
+    if ((long long)s.nblk * ((n_src + TJ - 1) / TJ) < (long long)sm_count * RB2_MINB) gran = 32;
+    const int max_ns = (n_src + gran - 1) / gran;
     if (ns > max_ns) ns = max_ns;
     if (ns < 1) ns = 1;
     int chunk = (n_src + ns - 1) / ns;
-    chunk = ((chunk + TJ - 1) / TJ) * TJ;
+    chunk = ((chunk + gran - 1) / gran) * gran;
     s.j_chunk = chunk;
     s.nsplit = (n_src + chunk - 1) / chunk;
     if (s.nsplit > 65535) {

@@ -19,7 +19,17 @@ try:
 except Exception as ex:
     I, nel = float("nan"), -1
 phase = [l for l in log if "wall clock per phase" in l]
-print(f"{name:28s} rc={rc} steps={steps} wall={e-s:7.2f}s  steps/s={steps/(e-s):8.1f}  I(last quarter)={I:.4e} A  nrElec(end)={nel}")
+loop = float("nan")
+try:  # time inside the main loop (the process start -- CUDA context, first touch of the libraries -- is 2-4 s on a fresh box)
+    import re
+    m = re.search(r"emission ([0-9.]+)\s+MD step ([0-9.]+)\s+removal ([0-9.]+)\s+writers ([0-9.]+)", phase[0])
+    loop = sum(float(x) for x in m.groups())
+    c = [l for l in log if "collisions:" in l]
+    if c:
+        loop += float(re.search(r"wall clock ([0-9.]+) s", c[0]).group(1))
+except Exception:
+    pass
+print(f"{name:28s} rc={rc} steps={steps} wall={e-s:7.2f}s  steps/s={steps/(e-s):8.1f} (main loop only: {steps/loop:8.1f})  I(last quarter)={I:.4e} A  nrElec(end)={nel}")
 print("   ", phase[0] if phase else log[-2:])
 for l in log:
     if "collisions:" in l or "emission split" in l or "work-unit lists" in l: print("   ", l)
