@@ -222,6 +222,16 @@ module mod_b200_bridge
       real(c_double), intent(out) :: eta_f_out(*), df_out(*), pos_out(3, *)
       real(c_double), intent(inout) :: a_rate_io, mh_std_io
     end function
+    ! supply sum over the tip's (xi, phi) grid on the device (nodes, normals, areas handed over once)
+    integer(c_int) function rb2_tip_supply_set_grid(M, pts, normals, area) bind(C, name='rb2_tip_supply_set_grid')
+      import :: c_int, c_double
+      integer(c_int), value :: M
+      real(c_double), intent(in) :: pts(3, *), normals(3, *), area(*)
+    end function
+    integer(c_int) function rb2_tip_supply(n_s_out, F_sum_out) bind(C, name='rb2_tip_supply')
+      import :: c_int, c_double
+      real(c_double), intent(out) :: n_s_out, F_sum_out
+    end function
     integer(c_int) function rb2_nearest_electron(dist_out, id_out) bind(C, name='rb2_nearest_electron')
       import :: c_int, c_double
       real(c_double), intent(out) :: dist_out(*)

@@ -285,6 +285,17 @@ int rb2_mh_planar_serial(const rb2_mh_config *cfg, const double *w_theta, int M,
 int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
                double *a_rate_io, double *mh_std_io);
 
+/* The tip's supply sum on the device: Do_Field_Emission_Tip_OLDCODE (src/mod_emission_tip.f90:431-481) adds
+ * Elec_Supply(A_k, F_k) (:1710-1718) over a 100 x 100 (xi, phi) midpoint grid of the tip surface in every time step.
+ * rb2_tip_supply_set_grid: the M nodes pts(3,M), unit surface normals normals(3,M) (surface_normal,
+ * src/mod_hyperboloid_tip.f90:25-34) and patch areas area(M) (Tip_Area) -- geometry only, handed over once.
+ * rb2_tip_supply: field of the resident particles at the nodes (the kernel of rb2_field_batch), F_k = normal . field,
+ * n_s = sum over F_k < 0 of A_k a_FN F_k^2 dt / (q_0 w_theta t_y(l)^2) with w_theta = 4.7 eV (:45), and the plain sum of
+ * the F_k (the caller divides by M for F_avg).  256 nodes per CTA are added in a fixed tree, the CTA sums in CTA order
+ * on the host: deterministic, but not the reference's serial order (agreement ~1e-15 relative). */
+int rb2_tip_supply_set_grid(int M, const double *pts, const double *normals, const double *area);
+int rb2_tip_supply(double *n_s_out, double *F_sum_out);
+
 /* ---- electron / N2 collisions (collision_mode 1 and 2) -------------------------
  * Do_Electron_Atom_Collisions (src/mod_collisions.F90:30-76, called from src/main.F90:202 through
  * Do_Collisions, src/mod_verlet.F90:164-170), one-time-step variants:

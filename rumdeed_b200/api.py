@@ -133,7 +133,7 @@ EXPORTS = (
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
     "rb2_add_particles", "rb2_capacity_left", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_get_ramo_sections", "rb2_accel_host",
-    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip",
+    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip", "rb2_tip_supply_set_grid", "rb2_tip_supply",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_set_devices", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
@@ -180,6 +180,8 @@ def load_library(path: str | None = None):
     lib.rb2_mh_planar.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
     lib.rb2_mh_planar_serial.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PI, _PD, _PD]
     lib.rb2_mh_tip.argtypes = [C.c_int, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
+    lib.rb2_tip_supply_set_grid.argtypes = [C.c_int, _PD, _PD, _PD]
+    lib.rb2_tip_supply.argtypes = [_PD, _PD]
     lib.rb2_set_partition.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_pair_rank.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_option.argtypes = [C.c_char_p, C.c_double]
@@ -507,6 +509,18 @@ class HotPath:
         ar, sd = C.c_double(a_rate), C.c_double(MH_std)
         self._check(self.lib.rb2_mh_tip(M, ndim, seed, _d(ef), _d(df), _d(pos), C.byref(ar), C.byref(sd)))
         return ef, df, pos, ar.value, sd.value
+
+    def tip_supply_set_grid(self, pts, normals, area):
+        """Nodes (M,3), unit normals (M,3) and patch areas (M,) of the tip's supply grid; kept on the device."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64); normals = np.ascontiguousarray(normals, dtype=np.float64)
+        area = np.ascontiguousarray(area, dtype=np.float64)
+        self._check(self.lib.rb2_tip_supply_set_grid(int(area.shape[0]), _d(pts), _d(normals), _d(area)))
+
+    def tip_supply(self):
+        """(n_s, sum of the normal field over the nodes): Elec_Supply summed over the resident grid, src/mod_emission_tip.f90:431-481."""
+        ns, fs = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.rb2_tip_supply(C.byref(ns), C.byref(fs)))
+        return ns.value, fs.value
 
     def Particles_To_Device(self):
         self._check(self.lib.rb2_field_window_open())

@@ -278,6 +278,8 @@ static void release_all(Rb2Ctx &c)
     if (c.h_pts) cudaFreeHost(c.h_pts);
     if (c.h_fld) cudaFreeHost(c.h_fld);
     if (c.h_stage) cudaFreeHost(c.h_stage);
+    cudaFree(c.d_sup_grid); cudaFree(c.d_tip_img);
+    if (c.h_sup) cudaFreeHost(c.h_sup);
     if (c.graph_exec) cudaGraphExecDestroy(c.graph_exec);
     cudaEvent_t evs[] = {c.ev_a0, c.ev_a1, c.ev_s0, c.ev_s1, c.ev_c};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -1124,6 +1126,21 @@ int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, doub
     if (M == 0) return RB2_OK;
     if (!eta_f_out || !df_out || !pos_out || !a_rate_io || !mh_std_io) return rb2_fail(RB2_ERR_ARG, "NULL argument");
     return rb2_launch_mh_tip(g_rb2, M, ndim, seed, eta_f_out, df_out, pos_out, a_rate_io, mh_std_io);
+}
+
+int rb2_tip_supply_set_grid(int M, const double *pts, const double *normals, const double *area)
+{
+    RB2_REQUIRE_INIT();
+    if (M < 1) return rb2_fail(RB2_ERR_ARG, "rb2_tip_supply_set_grid: M < 1");
+    if (!pts || !normals || !area) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    return rb2_tip_supply_set_grid_impl(g_rb2, M, pts, normals, area);
+}
+
+int rb2_tip_supply(double *n_s_out, double *F_sum_out)
+{
+    RB2_REQUIRE_INIT();
+    if (!n_s_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    return rb2_tip_supply_impl(g_rb2, n_s_out, F_sum_out);
 }
 
 int rb2_field_window_open(void) { RB2_REQUIRE_INIT(); return RB2_OK; }

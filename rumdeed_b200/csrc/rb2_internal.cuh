@@ -148,6 +148,8 @@ struct Rb2Ctx {
     double *d_stage_d = nullptr; size_t stage_d_cap = 0;  // doubles
     int *d_stage_i = nullptr; size_t stage_i_cap = 0;     // ints
     double *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned
+    double4 *d_tip_img = nullptr; size_t tip_img_cap = 0;           // tip accelerations: sphere image of every particle
+    double *d_sup_grid = nullptr, *h_sup = nullptr; int sup_M = 0;  // tip supply grid: nodes, normals, areas, fields, partial sums
 
     cudaEvent_t ev_a0 = nullptr, ev_a1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr, ev_c = nullptr;
     // CUDA graph of the fused step (rb2_step): captured the second time in a row that a step would queue exactly the same
@@ -195,6 +197,8 @@ inline cudaError_t rb2_event_record(Rb2Ctx &c, cudaEvent_t e)
     return c.capturing ? cudaEventRecordWithFlags(e, c.stream, cudaEventRecordExternal) : cudaEventRecord(e, c.stream);
 }
 int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
+int rb2_tip_supply_set_grid_impl(Rb2Ctx &ctx, int M, const double *pts, const double *nrm, const double *area);
+int rb2_tip_supply_impl(Rb2Ctx &ctx, double *n_s_out, double *F_sum_out);
 
 // pair / field kernels (rb2_pair.cu)
 int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, int i_begin, int i_end, double *acc_out);
@@ -282,6 +286,20 @@ __device__ __forceinline__ double rb2_inv_r3_far(double s)
     const double e = fma(-s, t, 1.0);
     const double p = fma(e, fma(1.875, e, 1.5), 1.0);
     return (y0 * t) * p;
+}
+
+// Softened and plain inverse cube of the same s from one seed (the tip's Coulomb term and its sphere-image term share
+// their distance): 8 FP64 instructions for both.
+__device__ __forceinline__ void rb2_inv_r3_both(double s, double &w_soft, double &w_plain)
+{
+    const double y0 = rb2_rsqrt_seed(s);
+    const double t = y0 * y0;
+    const double e = fma(-s, t, 1.0);
+    const double p0 = fma(e, fma(1.875, e, 1.5), 1.0);
+    const double p1 = fma(-3.0 * rb2k::soft, y0, p0);
+    const double y3 = y0 * t;
+    w_plain = y3 * p0;
+    w_soft = y3 * p1;
 }
 
 // The first-order softening above is good to 6 (eps/r)^2: 6e-14 at r = 1e-11 m, but 6e-10 at 1e-13 m.  Pairs whose

@@ -1244,7 +1244,8 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_tip_small(MhParams P, TipMh T, 
         __syncthreads();
         const double px = sp[0][lane], py = sp[1][lane], pz = sp[2][lane];
         TipImage im_i{};
-        if (Q.do_ic) im_i = tip_image_point(TP, px, py, pz);
+        double4 img_i = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (Q.do_ic) { im_i = tip_image_point(TP, px, py, pz); img_i = tip_image_packed(TP, px, py, pz); }
         double ax = 0.0, ay = 0.0, az = 0.0;
         for (int t = 0; t < s1 - s0; ++t) {
             const double4 *rr = &mine[t * TSUB + warp * RPW];
@@ -1252,7 +1253,9 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_tip_small(MhParams P, TipMh T, 
             for (int k = 0; k < RPW; ++k) {
                 const double4 pj = rr[k];
                 double fx, fy, fz;
-                tip_point_field(TP, im_i, Q.do_ic != 0, px, py, pz, pj, fx, fy, fz);
+                bool close = false;
+                tip_pair_fast_upper(img_i, Q.do_ic != 0, px, py, pz, pj, fx, fy, fz, close);
+                if (close) tip_point_field(TP, im_i, Q.do_ic != 0, px, py, pz, pj, fx, fy, fz);  // within 1e-11 m: literal arithmetic
                 ax = fma(pj.w, fx, ax); ay = fma(pj.w, fy, ay); az = fma(pj.w, fz, az);
             }
         }
@@ -1488,6 +1491,83 @@ int rb2_launch_mh_tip(Rb2Ctx &ctx, int M, int ndim, unsigned long long seed, dou
     RB2_CUDA(cudaStreamSynchronize(st));
     *mh_std_io = scal[0];
     *a_rate_io = scal[1];
+    return RB2_OK;
+}
+
+// ---- the tip's supply grid on the device ----------------------------------------------------------------------------
+// Do_Field_Emission_Tip_OLDCODE (src/mod_emission_tip.f90:431-481) sums Elec_Supply(A, F) (:1710-1718) over a 100 x 100
+// (xi, phi) midpoint grid of the tip surface every time step.  Nodes, unit normals and patch areas depend on the geometry
+// only: the host hands them over once (rb2_tip_supply_set_grid); a time step is then the tip field kernel on the
+// resident nodes + one kernel that projects the field on the normal, applies the supply function and reduces 256 nodes
+// per CTA in a fixed tree -- two numbers per CTA go back (the host adds them in CTA order) instead of 3M doubles each way
+// and M exp / log calls on the host.
+constexpr int SUPB = 256;
+__global__ void __launch_bounds__(SUPB) k_tip_supply(MhParams P, int M, const double *__restrict__ nrm, const double *__restrict__ area,
+                                                     const double *__restrict__ fld, double fac, double *__restrict__ part)
+{
+    __shared__ double s_ns[SUPB], s_F[SUPB];
+    const int k = blockIdx.x * SUPB + threadIdx.x;
+    double ns = 0.0, F = 0.0;
+    if (k < M) {
+        F = nrm[3 * k] * fld[3 * k] + nrm[3 * k + 1] * fld[3 * k + 1] + nrm[3 * k + 2] * fld[3 * k + 2];  // Field_normal
+        if (F < 0.0) {
+            const double t = t_y(P, F, TIP_W);
+            ns = area[k] * fac * (F * F) / (t * t);
+        }
+    }
+    s_ns[threadIdx.x] = ns; s_F[threadIdx.x] = F;
+    __syncthreads();
+    for (int o = SUPB / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_ns[threadIdx.x] += s_ns[threadIdx.x + o]; s_F[threadIdx.x] += s_F[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = s_ns[0]; part[2 * blockIdx.x + 1] = s_F[0]; }
+}
+
+int rb2_tip_supply_set_grid_impl(Rb2Ctx &ctx, int M, const double *pts, const double *nrm, const double *area)
+{
+    if (ctx.cfg.geometry != RB2_GEOM_TIP) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_tip_supply_set_grid: hyperboloid-tip geometry only");
+    RB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (ctx.d_sup_grid) RB2_CUDA(cudaFree(ctx.d_sup_grid));
+    if (ctx.h_sup) RB2_CUDA(cudaFreeHost(ctx.h_sup));
+    ctx.d_sup_grid = nullptr; ctx.h_sup = nullptr; ctx.sup_M = 0;
+    const int nb = (M + SUPB - 1) / SUPB;
+    RB2_CUDA(cudaMallocHost(&ctx.h_sup, (size_t)2 * nb * sizeof(double)));
+    // [3M] nodes | [3M] normals | [M] areas | [3M] fields | [2 nb] partial sums
+    RB2_CUDA(cudaMalloc(&ctx.d_sup_grid, ((size_t)10 * M + 2 * (size_t)nb) * sizeof(double)));
+    RB2_CUDA(cudaMemcpy(ctx.d_sup_grid, pts, (size_t)3 * M * sizeof(double), cudaMemcpyHostToDevice));
+    RB2_CUDA(cudaMemcpy(ctx.d_sup_grid + (size_t)3 * M, nrm, (size_t)3 * M * sizeof(double), cudaMemcpyHostToDevice));
+    RB2_CUDA(cudaMemcpy(ctx.d_sup_grid + (size_t)6 * M, area, (size_t)M * sizeof(double), cudaMemcpyHostToDevice));
+    ctx.sup_M = M;
+    return RB2_OK;
+}
+
+int rb2_tip_supply_impl(Rb2Ctx &ctx, double *n_s_out, double *F_sum_out)
+{
+    const rb2_config &gc = ctx.cfg;
+    if (gc.geometry != RB2_GEOM_TIP) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_tip_supply: hyperboloid-tip geometry only");
+    const int M = ctx.sup_M;
+    if (M < 1 || !ctx.d_sup_grid) return rb2_fail(RB2_ERR_ARG, "rb2_tip_supply without rb2_tip_supply_set_grid");
+    const int nb = (M + SUPB - 1) / SUPB;
+    double *pts = ctx.d_sup_grid, *nrm = pts + (size_t)3 * M, *area = nrm + (size_t)3 * M, *fld = area + M, *part = fld + (size_t)3 * M;
+    int rc = rb2_launch_field(ctx, ctx.a.pq, ctx.n, nullptr, 0, pts, M, fld);
+    if (rc) return rc;
+    const double pi = RB2_PI, h_bar = 6.62607015e-34 / (2.0 * pi);
+    MhParams P{};
+    P.c.image_charge = gc.image_charge;
+    P.l_const = rb2k::q_0 / (4.0 * pi * rb2k::epsilon_0);
+    const double a_FN = (rb2k::q_0 * rb2k::q_0) / (16.0 * (pi * pi) * h_bar);
+    const double fac = a_FN * gc.time_step / (rb2k::q_0 * TIP_W);  // Elec_Supply = A a_FN F^2 dt / (q_0 w t^2)
+    k_tip_supply<<<nb, SUPB, 0, ctx.stream>>>(P, M, nrm, area, fld, fac, part);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(1);
+    double *h = ctx.h_sup;
+    RB2_CUDA(cudaMemcpyAsync(h, part, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    RB2_CUDA(cudaStreamSynchronize(ctx.stream));
+    double ns = 0.0, Fs = 0.0;
+    for (int b = 0; b < nb; ++b) { ns += h[2 * b]; Fs += h[2 * b + 1]; }
+    *n_s_out = ns;
+    if (F_sum_out) *F_sum_out = Fs;
     return RB2_OK;
 }
 

@@ -92,6 +92,42 @@ __device__ __noinline__ Acc4 planar_tile_exact(double xi, double yi, double zi, 
     return a;
 }
 
+// Slow path of the tip tiles: the literal arithmetic (IEEE sqrt / divide, the source image recomputed per element).
+template <int NIC, bool FIELD>
+__device__ __noinline__ Acc4 tip_tile_exact(TipParams T, double xi, double yi, double zi, const double4 *tile, int cnt, int j0, int i)
+{
+    Acc4 a = {0.0, 0.0, 0.0, 0.0};
+    TipImage im_i{};
+    if (NIC >= 0) im_i = tip_image_point(T, xi, yi, zi);
+    for (int jj = 0; jj < cnt; ++jj) {
+        const double4 pj = tile[jj];
+        const int j = j0 + jj;
+        const double qe = (!FIELD && (j == i)) ? 0.0 : pj.w;
+        // Coulomb, src/mod_verlet.F90:1371-1379
+        const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+        const double r = sqrt(dx * dx + dy * dy + dz * dz) + rb2k::soft;
+        const double inv_r3 = 1.0 / (r * r * r);
+        double fx = inv_r3 * dx, fy = inv_r3 * dy, fz = inv_r3 * dz;
+        if (NIC >= 0 && !(!FIELD && j == i)) {
+            double ic_x, ic_y, ic_z;
+            if (FIELD || (j > i)) {
+                // a = target (the field point, or the lower-indexed particle i), b = source j
+                tip_ic_force(T, im_i, xi, yi, zi, pj.x, pj.y, pj.z, ic_x, ic_y, ic_z);
+                fx += ic_x; fy += ic_y; fz += ic_z;
+            } else {
+                // a = particle j (lower index), b = particle i; x, y mirrored (sgn_xy = -1)
+                const TipImage im_j = tip_image_point(T, pj.x, pj.y, pj.z);
+                tip_ic_force(T, im_j, pj.x, pj.y, pj.z, xi, yi, zi, ic_x, ic_y, ic_z);
+                fx -= ic_x; fy -= ic_y; fz += ic_z;
+            }
+        }
+        a.x = fma(qe, fx, a.x);
+        a.y = fma(qe, fy, a.y);
+        a.z = fma(qe, fz, a.z);
+    }
+    return a;
+}
+
 // ---- the tiled pair kernel --------------------------------------------------------------------
 // GEOM 1 planar / 2 tip.  NIC: -1 image charge off, 0, 1, 2 (= runtime N_ic_max loop); tip uses
 // NIC -1 / 0 for image charge off / on.  FIELD: targets are the M field points (no self
@@ -101,7 +137,8 @@ __device__ __noinline__ Acc4 planar_tile_exact(double xi, double yi, double zi, 
 template <int GEOM, int NIC, bool FIELD>
 __global__ void __launch_bounds__(BLOCK, RB2_MINB)
 k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ tgt_pq, const double *__restrict__ tgt_pts,
-       int i_begin, int i_end, int j_chunk, int slot0, PlanarParams P, TipParams T, double *__restrict__ partial)
+       int i_begin, int i_end, int j_chunk, int slot0, PlanarParams P, TipParams T, double *__restrict__ partial,
+       const double4 *__restrict__ src_img)  // tip accelerations: the sources' sphere images (tip_image_packed)
 {
     __shared__ __align__(128) double4 tiles[STAGES * TJ];
     __shared__ __align__(8) uint64_t full[STAGES];
@@ -151,8 +188,8 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
         for (int t = 0; t < STAGES - 1; ++t) issue(t);
     }
 
-    TipImage im_i;
-    if (GEOM == 2 && NIC >= 0) im_i = tip_image_point(T, xi, yi, zi);
+    double4 img_i = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (GEOM == 2 && NIC >= 0) img_i = tip_image_packed(T, xi, yi, zi);
 
     double ax = 0.0, ay = 0.0, az = 0.0;
     for (int t = 0; t < ntiles; ++t) {
@@ -208,32 +245,24 @@ k_pair(const double4 *__restrict__ src, int n_src, const double4 *__restrict__ t
                     }
                 }
             } else {
+                // tip: the fast pair forms of rb2_tip_math.cuh; a pair closer than 1e-11 m sends this thread's row of the
+                // tile to the literal arithmetic
+                bool close = false;
                 for (int jj = 0; jj < cnt; ++jj) {
                     const double4 pj = tile[jj];
                     const int j = j0 + jj;
-                    const double qe = (!FIELD && (j == i)) ? 0.0 : pj.w;
-                    // Coulomb, src/mod_verlet.F90:1371-1379 (IEEE sqrt / divide here)
-                    const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
-                    const double r = sqrt(dx * dx + dy * dy + dz * dz) + rb2k::soft;
-                    const double inv_r3 = 1.0 / (r * r * r);
-                    double fx = inv_r3 * dx, fy = inv_r3 * dy, fz = inv_r3 * dz;
-                    if (NIC >= 0 && !(!FIELD && j == i)) {
-                        double ic_x, ic_y, ic_z;
-                        if (FIELD || (j > i)) {
-                            // a = target (the field point, or the lower-indexed particle i), b = source j
-                            tip_ic_force(T, im_i, xi, yi, zi, pj.x, pj.y, pj.z, ic_x, ic_y, ic_z);
-                            fx += ic_x; fy += ic_y; fz += ic_z;
-                        } else {
-                            // a = particle j (lower index), b = particle i; x, y mirrored (sgn_xy = -1)
-                            const TipImage im_j = tip_image_point(T, pj.x, pj.y, pj.z);
-                            tip_ic_force(T, im_j, pj.x, pj.y, pj.z, xi, yi, zi, ic_x, ic_y, ic_z);
-                            fx -= ic_x; fy -= ic_y; fz += ic_z;
-                        }
-                    }
+                    const bool self = !FIELD && (j == i);
+                    const double qe = self ? 0.0 : pj.w;
+                    double fx, fy, fz;
+                    bool c1 = false;
+                    if (FIELD || j >= i) tip_pair_fast_upper(img_i, NIC >= 0, xi, yi, zi, pj, fx, fy, fz, c1);
+                    else tip_pair_fast_lower(NIC >= 0 ? src_img[j] : make_double4(0.0, 0.0, 0.0, 0.0), NIC >= 0, xi, yi, zi, pj, fx, fy, fz, c1);
+                    close = close || (c1 && !self);
                     a.x = fma(qe, fx, a.x);
                     a.y = fma(qe, fy, a.y);
                     a.z = fma(qe, fz, a.z);
                 }
+                if (close) a = tip_tile_exact<NIC, FIELD>(T, xi, yi, zi, tile, cnt, j0, i);
             }
             ax += a.x; ay += a.y; az += a.z;
         }
@@ -331,6 +360,12 @@ __global__ void __launch_bounds__(128) k_field_finalize_wide(const double *__res
     }
 }
 
+__global__ void k_tip_images(const double4 *__restrict__ pq, int n, TipParams T, double4 *__restrict__ img)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { const double4 p = pq[j]; img[j] = tip_image_packed(T, p.x, p.y, p.z); }
+}
+
 struct Split {
     int nblk, nsplit, j_chunk;
 };
@@ -380,12 +415,27 @@ template <bool FIELD>
 int launch_pair(Rb2Ctx &ctx, const double4 *src, int n_src, const double4 *tgt_pq, const double *tgt_pts, int i_begin,
                 int i_end, const Split &sp, int slot0, double *partial)
 {
+    const double4 *src_img = nullptr;
+    if (!FIELD && ctx.cfg.geometry == RB2_GEOM_TIP && ctx.cfg.image_charge) {
+        // the sphere image of every particle, once per evaluation (the pairs with a lower-indexed source need the SOURCE's)
+        if ((size_t)n_src > ctx.tip_img_cap) {
+            if (ctx.d_tip_img) RB2_CUDA(cudaFree(ctx.d_tip_img));
+            ctx.d_tip_img = nullptr; ctx.tip_img_cap = 0;
+            const size_t want = std::max((size_t)ctx.cap, (size_t)n_src);
+            RB2_CUDA(cudaMalloc(&ctx.d_tip_img, want * sizeof(double4)));
+            ctx.tip_img_cap = want;
+        }
+        k_tip_images<<<(n_src + 255) / 256, 256, 0, ctx.stream>>>(src, n_src, rb2_make_step_params(ctx.cfg).tip, ctx.d_tip_img);
+        RB2_CUDA(cudaGetLastError());
+        RB2_LAUNCHED(1);
+        src_img = ctx.d_tip_img;
+    }
     const rb2_config &c = ctx.cfg;
     StepParams P = rb2_make_step_params(c);
     P.pl.far_ok = P.pl.far_ok && ctx.sym_far;  // option "sym_far" (on by default) governs both pair kernels
     dim3 grid(sp.nblk, sp.nsplit), block(BLOCK);
     cudaStream_t st = ctx.stream;
-#define RB2_GO(G, N) k_pair<G, N, FIELD><<<grid, block, 0, st>>>(src, n_src, tgt_pq, tgt_pts, i_begin, i_end, sp.j_chunk, slot0, P.pl, P.tip, partial)
+#define RB2_GO(G, N) k_pair<G, N, FIELD><<<grid, block, 0, st>>>(src, n_src, tgt_pq, tgt_pts, i_begin, i_end, sp.j_chunk, slot0, P.pl, P.tip, partial, src_img)
     if (c.geometry == RB2_GEOM_PLANAR) {
         if (!c.image_charge) RB2_GO(1, -1);
         else if (c.N_ic_max == 0) RB2_GO(1, 0);
@@ -438,19 +488,17 @@ __global__ void __launch_bounds__(128) k_tip_field_point(const double4 *__restri
     const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double xi = pts[3 * k], yi = pts[3 * k + 1], zi = pts[3 * k + 2];
     TipImage im_i{};
-    if (do_ic) im_i = tip_image_point(T, xi, yi, zi);
+    double4 img_i = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (do_ic) { im_i = tip_image_point(T, xi, yi, zi); img_i = tip_image_packed(T, xi, yi, zi); }
     double ax = 0.0, ay = 0.0, az = 0.0;
     for (int j = tid; j < n; j += 128) {
         const double4 pj = src[j];
-        const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;  // Coulomb, src/mod_verlet.F90:1511-1518
-        const double r = sqrt(dx * dx + dy * dy + dz * dz) + rb2k::soft;
-        const double inv_r3 = 1.0 / (r * r * r);
-        double fx = inv_r3 * dx, fy = inv_r3 * dy, fz = inv_r3 * dz;
-        if (do_ic) {  // Sphere_IC_field(p, r_j): the field point is imaged (:1520)
-            double ic_x, ic_y, ic_z;
-            tip_ic_force(T, im_i, xi, yi, zi, pj.x, pj.y, pj.z, ic_x, ic_y, ic_z);
-            fx += ic_x; fy += ic_y; fz += ic_z;
-        }
+        double fx, fy, fz;
+        bool close = false;
+        // Coulomb (src/mod_verlet.F90:1511-1518) + Sphere_IC_field(p, r_j) (:1520, the field point is imaged), fast form;
+        // a source within 1e-11 m: the literal arithmetic
+        tip_pair_fast_upper(img_i, do_ic != 0, xi, yi, zi, pj, fx, fy, fz, close);
+        if (close) tip_point_field(T, im_i, do_ic != 0, xi, yi, zi, pj, fx, fy, fz);
         ax = fma(pj.w, fx, ax);
         ay = fma(pj.w, fy, ay);
         az = fma(pj.w, fz, az);

@@ -4,7 +4,13 @@
 
 #include "rb2_internal.cuh"
 
-// ---- hyperboloid tip math (IEEE sqrt / divide: N is small for this geometry) -----------------
+// ---- hyperboloid tip math ---------------------------------------------------------------------
+// Two forms of every pair term.  The literal one (IEEE sqrt / divide, operation by operation like the .inc files) is the
+// slow path and the per-particle set-up; the fast one rewrites the same sums on the MUFU-seeded inverse cubes of
+// rb2_internal.cuh (~36 FP64 instructions per pair instead of ~155):
+//   Coulomb + Sphere_IC_field of source b on target a (a imaged):  f = d (w_c + pre w_a) - pre k_a w_b (im_a - r_b)
+//   with d = r_a - r_b, w_c = 1/(|d| + eps)^3, w_a = 1/|d|^3, w_b = 1/|r_b - im_a|^3, k_a = r_tip / dis_a, pre = q_0/(4 pi eps_0).
+// Pairs closer than 1e-11 m raise the `close` flag (rb2_is_close on |d|^2) and are redone by the caller on the slow path.
 struct TipImage {
     double dis_a, x_im, y_im, z_im;
 };
@@ -51,4 +57,52 @@ __device__ __forceinline__ void tip_point_field(const TipParams &T, const TipIma
         tip_ic_force(T, im_i, xi, yi, zi, pj.x, pj.y, pj.z, ic_x, ic_y, ic_z);
         fx += ic_x; fy += ic_y; fz += ic_z;
     }
+}
+
+// Per-particle constants of the fast forms: the sphere image and kk = pre * r_tip / dis_a (exact arithmetic, once per
+// particle / field point).
+__device__ __forceinline__ double4 tip_image_packed(const TipParams &T, double x, double y, double z)
+{
+    const TipImage im = tip_image_point(T, x, y, z);
+    const double pre = 1.0 * rb2k::q_0 / (4.0 * RB2_PI * rb2k::epsilon_0);
+    return make_double4(im.x_im, im.y_im, im.z_im, pre * T.r_tip / im.dis_a);
+}
+// Target a = (xi, yi, zi) with image ia, source b = pj: the field-point form and the acceleration of a particle from a
+// HIGHER-indexed source (src/mod_verlet.F90:1511-1520, :1380-1400 with a = i).
+__device__ __forceinline__ void tip_pair_fast_upper(const double4 ia, bool do_ic, double xi, double yi, double zi, const double4 pj,
+                                                    double &fx, double &fy, double &fz, bool &close)
+{
+    const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+    const double s = fma(dz, dz, fma(dy, dy, fma(dx, dx, RB2_S_FLOOR)));
+    close = close || rb2_is_close(s);
+    double wc, wa;
+    rb2_inv_r3_both(s, wc, wa);
+    if (!do_ic) { fx = wc * dx; fy = wc * dy; fz = wc * dz; return; }
+    const double pre = 1.0 * rb2k::q_0 / (4.0 * RB2_PI * rb2k::epsilon_0);
+    const double ex = ia.x - pj.x, ey = ia.y - pj.y, ez = ia.z - pj.z;
+    const double V = ia.w * rb2_inv_r3_far(fma(ez, ez, fma(ey, ey, ex * ex)));
+    const double U = fma(pre, wa, wc);
+    fx = fma(dx, U, -(V * ex));
+    fy = fma(dy, U, -(V * ey));
+    fz = fma(dz, U, -(V * ez));
+}
+// Acceleration of particle i = (xi, yi, zi) from a LOWER-indexed source j = pj with image ij: the reference evaluates the
+// pair with a = j, b = i and mirrors x, y (sgn_xy = -1, src/mod_verlet.F90:1380-1400):
+//   f_xy = d (w_c + pre w_a) + pre k_j w_b (im_j - r_i),   f_z = d_z (w_c - pre w_a) - pre k_j w_b (im_j - r_i)_z
+__device__ __forceinline__ void tip_pair_fast_lower(const double4 ij, bool do_ic, double xi, double yi, double zi, const double4 pj,
+                                                    double &fx, double &fy, double &fz, bool &close)
+{
+    const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+    const double s = fma(dz, dz, fma(dy, dy, fma(dx, dx, RB2_S_FLOOR)));
+    close = close || rb2_is_close(s);
+    double wc, wa;
+    rb2_inv_r3_both(s, wc, wa);
+    if (!do_ic) { fx = wc * dx; fy = wc * dy; fz = wc * dz; return; }
+    const double pre = 1.0 * rb2k::q_0 / (4.0 * RB2_PI * rb2k::epsilon_0);
+    const double ex = ij.x - xi, ey = ij.y - yi, ez = ij.z - zi;
+    const double V = ij.w * rb2_inv_r3_far(fma(ez, ez, fma(ey, ey, ex * ex)));
+    const double U1 = fma(pre, wa, wc), U2 = fma(-pre, wa, wc);
+    fx = fma(dx, U1, V * ex);
+    fy = fma(dy, U1, V * ey);
+    fz = fma(dz, U2, -(V * ez));
 }

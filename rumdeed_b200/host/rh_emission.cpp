@@ -904,6 +904,20 @@ int Tip_Supply_Grid(Sim &s, int nr_xi, int nr_phi, double *n_s_out, double *F_av
             }
         s.tip_grid_key[0] = nr_xi; s.tip_grid_key[1] = nr_phi;
         s.tip_grid_geom[0] = s.max_xi; s.tip_grid_geom[1] = s.eta_1; s.tip_grid_geom[2] = s.a_foci; s.tip_grid_geom[3] = s.shift_z;
+        s.tip_grid_on_device = false;
+    }
+    if (s.g.mh_device) {
+        // the grid stays on the device: field, normal projection, supply function and the sum there, two numbers per
+        // 256 nodes back (rb2_tip_supply); the host loop below is the MH_DEVICE = .false. path
+        if (!s.tip_grid_on_device) {
+            if (s.check(rb2_tip_supply_set_grid(M, s.tip_grid_pts.data(), s.tip_grid_nrm.data(), s.tip_grid_area.data()), "rb2_tip_supply_set_grid")) return -1;
+            s.tip_grid_on_device = true;
+        }
+        double n_s = 0.0, F_sum = 0.0;
+        if (s.check(rb2_tip_supply(&n_s, &F_sum), "rb2_tip_supply")) return -1;
+        *n_s_out = n_s;
+        if (F_avg_out) *F_avg_out = F_sum / ((double)nr_phi * nr_xi);
+        return 0;
     }
     s.scratch_fld.resize((size_t)3 * M);
     if (s.Calc_Field_at_Batch(M, s.tip_grid_pts.data(), s.scratch_fld.data())) return -1;

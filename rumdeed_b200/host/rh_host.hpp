@@ -169,6 +169,7 @@ struct Sim {
     // tip supply grid (Tip_Supply_Grid): geometry-only quantities, computed once
     std::vector<double> tip_grid_pts, tip_grid_nrm, tip_grid_area;
     int tip_grid_key[2] = {0, 0};
+    bool tip_grid_on_device = false;  // rb2_tip_supply_set_grid done for the cached grid
     double tip_grid_geom[4] = {0, 0, 0, 0};
 
     int fail(const std::string &m) { err = m; return -1; }

@@ -324,6 +324,41 @@ def test_tip_supply_and_sampler_match_oracle(orc):
 
 
 @gpu
+def test_tip_supply_grid_on_the_device(orc):
+    """rb2_tip_supply (MH_DEVICE runs): the 100 x 100 supply sum of Do_Field_Emission_Tip_OLDCODE with the grid resident on
+    the device -- against the oracle's serial double loop, against the host loop over an rb2_field_batch of the same
+    nodes, without and with space charge, and again after the particle set changed (the grid stays, the field does not)."""
+    sim_h, p, st, em = _tip_pair(orc, 41)
+    with sim_h:
+        host0 = sim_h.Tip_Supply_Grid(100, 100)
+    sim, p, st, em = _tip_pair(orc, 41, mh_batch=2)
+    with sim:
+        dev0 = sim.Tip_Supply_Grid(100, 100)
+        n_o, F_o = em.tip_supply_grid(100, 100)
+        assert dev0[0] == pytest.approx(n_o, rel=1e-9) and dev0[1] == pytest.approx(F_o, rel=1e-9)
+        assert dev0[0] == pytest.approx(host0[0], rel=1e-12) and dev0[1] == pytest.approx(host0[1], rel=1e-12)
+        rng = np.random.default_rng(2)
+        pos = np.stack([rng.uniform(-30, 30, 60), rng.uniform(-30, 30, 60), rng.uniform(503, 700, 60)], axis=1) * NM
+        hp = rb.HotPath.attach()
+        hp.Add_Particles(pos, np.zeros((60, 3)), np.ones(60, dtype=np.int32), 0)
+        for r in pos:
+            st.add(p, r, [0, 0, 0], 1, 0, 1)
+        dev1 = sim.Tip_Supply_Grid(100, 100)
+        n_o1, F_o1 = em.tip_supply_grid(100, 100)
+        assert dev1[0] == pytest.approx(n_o1, rel=1e-9) and dev1[1] == pytest.approx(F_o1, rel=1e-9)
+        assert dev1[0] < dev0[0]                      # the space charge screens the apex
+        assert sim.Tip_Supply_Grid(100, 100) == dev1  # deterministic
+        # the raw entry points with a grid of our own: 7 nodes, unit weights, normals along z
+        nodes = pos[:7] * [0.2, 0.2, 0.0] + [0, 0, 600 * NM]
+        nrm = np.tile([0.0, 0.0, 1.0], (7, 1))
+        hp.tip_supply_set_grid(nodes, nrm, np.ones(7))
+        n_s, F_sum = hp.tip_supply()
+        fz = hp.Calc_Field_at_Batch(nodes)[:, 2]
+        assert F_sum == pytest.approx(fz.sum(), rel=1e-13)
+        assert (n_s > 0.0) == bool(np.any(fz < 0.0))
+
+
+@gpu
 def test_device_resident_tip_sampler(orc):
     """rb2_mh_tip: the lock-step tip chains with every jump queued on the device (proposal kernel, the tip field kernel
     of rb2_field_batch, accept kernel).  Same distributions as the oracle's serial chains and as the host lock-step

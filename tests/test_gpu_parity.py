@@ -439,10 +439,10 @@ def test_field_delta_is_linear(orc):
 
 
 # --------------------------------------------------------------------------------------------------
-def tip_setup(orc, V=2.0e3, cap=4096, dt=0.25e-3 * 1e-12, boxz=1000 * NM):
+def tip_setup(orc, V=2.0e3, cap=4096, dt=0.25e-3 * 1e-12, boxz=1000 * NM, ic=True):
     box = (100 * NM, 100 * NM, boxz)
-    cfg = rb.tip_config(V, 900 * NM, 100 * NM, 100 * NM, box, dt, True, capacity=cap)
-    p = orc.params_tip(V, 900 * NM, 100 * NM, 100 * NM, box, dt, True)
+    cfg = rb.tip_config(V, 900 * NM, 100 * NM, 100 * NM, box, dt, ic, capacity=cap)
+    p = orc.params_tip(V, 900 * NM, 100 * NM, 100 * NM, box, dt, ic)
     return cfg, p
 
 
@@ -470,6 +470,42 @@ def test_tip_reference_case(orc):
     assert relerr(acc, orc.accel_gather_ld(p, R, q, m)) < TOL
     assert relerr(batch, orc.calc_field_at_batch(p, R, q, pts, sp)) < TOL
     assert relerr(batch, singles) < 1e-13
+
+
+@pytest.mark.parametrize("ic", [True, False])
+def test_tip_close_pairs_and_large_cloud(orc, ic):
+    """The tip kernels run on MUFU-seeded inverse cubes (rb2_tip_math.cuh: Coulomb and sphere-image term rewritten on
+    shared distances); a pair closer than 1e-11 m goes back to the literal sqrt / divide arithmetic.  2600 particles (21
+    source tiles, pairs with lower- and higher-indexed sources in every row) with separations from 1e-15 to 3e-11 m planted
+    across tiles, field points 2e-14 m from a particle, image charge on and off; 260 rows against the long-double oracle."""
+    n = 2600
+    cfg, p = tip_setup(orc, ic=ic)
+    rng = np.random.default_rng(77)
+    pos = np.stack([rng.uniform(-40, 40, n), rng.uniform(-40, 40, n), rng.uniform(105, 900, n)], axis=1) * NM
+    ion = (np.arange(n) % 7) == 6
+    q = np.where(ion, Q_0, -Q_0); m = np.where(ion, M_N2P, M_0)
+    seps = [1e-15, 1e-14, 1e-13, 1e-12, 5e-12, 1e-11, 3e-11]
+    touched = []
+    for k, r in enumerate(seps):
+        for axis in range(3):
+            i = int(rng.integers(0, n)); j = (i + 1) % n if (k + axis) % 2 == 0 else (i + n // 2 + 31) % n
+            off = np.zeros(3); off[axis] = r
+            pos[j] = pos[i] + off
+            touched += [i, j]
+    rows = np.unique(np.concatenate([touched, rng.choice(n, 220, replace=False), [0, 127, 128, n - 1]]))
+    pts = np.concatenate([pos[touched[:6]] + [0, 0, 2e-14], np.stack([rng.uniform(-30, 30, 30), rng.uniform(-30, 30, 30), rng.uniform(101, 400, 30)], axis=1) * NM])
+    with rb.HotPath(cfg) as hp:
+        hp.upload(pos, q, m, species=np.where(ion, 2, 1).astype(np.int32))
+        hp.Calculate_Acceleration_Particles()
+        acc = hp.download(("acc",))["acc"]
+        fld = hp.Calc_Field_at_Batch(pts)
+        hp.set_option("tip_field_small", 0)
+        fld_tiled = hp.Calc_Field_at_Batch(pts)
+    assert np.all(np.isfinite(acc))
+    truth = orc.accel_gather_ld_rows(p, pos, q, m, rows)
+    assert relerr(acc[rows], truth) < TOL
+    want = np.stack([orc.calc_field_at(p, pos, q, pt, ld=True) for pt in pts])
+    assert relerr(fld, want) < TOL and relerr(fld_tiled, want) < TOL
 
 
 @pytest.mark.parametrize("n", [5, 130, 700])
