@@ -222,6 +222,15 @@ module mod_b200_bridge
       real(c_double), intent(out) :: eta_f_out(*), df_out(*), pos_out(3, *)
       real(c_double), intent(inout) :: a_rate_io, mh_std_io
     end function
+    ! one level of the planar supply quadrature on the device (nodes of K shifted lattices, field, integrand, per-shift sums)
+    integer(c_int) function rb2_planar_supply_level(cfg, w_theta, kind, K, shifts, n_done, n_new, sums_out, ez_sum_out) &
+        bind(C, name='rb2_planar_supply_level')
+      import :: c_int, c_double, rb2_mh_config
+      type(rb2_mh_config), intent(in) :: cfg
+      real(c_double), intent(in) :: w_theta(*), shifts(2, *)
+      integer(c_int), value :: kind, K, n_done, n_new
+      real(c_double), intent(out) :: sums_out(*), ez_sum_out
+    end function
     ! supply sum over the tip's (xi, phi) grid on the device (nodes, normals, areas handed over once)
     integer(c_int) function rb2_tip_supply_set_grid(M, pts, normals, area) bind(C, name='rb2_tip_supply_set_grid')
       import :: c_int, c_double

@@ -285,6 +285,17 @@ int rb2_mh_planar_serial(const rb2_mh_config *cfg, const double *w_theta, int M,
 int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, double *df_out, double *pos_out,
                double *a_rate_io, double *mh_std_io);
 
+/* One level of the planar supply quadrature on the device (Do_Surface_Integration_FE / _Simple,
+ * src/mod_field_emission_v2.F90:635-745, src/mod_field_thermo_emission.F90:394-466; the host's stand-in for Cuba is a
+ * rank-1 lattice with K <= 8 random shifts, refined level by level): the nodes k = n_done+1 .. n_done+n_new of every
+ * shifted lattice -- u = frac(k a1 + shift(1,r)), v = frac(k a2 + shift(2,r)) over the emitter rectangle of cfg -- are
+ * generated on the device, the cathode-plane field kernel of rb2_field_surface_z runs on them, and the integrand
+ * (kind 1: Elec_Supply_V2 :579-587; kind 2: J_GTF dt / q_0) at the node's work function is summed per shift in a fixed
+ * tree.  sums_out[r] = sum of the integrand over the new nodes of shift r (the caller multiplies by the emitter area),
+ * *ez_sum_out = sum of E_z over all new nodes.  Needs image_charge = 1 or 0 alike (E_z from the surface kernel). */
+int rb2_planar_supply_level(const rb2_mh_config *cfg, const double *w_theta, int kind, int K, const double *shifts, int n_done,
+                            int n_new, double *sums_out, double *ez_sum_out);
+
 /* The tip's supply sum on the device: Do_Field_Emission_Tip_OLDCODE (src/mod_emission_tip.f90:431-481) adds
  * Elec_Supply(A_k, F_k) (:1710-1718) over a 100 x 100 (xi, phi) midpoint grid of the tip surface in every time step.
  * rb2_tip_supply_set_grid: the M nodes pts(3,M), unit surface normals normals(3,M) (surface_normal,

@@ -133,7 +133,7 @@ EXPORTS = (
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
     "rb2_add_particles", "rb2_capacity_left", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_get_ramo_sections", "rb2_accel_host",
-    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip", "rb2_tip_supply_set_grid", "rb2_tip_supply",
+    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip", "rb2_tip_supply_set_grid", "rb2_tip_supply", "rb2_planar_supply_level",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_set_devices", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
@@ -182,6 +182,7 @@ def load_library(path: str | None = None):
     lib.rb2_mh_tip.argtypes = [C.c_int, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
     lib.rb2_tip_supply_set_grid.argtypes = [C.c_int, _PD, _PD, _PD]
     lib.rb2_tip_supply.argtypes = [_PD, _PD]
+    lib.rb2_planar_supply_level.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_int, _PD, C.c_int, C.c_int, _PD, _PD]
     lib.rb2_set_partition.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_pair_rank.argtypes = [C.c_int, C.c_int]
     lib.rb2_set_option.argtypes = [C.c_char_p, C.c_double]
@@ -509,6 +510,24 @@ class HotPath:
         ar, sd = C.c_double(a_rate), C.c_double(MH_std)
         self._check(self.lib.rb2_mh_tip(M, ndim, seed, _d(ef), _d(df), _d(pos), C.byref(ar), C.byref(sd)))
         return ef, df, pos, ar.value, sd.value
+
+    def planar_supply_level(self, emit_pos, emit_dim, w_theta, shifts, n_done, n_new, kind=1, T_temp=293.15):
+        """One level of the planar supply quadrature on the device (rb2_planar_supply_level): per-shift sums of the
+        integrand over lattice nodes n_done+1 .. n_done+n_new and the sum of E_z over them."""
+        w = np.ascontiguousarray(w_theta, dtype=np.float64)
+        if w.ndim != 2:
+            w = w.reshape(1, -1)
+        c = MhConfig()
+        c.kind = kind
+        c.y_num, c.x_num = w.shape
+        c.emit_pos[:] = list(emit_pos)[:2]
+        c.emit_dim[:] = list(emit_dim)[:2]
+        c.T_temp = T_temp
+        sh = np.ascontiguousarray(shifts, dtype=np.float64).reshape(-1, 2)
+        sums = np.zeros(sh.shape[0])
+        ez = C.c_double(0.0)
+        self._check(self.lib.rb2_planar_supply_level(C.byref(c), _d(w), kind, sh.shape[0], _d(sh), int(n_done), int(n_new), _d(sums), C.byref(ez)))
+        return sums, ez.value
 
     def tip_supply_set_grid(self, pts, normals, area):
         """Nodes (M,3), unit normals (M,3) and patch areas (M,) of the tip's supply grid; kept on the device."""

@@ -278,7 +278,8 @@ static void release_all(Rb2Ctx &c)
     if (c.h_pts) cudaFreeHost(c.h_pts);
     if (c.h_fld) cudaFreeHost(c.h_fld);
     if (c.h_stage) cudaFreeHost(c.h_stage);
-    cudaFree(c.d_sup_grid); cudaFree(c.d_tip_img);
+    cudaFree(c.d_sup_grid); cudaFree(c.d_tip_img); cudaFree(c.d_supq);
+    if (c.h_supq) cudaFreeHost(c.h_supq);
     if (c.h_sup) cudaFreeHost(c.h_sup);
     if (c.graph_exec) cudaGraphExecDestroy(c.graph_exec);
     cudaEvent_t evs[] = {c.ev_a0, c.ev_a1, c.ev_s0, c.ev_s1, c.ev_c};
@@ -1126,6 +1127,14 @@ int rb2_mh_tip(int M, int ndim, unsigned long long seed, double *eta_f_out, doub
     if (M == 0) return RB2_OK;
     if (!eta_f_out || !df_out || !pos_out || !a_rate_io || !mh_std_io) return rb2_fail(RB2_ERR_ARG, "NULL argument");
     return rb2_launch_mh_tip(g_rb2, M, ndim, seed, eta_f_out, df_out, pos_out, a_rate_io, mh_std_io);
+}
+
+int rb2_planar_supply_level(const rb2_mh_config *cfg, const double *w_theta, int kind, int K, const double *shifts, int n_done,
+                            int n_new, double *sums_out, double *ez_sum_out)
+{
+    RB2_REQUIRE_INIT();
+    if (!cfg || !w_theta || !shifts || !sums_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    return rb2_planar_supply_level_impl(g_rb2, cfg, w_theta, kind, K, shifts, n_done, n_new, sums_out, ez_sum_out);
 }
 
 int rb2_tip_supply_set_grid(int M, const double *pts, const double *normals, const double *area)

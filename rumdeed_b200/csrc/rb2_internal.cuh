@@ -148,6 +148,7 @@ struct Rb2Ctx {
     double *d_stage_d = nullptr; size_t stage_d_cap = 0;  // doubles
     int *d_stage_i = nullptr; size_t stage_i_cap = 0;     // ints
     double *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned
+    double *d_supq = nullptr, *h_supq = nullptr; size_t supq_cap = 0;  // planar supply quadrature: table, nodes, E_z, partial sums
     double4 *d_tip_img = nullptr; size_t tip_img_cap = 0;           // tip accelerations: sphere image of every particle
     double *d_sup_grid = nullptr, *h_sup = nullptr; int sup_M = 0;  // tip supply grid: nodes, normals, areas, fields, partial sums
 
@@ -199,6 +200,8 @@ inline cudaError_t rb2_event_record(Rb2Ctx &c, cudaEvent_t e)
 int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
 int rb2_tip_supply_set_grid_impl(Rb2Ctx &ctx, int M, const double *pts, const double *nrm, const double *area);
 int rb2_tip_supply_impl(Rb2Ctx &ctx, double *n_s_out, double *F_sum_out);
+int rb2_planar_supply_level_impl(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int kind, int K,
+                                 const double *shifts, int n_done, int n_new, double *sums_out, double *ez_sum_out);
 
 // pair / field kernels (rb2_pair.cu)
 int rb2_launch_accel(Rb2Ctx &ctx, const double4 *pq, const double *mass, int n, int i_begin, int i_end, double *acc_out);

@@ -1571,6 +1571,118 @@ int rb2_tip_supply_impl(Rb2Ctx &ctx, double *n_s_out, double *F_sum_out)
     return RB2_OK;
 }
 
+// ---- one level of the planar supply quadrature on the device -------------------------------------------------------
+// The host's stand-in for Cuba_Integrate (rh_emission.cpp) evaluates the integrand of Do_Surface_Integration_FE
+// (integrand_cuba_fe_v, src/mod_field_emission_v2.F90:668-745) or ..._Simple (integrand_cuba_simple,
+// src/mod_field_thermo_emission.F90:394-446) on K shifted copies of a rank-1 lattice, level by level.  A level here is:
+// the nodes generated on the device from the K shifts, the cathode-plane field kernel on them, the integrand
+// (Elec_Supply_V2 or J_GTF dt / q_0 at the node's work function) and a fixed-tree sum per shift and CTA -- 2 K nb
+// numbers come back instead of M fields, and the M exp / log evaluations leave the host.
+struct SupLevel {
+    int K, n_done, n_new, kind;
+    double shift[16];
+    double fe_fac, gtf_fac;  // (dt / q_0) a_FN;  dt / q_0
+};
+__global__ void k_supply_nodes(MhParams P, SupLevel S, double *__restrict__ pts)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= S.K * S.n_new) return;
+    const int r = m / S.n_new, k = m - r * S.n_new;
+    const double a1 = 0.7548776662466927600495088963585286919, a2 = 0.5698402909980532659113999581195686488;
+    const double kk = (double)(S.n_done + k + 1);
+    double u = kk * a1 + S.shift[2 * r], v = kk * a2 + S.shift[2 * r + 1];
+    u -= floor(u); v -= floor(v);
+    pts[3 * m] = P.c.emit_pos[0] + u * P.c.emit_dim[0];
+    pts[3 * m + 1] = P.c.emit_pos[1] + v * P.c.emit_dim[1];
+    pts[3 * m + 2] = 0.0;
+}
+__global__ void __launch_bounds__(SUPB) k_supply_planar(MhParams P, SupLevel S, const double *__restrict__ pts,
+                                                        const double *__restrict__ Ez, double *__restrict__ part)
+{
+    __shared__ double s_f[SUPB], s_E[SUPB];
+    const int r = blockIdx.y, k = blockIdx.x * SUPB + threadIdx.x;
+    double ff = 0.0, F = 0.0;
+    if (k < S.n_new) {
+        const int m = r * S.n_new + k;
+        F = Ez[m];
+        if (F < 0.0) {
+            const double w = w_theta_xy(P, pts[3 * m], pts[3 * m + 1]);
+            if (S.kind == 1) { const double t = t_y(P, F, w); ff = S.fe_fac / ((t * t) * w) * (F * F); }  // Elec_Supply_V2
+            else ff = kevin_jgtf_v2(F, P.c.T_temp, w) * S.gtf_fac;
+        }
+    }
+    s_f[threadIdx.x] = ff; s_E[threadIdx.x] = F;
+    __syncthreads();
+    for (int o = SUPB / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_f[threadIdx.x] += s_f[threadIdx.x + o]; s_E[threadIdx.x] += s_E[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const size_t o = ((size_t)r * gridDim.x + blockIdx.x) * 2;
+        part[o] = s_f[0]; part[o + 1] = s_E[0];
+    }
+}
+
+int rb2_planar_supply_level_impl(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int kind, int K,
+                                 const double *shifts, int n_done, int n_new, double *sums_out, double *ez_sum_out)
+{
+    const rb2_config &gc = ctx.cfg;
+    if (gc.geometry != RB2_GEOM_PLANAR) return rb2_fail(RB2_ERR_GEOMETRY, "rb2_planar_supply_level: planar geometry only");
+    if (K < 1 || K > 8 || n_new < 1 || n_done < 0) return rb2_fail(RB2_ERR_ARG, "rb2_planar_supply_level: K must be 1..8, n_new >= 1, n_done >= 0");
+    if (kind != 1 && kind != 2) return rb2_fail(RB2_ERR_ARG, "rb2_planar_supply_level: kind must be 1 (field emission) or 2 (thermal-field)");
+    const int nw = cfg->y_num * cfg->x_num;
+    if (nw < 1 || nw > 96 * 96) return rb2_fail(RB2_ERR_ARG, "work function table must have 1..9216 cells");
+    const size_t Mp = (size_t)K * n_new;
+    if (Mp > (size_t)1 << 26) return rb2_fail(RB2_ERR_ARG, "rb2_planar_supply_level: too many nodes in one level");
+    const int M = (int)Mp, nb = (n_new + SUPB - 1) / SUPB;
+    // own buffers (the field kernel reallocates the shared staging area): table | nodes | E_z | partial sums
+    const size_t need = (size_t)nw + 4 * (size_t)M + 2 * (size_t)K * nb + 8;
+    if (need > ctx.supq_cap) {
+        RB2_CUDA(cudaStreamSynchronize(ctx.stream));
+        if (ctx.d_supq) RB2_CUDA(cudaFree(ctx.d_supq));
+        if (ctx.h_supq) RB2_CUDA(cudaFreeHost(ctx.h_supq));
+        ctx.d_supq = nullptr; ctx.h_supq = nullptr; ctx.supq_cap = 0;
+        const size_t want = need + need / 2;
+        RB2_CUDA(cudaMalloc(&ctx.d_supq, want * sizeof(double)));
+        RB2_CUDA(cudaMallocHost(&ctx.h_supq, want * sizeof(double)));
+        ctx.supq_cap = want;
+    }
+    double *d_w = ctx.d_supq, *d_pts = d_w + ((nw + 1) & ~1), *d_Ez = d_pts + (size_t)3 * M, *d_part = d_Ez + M;
+    cudaStream_t st = ctx.stream;
+    memcpy(ctx.h_supq, w_theta_host, (size_t)nw * sizeof(double));
+    RB2_CUDA(cudaMemcpyAsync(d_w, ctx.h_supq, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double pi = RB2_PI, h_bar = 6.62607015e-34 / (2.0 * pi);
+    MhParams P;
+    P.c = *cfg;
+    P.c.image_charge = gc.image_charge;
+    P.w_theta = d_w;
+    P.b_FN = -4.0 / (3.0 * h_bar) * sqrt(2.0 * rb2k::m_0 * rb2k::q_0);
+    P.l_const = rb2k::q_0 / (4.0 * pi * rb2k::epsilon_0);
+    SupLevel S{};
+    S.K = K; S.n_done = n_done; S.n_new = n_new; S.kind = kind;
+    for (int i = 0; i < 2 * K; ++i) S.shift[i] = shifts[i];
+    S.gtf_fac = gc.time_step / rb2k::q_0;
+    S.fe_fac = S.gtf_fac * (rb2k::q_0 * rb2k::q_0) / (16.0 * (pi * pi) * h_bar);
+    k_supply_nodes<<<(M + 255) / 256, 256, 0, st>>>(P, S, d_pts);
+    RB2_CUDA(cudaGetLastError());
+    int rc = rb2_launch_surface_field(ctx, d_pts, M, d_Ez);
+    if (rc) return rc;
+    k_supply_planar<<<dim3(nb, K), SUPB, 0, st>>>(P, S, d_pts, d_Ez, d_part);
+    RB2_CUDA(cudaGetLastError());
+    RB2_LAUNCHED(2);
+    double *h = ctx.h_supq + ((nw + 1) & ~1);
+    RB2_CUDA(cudaMemcpyAsync(h, d_part, (size_t)2 * K * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    double ez = 0.0;
+    for (int r = 0; r < K; ++r) {
+        double f = 0.0;
+        for (int b = 0; b < nb; ++b) { f += h[((size_t)r * nb + b) * 2]; ez += h[((size_t)r * nb + b) * 2 + 1]; }
+        sums_out[r] = f;
+    }
+    if (ez_sum_out) *ez_sum_out = ez;
+    return RB2_OK;
+}
+
 // At most 512 chains (T <= 16 tiles) over at most 6 resident 128-record sub-tiles per CTA: the single-barrier kernel, with
 // 4 warps per CTA (two CTAs per SM) up to 4 tiles and 16 warps (one CTA per SM) beyond.
 // Returns RB2_ERR_ARG - 1000 ("does not apply") when the problem is too large for it.

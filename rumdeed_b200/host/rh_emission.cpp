@@ -197,6 +197,8 @@ double Sim::Tip_Area(double xi_1, double xi_2, double phi_1, double phi_2) const
     return 0.5 * (a_foci * a_foci) * sqrt(1.0 - e2) * (phi_2 - phi_1) * (fac_2 - fac_1);
 }
 
+static void fill_mh_config(const Sim &s, int kind, rb2_mh_config &c);
+
 // ---- surface integration: stand-in for Cuba_Integrate ----------------------------------------------------
 // Cuba (Divonne, src/mod_cuba_integration.F90:95-169) is not available.  The replacement is a
 // randomised rank-1 lattice (R2 sequence, 8 independent Cranley-Patterson shifts): the estimate is
@@ -218,6 +220,17 @@ int Cuba_Integrate(Sim &s, int kind, int emit, QuadResult *out)
     double fsum[3] = {0, 0, 0};
     for (;;) {
         const int n_new = n_next - n_done, M = n_new * K;
+        if (g.mh_device) {
+            // the level on the device (rb2_planar_supply_level): nodes, cathode-plane field, integrand and the per-shift
+            // sums there; the convergence test below is unchanged
+            rb2_mh_config c{};
+            fill_mh_config(s, kind == SUPPLY_FE ? 1 : 2, c);
+            double part[K], ez = 0.0;
+            if (s.check(rb2_planar_supply_level(&c, s.work.w_theta_arr.data(), kind == SUPPLY_FE ? 1 : 2, K, &shift[0][0], n_done, n_new, part, &ez),
+                        "rb2_planar_supply_level")) return -1;
+            for (int r = 0; r < K; ++r) sum[r] += A * part[r];
+            fsum[2] += ez;
+        } else {
         s.scratch_pts.resize((size_t)3 * M);
         s.scratch_fld.resize((size_t)3 * M);
         for (int r = 0; r < K; ++r)
@@ -243,6 +256,7 @@ int Cuba_Integrate(Sim &s, int kind, int emit, QuadResult *out)
                 }
                 sum[r] += A * ff;
             }
+        }
         n_done = n_next;
         q.neval = n_done * K;
         double mean = 0.0, var = 0.0;

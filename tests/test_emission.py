@@ -141,6 +141,32 @@ def test_supply_integral_matches_oracle_grid(orc, kind, mode, T):
             assert abs(val - truth) <= 4.0 * tol, (val, truth, err)
 
 
+@gpu
+@pytest.mark.parametrize("kind,mode,T", [(SUPPLY_FE, 10, 293.15), (SUPPLY_GTF, 9, 1400.0)])
+def test_supply_quadrature_on_the_device(orc, kind, mode, T):
+    """rb2_planar_supply_level (MH_DEVICE runs): every level of the lattice rule -- nodes, cathode-plane field, integrand,
+    per-shift sums -- on the device.  Same seed, same shifts: the same levels, evaluation count and (to the summation
+    order) the same integral and error as the host loop over rb2_field_surface_z; and the oracle's grid as before."""
+    w = ((2.0, 2.5), (2.5, 2.0))
+    res = {}
+    for mh_batch in (False, 2):
+        sim, p, st, em = _planar_pair(orc, 11, w=w, mode=mode, T=T, mh_batch=mh_batch)
+        with sim:
+            out = []
+            for n_pre in (0, 150):
+                if n_pre:
+                    _preload(sim, st, p, n_pre, 3)
+                truth, _ = em.supply_grid(kind, 96)
+                val, err, neval, fail = sim.Cuba_Integrate(kind)
+                tol = max(0.5, 1e-3 * abs(truth))
+                assert fail == 0 and err <= tol and abs(val - truth) <= 4.0 * tol, (mh_batch, val, truth, err)
+                out.append((val, err, neval))
+            res[mh_batch] = out
+    for (v0, e0, n0), (v1, e1, n1) in zip(res[False], res[2]):
+        assert n0 == n1
+        assert v1 == pytest.approx(v0, rel=1e-12) and e1 == pytest.approx(e0, rel=1e-6, abs=1e-12 * abs(v0))
+
+
 def _ks(a, b):
     from scipy.stats import ks_2samp
     return ks_2samp(a, b).pvalue
