@@ -1683,7 +1683,7 @@ int rb2_planar_supply_level_impl(Rb2Ctx &ctx, const rb2_mh_config *cfg, const do
     return RB2_OK;
 }
 
-// At most 512 chains (T <= 16 tiles) over at most 6 resident 128-record sub-tiles per CTA: the single-barrier kernel, with
+// At most 512 chains (T <= 16 tiles), the records of every CTA resident in shared memory (as many 128-record sub-tiles as fit): the single-barrier kernel, with
 // 4 warps per CTA (two CTAs per SM) up to 4 tiles and 16 warps (one CTA per SM) beyond.
 // Returns RB2_ERR_ARG - 1000 ("does not apply") when the problem is too large for it.
 static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int M, unsigned long long seed,
@@ -1701,7 +1701,13 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     Q.Gs = std::max(1, std::min(Q.S, max_ctas / Q.T));
     Q.G = Q.T * Q.Gs;
     Q.R = std::max(1, (Q.S + Q.Gs - 1) / Q.Gs);
-    if (Q.R > (WPB == 4 ? 4 : 6)) return RB2_ERR_ARG - 1000;
+    {   // the records of a CTA stay in shared memory: as many 8 KB sub-tiles as fit next to the join strands (one CTA of
+        // 16 warps per SM: ~216 KB; two CTAs of 4 warps: ~105 KB each).  Round 2 first capped this at 6 resp. 4 sub-tiles;
+        // the Ion deck (20 k particles, 12 per CTA) then fell to the many-chain kernel at 21.8 us per jump.
+        const size_t budget = (WPB == 4 ? 105 : 216) * 1024, strands = (size_t)Q.T * WPB * 32 * sizeof(double);
+        const int r_max = budget > strands ? (int)((budget - strands) / (MHB * sizeof(SurfRec))) : 0;
+        if (Q.R > r_max) return RB2_ERR_ARG - 1000;
+    }
     MhPlan L{};
     L.M = M; L.n = n; L.n_tiles = Q.T; L.max_init = max_init; L.seed = seed;
     L.two_d = 2.0 * gc.d;
