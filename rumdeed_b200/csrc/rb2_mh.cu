@@ -250,6 +250,26 @@ __device__ __forceinline__ double surf_block(const SurfRec *rr, double px, doubl
     return acc + part;
 }
 
+// the same for a run-time number of records (the partly filled last sub-tile of a CTA of k_mh_small)
+template <int NIC>
+__device__ __forceinline__ double surf_block_n(const SurfRec *rr, int cnt, double px, double py, double acc, const MhPlan &L)
+{
+    double part = 0.0;
+    bool close = false;
+    if (NIC == 1 && L.far) {
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) part = surf_term<NIC, false, true>(rr[k], px, py, part, L, close);
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) part = surf_term<NIC, false>(rr[k], px, py, part, L, close);
+    }
+    if (close) {
+        part = 0.0;
+        for (int k = 0; k < cnt; ++k) part = surf_term<NIC, true>(rr[k], px, py, part, L, close);
+    }
+    return acc + part;
+}
+
 __global__ void k_surf_pack(const double4 *__restrict__ pq, int n, double two_d, int nic, SurfRec *__restrict__ recs)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,15 +289,20 @@ __global__ void k_surf_pack(const double4 *__restrict__ pq, int n, double two_d,
 __device__ __forceinline__ void draw_jump_normals(const MhPlan &L, int iter, int k, double &g0, double &g1)
 {
     g0 = 0.0; g1 = 0.0;
-    for (int attempt = 0; attempt < 64; ++attempt) {  // Marsaglia polar method, src/mod_global.F90:578-595
+    // Marsaglia polar method, src/mod_global.F90:578-595.  The lanes of a warp leave the rejection loop at different
+    // attempts (78 % per attempt: ~3 rounds until all 32 are through), so only the cheap part is inside it; the
+    // log / divide / sqrt of the accepted point runs once, behind the loop (same values: same operations).
+    double a = 0.0, b = 0.0, w = 0.0;
+    bool found = false;
+    for (int attempt = 0; attempt < 64 && !found; ++attempt) {
         double u, v;
         rand2(L.seed, k, iter, 1, attempt, u, v);
-        const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
-        if (w < 1.0 && w > 0.0) {
-            const double f = sqrt((-2.0 * log(w)) / w);
-            g0 = a * f; g1 = b * f;
-            break;
-        }
+        a = 2.0 * u - 1.0; b = 2.0 * v - 1.0; w = a * a + b * b;
+        found = (w < 1.0 && w > 0.0);
+    }
+    if (found) {
+        const double f = sqrt((-2.0 * log(w)) / w);
+        g0 = a * f; g1 = b * f;
     }
 }
 __device__ __forceinline__ void propose_apply(const MhParams &P, int iter, double mh_std, double g0, double g1, double &x, double &y);
@@ -583,7 +608,7 @@ __global__ void __launch_bounds__(MHB, 4) k_mh_persistent(MhParams P, MhState S,
 //     parity (a CTA can only be one barrier ahead of the slowest one).
 // Proposals, targets and the generator keys are those of k_mh_persistent (propose_from, target_log, rand2).
 struct MhSmall {
-    int T, Gs, G, S, R;     // tiles, CTAs per tile, CTAs = T * Gs, 128-record sub-tiles in total, most sub-tiles per CTA
+    int T, Gs, G, S, R, U;  // tiles, CTAs per tile, CTAs = T * Gs, 128-record sub-tiles in total, most sub-tiles per CTA, 16-record units in total
     double *partial;        // [2][G][32]
     unsigned *bar;          // arrival counter, zeroed by the host
 };
@@ -603,11 +628,14 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
     __shared__ int s_acc[WPB], s_rej[WPB], s_bad[WPB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t_b = blockIdx.x / Q.Gs, g_b = blockIdx.x - t_b * Q.Gs;
-    const int s0 = (int)((long long)Q.S * g_b / Q.Gs), s1 = (int)((long long)Q.S * (g_b + 1) / Q.Gs);
-    for (int q = tid; q < (s1 - s0) * MHB; q += NT) {
-        const int j = s0 * MHB + q;
+    // this CTA's records: an even share in units of 16 records (whole 128-record sub-tiles left 6 sub-tiles to some CTAs
+    // and 5 to others at the deck's size, and every jump waited for the long ones: 7.2 vs 6.0 us of field sums)
+    const int u0 = (int)((long long)Q.U * g_b / Q.Gs), u1 = (int)((long long)Q.U * (g_b + 1) / Q.Gs);
+    const int cnt = (u1 - u0) * 16, nfull = cnt / MHB, rem = cnt - nfull * MHB, rem_w = rem / WPB;  // rem: a multiple of 16
+    for (int q = tid; q < (nfull + (rem ? 1 : 0)) * MHB; q += NT) {
+        const int j = u0 * 16 + q;
         SurfRec r;
-        if (j < L.n) r = S.recs[j];
+        if (q < cnt && j < L.n) r = S.recs[j];
         else { r.x = 1.0; r.y = 1.0; r.h0 = 1.0; r.g0 = 0.0; r.h1 = 1.0; r.g1 = 0.0; r.h2 = 1.0; r.g2 = 0.0; }
         mine[q] = r;
     }
@@ -623,6 +651,13 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
     bool searching = true;
     double ahead_g0 = 0.0, ahead_g1 = 0.0;
     int ahead_iter = 0;  // jump whose normals are in ahead_g0 / ahead_g1
+    // -DRB2_MH_TIMING: clock64 per phase, printed by the first and the last CTA (profiles/mh_small_phases_r02.log)
+#ifdef RB2_MH_TIMING
+    long long tk[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+#define RB2_TK(i) do { const long long now_ = clock64(); tk[i] += now_ - tc; tc = now_; } while (0)
+#else
+#define RB2_TK(i) do { } while (0)
+#endif
     for (;;) {
         // rounds of the search for a favourable start (generator iteration -(round + 1), like k_mh_persistent), then the
         // jump iterations 1 .. ndim
@@ -638,23 +673,33 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
         }
         if (warp == t_b) { sp_x[lane] = qx; sp_y[lane] = qy; }
         __syncthreads();
+        RB2_TK(0);  // propose
         const double px = sp_x[lane], py = sp_y[lane];
         double acc = 0.0;
-        for (int t = 0; t < s1 - s0; ++t) {
+        for (int t = 0; t < nfull; ++t) {
             const SurfRec *rr = &mine[t * MHB + warp * RPW];
             acc = surf_block<NIC, RPW>(rr, px, py, acc, L);
         }
+        if (rem_w > 0) acc = surf_block_n<NIC>(&mine[nfull * MHB + warp * rem_w], rem_w, px, py, acc, L);
         red[warp][lane] = acc;
         __syncthreads();
+        RB2_TK(1);  // field sums
         double *part = Q.partial + (size_t)(phase & 1u) * Q.G * 32;
-        if (warp == 0) {
+        // The LAST warp joins the CTA's sums, stores them and arrives at the barrier (release fence + counter): it owns no
+        // tile unless there are 16 of them, so the fence (~1 us until the stores are visible) no longer sits in front of
+        // the look-ahead of the warp that does (clock64 profile: arrive + look-ahead 2.3 us of a 13 us jump, serial in warp 0)
+        if (warp == WPB - 1) {
             double sum = red[0][lane];
 #pragma unroll
             for (int w = 1; w < WPB; ++w) sum += red[w][lane];
             part[(size_t)blockIdx.x * 32 + lane] = sum;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(Q.bar, 1u);
+            }
         }
         ++phase;
-        small_barrier_arrive(Q.bar);
         // while the other CTAs arrive: the normals of the NEXT jump (Philox + log + sqrt, ~1 us of dependent latency that
         // would otherwise open the next iteration)
         // ... and what the accept step needs besides the field sum: the work function at the proposal, log(u) of the test
@@ -668,7 +713,9 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
             }
         }
         if (live && !searching && jump < P.c.ndim) { ahead_iter = jump + 1; draw_jump_normals(L, ahead_iter, chain, ahead_g0, ahead_g1); }
+        RB2_TK(2);  // store, arrive, look-ahead
         small_barrier_wait(Q.bar, phase * (unsigned)Q.G);
+        RB2_TK(3);  // wait
         // join: for every tile, warp w adds the partial sums of that tile's CTAs w, w + WPB, ... (ascending); the WPB
         // strands are added in warp order by the warp that owns the tile.  The loads of four tiles are issued together:
         // tile after tile, each join paid its own L2 round trip.
@@ -689,6 +736,7 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
             }
         }
         __syncthreads();
+        RB2_TK(4);  // join loads
         bool acc_ = false, rej_ = false, bad_ = false;
         if (warp < Q.T) {
             const double *sw = strands + (size_t)warp * WPB * 32 + lane;
@@ -728,7 +776,13 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_small(MhParams P, MhState S, Mh
             }
             if (searching) { bad = nb; ++round; } else ++jump;
         }
+        RB2_TK(5);  // accept + bookkeeping
     }
+#ifdef RB2_MH_TIMING
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+        printf("k_mh_small cta %d (tile %d, %d records): clocks propose %lld field %lld arrive+ahead %lld wait %lld join %lld accept %lld\n",
+               (int)blockIdx.x, t_b, cnt, tk[0], tk[1], tk[2], tk[3], tk[4], tk[5]);
+#endif
     if (blockIdx.x == 0) {
         if (live) {
             const int k = chain;
@@ -1167,15 +1221,18 @@ struct TipSmall {
 __device__ __forceinline__ void tip_normals(unsigned long long seed, int iter, int k, double &g0, double &g1)
 {
     g0 = 0.0; g1 = 0.0;
-    for (int attempt = 0; attempt < 64; ++attempt) {  // box_muller = Marsaglia polar, src/mod_global.F90:578-595
+    // box_muller = Marsaglia polar, src/mod_global.F90:578-595; the tail behind the rejection loop (draw_jump_normals)
+    double a = 0.0, b = 0.0, w = 0.0;
+    bool found = false;
+    for (int attempt = 0; attempt < 64 && !found; ++attempt) {
         double u, v;
         rand2(seed, k, iter, 1, attempt, u, v);
-        const double a = 2.0 * u - 1.0, b = 2.0 * v - 1.0, w = a * a + b * b;
-        if (w < 1.0 && w > 0.0) {
-            const double f = sqrt((-2.0 * log(w)) / w);
-            g0 = a * f; g1 = b * f;
-            break;
-        }
+        a = 2.0 * u - 1.0; b = 2.0 * v - 1.0; w = a * a + b * b;
+        found = (w < 1.0 && w > 0.0);
+    }
+    if (found) {
+        const double f = sqrt((-2.0 * log(w)) / w);
+        g0 = a * f; g1 = b * f;
     }
 }
 
@@ -1262,14 +1319,22 @@ __global__ void __launch_bounds__(WPB * 32) k_mh_tip_small(MhParams P, TipMh T, 
         red[warp][0][lane] = ax; red[warp][1][lane] = ay; red[warp][2][lane] = az;
         __syncthreads();
         double *part = Q.partial + (size_t)(phase & 1u) * Q.G * 96;
-        if (warp < 3) {
-            double sum = red[0][warp][lane];
+        // the last warp (tile-free unless there are 16 tiles) joins, stores and arrives: see k_mh_small
+        if (warp == WPB - 1) {
 #pragma unroll
-            for (int w = 1; w < WPB; ++w) sum += red[w][warp][lane];
-            part[((size_t)blockIdx.x * 3 + warp) * 32 + lane] = sum;
+            for (int c = 0; c < 3; ++c) {
+                double sum = red[0][c][lane];
+#pragma unroll
+                for (int w = 1; w < WPB; ++w) sum += red[w][c][lane];
+                part[((size_t)blockIdx.x * 3 + c) * 32 + lane] = sum;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(Q.bar, 1u);
+            }
         }
         ++phase;
-        small_barrier_arrive(Q.bar);
         // while the other CTAs arrive: everything of the accept step that does not need the field sums -- the vacuum
         // field and the surface normal at the proposal, log(u) of the accept test -- and the normals of the NEXT jump
         double fE_x = 0.0, fE_y = 0.0, fE_z = 0.0, nrm[3] = {0.0, 0.0, 1.0}, log_u = 0.0;
@@ -1700,7 +1765,8 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     Q.S = (n + MHB - 1) / MHB;
     Q.Gs = std::max(1, std::min(Q.S, max_ctas / Q.T));
     Q.G = Q.T * Q.Gs;
-    Q.R = std::max(1, (Q.S + Q.Gs - 1) / Q.Gs);
+    Q.U = std::max(1, (n + 15) / 16);
+    Q.R = std::max(1, (((Q.U + Q.Gs - 1) / Q.Gs) * 16 + MHB - 1) / MHB);  // sub-tiles of shared memory for the largest share
     {   // the records of a CTA stay in shared memory: as many 8 KB sub-tiles as fit next to the join strands (one CTA of
         // 16 warps per SM: ~216 KB; two CTAs of 4 warps: ~105 KB each).  Round 2 first capped this at 6 resp. 4 sub-tiles;
         // the Ion deck (20 k particles, 12 per CTA) then fell to the many-chain kernel at 21.8 us per jump.
