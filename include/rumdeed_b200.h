@@ -220,6 +220,15 @@ int rb2_set_devices(int n_devices, const int *devices);
  * (1 / 0: single-barrier kernel for few chains), "mh_small_max" (its chain limit, <= 512), "mh_ctas_per_sm" (1..4,
  * many-chain kernel), "tip_field_small" (1 / 0: CTA-per-point tip field kernel for small batches). */
 int rb2_set_option(const char *name, double value);
+/* Host-only view of the planning of the pair-symmetric work (no device, no rb2_init needed): for n particles dealt to
+ * `world` ranks, shape_out[6] = {targets per lane T, K superblocks x G source tiles per work unit, source tiles per band,
+ * number of source tiles, number of target superblocks}, rank_cost_out[world] = tile pairs dealt to every rank,
+ * units_out[3 * cap] = (band, set, group) of THIS rank's units in launch order (n_units_out of them),
+ * table_hash_out = hash of the owner table every rank must agree on.  tpl 0 = auto; sm_count, waves, kmax, gmax,
+ * budget_mb as the options of the same names (148, 64, 12, 24, 2048 by default).  Used by the multi-process CPU tests. */
+int rb2_sym_plan_probe(int n, int tpl, int world, int rank, int sm_count, double waves, int kmax, int gmax, double budget_mb,
+                       int *shape_out, long long *rank_cost_out, int *units_out, int cap, int *n_units_out,
+                       unsigned long long *table_hash_out);
 /* Device pointer + byte size of the (3,capacity) acceleration buffer so that the
  * host plumbing (torch.distributed / NCCL) can all-gather the slices in place. */
 int rb2_device_buffer(const char *name, void **dev_ptr, size_t *bytes);

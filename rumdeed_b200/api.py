@@ -133,7 +133,7 @@ EXPORTS = (
     "rb2_upload_particles", "rb2_download_particles", "rb2_get_counts",
     "rb2_add_particles", "rb2_capacity_left", "rb2_mark_remove", "rb2_remove_marked", "rb2_get_life_time",
     "rb2_step", "rb2_update_position", "rb2_accel_only", "rb2_update_velocity", "rb2_get_events", "rb2_get_ramo_sections", "rb2_accel_host",
-    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip", "rb2_tip_supply_set_grid", "rb2_tip_supply", "rb2_planar_supply_level",
+    "rb2_field_batch", "rb2_field_batch_delta", "rb2_field_window_open", "rb2_field_window_close", "rb2_field_surface_z", "rb2_mh_planar", "rb2_mh_planar_serial", "rb2_mh_tip", "rb2_tip_supply_set_grid", "rb2_tip_supply", "rb2_planar_supply_level", "rb2_sym_plan_probe",
     "rb2_set_partition", "rb2_set_pair_rank", "rb2_accel_partial", "rb2_accel_finalize", "rb2_set_option", "rb2_device_buffer", "rb2_synchronize", "rb2_stream",
     "rb2_p2p_export", "rb2_p2p_attach", "rb2_p2p_detach", "rb2_set_devices", "rb2_nearest_electron",
     "rb2_collisions_init", "rb2_collision_data", "rb2_continuous_ionization", "rb2_discrete_recombination",
@@ -180,6 +180,9 @@ def load_library(path: str | None = None):
     lib.rb2_mh_planar.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
     lib.rb2_mh_planar_serial.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PI, _PD, _PD]
     lib.rb2_mh_tip.argtypes = [C.c_int, C.c_int, C.c_ulonglong, _PD, _PD, _PD, _PD, _PD]
+    lib.rb2_sym_plan_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                                       C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_ulonglong)]
     lib.rb2_tip_supply_set_grid.argtypes = [C.c_int, _PD, _PD, _PD]
     lib.rb2_tip_supply.argtypes = [_PD, _PD]
     lib.rb2_planar_supply_level.argtypes = [C.POINTER(MhConfig), _PD, C.c_int, C.c_int, _PD, C.c_int, C.c_int, _PD, _PD]
@@ -687,6 +690,28 @@ class HotPath:
         gx, gy, bl, js = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self._check(self.lib.rb2_last_accel_info(C.byref(ms), C.byref(gx), C.byref(gy), C.byref(bl), C.byref(js)))
         return dict(ms=ms.value, grid_x=gx.value, grid_y=gy.value, block=bl.value, j_chunk=js.value)
+
+
+def sym_plan_probe(n, world=1, rank=0, tpl=0, sm_count=148, waves=64.0, kmax=12, gmax=24, budget_mb=2048.0):
+    """Host-only planning of the pair-symmetric work (rb2_sym_plan_probe; needs no GPU): returns a dict with the unit shape
+    (T, K, G, band width, tiles, superblocks), the cost dealt to every rank, this rank's units (band, set, group) in launch
+    order and the hash of the owner table."""
+    lib = load_library()
+    shape = (C.c_int * 6)()
+    cost = (C.c_longlong * world)()
+    n_units = C.c_int(0)
+    h = C.c_ulonglong(0)
+    rc = lib.rb2_sym_plan_probe(n, tpl, world, rank, sm_count, waves, kmax, gmax, budget_mb, shape, cost, None, 0, C.byref(n_units), C.byref(h))
+    if rc:
+        raise Rb2Error(f"rb2 error {rc}: {lib.rb2_last_error_string().decode()}")
+    cap = max(1, n_units.value)
+    units = (C.c_int * (3 * cap))()
+    rc = lib.rb2_sym_plan_probe(n, tpl, world, rank, sm_count, waves, kmax, gmax, budget_mb, shape, cost, units, cap, C.byref(n_units), C.byref(h))
+    if rc:
+        raise Rb2Error(f"rb2 error {rc}: {lib.rb2_last_error_string().decode()}")
+    T, K, G, Wb, nsb, nIb = list(shape)
+    return dict(T=T, K=K, G=G, Wb=Wb, nsb=nsb, nIb=nIb, rank_cost=list(cost), table_hash=h.value,
+                units=np.array(list(units), dtype=np.int64).reshape(-1, 3)[: n_units.value])
 
 
 def device_available() -> bool:

@@ -400,6 +400,96 @@ int ensure_bytes(double **p, size_t *have, size_t want, size_t limit = 0)
 }  // namespace
 
 // Partial raw sums of this rank (rank 0 of 1: everything) into ctx.sym_raw[3][n_pad].
+// K x G of the work units (see rb2_launch_accel_sym_partial): host arithmetic only, shared with rb2_sym_plan_probe.
+static void sym_unit_shape(int nsb, int nIb, int T, int world, int sm_count, double waves, int kmax, int gmax, int &K_out, int &G_out)
+{
+    const int Gmax = (T == 1) ? 12 : 24;   // shared memory: 32 KB static + 3 KB x G, 3 (T = 1) or 2 CTAs per SM
+    // unit size from the whole triangle: about sym_waves waves of units per rank and evaluation (not per band: tying the
+    // unit to the band width shrank the units whenever the budget shrank the bands, which costs more scratch per tile,
+    // which shrinks the bands ...)
+    const double tri = 0.5 * (double)nIb * (double)nsb, slots = (double)sm_count * (4 / T) * world;
+    double KG = tri / (slots * waves);
+    // single-tile units pay ~5 % for their fixed cost (prologue, 6 KB of sums stored per 128T x 128 pairs): when the work
+    // per rank is small, prefer K G = 4 over the full number of waves, down to 16 waves (8 ranks at N = 1e5: the slowest
+    // rank's kernel at 95 % of 1/8 of the undivided one instead of 90 %, profiles/rank_emulation_r02.log)
+    if (KG < 4.0 && waves > 16.0) KG = std::min(4.0, tri / (slots * 16.0));
+    int G = (int)sqrt((double)T * KG);     // traffic per pair ~ T / G + 1 / K: G = T K at the optimum
+    if (G > Gmax) G = Gmax;
+    if (G > gmax) G = gmax;
+    if (G > nsb) G = nsb;
+    if (G < 1) G = 1;
+    int K = (int)(KG / G);
+    if (K > kmax) K = kmax;
+    if (K < 1) K = 1;
+    K_out = K; G_out = G;
+}
+
+// Source tiles per band: everything when it fits the budget, else whole groups of G tiles.
+static int sym_band_width(int nsb, double tile_bytes, int G, size_t budget)
+{
+    int Wb = nsb;
+    if (tile_bytes * nsb > (double)budget) {
+        Wb = (int)((double)budget / tile_bytes);
+        Wb = std::max(G, (Wb / G) * G);  // whole groups per band
+        if (Wb > nsb) Wb = nsb;
+    }
+    return Wb;
+}
+
+// The deal of the work units of every band to the ranks: by cost (tile pairs in the unit; the triangle clips the ones
+// near the diagonal), largest first to the least loaded rank, ties in group-major order.  tab: owner of unit (set, group)
+// per band (world > 1 only), mine: this rank's units in the order they were dealt.  Pure host arithmetic: every rank
+// computes the same table (tests/test_partition_gloo.py checks that through rb2_sym_plan_probe).
+static void sym_deal_units(int nsb, int nIb, int T, int K, int G, int Wb, int world, int rank, std::vector<unsigned char> &tab,
+                           std::vector<int2> &mine, std::vector<size_t> &unit_off, std::vector<int> &unit_cnt,
+                           std::vector<long long> *rank_cost)
+{
+    std::vector<size_t> owner_off;
+    size_t total = 0;
+    for (int b0 = 0; b0 < nsb; b0 += Wb) {
+        const int blen = (b0 + Wb <= nsb) ? Wb : (nsb - b0);
+        const int nI = (b0 + blen - 1) / T + 1;
+        owner_off.push_back(total);
+        total += (size_t)((nI + K - 1) / K) * ((blen + G - 1) / G);
+    }
+    tab.assign(world > 1 ? total : 0, 0);
+    mine.clear(); unit_off.clear(); unit_cnt.clear();
+    if (rank_cost) rank_cost->assign((size_t)world, 0);
+    constexpr bool order_gr_major = true;  // ties in group-major order: neighbouring CTAs share their source tiles (0.4 % at 8 ranks)
+    std::vector<std::pair<long long, int>> units;  // (-cost, index): ascending sort = largest first, index order on ties
+    size_t bi = 0;
+    for (int b0 = 0; b0 < nsb; b0 += Wb, ++bi) {
+        const int blen = (b0 + Wb <= nsb) ? Wb : (nsb - b0);
+        const int nI = (b0 + blen - 1) / T + 1, nsets = (nI + K - 1) / K, ngr = (blen + G - 1) / G;
+        units.clear();
+        for (int is = 0; is < nsets; ++is)
+            for (int gr = 0; gr < ngr; ++gr) {
+                const int J0 = b0 + gr * G, J1 = std::min(J0 + G, std::min(b0 + blen, nsb));
+                long long cost = 0;
+                for (int I = is * K; I < std::min(is * K + K, nIb); ++I) {
+                    const int Jb = std::max(J0, T * I);
+                    if (Jb >= J1) break;
+                    cost += (long long)T * (J1 - Jb);          // T sub-sets x tiles ...
+                    for (int J = Jb; J < std::min(J1, T * I + T); ++J) cost -= (T - 1 - (J - T * I));  // ... less what the diagonal clips
+                }
+                if (cost > 0) units.emplace_back(-cost, order_gr_major ? gr * nsets + is : is * ngr + gr);
+            }
+        std::sort(units.begin(), units.end());
+        std::vector<long long> load((size_t)world, 0);
+        unit_off.push_back(mine.size());
+        for (const auto &u : units) {
+            int best = 0;
+            for (int r = 1; r < world; ++r) if (load[(size_t)r] < load[(size_t)best]) best = r;
+            load[(size_t)best] += -u.first;
+            const int is = order_gr_major ? u.second % nsets : u.second / ngr, gr = order_gr_major ? u.second / nsets : u.second % ngr;
+            if (world > 1) tab[owner_off[bi] + (size_t)is * ngr + gr] = (unsigned char)best;
+            if (best == rank) mine.push_back(make_int2(is, gr));
+        }
+        unit_cnt.push_back((int)(mine.size() - unit_off.back()));
+        if (rank_cost) for (int r = 0; r < world; ++r) (*rank_cost)[(size_t)r] += load[(size_t)r];
+    }
+}
+
 int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
 {
     if (n < 1) return RB2_OK;
@@ -425,24 +515,8 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
     // the same table, cached until the geometry changes.  (Round 1 dealt them round-robin, (I + grp) % world, and needed
     // world^2 times more, i.e. smaller, units to balance: at N = 1e5 on 8 GPUs single-tile CTAs whose fixed cost was 10 %.)
     // The source tiles are processed in bands that fit the scratch budget (default 2 GiB).
-    const int Gmax = (T == 1) ? 12 : 24;   // shared memory: 32 KB static + 3 KB x G, 3 (T = 1) or 2 CTAs per SM
-    // unit size from the whole triangle: about sym_waves waves of units per rank and evaluation (not per band: tying the
-    // unit to the band width shrank the units whenever the budget shrank the bands, which costs more scratch per tile,
-    // which shrinks the bands ...)
-    const double tri = 0.5 * (double)g.nIb * (double)g.nsb, slots = (double)ctx.sm_count * (4 / T) * g.world;
-    double KG = tri / (slots * ctx.sym_waves);
-    // single-tile units pay ~5 % for their fixed cost (prologue, 6 KB of sums stored per 128T x 128 pairs): when the work
-    // per rank is small, prefer K G = 4 over the full number of waves, down to 16 waves (8 ranks at N = 1e5: the slowest
-    // rank's kernel at 95 % of 1/8 of the undivided one instead of 90 %, profiles/rank_emulation_r02.log)
-    if (KG < 4.0 && ctx.sym_waves > 16.0) KG = std::min(4.0, tri / (slots * 16.0));
-    int G = (int)sqrt((double)T * KG);     // traffic per pair ~ T / G + 1 / K: G = T K at the optimum
-    if (G > Gmax) G = Gmax;
-    if (G > ctx.sym_gmax) G = ctx.sym_gmax;
-    if (G > g.nsb) G = g.nsb;
-    if (G < 1) G = 1;
-    int K = (int)(KG / G);
-    if (K > ctx.sym_kmax) K = ctx.sym_kmax;
-    if (K < 1) K = 1;
+    int K = 1, G = 1;
+    sym_unit_shape(g.nsb, g.nIb, T, g.world, ctx.sm_count, ctx.sym_waves, ctx.sym_kmax, ctx.sym_gmax, K, G);
     // band width from the scratch budget.  The layout is not compacted by owner: over `world` ranks every rank fills
     // 1 / world of the slots it allocates, so the budget (2 GiB of partial sums a rank actually writes) scales with it.
     size_t budget = ctx.sym_budget_bytes * (size_t)g.world;
@@ -457,12 +531,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
             if (budget > cap) budget = cap;
         }
     }
-    int Wb = g.nsb;
-    if (tile_bytes * g.nsb > (double)budget) {
-        Wb = (int)((double)budget / tile_bytes);
-        Wb = std::max(G, (Wb / G) * G);  // whole groups per band
-        if (Wb > g.nsb) Wb = g.nsb;
-    }
+    const int Wb = sym_band_width(g.nsb, tile_bytes, G, budget);
     g.K = K;
     g.nIsets = (g.nIb + K - 1) / K;
     const int ngroups_max = (Wb + G - 1) / G;
@@ -502,41 +571,9 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         if (memcmp(key, ctx.sym_owner_key, sizeof(key)) != 0 || !ctx.sym_units) {
             if (ctx.capturing) return rb2_fail(RB2_ERR_CUDA, "pair-symmetric work units changed inside a graph capture");
             const auto t_plan0 = std::chrono::steady_clock::now();
-            std::vector<unsigned char> tab(g.world > 1 ? total : 0, 0);
+            std::vector<unsigned char> tab;
             std::vector<int2> mine;
-            ctx.sym_unit_off.clear(); ctx.sym_unit_cnt.clear();
-            constexpr bool order_gr_major = true;  // ties in group-major order: neighbouring CTAs share their source tiles (0.4 % at 8 ranks)
-            std::vector<std::pair<long long, int>> units;  // (-cost, index): ascending sort = largest first, index order on ties
-            size_t bi = 0;
-            for (int b0 = 0; b0 < g.nsb; b0 += Wb, ++bi) {
-                const int blen = (b0 + Wb <= g.nsb) ? Wb : (g.nsb - b0);
-                const int nI = (b0 + blen - 1) / T + 1, nsets = (nI + K - 1) / K, ngr = (blen + G - 1) / G;
-                units.clear();
-                for (int is = 0; is < nsets; ++is)
-                    for (int gr = 0; gr < ngr; ++gr) {
-                        const int J0 = b0 + gr * G, J1 = std::min(J0 + G, std::min(b0 + blen, g.nsb));
-                        long long cost = 0;
-                        for (int I = is * K; I < std::min(is * K + K, g.nIb); ++I) {
-                            const int Jb = std::max(J0, T * I);
-                            if (Jb >= J1) break;
-                            cost += (long long)T * (J1 - Jb);          // T sub-sets x tiles ...
-                            for (int J = Jb; J < std::min(J1, T * I + T); ++J) cost -= (T - 1 - (J - T * I));  // ... less what the diagonal clips
-                        }
-                        if (cost > 0) units.emplace_back(-cost, order_gr_major ? gr * nsets + is : is * ngr + gr);
-                    }
-                std::sort(units.begin(), units.end());
-                std::vector<long long> load((size_t)g.world, 0);
-                ctx.sym_unit_off.push_back(mine.size());
-                for (const auto &u : units) {
-                    int best = 0;
-                    for (int r = 1; r < g.world; ++r) if (load[(size_t)r] < load[(size_t)best]) best = r;
-                    load[(size_t)best] += -u.first;
-                    const int is = order_gr_major ? u.second % nsets : u.second / ngr, gr = order_gr_major ? u.second / nsets : u.second % ngr;
-                    if (g.world > 1) tab[owner_off[bi] + (size_t)is * ngr + gr] = (unsigned char)best;
-                    if (best == g.rank) mine.push_back(make_int2(is, gr));
-                }
-                ctx.sym_unit_cnt.push_back((int)(mine.size() - ctx.sym_unit_off.back()));
-            }
+            sym_deal_units(g.nsb, g.nIb, T, K, G, Wb, g.world, g.rank, tab, mine, ctx.sym_unit_off, ctx.sym_unit_cnt, nullptr);
             if (g.world > 1 && total > ctx.sym_owner_cap) {
                 if (ctx.sym_owner) RB2_CUDA(cudaFree(ctx.sym_owner));
                 ctx.sym_owner = nullptr; ctx.sym_owner_cap = 0;
@@ -608,5 +645,48 @@ int rb2_launch_accel_sym_finalize(Rb2Ctx &ctx, const double4 *pq, const double *
     RB2_CUDA(cudaGetLastError());
     RB2_LAUNCHED(1);
     RB2_CUDA(rb2_event_record(ctx, ctx.ev_a1));
+    return RB2_OK;
+}
+
+
+// Host-only view of the planning above (no device needed, no context): the unit shape, the band width and THIS rank's
+// work units for a system of n particles dealt to `world` ranks.  The multi-process tests run it on every rank and check
+// that the lists are disjoint, cover the triangle and balance the cost (tests/test_partition_gloo.py).
+extern "C" int rb2_sym_plan_probe(int n, int tpl, int world, int rank, int sm_count, double waves, int kmax, int gmax, double budget_mb,
+                                  int *shape_out, long long *rank_cost_out, int *units_out, int cap, int *n_units_out,
+                                  unsigned long long *table_hash_out)
+{
+    if (n < 1 || world < 1 || world > 255 || rank < 0 || rank >= world || sm_count < 1 || waves < 1.0 || kmax < 1 || gmax < 1 || budget_mb <= 0.0)
+        return rb2_fail(RB2_ERR_ARG, "rb2_sym_plan_probe: bad argument");
+    const int T = tpl == 1 ? 1 : (tpl == 2 ? 2 : (n >= 25000 ? 2 : 1));
+    const int nsb = (n + SB - 1) / SB, nIb = (nsb + T - 1) / T, n_pad = nIb * T * SB;
+    int K = 1, G = 1;
+    sym_unit_shape(nsb, nIb, T, world, sm_count, waves, kmax, gmax, K, G);
+    const size_t budget = (size_t)(budget_mb * 1048576.0) * (size_t)world;
+    const size_t nsets = (size_t)(nIb + K - 1) / K;
+    const double tile_bytes = (double)nsets * 3 * SB * sizeof(double) + 3.0 * n_pad * sizeof(double) / G;
+    const int Wb = sym_band_width(nsb, tile_bytes, G, budget);
+    std::vector<unsigned char> tab;
+    std::vector<int2> mine;
+    std::vector<size_t> unit_off;
+    std::vector<int> unit_cnt;
+    std::vector<long long> cost;
+    sym_deal_units(nsb, nIb, T, K, G, Wb, world, rank, tab, mine, unit_off, unit_cnt, &cost);
+    if (shape_out) { shape_out[0] = T; shape_out[1] = K; shape_out[2] = G; shape_out[3] = Wb; shape_out[4] = nsb; shape_out[5] = nIb; }
+    if (rank_cost_out) for (int r = 0; r < world; ++r) rank_cost_out[r] = cost[(size_t)r];
+    if (n_units_out) *n_units_out = (int)mine.size();
+    if (units_out) {
+        size_t k = 0;
+        for (size_t b = 0; b < unit_off.size(); ++b)
+            for (int u = 0; u < unit_cnt[b] && (int)k < cap; ++u, ++k) {
+                const int2 v = mine[unit_off[b] + (size_t)u];
+                units_out[3 * k] = (int)b; units_out[3 * k + 1] = v.x; units_out[3 * k + 2] = v.y;
+            }
+    }
+    if (table_hash_out) {
+        unsigned long long h = 1469598103934665603ull;
+        for (unsigned char c : tab) { h ^= c; h *= 1099511628211ull; }
+        *table_hash_out = h;
+    }
     return RB2_OK;
 }
