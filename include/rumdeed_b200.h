@@ -212,7 +212,8 @@ int rb2_p2p_detach(void);
 int rb2_set_devices(int n_devices, const int *devices);
 /* Tunables: "pair_mode" 0 auto / 1 gather / 2 pair-symmetric, "sym_min_n", "sym_budget_mb", "sym_waves", "sym_kmax", "sym_gmax",
  * "sym_far" (1 / 0: with d >= 1 um the acceleration kernels evaluate the three image partners that are at least d away
- * without the softening term, a change of <= 3e-12 of those terms; 1 by default),
+ * without the softening term, a change of <= 3e-12 of those terms; 1 by default; it switches itself off while a particle
+ * handed in by the caller lies outside 0 <= z <= d),
  * "sym_tpl" (targets per lane of the pair-symmetric kernel: 0 auto, 1, 2), "step_graph" (1 / 0: replay rb2_step as a CUDA graph while
  * consecutive steps queue identical work), "ramo_sections" / "ramo_emitters" (size
  * of the per-section Ramo table, 0 sections = off), "event_buffer" (initial number of

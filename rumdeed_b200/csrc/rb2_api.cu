@@ -53,7 +53,8 @@ StepParams rb2_make_step_params(const rb2_config &c)
     P.pl.E_z = c.E_z;
     P.pl.nic = c.N_ic_max;
     P.pl.do_ic = c.image_charge;
-    P.pl.far_ok = (c.d >= 1.0e-6) ? 1 : 0;
+    // far image partners without the softening term: gap of at least 1 um, and no charged particle survives outside it
+    P.pl.far_ok = (c.d >= 1.0e-6 && c.box_dim[2] <= c.d * (1.0 + 1.0e-9)) ? 1 : 0;
     P.tip.a_foci = c.a_foci;
     P.tip.shift_z = c.shift_z;
     P.tip.pre_fac_E_tip = c.pre_fac_E_tip;
@@ -468,9 +469,11 @@ static int upload_particles_one(int n, const double *pos, const double *prev_pos
     if (n > 0 && (!pos || !charge || !mass)) return rb2_fail(RB2_ERR_ARG, "pos, charge and mass are required");
     const size_t b3 = (size_t)n * 3 * sizeof(double), b1 = (size_t)n * sizeof(double), bi = (size_t)n * sizeof(int);
     cudaStream_t st = c.stream;
+    c.far_state_ok = true;
     if (n > 0) {
         // pos + charge travel through the spare set and are packed into pq on the device
         RB2_CUDA(cudaMemcpyAsync(c.b.prev_pos, pos, b3, cudaMemcpyHostToDevice, st));
+        if (c.cfg.geometry == RB2_GEOM_PLANAR) c.far_state_ok = rb2_all_between_plates(pos, n, c.cfg.d);  // (while the copy runs)
         RB2_CUDA(cudaMemcpyAsync(c.b.mass, charge, b1, cudaMemcpyHostToDevice, st));
         int rc = rb2_launch_pack(c, c.b.prev_pos, c.b.mass, n, c.a.pq);
         if (rc) return rc;
@@ -593,6 +596,7 @@ static int add_particles_one(int k, const double *pos, const double *vel, const 
         tmp[2 * kk + t] = life ? life[t] : -1;
     }
     cudaStream_t st = c.stream;
+    if (c.cfg.geometry == RB2_GEOM_PLANAR && c.far_state_ok) c.far_state_ok = rb2_all_between_plates(pos, kk, c.cfg.d);
     double *d_pos = c.d_stage_d, *d_vel = c.d_stage_d + (size_t)3 * kk;
     int *d_sp = c.d_stage_i, *d_emit = d_sp + kk, *d_sec = d_sp + 2 * kk, *d_life = d_sp + 3 * kk;
     RB2_CUDA(cudaMemcpyAsync(d_pos, pos, (size_t)3 * kk * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -785,7 +789,7 @@ static unsigned long long step_key(const Rb2Ctx &c)
     k.n = c.n; k.cap = c.cap; k.pair_mode = c.pair_mode; k.sym_min_n = c.sym_min_n; k.pair_rank = c.pair_rank; k.pair_world = c.pair_world;
     k.sym_tpl = c.sym_tpl; k.ramo_n_sec = c.ramo_n_sec; k.ramo_n_emit = c.ramo_n_emit; k.ramo_blocks = c.ramo_blocks; k.ev_cap = c.ev_cap;
     k.redpart_blocks = c.redpart_blocks; k.part_begin = c.part_begin; k.part_end = c.part_end; k.sm_count = c.sm_count;
-    k.pad = (c.sym_kmax * 64 + c.sym_gmax) * 2 + c.sym_far;
+    k.pad = (c.sym_kmax * 64 + c.sym_gmax) * 2 + (rb2_far_allowed(c) ? 1 : 0);
     k.sym_waves = c.sym_waves; k.sym_budget = c.sym_budget_bytes; k.partial_bytes = c.partial_bytes;
     k.bufI_bytes = c.sym_bufI_bytes; k.bufJ_bytes = c.sym_bufJ_bytes; k.raw_bytes = c.sym_raw_bytes;
     const void *ptrs[] = {c.a.pq, c.a.prev_pos, c.a.vel, c.a.acc, c.a.acc_prev, c.a.acc_prev2, c.a.mass, c.a.species, c.a.step, c.a.emitter,
@@ -934,6 +938,7 @@ int rb2_accel_host(int n, const double *pos, const double *charge, const double 
     if (n < 0 || n > g_rb2.cap) return rb2_fail(RB2_ERR_CAPACITY, "n = %d exceeds capacity %d", n, g_rb2.cap);
     if (n == 0) return RB2_OK;
     if (!pos || !charge || !mass || !acc_out) return rb2_fail(RB2_ERR_ARG, "NULL argument");
+    int inside = -1;  // this call's particle set between the plates?  (scanned once, while the first copies run)
     // every device gets the inputs and queues its share of the pair work; the first one returns the accelerations
     const int rc = each_device([&]() -> int {
         Rb2Ctx &c = g_rb2;
@@ -945,11 +950,17 @@ int rb2_accel_host(int n, const double *pos, const double *charge, const double 
         RB2_CUDA(cudaMemcpyAsync(c.b.vel, mass, b1, cudaMemcpyHostToDevice, st));
         int rc1 = rb2_launch_pack(c, c.b.prev_pos, c.b.mass, n, c.b.pq);
         if (rc1) return rc1;
+        if (inside < 0) inside = (c.cfg.geometry != RB2_GEOM_PLANAR || rb2_all_between_plates(pos, n, c.cfg.d)) ? 1 : 0;
+        const bool state_ok = c.far_state_ok;
+        c.far_state_ok = true;  // the resident particles do not take part in this evaluation
+        c.far_call_ok = inside == 1;
         // honours the i-partition: this process evaluates and returns rows [i0, i1) only
         int i0 = c.part_begin < 0 ? 0 : c.part_begin;
         int i1 = (c.part_end < 0 || c.part_end > n) ? n : c.part_end;
         if (i0 > i1) i0 = i1;
         rc1 = launch_accel_any(c, c.b.pq, c.b.vel, n, i0, i1, c.b.acc);
+        c.far_state_ok = state_ok;
+        c.far_call_ok = true;
         if (rc1) return rc1;
         c.accel_timed = (i1 > i0);
         return RB2_OK;

@@ -113,6 +113,11 @@ struct Rb2Ctx {
     size_t sym_budget_bytes = (size_t)2048 << 20;  // scratch for the (set, source tile) / (group, target) partial sums
     int    sym_tpl = 0;                   // targets per lane of the pair-symmetric kernel: 0 auto, 1, 2
     int    sym_far = 1;                   // option "sym_far": allow the cheaper far-partner inverse cube when d >= 1 um
+    // ... which also needs every charged particle between the plates (0 <= z <= d): true for anything the time step
+    // produces (a particle that leaves the gap is marked and loses its charge in the same kernel), checked on the host
+    // for whatever the caller hands in (rb2_upload_particles, rb2_add_particles, rb2_accel_host)
+    bool   far_state_ok = true;           // the resident particles
+    bool   far_call_ok = true;            // the particle set of the rb2_accel_host call in flight
     int    sym_kmax = 12, sym_gmax = 24;  // caps of the work-unit shape (options "sym_kmax", "sym_gmax"; tools/sym_unit_sweep.py)
     double sym_waves = 64.0;              // work units are sized for about this many waves per band launch and rank (tools/run_r2_2gpu_waves.sh)
     double *sym_bufI = nullptr, *sym_bufJ = nullptr, *sym_raw = nullptr;
@@ -198,6 +203,15 @@ inline cudaError_t rb2_event_record(Rb2Ctx &c, cudaEvent_t e)
     return c.capturing ? cudaEventRecordWithFlags(e, c.stream, cudaEventRecordExternal) : cudaEventRecord(e, c.stream);
 }
 int rb2_ensure_stage(Rb2Ctx &ctx, size_t n_doubles, size_t n_ints);
+inline bool rb2_far_allowed(const Rb2Ctx &c) { return c.sym_far && c.far_state_ok && c.far_call_ok; }
+inline bool rb2_all_between_plates(const double *pos3, int n, double d)
+{
+    for (int k = 0; k < n; ++k) {
+        const double z = pos3[3 * (size_t)k + 2];
+        if (!(z >= 0.0 && z <= d)) return false;
+    }
+    return true;
+}
 int rb2_tip_supply_set_grid_impl(Rb2Ctx &ctx, int M, const double *pts, const double *nrm, const double *area);
 int rb2_tip_supply_impl(Rb2Ctx &ctx, double *n_s_out, double *F_sum_out);
 int rb2_planar_supply_level_impl(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *w_theta_host, int kind, int K,

@@ -1006,7 +1006,7 @@ MhPlan make_plan(const Rb2Ctx &ctx, int M, int G_max)
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
     L.nic = gc.N_ic_max;
-    L.far = (rb2_make_step_params(gc).pl.far_ok && ctx.sym_far) ? 1 : 0;
+    L.far = (rb2_make_step_params(gc).pl.far_ok && rb2_far_allowed(ctx)) ? 1 : 0;
     return L;
 }
 
@@ -1780,7 +1780,7 @@ static int launch_mh_small(Rb2Ctx &ctx, const rb2_mh_config *cfg, const double *
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
     L.nic = gc.N_ic_max;
-    L.far = (rb2_make_step_params(gc).pl.far_ok && ctx.sym_far) ? 1 : 0;
+    L.far = (rb2_make_step_params(gc).pl.far_ok && rb2_far_allowed(ctx)) ? 1 : 0;
     L.mh_std0 = *mh_std_io; L.a_rate0 = *a_rate_io;
     // scratch (doubles): 5M outputs + 2 scalars + table + 2 x G x 32 partials + 8n records; (ints): the arrival counter
     size_t off_part = (size_t)5 * M + 2 + nw;
@@ -1851,7 +1851,7 @@ int rb2_launch_mh_planar_serial(Rb2Ctx &ctx, const rb2_mh_config *cfg, const dou
     L.E_vac = rb2_make_step_params(gc).pl.E_z;
     L.fac = (gc.image_charge ? 2.0 : 1.0) * rb2k::div_fac_c;
     L.nic = gc.N_ic_max;
-    L.far = (rb2_make_step_params(gc).pl.far_ok && ctx.sym_far) ? 1 : 0;
+    L.far = (rb2_make_step_params(gc).pl.far_ok && rb2_far_allowed(ctx)) ? 1 : 0;
     MhSerial Q{};
     Q.M = M; Q.n = n;
     Q.mh_std0 = *mh_std_io; Q.a_rate0 = *a_rate_io;

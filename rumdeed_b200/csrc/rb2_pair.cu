@@ -432,7 +432,7 @@ int launch_pair(Rb2Ctx &ctx, const double4 *src, int n_src, const double4 *tgt_p
     }
     const rb2_config &c = ctx.cfg;
     StepParams P = rb2_make_step_params(c);
-    P.pl.far_ok = P.pl.far_ok && ctx.sym_far;  // option "sym_far" (on by default) governs both pair kernels
+    P.pl.far_ok = P.pl.far_ok && rb2_far_allowed(ctx);  // option "sym_far" (on by default), sources between the plates
     dim3 grid(sp.nblk, sp.nsplit), block(BLOCK);
     cudaStream_t st = ctx.stream;
 #define RB2_GO(G, N) k_pair<G, N, FIELD><<<grid, block, 0, st>>>(src, n_src, tgt_pq, tgt_pts, i_begin, i_end, sp.j_chunk, slot0, P.pl, P.tip, partial, src_img)

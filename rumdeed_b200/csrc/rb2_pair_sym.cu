@@ -622,7 +622,7 @@ int rb2_launch_accel_sym_partial(Rb2Ctx &ctx, const double4 *pq, int n)
         if (grid.x == 0) { /* nothing of this band is ours */ }
         else if (!c.image_charge) RB2_GO(-1, false);
         else if (c.N_ic_max == 0) RB2_GO(0, false);
-        else if (c.N_ic_max == 1) { if (SP.pl.far_ok && ctx.sym_far) RB2_GO(1, true); else RB2_GO(1, false); }
+        else if (c.N_ic_max == 1) { if (SP.pl.far_ok && rb2_far_allowed(ctx)) RB2_GO(1, true); else RB2_GO(1, false); }
         else RB2_GO(2, false);
 #undef RB2_GO
         RB2_CUDA(cudaGetLastError());

@@ -242,6 +242,24 @@ def test_far_partner_shortcut_stays_inside_the_bar(orc, d_nm, mode, tpl):
         assert not np.array_equal(res[1], res[0])  # the shortcut is actually taken
     else:
         assert np.array_equal(res[1], res[0])
+    # a charged particle OUTSIDE the plates (only a caller can put it there: the time step strips such a particle of its
+    # charge) brings "far" partners close: the shortcut must switch itself off -- bit-identical with and without the
+    # option, through the resident state and through rb2_accel_host
+    pos2 = pos.copy()
+    pos2[5, 2] = 1.99 * d
+    pos2[6, 2] = -0.3 * d
+    with rb.HotPath(cfg) as hp:
+        hp.set_option("pair_mode", mode)
+        if tpl:
+            hp.set_option("sym_tpl", tpl)
+        out = {}
+        for far in (1, 0):
+            hp.set_option("sym_far", far)
+            hp.upload(pos2, q, m, species=sp)
+            hp.Calculate_Acceleration_Particles()
+            out[far] = (hp.download(("acc",))["acc"], hp.accel_host(pos2, q, m))
+    assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
+    assert relerr(out[1][0], orc.accel_gather_ld(p, pos2, q, m)) < TOL
 
 
 @pytest.mark.parametrize("mode,tpl", [(1, 0), (2, 1), (2, 2)])
